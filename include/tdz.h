@@ -1,0 +1,170 @@
+/* tdz.h - C ABI of libtdz.so, the B200 (sm_100a) implementation of TargetDiarization's
+ * target-speaker separation + scoring stage.
+ *
+ * The reference has no FFI: its seam for this path is two Python callables and one method
+ * (SURVEY.md section 8b).  Each entry point below states which reference call it stands behind; the
+ * Python host code in targetdiarization_b200/ mirrors those callables and reaches this library
+ * through ctypes (INTEGRATION.md shows the binding).
+ *
+ *   AudioProcessor.separater(tensor[1,T]) -> [1,2,T]          AudioProcessor.py:271-273,943
+ *       -> tdz_separate()                                      (look2hear/models/mossformer2.py:563-589)
+ *   look2hear.utils.wav_chunk_inference (overlap-add)          look2hear/utils/separator.py:72-132
+ *       -> tdz_gather_segments() + tdz_separate() + tdz_stitch_ola()
+ *   AudioProcessor.separate_speaker chunk concat               AudioProcessor.py:920-948
+ *       -> tdz_stitch_concat()
+ *   TargetASR.embedding['eres2netv2_large'](wav, output_emb)   TargetASR.py:102-103,155-163
+ *       -> tdz_fbank() + tdz_embed()
+ *   TargetASR.cosine_similarity                                TargetASR.py:144-152
+ *       -> tdz_cosine_scores()
+ *
+ * Conventions: all pointers named *_dev are device pointers owned by the caller (PyTorch allocates);
+ * the library never allocates on the hot path, the caller passes a workspace sized by the matching
+ * *_workspace_bytes().  Every call returns 0 on success or a non-zero code, with text in
+ * tdz_last_error(); there is no CPU fallback.  `stream` is a cudaStream_t passed as void*.
+ * A handle serialises its own calls; different handles may be used from different threads.
+ */
+#ifndef TDZ_H_
+#define TDZ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tdz_ctx tdz_ctx;
+
+#define TDZ_NUM_LAYERS 24
+
+/* Packed weights of one FLASH_ShareA_FFConvM + GatedFSMNBlockDilated pair
+ * (look2hear/models/mossformer_block.py:143-220, 391-425; fsmn.py:76-144).  Norm gains that commute
+ * with the following matmul are folded into it by the packer (targetdiarization_b200/weights.py). */
+typedef struct tdz_layer_weights {
+  const void* w_in;        /* bf16 [2176][512]: to_hidden (2048 rows, ScaleNorm g folded) | to_qk (128 rows) */
+  const float* b_in;       /* [2176] */
+  const float* dw_in;      /* [2176][17] depthwise taps of the two ConvModules */
+  const float* os_gamma;   /* [4][128] OffsetScale */
+  const float* os_beta;    /* [4][128] */
+  const void* w_out;       /* bf16 [512][1024], ScaleNorm g folded */
+  const float* b_out;      /* [512] */
+  const float* dw_out;     /* [512][17] */
+  const float* w_c1;       /* fp32 [256][512] fsmn.conv1 (tf32 operand) */
+  const float* b_c1;       /* [256] */
+  const float* prelu_c1;   /* [1] */
+  const float* ln1_g;      /* [256] norm1 */
+  const float* ln1_b;      /* [256] */
+  const void* w_uv;        /* bf16 [512][256]: to_u | to_v with their LayerNorm affine folded */
+  const float* b_uv;       /* [512] */
+  const float* dw_uv;      /* [512][17] */
+  const void* w_lin;       /* bf16 [256][256] fsmn.linear */
+  const float* b_lin;      /* [256] */
+  const void* w_proj;      /* bf16 [256][256] fsmn.project (no bias) */
+  const float* dd_w1;      /* [256][39] DilatedDenseNet conv1 */
+  const float* in1_g;      /* [256] InstanceNorm affine */
+  const float* in1_b;
+  const float* dd_prelu1;  /* [256] */
+  const float* dd_w2;      /* [256][2][39] conv2 (dilation 2) */
+  const float* in2_g;
+  const float* in2_b;
+  const float* dd_prelu2;
+  const float* w_c2;       /* fp32 [512][256] fsmn.conv2 with norm2 gain folded (tf32 operand) */
+  const float* b_c2;       /* [512] with norm2 bias folded */
+} tdz_layer_weights;
+
+/* Whole MossFormer2 (look2hear/models/mossformer2.py:525-589), default architecture:
+ * 512 channels, 24 blocks, kernel 16 / stride 8, 2 speakers. */
+typedef struct tdz_mossformer2_weights {
+  const float* enc_w;        /* [512][16] enc.conv1d */
+  const float* w_enc1x1;     /* fp32 [512][512] mask_net.conv1d_encoder with GroupNorm gain folded */
+  const float* enc1x1_colsum;/* [512] row sums of the folded matrix (GroupNorm mean term) */
+  const float* enc1x1_bias;  /* [512] W @ beta (GroupNorm bias term) */
+  const float* pos_inv_freq; /* [256] */
+  const float* pos_scale;    /* [1] */
+  const float* rot_freqs;    /* [16] rotary_pos_emb.freqs */
+  tdz_layer_weights layers[TDZ_NUM_LAYERS];
+  const float* fln_g;        /* [512] mdl.intra_mdl.norm (LayerNorm eps 1e-6) */
+  const float* fln_b;
+  const float* fgn_g;        /* [512] mdl.intra_norm (GroupNorm eps 1e-8) */
+  const float* fgn_b;
+  const float* mask_prelu;   /* [1] */
+  const float* w_out1;       /* fp32 [1024][512] conv1d_out */
+  const float* b_out1;       /* [1024] */
+  const float* w_tg;         /* fp32 [1024][512]: output.0 (tanh) rows 0..511 | output_gate.0 rows 512..1023 */
+  const float* b_tg;         /* [1024] */
+  const float* w_dec1;       /* fp32 [512][512] conv1_decoder */
+  const float* dec_w;        /* [512][16] dec (ConvTranspose1d) */
+} tdz_mossformer2_weights;
+
+/* ---- handle ---------------------------------------------------------------------------------- */
+int tdz_create(int device, tdz_ctx** out);
+void tdz_destroy(tdz_ctx* ctx);
+const char* tdz_last_error(tdz_ctx* ctx);
+int tdz_num_sms(tdz_ctx* ctx);
+const char* tdz_version(void);
+
+/* ---- separator ------------------------------------------------------------------------------- */
+/* Stores the pointer table (the tensors stay owned by the caller and must outlive the handle's use). */
+int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_weights* w);
+
+/* Frames produced by the encoder for T samples: floor((T-16)/8)+1 (mossformer2.py:178-185). */
+int64_t tdz_num_frames(int64_t T);
+/* Frames per sample in the padded token space: S rounded up to a multiple of 256 (group size). */
+int64_t tdz_padded_frames(int64_t T);
+size_t tdz_separate_workspace_bytes(int64_t B, int64_t T);
+
+/* MossFormer2.forward on B chunks of T samples each: mix_dev fp32 [B][T] -> out_dev fp32 [B][2][T].
+ * Replaces `self.separater(audio_data_tensor)` (AudioProcessor.py:943). */
+int tdz_separate(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* workspace_dev,
+                 size_t workspace_bytes, void* stream);
+
+/* Test hook: run only the first `num_layers` layer pairs, and of the launch sequence only the steps whose
+ * index lies in [step_lo, step_hi] (step numbering: enum Step in csrc/tdz_api.cu; 0..24).  The tests write
+ * oracle intermediates into the workspace, run one step and compare its outputs.  Offsets (bytes) of the
+ * named intermediates inside the workspace are returned by tdz_separate_layout(). */
+int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* workspace_dev,
+                       size_t workspace_bytes, void* stream, int num_layers, int step_lo, int step_hi);
+
+typedef struct tdz_sep_layout {
+  size_t enc, x0, x, xbf, ss, h, vu, qk4, P, o, o_ss, y, c, nhat, uvpre, xuv, xubf, f1, p, y1, y2, g, kv_part, kv,
+      gn_stats, in_stats, samp, rot, total;
+  int64_t S, Sp, Mtot;
+  int32_t kv_nsplit, kv_kb_per_split;
+} tdz_sep_layout;
+int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_layout* out);
+
+/* ---- chunk stitching ------------------------------------------------------------------------- */
+/* wav_chunk_inference segmenting (separator.py:95-112): seg_dev[i][:] = padded_mix[i*hop : i*hop+session],
+ * zero where outside; padded_mix = zeros(session-hop) | mix | zeros(session-hop).  Segments
+ * [seg_begin, seg_begin+n_seg). */
+int tdz_gather_segments(tdz_ctx* ctx, const float* mix_dev, int64_t L, int64_t session, int64_t hop,
+                        int64_t seg_begin, int64_t n_seg, float* seg_dev, void* stream);
+/* Overlap-add (separator.py:126-130): out[trk][n] = (1/ratio) * sum_i est[i][trk][n + (session-hop) - i*hop]
+ * over the segments covering n, ascending i (fixed order -> bit-reproducible across shardings).
+ * est_dev fp32 [n_seg][2][session] holds segments [seg_begin, seg_begin+n_seg); out_dev fp32 [2][n_out]
+ * receives samples [out_begin, out_begin+n_out) of the stitched streams. */
+int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t session, int64_t hop, int64_t seg_begin,
+                   int64_t n_seg, int64_t L, int64_t out_begin, int64_t n_out, float ratio, float* out_dev,
+                   void* stream);
+/* separate_speaker concat (AudioProcessor.py:947-948): copies est_dev [2][len] of one chunk into
+ * out_dev [2][L] at sample offset `start`. */
+int tdz_stitch_concat(tdz_ctx* ctx, const float* est_dev, int64_t len, int64_t start, int64_t L, float* out_dev,
+                      void* stream);
+
+/* ---- speaker scoring ------------------------------------------------------------------------- */
+/* Kaldi fbank (80 mel bins, 25 ms / 10 ms, povey window, pre-emphasis 0.97, DC removal, power, log,
+ * snip_edges) + per-utterance mean normalisation, as the modelscope ERes2NetV2 pipeline computes it
+ * (torchaudio/compliance/kaldi.py:514-646).  wav_dev fp32 [N][T] -> feat_dev fp32 [N][frames][80],
+ * frames = 1 + (T-400)/160. */
+int64_t tdz_fbank_frames(int64_t T);
+int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t T, float* feat_dev, void* stream);
+
+/* cosine similarity of N embeddings against one target, TargetASR.cosine_similarity semantics
+ * (all-zero vector -> 1.0; result clamped to [0,1]).  emb_dev [N][dim], target_dev [dim] -> scores_dev [N]. */
+int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float* target_dev, int64_t N, int64_t dim,
+                      float* scores_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDZ_H_ */

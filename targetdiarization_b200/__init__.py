@@ -1,0 +1,11 @@
+"""tdz: B200-native (sm_100a) target-speaker separation + scoring stage of TargetDiarization.
+
+Drop-in pieces:
+  Separator         <-> AudioProcessor.separater                       (AudioProcessor.py:268-274, 943)
+  separate_speaker  <-> AudioProcessor.separate_speaker                (AudioProcessor.py:885-956)
+  wav_chunk_inference <-> look2hear.utils.wav_chunk_inference          (look2hear/utils/separator.py:72-132)
+  Embedder          <-> TargetASR.embedding['eres2netv2_large']        (TargetASR.py:102-103, 155-163)
+  cosine_similarity / pick_target <-> TargetASR.cosine_similarity, :612-625
+"""
+from ._lib import Handle, load  # noqa: F401
+from .separator import Separator  # noqa: F401

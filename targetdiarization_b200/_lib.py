@@ -1,0 +1,112 @@
+"""ctypes binding of libtdz.so (include/tdz.h).  The product path has no fallback: if the CUDA library is
+missing or cannot be loaded this module raises, it never routes to a CPU implementation."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtdz.so")
+
+NUM_LAYERS = 24
+c_f32p = ctypes.c_void_p  # device pointers travel as integers
+
+
+class LayerWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "w_in", "b_in", "dw_in", "os_gamma", "os_beta", "w_out", "b_out", "dw_out", "w_c1", "b_c1", "prelu_c1",
+        "ln1_g", "ln1_b", "w_uv", "b_uv", "dw_uv", "w_lin", "b_lin", "w_proj", "dd_w1", "in1_g", "in1_b",
+        "dd_prelu1", "dd_w2", "in2_g", "in2_b", "dd_prelu2", "w_c2", "b_c2")]
+
+
+class MossFormer2Weights(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in (
+        "enc_w", "w_enc1x1", "enc1x1_colsum", "enc1x1_bias", "pos_inv_freq", "pos_scale", "rot_freqs")]
+        + [("layers", LayerWeights * NUM_LAYERS)]
+        + [(n, ctypes.c_void_p) for n in (
+            "fln_g", "fln_b", "fgn_g", "fgn_b", "mask_prelu", "w_out1", "b_out1", "w_tg", "b_tg", "w_dec1",
+            "dec_w")])
+
+
+class SepLayout(ctypes.Structure):
+    _names = ("enc", "x0", "x", "xbf", "ss", "h", "vu", "qk4", "P", "o", "o_ss", "y", "c", "nhat", "uvpre", "xuv",
+              "xubf", "f1", "p", "y1", "y2", "g", "kv_part", "kv", "gn_stats", "in_stats", "samp", "rot", "total")
+    _fields_ = ([(n, ctypes.c_size_t) for n in _names]
+                + [("S", ctypes.c_int64), ("Sp", ctypes.c_int64), ("Mtot", ctypes.c_int64),
+                   ("kv_nsplit", ctypes.c_int32), ("kv_kb_per_split", ctypes.c_int32)])
+
+
+# name -> (restype, argtypes); mirrors include/tdz.h one to one
+_vp, _i64, _sz, _int, _f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
+SIGNATURES = {
+    "tdz_create": (_int, [_int, ctypes.POINTER(_vp)]),
+    "tdz_destroy": (None, [_vp]),
+    "tdz_last_error": (ctypes.c_char_p, [_vp]),
+    "tdz_num_sms": (_int, [_vp]),
+    "tdz_version": (ctypes.c_char_p, []),
+    "tdz_set_mossformer2_weights": (_int, [_vp, ctypes.POINTER(MossFormer2Weights)]),
+    "tdz_num_frames": (_i64, [_i64]),
+    "tdz_padded_frames": (_i64, [_i64]),
+    "tdz_separate_workspace_bytes": (_sz, [_i64, _i64]),
+    "tdz_separate": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "tdz_separate_debug": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _int, _int, _int]),
+    "tdz_separate_layout": (_int, [_i64, _i64, _int, ctypes.POINTER(SepLayout)]),
+    "tdz_gather_segments": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "tdz_stitch_ola": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _vp, _vp]),
+    "tdz_stitch_concat": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "tdz_fbank_frames": (_i64, [_i64]),
+    "tdz_fbank": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "tdz_cosine_scores": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads libtdz.so (built by __graft_entry__.build()).  Raises if it is absent -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "the tdz hot path has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Handle:
+    """Owns one tdz_ctx.  check() turns non-zero return codes into RuntimeError (the reference's convention
+    is Python exceptions caught at init, AudioProcessor.py:187-194)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        ptr = ctypes.c_void_p()
+        rc = self.lib.tdz_create(int(device), ctypes.byref(ptr))
+        if rc != 0 or not ptr.value:
+            raise RuntimeError(f"tdz_create(device={device}) failed with code {rc}: an sm_100 GPU is required "
+                               "(no CPU fallback)")
+        self.ptr = ptr
+        self.device = int(device)
+
+    def check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.tdz_last_error(self.ptr)
+            raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc}")
+
+    @property
+    def num_sms(self):
+        return self.lib.tdz_num_sms(self.ptr)
+
+    def close(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value:
+            self.lib.tdz_destroy(self.ptr)
+            self.ptr = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

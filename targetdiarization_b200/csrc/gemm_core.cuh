@@ -1,0 +1,181 @@
+// Warp-specialised persistent tcgen05 GEMM core for sm_100a.
+//
+//   warp 0 (lane 0) : TMA producer   - fills a ring of {A,B} shared-memory stages (128 B swizzle)
+//   warp 1 (lane 0) : MMA issuer     - tcgen05.mma cta_group::1, M=128, N=BLOCK_N, fp32 accumulators in TMEM
+//   warps 2..5      : epilogue       - tcgen05.ld of the finished accumulator, fused elementwise work, stores
+//
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  What is loaded
+// for a k-block and what the epilogue does are supplied by a Cfg class, so every dense op of the
+// separator is an instance of this one pipeline.
+#pragma once
+#include "ptx.cuh"
+
+namespace tdz {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_STAGE_A_BYTES = GEMM_BLOCK_M * 128;  // 128 rows x 128 B (K-major) or 64 k-rows x 2 atoms (MN-major)
+
+struct TileInfo {
+  int m0;   // first row of the tile in the padded token space [B*Sp]
+  int n0;   // first output column
+  int b;    // sample index
+  int t0;   // first frame of the tile inside the sample
+  int nkb;  // k-blocks to accumulate
+  int aux;  // Cfg specific (group index, split index ...)
+};
+
+template <int BLOCK_N, int STAGES>
+constexpr int gemm_smem_bytes() {
+  return STAGES * (GEMM_STAGE_A_BYTES + BLOCK_N * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ typename Cfg::Params P) {
+  constexpr int BLOCK_N = Cfg::BLOCK_N;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGE_B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    Cfg::prefetch(P);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int ntiles = Cfg::num_tiles(P);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        TileInfo ti;
+        Cfg::tile_info(P, tile, ti);
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          Cfg::load(P, ti, kb, sa, sa + GEMM_STAGE_A_BYTES, full_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc(Cfg::FMT, GEMM_BLOCK_M, BLOCK_N, Cfg::A_MN, Cfg::B_MN);
+      // K-major: 32 B per UMMA_K step inside the 128 B swizzle row; 8-row groups 1024 B apart.
+      // MN-major: 16 k-rows (2 KB) per step; next 64-wide MN atom one 64-row box (8 KB) further.
+      constexpr uint32_t A_STEP = Cfg::A_MN ? 2048u : 32u;
+      constexpr uint32_t B_STEP = Cfg::B_MN ? 2048u : 32u;
+      constexpr uint32_t A_LBO = Cfg::A_MN ? 8192u : 16u;
+      constexpr uint32_t B_LBO = Cfg::B_MN ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        TileInfo ti;
+        Cfg::tile_info(P, tile, ti);
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * A_STEP, A_LBO, 1024u);
+            const uint64_t db = umma_smem_desc(sb + k * B_STEP, B_LBO, 1024u);
+            if (Cfg::FMT == 2)
+              umma_tf32(tacc, da, db, IDESC, (kb | k) != 0);
+            else
+              umma_f16(tacc, da, db, IDESC, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == ti.nkb - 1) umma_commit(tfull_bar(as));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // epilogue warps: TMEM lane quarter is fixed by warp id % 4
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      TileInfo ti;
+      Cfg::tile_info(P, tile, ti);
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      Cfg::epilogue(P, ti, tacc, row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <class Cfg>
+cudaError_t launch_gemm(const typename Cfg::Params& P, int ntiles, int num_sms, cudaStream_t st) {
+  constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (ntiles <= 0) return cudaSuccess;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  gemm_kernel<Cfg><<<grid, GEMM_THREADS, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace tdz

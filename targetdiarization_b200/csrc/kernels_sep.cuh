@@ -1,0 +1,559 @@
+// Memory-bound kernels of the MossFormer2 separator (everything that is not a dense contraction).
+// Activations are token-major fp32 [B*Sp][C]; Sp = frames per sample rounded up to the 256-frame attention
+// group (mossformer_block.py:236-250), frames t >= S are padding.  Time convolutions keep a register
+// sliding window per thread so every input element is loaded once; lanes run along channels so every
+// global access is a fully coalesced 256 B row segment.
+#pragma once
+#include "ptx.cuh"
+
+namespace tdz {
+
+// ---------------------------------------------------------------- encoder  (mossformer2.py:178-208)
+// enc[b,t,c] = relu(sum_j w[c,j] * mix[b, 8t+j]),  + per-sample sum / sum^2 for GroupNorm(1,512).
+constexpr int ENC_FRAMES = 64;
+__global__ void __launch_bounds__(512) encoder_kernel(const float* __restrict__ mix, int T, const float* __restrict__ w,
+                                                      float* __restrict__ enc, double* __restrict__ gn_stats, int B,
+                                                      int Sp, int S) {
+  __shared__ float xs[ENC_FRAMES * 8 + 8];
+  __shared__ float red[2][16];
+  const int strips = Sp / ENC_FRAMES;
+  const int b = blockIdx.x / strips;
+  const int t0 = (blockIdx.x - b * strips) * ENC_FRAMES;
+  const int c = threadIdx.x;
+  for (int i = threadIdx.x; i < ENC_FRAMES * 8 + 8; i += 512) {
+    const int n = t0 * 8 + i;
+    xs[i] = (n < T) ? mix[static_cast<size_t>(b) * T + n] : 0.f;
+  }
+  float wr[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wr[j] = w[c * 16 + j];
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  for (int f = 0; f < ENC_FRAMES; ++f) {
+    const int t = t0 + f;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaf(wr[j], xs[f * 8 + j], acc);
+    acc = (t < S) ? fmaxf(acc, 0.f) : 0.f;
+    enc[(static_cast<size_t>(b) * Sp + t) * 512 + c] = acc;
+    s1 += acc;
+    s2 += acc * acc;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s1;
+    red[1][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float a = threadIdx.x < 16 ? red[0][threadIdx.x] : 0.f;
+    float q = threadIdx.x < 16 ? red[1][threadIdx.x] : 0.f;
+    a = warp_sum(a);
+    q = warp_sum(q);
+    if (threadIdx.x == 0) {
+      atomicAdd(gn_stats + 2 * b, static_cast<double>(a));
+      atomicAdd(gn_stats + 2 * b + 1, static_cast<double>(q));
+    }
+  }
+}
+
+// GroupNorm(1,C,eps) statistics -> per-sample scale/shift (mossformer2.py:152).  A = rstd, Bv = -rstd*mean.
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, float* __restrict__ sampA,
+                                   float* __restrict__ sampB, int B, double count, double eps) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double mean = stats[2 * b] / count;
+  double var = stats[2 * b + 1] / count - mean * mean;
+  if (var < 0) var = 0;
+  const double rstd = 1.0 / sqrt(var + eps);
+  sampA[b] = static_cast<float>(rstd);
+  sampB[b] = static_cast<float>(-rstd * mean);
+}
+
+// Rotary angle table (rotary_embedding_torch: angle[t,j] = t * freqs[j]); fp32 positions.
+__global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __restrict__ tab, int Sp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Sp * 16) return;
+  const int t = i >> 4, j = i & 15;
+  const float a = static_cast<float>(t) * freqs[j];
+  tab[i] = make_float2(cosf(a), sinf(a));
+}
+
+// ---------------------------------------------------------------- depthwise conv k=17 + residual
+// ConvModule: y = x + depthwise_conv1d(x, k=17, pad=8) over time (conv_module.py:209-220).
+// Thread = 2 adjacent channels x DW_TT consecutive frames per step; block = 128 threads = 256 channels.
+constexpr int DW_TT = 16;
+constexpr int DW_STRIP = 128;
+
+template <class Epi>
+__global__ void __launch_bounds__(128) dwconv17_kernel(const float* __restrict__ in, int ld_in, int c_begin,
+                                                       const float* __restrict__ taps, int C, int Sp, int S,
+                                                       Epi epi) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (c >= C) return;
+  const int strips = Sp / DW_STRIP;
+  const int b = blockIdx.y / strips;
+  const int ts = (blockIdx.y - b * strips) * DW_STRIP;
+  if (ts >= S) {
+    // whole strip is padding: the epilogue still has to write zeros where buffers require it
+    for (int t = ts; t < ts + DW_STRIP; ++t) epi(b, t, static_cast<size_t>(b) * Sp + t, c, 0.f, 0.f, false);
+    return;
+  }
+  float2 w[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) w[k] = make_float2(taps[c * 17 + k], taps[(c + 1) * 17 + k]);
+  const float* base = in + static_cast<size_t>(b) * Sp * ld_in + c_begin + c;
+  auto ld = [&](int t) -> float2 {
+    if (t < 0 || t >= S) return make_float2(0.f, 0.f);
+    return *reinterpret_cast<const float2*>(base + static_cast<size_t>(t) * ld_in);
+  };
+  float2 buf[DW_TT + 16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) buf[DW_TT + i] = ld(ts - 8 + i);
+#pragma unroll 1
+  for (int t = ts; t < ts + DW_STRIP; t += DW_TT) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) buf[i] = buf[DW_TT + i];
+#pragma unroll
+    for (int i = 0; i < DW_TT; ++i) buf[16 + i] = ld(t + 8 + i);
+#pragma unroll
+    for (int j = 0; j < DW_TT; ++j) {
+      float a0 = buf[j + 8].x, a1 = buf[j + 8].y;
+#pragma unroll
+      for (int k = 0; k < 17; ++k) {
+        a0 = fmaf(w[k].x, buf[j + k].x, a0);
+        a1 = fmaf(w[k].y, buf[j + k].y, a1);
+      }
+      const int tt = t + j;
+      epi(b, tt, static_cast<size_t>(b) * Sp + tt, c, a0, a1, tt < S);
+    }
+  }
+}
+
+// to_hidden tail: (v|u) = h + dwconv(h) -> bf16 operand copy, zero in padded frames
+struct EpiVU {
+  __nv_bfloat16* vu;  // [Mtot][2048]
+  __device__ void operator()(int, int, size_t grow, int c, float a0, float a1, bool valid) const {
+    *reinterpret_cast<uint32_t*>(vu + grow * 2048 + c) = valid ? pack_bf16(a0, a1) : 0u;
+  }
+};
+// to_qk tail: OffsetScale (4 heads) + rotary on dims 0..31 (interleaved pairs) -> qk4 bf16
+// (mossformer_block.py:76-86,214,230-233).  Head order: quad_q, lin_q, quad_k, lin_k.
+struct EpiQK {
+  __nv_bfloat16* qk4;    // [Mtot][512]
+  const float* gamma;    // [4][128]
+  const float* beta;     // [4][128]
+  const float2* rot;     // [Sp][16] (cos, sin)
+  __device__ void operator()(int, int t, size_t grow, int c, float a0, float a1, bool valid) const {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint32_t packed = 0u;
+      if (valid) {
+        float x0 = a0 * gamma[h * 128 + c] + beta[h * 128 + c];
+        float x1 = a1 * gamma[h * 128 + c + 1] + beta[h * 128 + c + 1];
+        if (c < 32) {
+          const float2 cs = rot[t * 16 + (c >> 1)];
+          const float r0 = x0 * cs.x - x1 * cs.y;
+          const float r1 = x1 * cs.x + x0 * cs.y;
+          x0 = r0;
+          x1 = r1;
+        }
+        packed = pack_bf16(x0, x1);
+      }
+      *reinterpret_cast<uint32_t*>(qk4 + grow * 512 + h * 128 + c) = packed;
+    }
+  }
+};
+// to_out tail + FLASH residual: x_out = x_in + y + dwconv(y)   (mossformer_block.py:219)
+struct EpiResX {
+  const float* x_in;  // [Mtot][512]
+  float* x_out;
+  __device__ void operator()(int, int, size_t grow, int c, float a0, float a1, bool valid) const {
+    if (!valid) return;
+    const float2 r = *reinterpret_cast<const float2*>(x_in + grow * 512 + c);
+    *reinterpret_cast<float2*>(x_out + grow * 512 + c) = make_float2(r.x + a0, r.y + a1);
+  }
+};
+// to_u | to_v tail: xuv fp32 (u = cols 0..255, v = 256..511) and bf16 copy of x_u for fsmn.linear
+struct EpiUV {
+  float* xuv;          // [Mtot][512]
+  __nv_bfloat16* xu;   // [Mtot][256]
+  __device__ void operator()(int, int, size_t grow, int c, float a0, float a1, bool valid) const {
+    if (valid) *reinterpret_cast<float2*>(xuv + grow * 512 + c) = make_float2(a0, a1);
+    if (c < 256) *reinterpret_cast<uint32_t*>(xu + grow * 256 + c) = valid ? pack_bf16(a0, a1) : 0u;
+  }
+};
+
+// ---------------------------------------------------------------- DilatedDenseNet  (fsmn.py:76-111)
+// stage 1: y1 = depthwise conv (39 taps, pad 19) of p; statistics for InstanceNorm over all S frames.
+// stage 2: y2[c] = sum_{j<2} conv39_dilation2( cat[2c+j] ), cat = [PReLU(IN(y1)) ; p], pad 38.
+// A thread owns 2 adjacent channels (stage 1) or one output channel = 2 adjacent input channels (stage 2)
+// and DD_TT frames of one parity, with the taps in shared memory (conflict-free: lanes = channels).
+constexpr int DD_TT = 16;
+constexpr int DD_STRIP = 256;
+
+__global__ void __launch_bounds__(128) dd_conv1_kernel(const float* __restrict__ p, const float* __restrict__ taps,
+                                                       float* __restrict__ y1, double* __restrict__ stats, int Sp,
+                                                       int S) {
+  __shared__ float2 ws[39][128];
+  const int c = threadIdx.x * 2;
+  const int strips = Sp / DD_STRIP;
+  const int b = blockIdx.x / strips;
+  const int ts = (blockIdx.x - b * strips) * DD_STRIP;
+  if (ts >= S) return;
+  for (int k = 0; k < 39; ++k) ws[k][threadIdx.x] = make_float2(taps[c * 39 + k], taps[(c + 1) * 39 + k]);
+  const float* base = p + static_cast<size_t>(b) * Sp * 256 + c;
+  auto ld = [&](int t) -> float2 {
+    if (t < 0 || t >= S) return make_float2(0.f, 0.f);
+    return *reinterpret_cast<const float2*>(base + static_cast<size_t>(t) * 256);
+  };
+  float2 buf[DD_TT + 38];
+#pragma unroll
+  for (int i = 0; i < 38; ++i) buf[DD_TT + i] = ld(ts - 19 + i);
+  float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+#pragma unroll 1
+  for (int t = ts; t < ts + DD_STRIP && t < S; t += DD_TT) {
+#pragma unroll
+    for (int i = 0; i < 38; ++i) buf[i] = buf[DD_TT + i];
+#pragma unroll
+    for (int i = 0; i < DD_TT; ++i) buf[38 + i] = ld(t + 19 + i);
+    float2 acc[DD_TT];
+#pragma unroll
+    for (int j = 0; j < DD_TT; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 39; ++k) {
+      const float2 wk = ws[k][threadIdx.x];
+#pragma unroll
+      for (int j = 0; j < DD_TT; ++j) {
+        acc[j].x = fmaf(wk.x, buf[j + k].x, acc[j].x);
+        acc[j].y = fmaf(wk.y, buf[j + k].y, acc[j].y);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DD_TT; ++j) {
+      const int tt = t + j;
+      if (tt < S) {
+        *reinterpret_cast<float2*>(y1 + (static_cast<size_t>(b) * Sp + tt) * 256 + c) = acc[j];
+        s1x += acc[j].x;
+        s1y += acc[j].y;
+        s2x += acc[j].x * acc[j].x;
+        s2y += acc[j].y * acc[j].y;
+      }
+    }
+  }
+  double* st = stats + (static_cast<size_t>(b) * 256 + c) * 2;
+  atomicAdd(st + 0, static_cast<double>(s1x));
+  atomicAdd(st + 1, static_cast<double>(s2x));
+  atomicAdd(st + 2, static_cast<double>(s1y));
+  atomicAdd(st + 3, static_cast<double>(s2y));
+}
+
+// InstanceNorm2d(affine) parameters from the accumulated statistics: biased variance, eps 1e-5.
+__device__ __forceinline__ float2 in_scale_shift(const double* st, double count, float g, float bt) {
+  const double mean = st[0] / count;
+  double var = st[1] / count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  return make_float2(rstd * g, bt - static_cast<float>(mean) * rstd * g);
+}
+
+__global__ void __launch_bounds__(128) dd_conv2_kernel(const float* __restrict__ y1, const float* __restrict__ p,
+                                                       const double* __restrict__ stats1,
+                                                       const float* __restrict__ in1_g, const float* __restrict__ in1_b,
+                                                       const float* __restrict__ prelu1,
+                                                       const float* __restrict__ taps /*[256][2][39]*/,
+                                                       float* __restrict__ y2, double* __restrict__ stats2, int Sp,
+                                                       int S) {
+  __shared__ float2 ws[39][128];
+  const int c = blockIdx.y * 128 + threadIdx.x;  // output channel
+  const int strips = Sp / DD_STRIP;
+  const int b = blockIdx.x / strips;
+  const int ts = (blockIdx.x - b * strips) * DD_STRIP;
+  if (ts >= S) return;
+  for (int k = 0; k < 39; ++k)
+    ws[k][threadIdx.x] = make_float2(taps[(c * 2 + 0) * 39 + k], taps[(c * 2 + 1) * 39 + k]);
+  const bool from_y1 = c < 128;
+  const int ic = from_y1 ? 2 * c : 2 * (c - 128);  // first of the two adjacent input channels
+  float2 sc0 = make_float2(1.f, 0.f), sc1 = make_float2(1.f, 0.f);
+  float a0 = 1.f, a1 = 1.f;
+  if (from_y1) {
+    const double* st = stats1 + (static_cast<size_t>(b) * 256 + ic) * 2;
+    sc0 = in_scale_shift(st, static_cast<double>(S), in1_g[ic], in1_b[ic]);
+    sc1 = in_scale_shift(st + 2, static_cast<double>(S), in1_g[ic + 1], in1_b[ic + 1]);
+    a0 = prelu1[ic];
+    a1 = prelu1[ic + 1];
+  }
+  const float* base = (from_y1 ? y1 : p) + static_cast<size_t>(b) * Sp * 256 + ic;
+  auto ld = [&](int t) -> float2 {
+    if (t < 0 || t >= S) return make_float2(0.f, 0.f);
+    float2 v = *reinterpret_cast<const float2*>(base + static_cast<size_t>(t) * 256);
+    if (from_y1) {
+      v.x = v.x * sc0.x + sc0.y;
+      v.y = v.y * sc1.x + sc1.y;
+      v.x = v.x >= 0.f ? v.x : a0 * v.x;
+      v.y = v.y >= 0.f ? v.y : a1 * v.y;
+    }
+    return v;
+  };
+  float s1 = 0.f, s2 = 0.f;
+  // two passes over the strip, one per frame parity (dilation 2 keeps parities independent)
+#pragma unroll 1
+  for (int par = 0; par < 2; ++par) {
+    float2 buf[DD_TT + 38];
+#pragma unroll
+    for (int i = 0; i < 38; ++i) buf[DD_TT + i] = ld(ts + par - 38 + 2 * i);
+#pragma unroll 1
+    for (int t = ts + par; t < ts + DD_STRIP && t < S; t += 2 * DD_TT) {
+#pragma unroll
+      for (int i = 0; i < 38; ++i) buf[i] = buf[DD_TT + i];
+#pragma unroll
+      for (int i = 0; i < DD_TT; ++i) buf[38 + i] = ld(t + 38 + 2 * i);
+      float acc[DD_TT];
+#pragma unroll
+      for (int j = 0; j < DD_TT; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 39; ++k) {
+        const float2 wk = ws[k][threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < DD_TT; ++j) acc[j] = fmaf(wk.x, buf[j + k].x, fmaf(wk.y, buf[j + k].y, acc[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < DD_TT; ++j) {
+        const int tt = t + 2 * j;
+        if (tt < S) {
+          y2[(static_cast<size_t>(b) * Sp + tt) * 256 + c] = acc[j];
+          s1 += acc[j];
+          s2 += acc[j] * acc[j];
+        }
+      }
+    }
+  }
+  double* st = stats2 + (static_cast<size_t>(b) * 256 + c) * 2;
+  atomicAdd(st + 0, static_cast<double>(s1));
+  atomicAdd(st + 1, static_cast<double>(s2));
+}
+
+// FSMN tail: o2 = PReLU(IN(y2)); f = x_u + o2 (fsmn.py:144); g = x_v*f + c (mossformer_block.py:324);
+// CLayerNorm(256) (norm2, :423) with its affine folded into conv2 -> bf16 operand.  One warp per frame.
+__global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict__ y2, const double* __restrict__ stats2,
+                                                        const float* __restrict__ in2_g,
+                                                        const float* __restrict__ in2_b,
+                                                        const float* __restrict__ prelu2,
+                                                        const float* __restrict__ xuv, const float* __restrict__ cres,
+                                                        float* __restrict__ gout, int B, int Sp, int S) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * Sp) return;
+  const int b = warp / Sp;
+  const int t = warp - b * Sp;
+  const size_t grow = warp;
+  float g[8];
+  if (t >= S) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gout[grow * 256 + lane * 8 + i] = 0.f;
+    return;
+  }
+  const int c0 = lane * 8;
+  const float4* yp = reinterpret_cast<const float4*>(y2 + grow * 256 + c0);
+  const float4* up = reinterpret_cast<const float4*>(xuv + grow * 512 + c0);
+  const float4* vp = reinterpret_cast<const float4*>(xuv + grow * 512 + 256 + c0);
+  const float4* cp = reinterpret_cast<const float4*>(cres + grow * 256 + c0);
+  float y[8], u[8], v[8], cr[8];
+  *reinterpret_cast<float4*>(y) = yp[0];
+  *reinterpret_cast<float4*>(y + 4) = yp[1];
+  *reinterpret_cast<float4*>(u) = up[0];
+  *reinterpret_cast<float4*>(u + 4) = up[1];
+  *reinterpret_cast<float4*>(v) = vp[0];
+  *reinterpret_cast<float4*>(v + 4) = vp[1];
+  *reinterpret_cast<float4*>(cr) = cp[0];
+  *reinterpret_cast<float4*>(cr + 4) = cp[1];
+  float s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    const float2 ss = in_scale_shift(stats2 + (static_cast<size_t>(b) * 256 + c) * 2, static_cast<double>(S),
+                                     in2_g[c], in2_b[c]);
+    float o = y[i] * ss.x + ss.y;
+    o = o >= 0.f ? o : prelu2[c] * o;
+    g[i] = v[i] * (u[i] + o) + cr[i];
+    s1 += g[i];
+  }
+  const float mean = warp_sum(s1) * (1.f / 256.f);
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = g[i] - mean;
+    s2 += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(s2) * (1.f / 256.f) + 1e-5f);
+  float4* op = reinterpret_cast<float4*>(gout + grow * 256 + c0);
+  op[0] = make_float4((g[0] - mean) * rstd, (g[1] - mean) * rstd, (g[2] - mean) * rstd, (g[3] - mean) * rstd);
+  op[1] = make_float4((g[4] - mean) * rstd, (g[5] - mean) * rstd, (g[6] - mean) * rstd, (g[7] - mean) * rstd);
+}
+
+// lin_kv reduce: KV[b][d][e] = (sum_s part[b][s][d][e]) / S  -> bf16  (mossformer_block.py:286,289)
+__global__ void kv_reduce_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ kv, int nsplit,
+                                 float inv_n, size_t per_sample /*128*2048*/, size_t total4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const size_t e = i * 4;
+  const size_t b = e / per_sample;
+  const size_t r = e - b * per_sample;
+  const float* src = part + b * nsplit * per_sample + r;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nsplit; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(src + s * per_sample);
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  uint2 o = make_uint2(pack_bf16(acc.x * inv_n, acc.y * inv_n), pack_bf16(acc.z * inv_n, acc.w * inv_n));
+  *reinterpret_cast<uint2*>(kv + e) = o;
+}
+
+// ---------------------------------------------------------------- after the 24 layers
+// LayerNorm(512, eps 1e-6) per frame (mossformer2.py:307,320) + per-sample statistics of its output
+// for the GroupNorm(1,512) that follows (mossformer2.py:388-390).  One warp per frame.
+__global__ void __launch_bounds__(256) final_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                       const float* __restrict__ bta, float* __restrict__ out,
+                                                       double* __restrict__ gn_stats, int B, int Sp, int S) {
+  __shared__ float red[2][8];
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warp = blockIdx.x * 8 + warp_in_block;
+  const int lane = threadIdx.x & 31;
+  // all 8 frames of a block belong to one sample: Sp is a multiple of 8
+  const int b = (blockIdx.x * 8) / Sp;
+  const int t = warp - b * Sp;
+  float q1 = 0.f, q2 = 0.f;
+  if (t < S) {
+    const size_t grow = warp;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(v + 4 * i) = *reinterpret_cast<const float4*>(x + grow * 512 + i * 128 + lane * 4);
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s1 += v[i];
+    const float mean = warp_sum(s1) * (1.f / 512.f);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = v[i] - mean;
+      s2 += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(s2) * (1.f / 512.f) + 1e-6f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 128 + lane * 4;
+      float4 o;
+      o.x = (v[4 * i + 0] - mean) * rstd * g[c + 0] + bta[c + 0];
+      o.y = (v[4 * i + 1] - mean) * rstd * g[c + 1] + bta[c + 1];
+      o.z = (v[4 * i + 2] - mean) * rstd * g[c + 2] + bta[c + 2];
+      o.w = (v[4 * i + 3] - mean) * rstd * g[c + 3] + bta[c + 3];
+      *reinterpret_cast<float4*>(out + grow * 512 + c) = o;
+      q1 += o.x + o.y + o.z + o.w;
+      q2 += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+    }
+  }
+  q1 = warp_sum(q1);
+  q2 = warp_sum(q2);
+  if (lane == 0) {
+    red[0][warp_in_block] = q1;
+    red[1][warp_in_block] = q2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      a += red[0][i];
+      q += red[1][i];
+    }
+    atomicAdd(gn_stats + 2 * b, static_cast<double>(a));
+    atomicAdd(gn_stats + 2 * b + 1, static_cast<double>(q));
+  }
+}
+
+// GroupNorm apply (per-channel affine) + skip around the block (mossformer2.py:393-394) + mask-net PReLU
+// (mossformer2.py:500).
+__global__ void final_gn_kernel(const float* __restrict__ ln, const float* __restrict__ sampA,
+                                const float* __restrict__ sampB, const float* __restrict__ g,
+                                const float* __restrict__ bta, const float* __restrict__ x0,
+                                const float* __restrict__ alpha, float* __restrict__ out, int Sp, int S,
+                                size_t total4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const size_t e = i * 4;
+  const size_t grow = e / 512;
+  const int c = static_cast<int>(e - grow * 512);
+  const int b = static_cast<int>(grow / Sp);
+  const int t = static_cast<int>(grow - static_cast<size_t>(b) * Sp);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < S) {
+    const float4 v = *reinterpret_cast<const float4*>(ln + e);
+    const float4 r = *reinterpret_cast<const float4*>(x0 + e);
+    const float A = sampA[b], Bv = sampB[b], al = alpha[0];
+    float z;
+    z = (v.x * A + Bv) * g[c + 0] + bta[c + 0] + r.x;
+    o.x = z >= 0.f ? z : al * z;
+    z = (v.y * A + Bv) * g[c + 1] + bta[c + 1] + r.y;
+    o.y = z >= 0.f ? z : al * z;
+    z = (v.z * A + Bv) * g[c + 2] + bta[c + 2] + r.z;
+    o.z = z >= 0.f ? z : al * z;
+    z = (v.w * A + Bv) * g[c + 3] + bta[c + 3] + r.w;
+    o.w = z >= 0.f ? z : al * z;
+  }
+  *reinterpret_cast<float4*>(out + e) = o;
+}
+
+// ---------------------------------------------------------------- decoder  (mossformer2.py:213-257,579-589)
+// ConvTranspose1d(512->1,k=16,stride=8): out[8t+j] += sum_c sep[t,c] * w[c,j]; then zero-pad / trim to T.
+// Block = 32 output frames (+1 halo frame) of one (speaker, sample); warp per frame for the 16 dot products.
+constexpr int DEC_FRAMES = 32;
+__global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ sep /*[2][Mtot][512]*/,
+                                                      const float* __restrict__ w /*[512][16]*/,
+                                                      float* __restrict__ out /*[B][2][T]*/, int B, int Sp, int S,
+                                                      int T) {
+  __shared__ float ws[512 * 17];
+  __shared__ float F[DEC_FRAMES + 1][16];
+  const int strips = Sp / DEC_FRAMES;
+  const int spk = blockIdx.y;
+  const int b = blockIdx.x / strips;
+  const int t0 = (blockIdx.x - b * strips) * DEC_FRAMES;
+  for (int i = threadIdx.x; i < 512 * 16; i += 256) ws[(i >> 4) * 17 + (i & 15)] = w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = sep + (static_cast<size_t>(spk) * B * Sp + static_cast<size_t>(b) * Sp) * 512;
+  for (int f = warp; f < DEC_FRAMES + 1; f += 8) {
+    const int t = t0 - 1 + f;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    if (t >= 0 && t < S) {
+      for (int i = 0; i < 16; ++i) {
+        const int c = i * 32 + lane;
+        const float s = base[static_cast<size_t>(t) * 512 + c];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(s, ws[c * 17 + j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) F[f][j] = acc[j];
+    }
+  }
+  __syncthreads();
+  // sample n = 8t + j (j<8) gets F[t][j] + F[t-1][8+j]
+  const int f = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const int t = t0 + f;
+  const int n = t * 8 + j;
+  if (n < T) {
+    const float v = F[f + 1][j] + F[f][8 + j];  // frames >= S contribute zeros
+    out[(static_cast<size_t>(b) * 2 + spk) * T + n] = v;
+  }
+}
+
+}  // namespace tdz

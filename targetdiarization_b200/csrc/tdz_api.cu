@@ -1,0 +1,550 @@
+// libtdz.so: C-ABI entry points (include/tdz.h) and the host-side launch sequence of the separator.
+// One tdz_separate() call = the whole MossFormer2 forward (look2hear/models/mossformer2.py:563-589 of the
+// reference) on B chunks, launched on the caller's stream, no allocation, no host synchronisation.
+#include "../../include/tdz.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "gemm_cfgs.cuh"
+#include "kernels_misc.cuh"
+#include "kernels_sep.cuh"
+
+using namespace tdz;
+
+// ------------------------------------------------------------------------------------------------ ctx
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct tdz_ctx {
+  int device = 0;
+  int num_sms = 0;
+  EncodeTiledFn encode = nullptr;
+  std::string err;
+  std::mutex mu;
+  bool have_sep = false;
+  tdz_mossformer2_weights sep;
+  // weight tensor maps (built once per tdz_set_mossformer2_weights)
+  struct LayerMaps {
+    CUtensorMap w_in, w_out, w_c1, w_uv, w_lin, w_proj, w_c2;
+  } lm[TDZ_NUM_LAYERS];
+  CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1;
+};
+
+static int fail(tdz_ctx* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return 1;
+}
+#define CUDA_OK(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                        \
+  } while (0)
+
+extern "C" const char* tdz_version(void) { return "tdz 0.1 (sm_100a)"; }
+
+extern "C" int tdz_create(int device, tdz_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return 2;
+  if (cudaSetDevice(device) != cudaSuccess) return 3;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 4;
+  if (prop.major != 10) return 5;  // hand-written for sm_100a; no fallback
+  tdz_ctx* c = new tdz_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    delete c;
+    return 6;
+  }
+  c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = c;
+  return 0;
+}
+extern "C" void tdz_destroy(tdz_ctx* ctx) { delete ctx; }
+extern "C" const char* tdz_last_error(tdz_ctx* ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
+extern "C" int tdz_num_sms(tdz_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+// rank-2/3 row-major tensor, innermost dimension contiguous, 128 B swizzle.
+static int make_tmap(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int rank, const uint64_t* dims,
+                     const uint32_t* box) {
+  const uint64_t es = f32 ? 4 : 2;
+  cuuint64_t gdim[3] = {1, 1, 1};
+  cuuint64_t gstr[2] = {0, 0};
+  cuuint32_t bx[3] = {1, 1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  uint64_t stride = es;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  if (bx[0] * es > 128) return fail(ctx, "tensor map inner box exceeds the 128 B swizzle span");
+  CUresult r = ctx->encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                           const_cast<void*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+// activation [B][Sp][C] -> 3-D map {C, Sp, B}
+static int act_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int C, int64_t Sp, int64_t B,
+                   uint32_t box_c, uint32_t box_rows) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Sp), static_cast<uint64_t>(B)};
+  const uint32_t box[3] = {box_c, box_rows, 1};
+  return make_tmap(ctx, m, ptr, f32, 3, dims, box);
+}
+// weight [N][K] -> 2-D map {K, N}
+static int w_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int N, int K, uint32_t box_rows) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+  const uint32_t box[2] = {f32 ? 32u : 64u, box_rows};
+  return make_tmap(ctx, m, ptr, f32, 2, dims, box);
+}
+
+extern "C" int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_weights* w) {
+  if (!ctx || !w) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->sep = *w;
+  for (int i = 0; i < TDZ_NUM_LAYERS; ++i) {
+    const tdz_layer_weights& L = w->layers[i];
+    auto& M = ctx->lm[i];
+    if (w_map(ctx, &M.w_in, L.w_in, false, 2176, 512, 256)) return 1;
+    if (w_map(ctx, &M.w_out, L.w_out, false, 512, 1024, 256)) return 1;
+    if (w_map(ctx, &M.w_c1, L.w_c1, true, 256, 512, 256)) return 1;
+    if (w_map(ctx, &M.w_uv, L.w_uv, false, 512, 256, 256)) return 1;
+    if (w_map(ctx, &M.w_lin, L.w_lin, false, 256, 256, 256)) return 1;
+    if (w_map(ctx, &M.w_proj, L.w_proj, false, 256, 256, 256)) return 1;
+    if (w_map(ctx, &M.w_c2, L.w_c2, true, 512, 256, 256)) return 1;
+  }
+  if (w_map(ctx, &ctx->m_enc1x1, w->w_enc1x1, true, 512, 512, 256)) return 1;
+  if (w_map(ctx, &ctx->m_out1, w->w_out1, true, 1024, 512, 256)) return 1;
+  if (w_map(ctx, &ctx->m_tg, w->w_tg, true, 1024, 512, 128)) return 1;  // split-N: two 128-row boxes per tile
+  if (w_map(ctx, &ctx->m_dec1, w->w_dec1, true, 512, 512, 256)) return 1;
+  ctx->have_sep = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+extern "C" int64_t tdz_num_frames(int64_t T) { return T < 16 ? 0 : (T - 16) / 8 + 1; }
+extern "C" int64_t tdz_padded_frames(int64_t T) {
+  const int64_t S = tdz_num_frames(T);
+  return (S + 255) / 256 * 256;
+}
+
+extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_layout* L) {
+  if (!L || B <= 0 || T < 16) return 1;
+  memset(L, 0, sizeof *L);
+  const int64_t S = tdz_num_frames(T), Sp = tdz_padded_frames(T), M = B * Sp;
+  L->S = S;
+  L->Sp = Sp;
+  L->Mtot = M;
+  // split the frame axis of the lin_kv GEMM until there are about two work items per SM
+  const int total_kb = static_cast<int>(Sp / 64);
+  int nsplit = 1;
+  const int64_t want = 2 * static_cast<int64_t>(num_sms > 0 ? num_sms : 148);
+  while (B * 8 * nsplit < want && nsplit * 2 <= total_kb && nsplit < 64) nsplit *= 2;
+  int kbps = (total_kb + nsplit - 1) / nsplit;
+  nsplit = (total_kb + kbps - 1) / kbps;
+  L->kv_nsplit = nsplit;
+  L->kv_kb_per_split = kbps;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return o;
+  };
+  const size_t m = static_cast<size_t>(M);
+  L->enc = take(m * 512 * 4);
+  L->x0 = take(m * 512 * 4);
+  L->x = take(m * 512 * 4);
+  L->xbf = take(m * 512 * 2);
+  L->ss = take(m * 2 * 4);
+  L->h = take(m * 2176 * 4);
+  L->vu = take(m * 2048 * 2);
+  L->qk4 = take(m * 512 * 2);
+  L->P = take(m * 256 * 2);
+  L->o = take(m * 1024 * 2);
+  L->o_ss = take(m * 8 * 4);
+  L->y = take(m * 512 * 4);
+  L->c = take(m * 256 * 4);
+  L->nhat = take(m * 256 * 2);
+  L->uvpre = take(m * 512 * 4);
+  L->xuv = take(m * 512 * 4);
+  L->xubf = take(m * 256 * 2);
+  L->f1 = take(m * 256 * 2);
+  L->p = take(m * 256 * 4);
+  L->y1 = take(m * 256 * 4);
+  L->y2 = take(m * 256 * 4);
+  L->g = take(m * 256 * 4);
+  L->kv_part = take(static_cast<size_t>(B) * nsplit * 128 * 2048 * 4);
+  L->kv = take(static_cast<size_t>(B) * 128 * 2048 * 2);
+  L->gn_stats = take(static_cast<size_t>(B) * 2 * 8 * 2);       // two GroupNorms
+  L->in_stats = take(static_cast<size_t>(B) * 256 * 2 * 8 * 2); // two InstanceNorms (re-zeroed per layer)
+  L->samp = take(static_cast<size_t>(B) * 4 * 4);               // A,B for each GroupNorm
+  L->rot = take(static_cast<size_t>(Sp) * 16 * 8);
+  L->total = off;
+  return 0;
+}
+
+extern "C" size_t tdz_separate_workspace_bytes(int64_t B, int64_t T) {
+  tdz_sep_layout L;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (tdz_separate_layout(B, T, sms, &L)) return 0;
+  return L.total;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+
+// Launch steps, selectable through tdz_separate_debug (tests drive single kernels with oracle inputs).
+enum Step : int {
+  ST_ENCODER = 0, ST_ENC1X1, ST_FLASH_IN, ST_DW_VU, ST_DW_QK, ST_SIM, ST_KV, ST_ATT_OUT, ST_TO_OUT, ST_DW_RESX,
+  ST_FSMN_C1, ST_FSMN_UV, ST_DW_UV, ST_FSMN_LIN, ST_FSMN_PROJ, ST_DD1, ST_DD2, ST_FSMN_TAIL, ST_FSMN_C2,
+  ST_FINAL_LN, ST_FINAL_GN, ST_OUT1, ST_TANHSIG, ST_DEC1, ST_DECODER, ST_COUNT
+};
+
+static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64, float* out, void* ws, size_t ws_bytes,
+                        cudaStream_t st, int num_layers, int step_lo, int step_hi) {
+#define STEP(k) if ((k) >= step_lo && (k) <= step_hi)
+  if (!ctx->have_sep) return fail(ctx, "tdz_separate: weights not set");
+  if (B64 <= 0 || T64 < 16 || B64 > 65535) return fail(ctx, "tdz_separate: bad shape B=%lld T=%lld", (long long)B64, (long long)T64);
+  tdz_sep_layout L;
+  tdz_separate_layout(B64, T64, ctx->num_sms, &L);
+  if (ws_bytes < L.total) return fail(ctx, "tdz_separate: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(ctx, "tdz_separate: workspace must be 1024 B aligned");
+  const int B = static_cast<int>(B64), T = static_cast<int>(T64);
+  const int S = static_cast<int>(L.S), Sp = static_cast<int>(L.Sp);
+  const size_t M = static_cast<size_t>(L.Mtot);
+  if (M * 2176 > 0x7fffffffull * 4) return fail(ctx, "tdz_separate: batch too large for one call");
+  const int sms = ctx->num_sms;
+  const tdz_mossformer2_weights& W = ctx->sep;
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+  auto H = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
+  float *enc = F(L.enc), *x0 = F(L.x0), *x = F(L.x), *ss = F(L.ss), *h = F(L.h), *o_ss = F(L.o_ss), *y = F(L.y),
+        *c = F(L.c), *uvpre = F(L.uvpre), *xuv = F(L.xuv), *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g),
+        *kv_part = F(L.kv_part), *samp = F(L.samp);
+  __nv_bfloat16 *xbf = H(L.xbf), *vu = H(L.vu), *qk4 = H(L.qk4), *Pm = H(L.P), *o = H(L.o), *nhat = H(L.nhat),
+                *xubf = H(L.xubf), *f1 = H(L.f1), *kv = H(L.kv);
+  double* gn_stats = reinterpret_cast<double*>(base + L.gn_stats);
+  double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
+  float2* rot = reinterpret_cast<float2*>(base + L.rot);
+  // aliases used after the layer loop
+  float* lnb = y;                        // [M][512]
+  float* ab = uvpre;                     // [M][512]
+  float* mb = h;                         // [M][1024]
+  float* gated = h + M * 1024;           // [2][M][512]
+  float* sep = reinterpret_cast<float*>(vu);  // [2][M][512]
+
+  // ---- activation tensor maps (buffers are reused by every layer)
+  CUtensorMap m_enc, m_xbf, m_x, m_o, m_nhat, m_xubf, m_f1, m_g, m_ab, m_mb, m_gated0, m_gated1;
+  if (act_map(ctx, &m_enc, enc, true, 512, Sp, B, 32, 128)) return 1;
+  if (act_map(ctx, &m_xbf, xbf, false, 512, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &m_x, x, true, 512, Sp, B, 32, 128)) return 1;
+  if (act_map(ctx, &m_o, o, false, 1024, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &m_nhat, nhat, false, 256, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &m_xubf, xubf, false, 256, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &m_f1, f1, false, 256, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &m_g, g, true, 256, Sp, B, 32, 128)) return 1;
+  if (act_map(ctx, &m_ab, ab, true, 512, Sp, B, 32, 128)) return 1;
+  if (act_map(ctx, &m_mb, mb, true, 1024, Sp, B, 32, 128)) return 1;
+  if (act_map(ctx, &m_gated0, gated, true, 512, Sp, B, 32, 128)) return 1;
+  if (act_map(ctx, &m_gated1, gated + M * 512, true, 512, Sp, B, 32, 128)) return 1;
+  AttnParams AP;
+  memset(&AP, 0, sizeof AP);
+  if (act_map(ctx, &AP.tmQK, qk4, false, 512, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &AP.tmQKb, qk4, false, 512, Sp, B, 64, 256)) return 1;
+  if (act_map(ctx, &AP.tmQKmn, qk4, false, 512, Sp, B, 64, 64)) return 1;
+  if (act_map(ctx, &AP.tmVUmn, vu, false, 2048, Sp, B, 64, 64)) return 1;
+  if (act_map(ctx, &AP.tmP, Pm, false, 256, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &AP.tmKVmn, kv, false, 2048, 128, B, 64, 64)) return 1;
+  AP.B = B;
+  AP.Sp = Sp;
+  AP.S = S;
+  AP.nsplit = L.kv_nsplit;
+  AP.kb_per_split = L.kv_kb_per_split;
+  AP.P = Pm;
+  AP.kv_part = kv_part;
+  AP.vu = vu;
+  AP.o = o;
+  AP.o_ss = o_ss;
+
+  const int mtiles = static_cast<int>(M / 128);
+  auto lin_base = [&](LinearParams& P, const CUtensorMap& a, const CUtensorMap& w, int N, int K, int block_n) {
+    memset(&P, 0, sizeof P);
+    P.tmA = a;
+    P.tmB = w;
+    P.B = B;
+    P.Sp = Sp;
+    P.S = S;
+    P.N = N;
+    P.K = K;
+    P.n_tiles = (N + block_n - 1) / block_n;
+  };
+
+  // ---- front: encoder -> GroupNorm -> conv1d_encoder (+pos enc)   (mossformer2.py:573,487-496)
+  STEP(ST_ENCODER) {
+    CUDA_OK(cudaMemsetAsync(gn_stats, 0, static_cast<size_t>(B) * 4 * 8, st));
+    if (static_cast<int64_t>(Sp) * 8 < T) CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(B) * 2 * T * 4, st));
+    encoder_kernel<<<B * (Sp / ENC_FRAMES), 512, 0, st>>>(mix, T, W.enc_w, enc, gn_stats, B, Sp, S);
+    gn_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(gn_stats, samp, samp + B, B, 512.0 * S, 1e-8);
+    rotary_table_kernel<<<(Sp * 16 + 255) / 256, 256, 0, st>>>(W.rot_freqs, rot, Sp);
+  }
+  STEP(ST_ENC1X1) {
+    LinearParams P;
+    lin_base(P, m_enc, ctx->m_enc1x1, 512, 512, 256);
+    P.e.sampA = samp;
+    P.e.sampB = samp + B;
+    P.e.colsum = W.enc1x1_colsum;
+    P.e.bias = W.enc1x1_bias;
+    P.e.pos_inv_freq = W.pos_inv_freq;
+    P.e.pos_scale = W.pos_scale;
+    P.e.out_f32 = x0;
+    P.e.out_ld = 512;
+    P.e.out_bf16 = xbf;
+    P.e.out_bf_ld = 512;
+    P.e.ss_out = ss;
+    P.e.ss_out_ld = 2;
+    P.e.zero_pad_rows = 1;
+    CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+  }
+
+  const dim3 dw_grid_y(1, B * (Sp / DW_STRIP));
+  for (int li = 0; li < num_layers; ++li) {
+    const tdz_layer_weights& LW = W.layers[li];
+    const auto& LM = ctx->lm[li];
+    const float* x_in = (li == 0) ? x0 : x;
+    // ---------------- FLASH_ShareA_FFConvM (mossformer_block.py:191-220)
+    STEP(ST_FLASH_IN) {  // token shift + ScaleNorm + to_hidden|to_qk Linear + SiLU
+      LinearParams P;
+      lin_base(P, m_xbf, LM.w_in, 2176, 512, 256);
+      P.shift_kblocks = 4;
+      P.e.ss_in = ss;
+      P.e.ss_mode = 1;
+      P.e.ss_dim_rsqrt = 0.044194173824159216f;  // 512^-0.5
+      P.e.bias = LW.b_in;
+      P.e.act = ACT_SILU;
+      P.e.out_f32 = h;
+      P.e.out_ld = 2176;
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    }
+    STEP(ST_DW_VU) dwconv17_kernel<EpiVU><<<dim3(8, dw_grid_y.y), 128, 0, st>>>(h, 2176, 0, LW.dw_in, 2048, Sp, S, EpiVU{vu});
+    STEP(ST_DW_QK) dwconv17_kernel<EpiQK><<<dim3(1, dw_grid_y.y), 128, 0, st>>>(h, 2176, 2048, LW.dw_in + 2048 * 17, 128, Sp, S,
+                                                                EpiQK{qk4, LW.os_gamma, LW.os_beta, rot});
+    STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
+    STEP(ST_KV) {
+      CUDA_OK((launch_gemm<AttnKV>(AP, B * AP.nsplit * 8, sms, st)));
+      const size_t total4 = static_cast<size_t>(B) * 128 * 2048 / 4;
+      kv_reduce_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
+          kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
+    }
+    STEP(ST_ATT_OUT) CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
+    STEP(ST_TO_OUT) {  // ScaleNorm(1024) + to_out Linear + SiLU
+      LinearParams P;
+      lin_base(P, m_o, LM.w_out, 512, 1024, 256);
+      P.e.ss_in = o_ss;
+      P.e.ss_mode = 2;
+      P.e.ss_parts = 8;
+      P.e.ss_dim_rsqrt = 0.03125f;  // 1024^-0.5
+      P.e.bias = LW.b_out;
+      P.e.act = ACT_SILU;
+      P.e.out_f32 = y;
+      P.e.out_ld = 512;
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    }
+    STEP(ST_DW_RESX) dwconv17_kernel<EpiResX><<<dim3(2, dw_grid_y.y), 128, 0, st>>>(y, 512, 0, LW.dw_out, 512, Sp, S, EpiResX{x_in, x});
+    // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
+    STEP(ST_FSMN_C1) {  // conv1 + PReLU + norm1 + inner LayerNorm statistics
+      LinearParams P;
+      lin_base(P, m_x, LM.w_c1, 256, 512, 256);
+      P.e.bias = LW.b_c1;
+      P.e.alpha = LW.prelu_c1;
+      P.ln_g1 = LW.ln1_g;
+      P.ln_b1 = LW.ln1_b;
+      P.e.out_f32 = c;
+      P.e.out_bf16 = nhat;
+      CUDA_OK((launch_gemm<LinearLN256<2, 4>>(P, mtiles, sms, st)));
+    }
+    STEP(ST_FSMN_UV) {  // to_u | to_v Linear + SiLU
+      LinearParams P;
+      lin_base(P, m_nhat, LM.w_uv, 512, 256, 256);
+      P.e.bias = LW.b_uv;
+      P.e.act = ACT_SILU;
+      P.e.out_f32 = uvpre;
+      P.e.out_ld = 512;
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    }
+    STEP(ST_DW_UV) dwconv17_kernel<EpiUV><<<dim3(2, dw_grid_y.y), 128, 0, st>>>(uvpre, 512, 0, LW.dw_uv, 512, Sp, S, EpiUV{xuv, xubf});
+    STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
+      LinearParams P;
+      lin_base(P, m_xubf, LM.w_lin, 256, 256, 256);
+      P.e.bias = LW.b_lin;
+      P.e.act = ACT_RELU;
+      P.e.out_bf16 = f1;
+      P.e.out_bf_ld = 256;
+      P.e.zero_pad_rows = 1;
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles, sms, st)));
+    }
+    STEP(ST_FSMN_PROJ) {  // fsmn.project
+      LinearParams P;
+      lin_base(P, m_f1, LM.w_proj, 256, 256, 256);
+      P.e.out_f32 = p;
+      P.e.out_ld = 256;
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles, sms, st)));
+    }
+    double* st1 = in_stats;
+    double* st2 = in_stats + static_cast<size_t>(B) * 512;
+    STEP(ST_DD1) {
+      CUDA_OK(cudaMemsetAsync(in_stats, 0, static_cast<size_t>(B) * 256 * 2 * 8 * 2, st));
+      dd_conv1_kernel<<<B * (Sp / DD_STRIP), 128, 0, st>>>(p, LW.dd_w1, y1, st1, Sp, S);
+    }
+    STEP(ST_DD2) dd_conv2_kernel<<<dim3(B * (Sp / DD_STRIP), 2), 128, 0, st>>>(y1, p, st1, LW.in1_g, LW.in1_b,
+                                                                      LW.dd_prelu1, LW.dd_w2, y2, st2, Sp, S);
+    STEP(ST_FSMN_TAIL) fsmn_tail_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st>>>(y2, st2, LW.in2_g, LW.in2_b,
+                                                                                  LW.dd_prelu2, xuv, c, g, B, Sp, S);
+    STEP(ST_FSMN_C2) {  // conv2 + residual; also the bf16 copy and ScaleNorm sums the next FLASH layer needs
+      LinearParams P;
+      lin_base(P, m_g, LM.w_c2, 512, 256, 256);
+      P.e.bias = LW.b_c2;
+      P.e.resid = x;
+      P.e.resid_ld = 512;
+      P.e.out_f32 = x;
+      P.e.out_ld = 512;
+      P.e.out_bf16 = xbf;
+      P.e.out_bf_ld = 512;
+      P.e.ss_out = ss;
+      P.e.ss_out_ld = 2;
+      P.e.zero_pad_rows = 1;
+      CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+  // ---- back: LayerNorm -> GroupNorm + skip -> PReLU -> mask head -> decoder (mossformer2.py:320,388-396,500-523,575-589)
+  const float* x_fin = (num_layers == 0) ? x0 : x;
+  STEP(ST_FINAL_LN) {
+    CUDA_OK(cudaMemsetAsync(gn_stats + 2 * B, 0, static_cast<size_t>(B) * 2 * 8, st));
+    final_ln_kernel<<<static_cast<unsigned>(M / 8), 256, 0, st>>>(x_fin, W.fln_g, W.fln_b, lnb, gn_stats + 2 * B, B, Sp,
+                                                                  S);
+    gn_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(gn_stats + 2 * B, samp + 2 * B, samp + 3 * B, B, 512.0 * S,
+                                                        1e-8);
+  }
+  STEP(ST_FINAL_GN) {
+    const size_t total4 = M * 512 / 4;
+    final_gn_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
+        lnb, samp + 2 * B, samp + 3 * B, W.fgn_g, W.fgn_b, x0, W.mask_prelu, ab, Sp, S, total4);
+  }
+  STEP(ST_OUT1) {  // conv1d_out 512 -> 1024 (+bias)
+    LinearParams P;
+    lin_base(P, m_ab, ctx->m_out1, 1024, 512, 256);
+    P.e.bias = W.b_out1;
+    P.e.out_f32 = mb;
+    P.e.out_ld = 1024;
+    P.e.zero_pad_rows = 1;
+    CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+  }
+  for (int spk = 0; spk < 2; ++spk) {
+    STEP(ST_TANHSIG) {  // tanh(output) * sigmoid(output_gate)
+      LinearParams P;
+      lin_base(P, m_mb, ctx->m_tg, 1024, 512, 256);
+      P.a_k0 = spk * 512;
+      P.split_n = 512;
+      P.e.bias = W.b_tg;
+      P.e.out_f32 = gated + static_cast<size_t>(spk) * M * 512;
+      P.e.out_ld = 512;
+      CUDA_OK((launch_gemm<LinearTanhSig<2, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    }
+    STEP(ST_DEC1) {  // conv1_decoder + ReLU, times the encoder output
+      LinearParams P;
+      lin_base(P, spk == 0 ? m_gated0 : m_gated1, ctx->m_dec1, 512, 512, 256);
+      P.e.act = ACT_RELU;
+      P.e.mul = enc;
+      P.e.mul_ld = 512;
+      P.e.out_f32 = sep + static_cast<size_t>(spk) * M * 512;
+      P.e.out_ld = 512;
+      P.e.zero_pad_rows = 1;
+      CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    }
+  }
+  STEP(ST_DECODER) decoder_kernel<<<dim3(B * (Sp / DEC_FRAMES), 2), 256, 0, st>>>(sep, W.dec_w, out, B, Sp, S, T);
+  CUDA_OK(cudaGetLastError());
+#undef STEP
+  return 0;
+}
+
+extern "C" int tdz_separate(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* ws,
+                            size_t ws_bytes, void* stream) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return run_separate(ctx, mix_dev, B, T, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), TDZ_NUM_LAYERS, 0, ST_COUNT);
+}
+extern "C" int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* ws,
+                                  size_t ws_bytes, void* stream, int num_layers, int step_lo, int step_hi) {
+  if (!ctx) return 1;
+  if (num_layers < 0 || num_layers > TDZ_NUM_LAYERS) return fail(ctx, "bad num_layers");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return run_separate(ctx, mix_dev, B, T, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), num_layers,
+                      step_lo, step_hi);
+}
+
+// ------------------------------------------------------------------------------------------------ stitching / scoring
+extern "C" int tdz_gather_segments(tdz_ctx* ctx, const float* mix_dev, int64_t L, int64_t session, int64_t hop,
+                                   int64_t seg_begin, int64_t n_seg, float* seg_dev, void* stream) {
+  if (!ctx) return 1;
+  if (n_seg <= 0) return 0;
+  const size_t total = static_cast<size_t>(n_seg) * session;
+  gather_segments_kernel<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mix_dev, L, session, hop, seg_begin, n_seg, seg_dev);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t session, int64_t hop, int64_t seg_begin,
+                              int64_t n_seg, int64_t L, int64_t out_begin, int64_t n_out, float ratio, float* out_dev,
+                              void* stream) {
+  if (!ctx) return 1;
+  if (n_out <= 0) return 0;
+  const size_t total = static_cast<size_t>(n_out) * 2;
+  stitch_ola_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      est_dev, session, hop, seg_begin, n_seg, L, out_begin, n_out, ratio, out_dev);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" int tdz_stitch_concat(tdz_ctx* ctx, const float* est_dev, int64_t len, int64_t start, int64_t L,
+                                 float* out_dev, void* stream) {
+  if (!ctx) return 1;
+  if (start < 0 || start + len > L) return fail(ctx, "tdz_stitch_concat: chunk outside the output");
+  CUDA_OK(cudaMemcpy2DAsync(out_dev + start, static_cast<size_t>(L) * 4, est_dev, static_cast<size_t>(len) * 4,
+                            static_cast<size_t>(len) * 4, 2, cudaMemcpyDeviceToDevice,
+                            static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float* target_dev, int64_t N, int64_t dim,
+                                 float* scores_dev, void* stream) {
+  if (!ctx) return 1;
+  if (N <= 0) return 0;
+  cosine_scores_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      emb_dev, target_dev, static_cast<int>(N), static_cast<int>(dim), scores_dev);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// fbank: implemented in kernels_fbank.cuh
+extern "C" int64_t tdz_fbank_frames(int64_t T) { return T < 400 ? 0 : 1 + (T - 400) / 160; }
+extern "C" int tdz_fbank(tdz_ctx* ctx, const float*, int64_t, int64_t, float*, void*) {
+  return fail(ctx, "tdz_fbank: not built yet");
+}
