@@ -157,6 +157,10 @@ int tdz_stitch_concat(tdz_ctx* ctx, const float* est_dev, int64_t len, int64_t s
  * (torchaudio/compliance/kaldi.py:514-646).  wav_dev fp32 [N][T] -> feat_dev fp32 [N][frames][80],
  * frames = 1 + (T-400)/160. */
 int64_t tdz_fbank_frames(int64_t T);
+/* Constant tables (povey window [400], FFT twiddles [256][2], mel filters [80][257], first/last non-zero
+ * bin per filter [80]) computed by targetdiarization_b200/fbank.py; device pointers, caller-owned. */
+int tdz_set_fbank_tables(tdz_ctx* ctx, const float* window_dev, const float* twiddle_dev, const float* mel_dev,
+                         const int32_t* mel_lo_dev, const int32_t* mel_hi_dev);
 int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t T, float* feat_dev, void* stream);
 
 /* cosine similarity of N embeddings against one target, TargetASR.cosine_similarity semantics

@@ -269,7 +269,7 @@ struct LinearTanhSig : LinearBase<FMT_, 256, STAGES_> {
   __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
-    if (t >= P.S) return;
+    const bool valid = t < P.S;  // no early return: tcgen05.ld is warp-collective
     const size_t grow = static_cast<size_t>(ti.m0) + row;
     const int oc0 = ti.n0 / 2;  // first output column of this tile
 #pragma unroll 1
@@ -278,6 +278,7 @@ struct LinearTanhSig : LinearBase<FMT_, 256, STAGES_> {
       tmem_ld16(tacc + c0, a);
       tmem_ld16(tacc + 128 + c0, g);
       tmem_ld_wait();
+      if (!valid) continue;
       float o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {

@@ -51,9 +51,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // barrier is never satisfied (a protocol bug), so a bad launch surfaces as a CUDA error.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if TDZ_HANG_GUARD
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz: far beyond any legitimate wait
   }
 #else
   while (!mbar_try_wait(bar, parity)) {

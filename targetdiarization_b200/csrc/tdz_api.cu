@@ -10,6 +10,7 @@
 #include <string>
 
 #include "gemm_cfgs.cuh"
+#include "kernels_fbank.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_sep.cuh"
 
@@ -33,6 +34,8 @@ struct tdz_ctx {
     CUtensorMap w_in, w_out, w_c1, w_uv, w_lin, w_proj, w_c2;
   } lm[TDZ_NUM_LAYERS];
   CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1;
+  bool have_fbank = false;
+  FbankTables fb;
 };
 
 static int fail(tdz_ctx* c, const char* fmt, ...) {
@@ -543,8 +546,30 @@ extern "C" int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float
   return 0;
 }
 
-// fbank: implemented in kernels_fbank.cuh
-extern "C" int64_t tdz_fbank_frames(int64_t T) { return T < 400 ? 0 : 1 + (T - 400) / 160; }
-extern "C" int tdz_fbank(tdz_ctx* ctx, const float*, int64_t, int64_t, float*, void*) {
-  return fail(ctx, "tdz_fbank: not built yet");
+// ------------------------------------------------------------------------------------------------ fbank
+extern "C" int64_t tdz_fbank_frames(int64_t T) { return T < FB_WIN ? 0 : 1 + (T - FB_WIN) / FB_SHIFT; }
+extern "C" int tdz_set_fbank_tables(tdz_ctx* ctx, const float* window_dev, const float* twiddle_dev,
+                                    const float* mel_dev, const int32_t* mel_lo_dev, const int32_t* mel_hi_dev) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->fb.window = window_dev;
+  ctx->fb.twiddle = reinterpret_cast<const float2*>(twiddle_dev);
+  ctx->fb.mel = mel_dev;
+  ctx->fb.mel_lo = mel_lo_dev;
+  ctx->fb.mel_hi = mel_hi_dev;
+  ctx->have_fbank = true;
+  return 0;
+}
+extern "C" int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t T, float* feat_dev, void* stream) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->have_fbank) return fail(ctx, "tdz_fbank: tables not set");
+  const int64_t frames = tdz_fbank_frames(T);
+  if (N <= 0 || frames <= 0) return fail(ctx, "tdz_fbank: input shorter than one 25 ms window");
+  const int64_t total = N * frames;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fbank_kernel<<<static_cast<unsigned>((total + 3) / 4), 128, 0, st>>>(wav_dev, T, frames, total, ctx->fb, feat_dev);
+  fbank_meannorm_kernel<<<static_cast<unsigned>(N), 240, 0, st>>>(feat_dev, frames);
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }

@@ -95,6 +95,28 @@ class Separator:
 
     forward = __call__
 
+    STEP_NAMES = ("ENCODER", "ENC1X1", "FLASH_IN", "DW_VU", "DW_QK", "SIM", "KV", "ATT_OUT", "TO_OUT", "DW_RESX",
+                  "FSMN_C1", "FSMN_UV", "DW_UV", "FSMN_LIN", "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2",
+                  "FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1", "DECODER")
+    KERNELS_PER_FORWARD = 4 + 24 * 18 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
+
+    def time_steps(self, mix, reps=5):
+        """CUDA-event time (ms) of every launch step of the forward run alone (layer 0 instance), after a
+        full forward has populated the workspace.  Used by bench.py for the roofline of the dominant kernel."""
+        self(mix)
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for k, name in enumerate(self.STEP_NAMES):
+            self(mix, _debug=(1, k, k))  # warm
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                self(mix, _debug=(1, k, k))
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            out[name] = e0.elapsed_time(e1) / reps
+        return out
+
     def debug_buffer(self, B, T, name, dtype, cols):
         """Test hook: view of a named intermediate inside the workspace after a call ([B, Sp, cols])."""
         lay = self.layout(B, T)

@@ -339,7 +339,7 @@ def worker(first, out_path):
     return 0
 
 
-def run_all(out_path, timeout=600):
+def run_all(out_path, timeout=300):
     if os.path.exists(out_path):
         os.remove(out_path)
     first = 0
@@ -348,8 +348,12 @@ def run_all(out_path, timeout=600):
             subprocess.run([sys.executable, "-m", "tests.sep_steps", "--worker", str(first), "--out", out_path],
                            cwd=ROOT, timeout=timeout)
         except subprocess.TimeoutExpired:
+            n_done = 0
+            if os.path.exists(out_path):
+                with open(out_path) as f:
+                    n_done = sum(1 for line in f if line.strip())
             with open(out_path, "a") as f:
-                f.write(json.dumps({"step": STEPS[first], "ok": False, "error": "timeout", "fatal": True}) + "\n")
+                f.write(json.dumps({"step": STEPS[n_done], "ok": False, "error": "timeout", "fatal": True}) + "\n")
         done = []
         if os.path.exists(out_path):
             with open(out_path) as f:
