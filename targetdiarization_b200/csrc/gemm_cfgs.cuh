@@ -7,39 +7,46 @@
 
 namespace tdz {
 
-enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_PRELU = 3, ACT_HARDTANH20 = 4 };
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_HARDTANH20 = 3, ACT_AFF = 4 };
 
-// ------------------------------------------------------------------------------------------------
-// Generic fused elementwise epilogue.  Order of operations on an accumulator value v at (row, col):
-//   v *= rowscale(row)                   ScaleNorm folded behind the GEMM (mossformer_block.py:44-54)
-//   v  = v*sampA[b] + sampB[b]*colsum[col]   GroupNorm(1,C) folded behind the GEMM (mossformer2.py:487-490)
-//   v += bias[col]; v = act(v); v += resid[row,col]; v *= mul[row,col]; v += posenc(t,col)
-// then optional fp32 / bf16 stores and a per-row sum of squares over the tile's columns.
+// Compile-time switches of the generic fused epilogue (a bit mask template argument): the epilogue warps
+// run one warp per scheduler, so runtime-uniform branches per element would leave them latency bound.
+enum EpiFlags : unsigned {
+  EF_SS_SHIFT = 1u << 0,    // ScaleNorm row scale from token-shifted half sums (mossformer_block.py:44-54,204-207)
+  EF_SS_PARTS = 1u << 1,    // ScaleNorm row scale from 16 partial sums (dim 1024)
+  EF_SAMP = 1u << 2,        // GroupNorm(1,C) folded behind the GEMM: v*A[b] + B[b]*colsum[col]
+  EF_BIAS = 1u << 3,
+  EF_RESID = 1u << 4,       // + resid[row,col] after the activation
+  EF_RESID_PRE = 1u << 5,   // + resid[row,col] before the activation (ResNet block end)
+  EF_MUL = 1u << 6,         // * mul[row,col]
+  EF_POS = 1u << 7,         // + ScaledSinuEmbedding (mossformer_block.py:60-73)
+  EF_OUT_F32 = 1u << 8,
+  EF_OUT_BF16 = 1u << 9,
+  EF_SS_OUT = 1u << 10,     // per-row sum of squares of the stored values, one partial per 128 columns
+  EF_ZERO_PAD = 1u << 11,   // padded frames (t >= S) are written as zeros instead of skipped
+  EF_ROUND_TF32 = 1u << 12, // fp32 output rounded to nearest tf32 (buffer is only a tf32 MMA operand)
+};
+
 struct EpiGeneric {
-  const float* ss_in;      // ss_mode 1: [Mtot][2] (lo,hi halves); ss_mode 2: [Mtot][ss_parts] partial sums
-  int ss_mode;             // 0 none, 1 token-shifted halves (dim 512), 2 partial sums
-  int ss_parts;
+  const float* ss_in;      // EF_SS_SHIFT: [Mtot][4] (128-column partial sums); EF_SS_PARTS: [Mtot][16]
   float ss_dim_rsqrt;      // dim^-0.5 of the ScaleNorm
   const float* sampA;      // [B]
   const float* sampB;      // [B]
   const float* colsum;     // [N]
   const float* bias;       // [N]
-  int act;
-  const float* alpha;      // PReLU slope (1 value)
   const float* resid;      // [Mtot][resid_ld]
   int resid_ld;
   const float* mul;        // [Mtot][mul_ld]
   int mul_ld;
-  const float* pos_inv_freq;  // [N/2]  ScaledSinuEmbedding (mossformer_block.py:60-73)
+  const float* pos_inv_freq;  // [N/2]
   const float* pos_scale;     // [1]
   float* out_f32;
   int out_ld;
   int out_col0;            // column offset added when storing
   __nv_bfloat16* out_bf16;
   int out_bf_ld;
-  float* ss_out;           // [Mtot][ss_out_ld], entry n_tile
+  float* ss_out;           // [Mtot][ss_out_ld], entry = global column / 128
   int ss_out_ld;
-  int zero_pad_rows;       // rows with t >= S are written as zeros instead of skipped
 };
 
 struct LinearParams {
@@ -52,9 +59,9 @@ struct LinearParams {
   int split_n;        // >0: tile columns [0,BN/2) come from W rows n0/2.., [BN/2,BN) from rows split_n+n0/2..
   EpiGeneric e;
   // epilogue specific extras
-  const float* ln_g1;  // LN256 epilogue
+  const float* alpha;  // PReLU slope (LN256 epilogue)
+  const float* ln_g1;
   const float* ln_b1;
-  float* out2_f32;
 };
 
 template <int FMT_, int BLOCK_N_, int STAGES_>
@@ -79,7 +86,7 @@ struct LinearBase {
     ti.n0 = nt * BLOCK_N;
     ti.b = ti.m0 / P.Sp;
     ti.t0 = ti.m0 - ti.b * P.Sp;
-    ti.nkb = P.K / KB;
+    ti.nkb = (P.K + KB - 1) / KB;  // a partial last k-block is zero-filled by TMA
     ti.aux = nt;
   }
   __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
@@ -94,94 +101,160 @@ struct LinearBase {
   }
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
-  switch (act) {
-    case ACT_SILU: return silu_f(v);
-    case ACT_RELU: return fmaxf(v, 0.f);
-    case ACT_PRELU: return v >= 0.f ? v : alpha * v;
-    case ACT_HARDTANH20: return fminf(fmaxf(v, 0.f), 20.f);
-    default: return v;
-  }
-}
-
 __device__ __forceinline__ float scalenorm_rscale(float ss, float dim_rsqrt) {
   // x / clamp(||x|| * dim^-0.5, 1e-5)   (mossformer_block.py:52-54)
   return 1.f / fmaxf(sqrtf(ss) * dim_rsqrt, 1e-5f);
 }
 
-template <int FMT_, int BLOCK_N_, int STAGES_>
+template <int ACT>
+__device__ __forceinline__ float act_apply(float v) {
+  if constexpr (ACT == ACT_SILU) return silu_f(v);
+  if constexpr (ACT == ACT_RELU) return fmaxf(v, 0.f);
+  if constexpr (ACT == ACT_HARDTANH20) return fminf(fmaxf(v, 0.f), 20.f);
+  return v;
+}
+
+__device__ __forceinline__ void ld_f32x16(const float* p, float* v) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(q + j);
+    v[4 * j] = t.x;
+    v[4 * j + 1] = t.y;
+    v[4 * j + 2] = t.z;
+    v[4 * j + 3] = t.w;
+  }
+}
+// same for data written earlier in the same stream (plain loads, no read-only path assumption needed)
+__device__ __forceinline__ void ld_f32x16_rw(const float* p, float* v, bool full) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < 2 || full) t = q[j];
+    v[4 * j] = t.x;
+    v[4 * j + 1] = t.y;
+    v[4 * j + 2] = t.z;
+    v[4 * j + 3] = t.w;
+  }
+}
+
+// Generic linear layer: out = epilogue(A @ W^T).  Order of operations on an accumulator value v:
+//   v *= rowscale; v = v*sampA + sampB*colsum; v += bias; [v += resid]; v = act(v); [v += resid]; v *= mul;
+//   v += posenc; stores; row sum of squares.
+// Work is done in chunks of 16 columns; N must be a multiple of 8 (a partial chunk has exactly 8 columns;
+// per-column vectors (bias, colsum) must be readable up to the next multiple of 16).
+template <int FMT_, int BLOCK_N_, int STAGES_, unsigned EF, int ACT>
 struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   using Params = LinearParams;
   static constexpr int BLOCK_N = BLOCK_N_;
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
+  static constexpr int EPI_SPLIT = (BLOCK_N_ >= 64) ? 2 : 1;
+  static constexpr int COLS = BLOCK_N_ / EPI_SPLIT;  // columns handled by one epilogue warp
+
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
     const bool valid = t < P.S;
     const size_t grow = static_cast<size_t>(ti.m0) + row;
     float rs = 1.f;
-    if (e.ss_mode == 1) {
-      float ss = e.ss_in[grow * 2 + 1];
-      if (t > 0) ss += e.ss_in[(grow - 1) * 2];
+    if constexpr ((EF & EF_SS_SHIFT) != 0) {
+      const float4 cur = *reinterpret_cast<const float4*>(e.ss_in + grow * 4);
+      float ss = cur.z + cur.w;  // channels 256..511 of this frame
+      if (t > 0) {
+        const float4 prv = *reinterpret_cast<const float4*>(e.ss_in + (grow - 1) * 4);
+        ss += prv.x + prv.y;     // channels 0..255 of the previous frame
+      }
       rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
-    } else if (e.ss_mode == 2) {
+    }
+    if constexpr ((EF & EF_SS_PARTS) != 0) {
       float ss = 0.f;
-      for (int i = 0; i < e.ss_parts; ++i) ss += e.ss_in[grow * e.ss_parts + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(e.ss_in + grow * 16 + 4 * i);
+        ss += (a.x + a.y) + (a.z + a.w);
+      }
       rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
     }
     float sA = 1.f, sB = 0.f;
-    if (e.sampA) {
+    if constexpr ((EF & EF_SAMP) != 0) {
       sA = e.sampA[ti.b];
       sB = e.sampB[ti.b];
     }
-    const float alpha = e.alpha ? e.alpha[0] : 0.f;
-    const float pscale = e.pos_scale ? e.pos_scale[0] : 0.f;
+    float pscale = 0.f;
+    if constexpr ((EF & EF_POS) != 0) pscale = e.pos_scale[0];
     float ssq = 0.f;
+    const int cbase = half * COLS;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int cc = 0; cc < COLS; cc += 16) {
+      const int c0 = cbase + cc;
       const int col0 = ti.n0 + c0;
-      if (col0 >= P.N) break;  // warp-uniform: N is a multiple of 32
-      float v[32];
+      if (col0 >= P.N) break;  // warp-uniform
+      const bool full = col0 + 16 <= P.N;  // else exactly 8 columns exist
+      float v[16];
       tmem_ld16(tacc + c0, v);
-      tmem_ld16(tacc + c0 + 16, v + 16);
+      float bias[16], cs[16], rsd[16], ml[16];
+      if constexpr ((EF & EF_BIAS) != 0) ld_f32x16(e.bias + col0, bias);
+      if constexpr ((EF & EF_SAMP) != 0) ld_f32x16(e.colsum + col0, cs);
+      if (valid) {
+        if constexpr ((EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF)
+          ld_f32x16_rw(e.resid + grow * e.resid_ld + col0, rsd, full);
+        if constexpr ((EF & EF_MUL) != 0 || ACT == ACT_AFF)
+          ld_f32x16_rw(e.mul + grow * e.mul_ld + col0, ml, full);
+      }
       tmem_ld_wait();
       if (!valid) {
-        if (!e.zero_pad_rows) continue;
+        if constexpr ((EF & EF_ZERO_PAD) == 0) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
+        for (int j = 0; j < 16; ++j) {
           float x = v[j] * rs;
-          if (e.sampA) x = x * sA + sB * __ldg(e.colsum + col);
-          if (e.bias) x += __ldg(e.bias + col);
-          x = apply_act(x, e.act, alpha);
-          if (e.resid) x += e.resid[grow * e.resid_ld + col];
-          if (e.mul) x *= e.mul[grow * e.mul_ld + col];
-          if (e.pos_inv_freq) {
-            const int half = P.N >> 1;
-            const float f = __ldg(e.pos_inv_freq + (col < half ? col : col - half));
-            const float a = static_cast<float>(t) * f;
-            x += pscale * (col < half ? sinf(a) : cosf(a));
+          if constexpr ((EF & EF_SAMP) != 0) x = x * sA + sB * cs[j];
+          if constexpr ((EF & EF_BIAS) != 0) x += bias[j];
+          if constexpr (ACT == ACT_AFF) {
+            // AFF gate: att = 1 + tanh(x); out = a*att + b*(2-att)   (ERes2NetV2 AFF)
+            const float att = 1.f + tanhf(x);
+            x = ml[j] * att + rsd[j] * (2.f - att);
+          } else {
+            if constexpr ((EF & EF_RESID_PRE) != 0) x += rsd[j];
+            x = act_apply<ACT>(x);
+            if constexpr ((EF & EF_RESID) != 0) x += rsd[j];
+            if constexpr ((EF & EF_MUL) != 0) x *= ml[j];
           }
+          if constexpr ((EF & EF_POS) != 0) {
+            const int col = col0 + j;
+            const int hlf = P.N >> 1;
+            const float f = __ldg(e.pos_inv_freq + (col < hlf ? col : col - hlf));
+            const float a = static_cast<float>(t) * f;
+            x += pscale * (col < hlf ? sinf(a) : cosf(a));
+          }
+          if constexpr ((EF & EF_SS_OUT) != 0) ssq += x * x;
+          if constexpr ((EF & EF_ROUND_TF32) != 0) x = round_tf32_rn(x);
           v[j] = x;
-          ssq += x * x;
         }
       }
-      if (e.out_f32) {
+      if constexpr ((EF & EF_OUT_F32) != 0) {
         float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.out_ld + e.out_col0 + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (full) {
+          o[2] = make_float4(v[8], v[9], v[10], v[11]);
+          o[3] = make_float4(v[12], v[13], v[14], v[15]);
+        }
       }
-      if (e.out_bf16) {
+      if constexpr ((EF & EF_OUT_BF16) != 0) {
         uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.out_bf_ld + e.out_col0 + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        if (full)
+          o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                            pack_bf16(v[14], v[15]));
       }
     }
-    if (e.ss_out) e.ss_out[grow * e.ss_out_ld + ti.aux] = valid ? ssq : 0.f;
+    if constexpr ((EF & EF_SS_OUT) != 0) {
+      // one partial per 128 output columns (COLS == 128 for the instances that use it)
+      e.ss_out[grow * e.ss_out_ld + (ti.n0 + cbase) / 128] = valid ? ssq : 0.f;
+    }
   }
 };
 
@@ -192,22 +265,23 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
 template <int FMT_, int STAGES_>
 struct LinearLN256 : LinearBase<FMT_, 256, STAGES_> {
   using Params = LinearParams;
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
+  static constexpr int EPI_SPLIT = 1;
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
     const bool valid = t < P.S;
     const size_t grow = static_cast<size_t>(ti.m0) + row;
-    const float alpha = e.alpha[0];
+    const float alpha = P.alpha[0];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-      float v[32];
+    for (int c0 = 0; c0 < 256; c0 += 16) {
+      float v[16], bias[16];
       tmem_ld16(tacc + c0, v);
-      tmem_ld16(tacc + c0 + 16, v + 16);
+      ld_f32x16(e.bias + c0, bias);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = v[j] + __ldg(e.bias + c0 + j);
+      for (int j = 0; j < 16; ++j) {
+        float x = v[j] + bias[j];
         x = x >= 0.f ? x : alpha * x;
         s1 += x;
         s2 += x * x;
@@ -217,16 +291,18 @@ struct LinearLN256 : LinearBase<FMT_, 256, STAGES_> {
     const float rstd1 = rsqrtf(fmaxf(s2 * (1.f / 256.f) - mean1 * mean1, 0.f) + 1e-5f);
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-      float v[32];
+    for (int c0 = 0; c0 < 256; c0 += 16) {
+      float v[16], bias[16], g1[16], b1[16];
       tmem_ld16(tacc + c0, v);
-      tmem_ld16(tacc + c0 + 16, v + 16);
+      ld_f32x16(e.bias + c0, bias);
+      ld_f32x16(P.ln_g1 + c0, g1);
+      ld_f32x16(P.ln_b1 + c0, b1);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = v[j] + __ldg(e.bias + c0 + j);
+      for (int j = 0; j < 16; ++j) {
+        float x = v[j] + bias[j];
         x = x >= 0.f ? x : alpha * x;
-        x = (x - mean1) * rstd1 * __ldg(P.ln_g1 + c0 + j) + __ldg(P.ln_b1 + c0 + j);
+        x = (x - mean1) * rstd1 * g1[j] + b1[j];
         v[j] = x;
         c1 += x;
         c2 += x * x;
@@ -234,27 +310,29 @@ struct LinearLN256 : LinearBase<FMT_, 256, STAGES_> {
       if (valid) {
         float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * 256 + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
     const float mean2 = c1 * (1.f / 256.f);
     const float rstd2 = rsqrtf(fmaxf(c2 * (1.f / 256.f) - mean2 * mean2, 0.f) + 1e-5f);
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
-      float v[32];
+    for (int c0 = 0; c0 < 256; c0 += 16) {
+      float v[16], bias[16], g1[16], b1[16];
       tmem_ld16(tacc + c0, v);
-      tmem_ld16(tacc + c0 + 16, v + 16);
+      ld_f32x16(e.bias + c0, bias);
+      ld_f32x16(P.ln_g1 + c0, g1);
+      ld_f32x16(P.ln_b1 + c0, b1);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = v[j] + __ldg(e.bias + c0 + j);
+      for (int j = 0; j < 16; ++j) {
+        float x = v[j] + bias[j];
         x = x >= 0.f ? x : alpha * x;
-        x = (x - mean1) * rstd1 * __ldg(P.ln_g1 + c0 + j) + __ldg(P.ln_b1 + c0 + j);
+        x = (x - mean1) * rstd1 * g1[j] + b1[j];
         v[j] = valid ? (x - mean2) * rstd2 : 0.f;
       }
       uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * 256 + c0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 2; ++j)
         o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
     }
@@ -266,25 +344,29 @@ struct LinearLN256 : LinearBase<FMT_, 256, STAGES_> {
 template <int FMT_, int STAGES_>
 struct LinearTanhSig : LinearBase<FMT_, 256, STAGES_> {
   using Params = LinearParams;
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
+  static constexpr int EPI_SPLIT = 2;
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
     const bool valid = t < P.S;  // no early return: tcgen05.ld is warp-collective
     const size_t grow = static_cast<size_t>(ti.m0) + row;
     const int oc0 = ti.n0 / 2;  // first output column of this tile
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 16) {
-      float a[16], g[16];
+    for (int cc = 0; cc < 64; cc += 16) {
+      const int c0 = half * 64 + cc;
+      float a[16], g[16], ba[16], bg[16];
       tmem_ld16(tacc + c0, a);
       tmem_ld16(tacc + 128 + c0, g);
+      ld_f32x16(e.bias + oc0 + c0, ba);
+      ld_f32x16(e.bias + P.split_n + oc0 + c0, bg);
       tmem_ld_wait();
       if (!valid) continue;
       float o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float xa = a[j] + __ldg(e.bias + oc0 + c0 + j);
-        const float xg = g[j] + __ldg(e.bias + P.split_n + oc0 + c0 + j);
-        o[j] = tanhf(xa) * (1.f / (1.f + expf(-xg)));
+        const float xa = a[j] + ba[j];
+        const float xg = g[j] + bg[j];
+        o[j] = round_tf32_rn(tanhf(xa) * (1.f / (1.f + expf(-xg))));
       }
       float4* dst = reinterpret_cast<float4*>(e.out_f32 + grow * e.out_ld + e.out_col0 + oc0 + c0);
 #pragma unroll
@@ -311,13 +393,13 @@ struct AttnParams {
   float* kv_part;          // [B][nsplit][128][2048]
   const __nv_bfloat16* vu; // [Mtot][2048]
   __nv_bfloat16* o;        // [Mtot][1024] gated output
-  float* o_ss;             // [Mtot][8]   partial sums of squares of o (ScaleNorm(1024) of to_out)
+  float* o_ss;             // [Mtot][16]  partial sums of squares of o (ScaleNorm(1024) of to_out)
 };
 
 // sim = quad_q quad_k^T / 256 ; attn = relu(sim)^2    (mossformer_block.py:256-258)
 struct AttnSim {
   using Params = AttnParams;
-  static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 0;
+  static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 0, EPI_SPLIT = 2;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmQK);
     tma_prefetch_desc(&P.tmQKb);
@@ -335,10 +417,11 @@ struct AttnSim {
     tma_load_3d(sa, &P.tmQK, bar, 0 + kb * 64, ti.t0, ti.b);      // quad_q
     tma_load_3d(sb, &P.tmQKb, bar, 256 + kb * 64, ti.aux, ti.b);  // quad_k of the whole group
   }
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
     const size_t grow = static_cast<size_t>(ti.m0) + row;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
+    for (int cc = 0; cc < 128; cc += 32) {
+      const int c0 = half * 128 + cc;
       float v[32];
       tmem_ld16(tacc + c0, v);
       tmem_ld16(tacc + c0 + 16, v + 16);
@@ -362,7 +445,7 @@ struct AttnSim {
 // Both operands are read MN-major straight from the token-major buffers.
 struct AttnKV {
   using Params = AttnParams;
-  static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 1, B_MN = 1;
+  static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 1, B_MN = 1, EPI_SPLIT = 2;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmQKmn);
     tma_prefetch_desc(&P.tmVUmn);
@@ -387,10 +470,11 @@ struct AttnKV {
 #pragma unroll
     for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 8192, &P.tmVUmn, bar, ti.n0 + j * 64, trow, ti.b);
   }
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
     float* dst = P.kv_part + ((static_cast<size_t>(ti.b) * P.nsplit + ti.aux) * 128 + row) * 2048 + ti.n0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
+    for (int cc = 0; cc < 128; cc += 32) {
+      const int c0 = half * 128 + cc;
       float v[32];
       tmem_ld16(tacc + c0, v);
       tmem_ld16(tacc + c0 + 16, v + 16);
@@ -407,7 +491,7 @@ struct AttnKV {
 // 128 u-columns, so the gate runs in the epilogue and the [.,2048] attention output never reaches HBM.
 struct AttnOut {
   using Params = AttnParams;
-  static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 1;
+  static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 1, EPI_SPLIT = 2;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmP);
     tma_prefetch_desc(&P.tmVUmn);
@@ -444,22 +528,29 @@ struct AttnOut {
       }
     }
   }
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row) {
+  // o_ss holds 16 partial sums per row: index = 2 * n_tile + half (the consumer adds them in index order)
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
     const int t = ti.t0 + row;
     const bool valid = t < P.S;
     const size_t grow = static_cast<size_t>(ti.m0) + row;
     float ssq = 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 16) {
+    for (int cc = 0; cc < 64; cc += 16) {
+      const int c0 = half * 64 + cc;
       float av[16], au[16];
       tmem_ld16(tacc + c0, av);
       tmem_ld16(tacc + 128 + c0, au);
+      uint4 vr[2], ur[2];
+      if (valid) {
+        const uint4* vp = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + ti.n0 + c0);
+        const uint4* up = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + 1024 + ti.n0 + c0);
+        vr[0] = vp[0];
+        vr[1] = vp[1];
+        ur[0] = up[0];
+        ur[1] = up[1];
+      }
       tmem_ld_wait();
       if (!valid) continue;
-      const uint4* vp = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + ti.n0 + c0);
-      const uint4* up = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + 1024 + ti.n0 + c0);
-      uint4 vr[2] = {vp[0], vp[1]};
-      uint4 ur[2] = {up[0], up[1]};
       const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(vr);
       const __nv_bfloat16* ub = reinterpret_cast<const __nv_bfloat16*>(ur);
       float o[16];
@@ -477,7 +568,7 @@ struct AttnOut {
         dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
                             pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
     }
-    P.o_ss[grow * 8 + ti.aux] = valid ? ssq : 0.f;
+    P.o_ss[grow * 16 + ti.aux * 2 + half] = valid ? ssq : 0.f;
   }
 };
 

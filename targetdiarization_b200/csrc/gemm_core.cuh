@@ -2,7 +2,8 @@
 //
 //   warp 0 (lane 0) : TMA producer   - fills a ring of {A,B} shared-memory stages (128 B swizzle)
 //   warp 1 (lane 0) : MMA issuer     - tcgen05.mma cta_group::1, M=128, N=BLOCK_N, fp32 accumulators in TMEM
-//   warps 2..5      : epilogue       - tcgen05.ld of the finished accumulator, fused elementwise work, stores
+//   warps 2..5(9)   : epilogue       - tcgen05.ld of the finished accumulator, fused elementwise work, stores
+//                                      (Cfg::EPI_SPLIT = 2: two warps per TMEM lane quarter, each half the columns)
 //
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  What is loaded
 // for a k-block and what the epilogue does are supplied by a Cfg class, so every dense op of the
@@ -13,7 +14,7 @@
 namespace tdz {
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int gemm_threads(int epi_split) { return 64 + 128 * epi_split; }
 constexpr int GEMM_STAGE_A_BYTES = GEMM_BLOCK_M * 128;  // 128 rows x 128 B (K-major) or 64 k-rows x 2 atoms (MN-major)
 
 struct TileInfo {
@@ -31,7 +32,7 @@ constexpr int gemm_smem_bytes() {
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ typename Cfg::Params P) {
+__global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(const __grid_constant__ typename Cfg::Params P) {
   constexpr int BLOCK_N = Cfg::BLOCK_N;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int STAGE_B_BYTES = BLOCK_N * 128;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 4 * Cfg::EPI_SPLIT);
     }
     fence_barrier_init();
   }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     // epilogue warps: TMEM lane quarter is fixed by warp id % 4
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int half = (warp - 2) >> 2;  // which column half this warp owns (always 0 when EPI_SPLIT == 1)
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       TileInfo ti;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       mbar_wait(tfull_bar(as), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-      Cfg::epilogue(P, ti, tacc, row);
+      Cfg::epilogue(P, ti, tacc, row, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -174,7 +176,7 @@ cudaError_t launch_gemm(const typename Cfg::Params& P, int ntiles, int num_sms, 
   }
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  gemm_kernel<Cfg><<<grid, GEMM_THREADS, smem, st>>>(P);
+  gemm_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT), smem, st>>>(P);
   return cudaGetLastError();
 }
 

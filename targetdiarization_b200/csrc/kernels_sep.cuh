@@ -388,8 +388,11 @@ __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict_
   }
   const float rstd = rsqrtf(warp_sum(s2) * (1.f / 256.f) + 1e-5f);
   float4* op = reinterpret_cast<float4*>(gout + grow * 256 + c0);
-  op[0] = make_float4((g[0] - mean) * rstd, (g[1] - mean) * rstd, (g[2] - mean) * rstd, (g[3] - mean) * rstd);
-  op[1] = make_float4((g[4] - mean) * rstd, (g[5] - mean) * rstd, (g[6] - mean) * rstd, (g[7] - mean) * rstd);
+  // g is only the tf32 operand of conv2: round to nearest here (the MMA would truncate)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = round_tf32_rn((g[i] - mean) * rstd);
+  op[0] = make_float4(g[0], g[1], g[2], g[3]);
+  op[1] = make_float4(g[4], g[5], g[6], g[7]);
 }
 
 // lin_kv reduce: KV[b][d][e] = (sum_s part[b][s][d][e]) / S  -> bf16  (mossformer_block.py:286,289)
@@ -495,14 +498,15 @@ __global__ void final_gn_kernel(const float* __restrict__ ln, const float* __res
     const float4 r = *reinterpret_cast<const float4*>(x0 + e);
     const float A = sampA[b], Bv = sampB[b], al = alpha[0];
     float z;
+    // the result is only the tf32 operand of conv1d_out: round to nearest (the MMA would truncate)
     z = (v.x * A + Bv) * g[c + 0] + bta[c + 0] + r.x;
-    o.x = z >= 0.f ? z : al * z;
+    o.x = round_tf32_rn(z >= 0.f ? z : al * z);
     z = (v.y * A + Bv) * g[c + 1] + bta[c + 1] + r.y;
-    o.y = z >= 0.f ? z : al * z;
+    o.y = round_tf32_rn(z >= 0.f ? z : al * z);
     z = (v.z * A + Bv) * g[c + 2] + bta[c + 2] + r.z;
-    o.z = z >= 0.f ? z : al * z;
+    o.z = round_tf32_rn(z >= 0.f ? z : al * z);
     z = (v.w * A + Bv) * g[c + 3] + bta[c + 3] + r.w;
-    o.w = z >= 0.f ? z : al * z;
+    o.w = round_tf32_rn(z >= 0.f ? z : al * z);
   }
   *reinterpret_cast<float4*>(out + e) = o;
 }

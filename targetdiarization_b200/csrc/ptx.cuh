@@ -167,6 +167,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// fp32 -> nearest tf32 (ties away), kept in fp32 storage; used where a buffer is only a tf32 MMA operand,
+// because the tensor core itself truncates the low 13 mantissa bits (a biased rounding).
+__device__ __forceinline__ float round_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

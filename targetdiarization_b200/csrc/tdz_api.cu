@@ -177,13 +177,13 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->x0 = take(m * 512 * 4);
   L->x = take(m * 512 * 4);
   L->xbf = take(m * 512 * 2);
-  L->ss = take(m * 2 * 4);
+  L->ss = take(m * 4 * 4);
   L->h = take(m * 2176 * 4);
   L->vu = take(m * 2048 * 2);
   L->qk4 = take(m * 512 * 2);
   L->P = take(m * 256 * 2);
   L->o = take(m * 1024 * 2);
-  L->o_ss = take(m * 8 * 4);
+  L->o_ss = take(m * 16 * 4);
   L->y = take(m * 512 * 4);
   L->c = take(m * 256 * 4);
   L->nhat = take(m * 256 * 2);
@@ -323,9 +323,10 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     P.e.out_bf16 = xbf;
     P.e.out_bf_ld = 512;
     P.e.ss_out = ss;
-    P.e.ss_out_ld = 2;
-    P.e.zero_pad_rows = 1;
-    CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    P.e.ss_out_ld = 4;
+    CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4,
+                                       EF_SAMP | EF_BIAS | EF_POS | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT | EF_ZERO_PAD,
+                                       ACT_NONE>>(P, mtiles * P.n_tiles, sms, st)));
   }
 
   const dim3 dw_grid_y(1, B * (Sp / DW_STRIP));
@@ -339,13 +340,12 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       lin_base(P, m_xbf, LM.w_in, 2176, 512, 256);
       P.shift_kblocks = 4;
       P.e.ss_in = ss;
-      P.e.ss_mode = 1;
       P.e.ss_dim_rsqrt = 0.044194173824159216f;  // 512^-0.5
       P.e.bias = LW.b_in;
-      P.e.act = ACT_SILU;
       P.e.out_f32 = h;
       P.e.out_ld = 2176;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_SS_SHIFT | EF_BIAS | EF_OUT_F32, ACT_SILU>>(
+          P, mtiles * P.n_tiles, sms, st)));
     }
     STEP(ST_DW_VU) dwconv17_kernel<EpiVU><<<dim3(8, dw_grid_y.y), 128, 0, st>>>(h, 2176, 0, LW.dw_in, 2048, Sp, S, EpiVU{vu});
     STEP(ST_DW_QK) dwconv17_kernel<EpiQK><<<dim3(1, dw_grid_y.y), 128, 0, st>>>(h, 2176, 2048, LW.dw_in + 2048 * 17, 128, Sp, S,
@@ -362,14 +362,12 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       LinearParams P;
       lin_base(P, m_o, LM.w_out, 512, 1024, 256);
       P.e.ss_in = o_ss;
-      P.e.ss_mode = 2;
-      P.e.ss_parts = 8;
       P.e.ss_dim_rsqrt = 0.03125f;  // 1024^-0.5
       P.e.bias = LW.b_out;
-      P.e.act = ACT_SILU;
       P.e.out_f32 = y;
       P.e.out_ld = 512;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_SS_PARTS | EF_BIAS | EF_OUT_F32, ACT_SILU>>(
+          P, mtiles * P.n_tiles, sms, st)));
     }
     STEP(ST_DW_RESX) dwconv17_kernel<EpiResX><<<dim3(2, dw_grid_y.y), 128, 0, st>>>(y, 512, 0, LW.dw_out, 512, Sp, S, EpiResX{x_in, x});
     // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
@@ -377,7 +375,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       LinearParams P;
       lin_base(P, m_x, LM.w_c1, 256, 512, 256);
       P.e.bias = LW.b_c1;
-      P.e.alpha = LW.prelu_c1;
+      P.alpha = LW.prelu_c1;
       P.ln_g1 = LW.ln1_g;
       P.ln_b1 = LW.ln1_b;
       P.e.out_f32 = c;
@@ -388,28 +386,27 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       LinearParams P;
       lin_base(P, m_nhat, LM.w_uv, 512, 256, 256);
       P.e.bias = LW.b_uv;
-      P.e.act = ACT_SILU;
       P.e.out_f32 = uvpre;
       P.e.out_ld = 512;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_BIAS | EF_OUT_F32, ACT_SILU>>(P, mtiles * P.n_tiles, sms,
+                                                                                     st)));
     }
     STEP(ST_DW_UV) dwconv17_kernel<EpiUV><<<dim3(2, dw_grid_y.y), 128, 0, st>>>(uvpre, 512, 0, LW.dw_uv, 512, Sp, S, EpiUV{xuv, xubf});
     STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;
       lin_base(P, m_xubf, LM.w_lin, 256, 256, 256);
       P.e.bias = LW.b_lin;
-      P.e.act = ACT_RELU;
       P.e.out_bf16 = f1;
       P.e.out_bf_ld = 256;
-      P.e.zero_pad_rows = 1;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_BIAS | EF_OUT_BF16 | EF_ZERO_PAD, ACT_RELU>>(P, mtiles, sms,
+                                                                                                    st)));
     }
     STEP(ST_FSMN_PROJ) {  // fsmn.project
       LinearParams P;
       lin_base(P, m_f1, LM.w_proj, 256, 256, 256);
       P.e.out_f32 = p;
       P.e.out_ld = 256;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4>>(P, mtiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_OUT_F32, ACT_NONE>>(P, mtiles, sms, st)));
     }
     double* st1 = in_stats;
     double* st2 = in_stats + static_cast<size_t>(B) * 512;
@@ -432,9 +429,10 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.out_bf16 = xbf;
       P.e.out_bf_ld = 512;
       P.e.ss_out = ss;
-      P.e.ss_out_ld = 2;
-      P.e.zero_pad_rows = 1;
-      CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+      P.e.ss_out_ld = 4;
+      CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4,
+                                         EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT | EF_ZERO_PAD,
+                                         ACT_NONE>>(P, mtiles * P.n_tiles, sms, st)));
     }
     CUDA_OK(cudaGetLastError());
   }
@@ -458,8 +456,9 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     P.e.bias = W.b_out1;
     P.e.out_f32 = mb;
     P.e.out_ld = 1024;
-    P.e.zero_pad_rows = 1;
-    CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+    // m is only the tf32 operand of the two gate convs: rounded to nearest tf32 on store
+    CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4, EF_BIAS | EF_OUT_F32 | EF_ZERO_PAD | EF_ROUND_TF32, ACT_NONE>>(
+        P, mtiles * P.n_tiles, sms, st)));
   }
   for (int spk = 0; spk < 2; ++spk) {
     STEP(ST_TANHSIG) {  // tanh(output) * sigmoid(output_gate)
@@ -475,13 +474,12 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     STEP(ST_DEC1) {  // conv1_decoder + ReLU, times the encoder output
       LinearParams P;
       lin_base(P, spk == 0 ? m_gated0 : m_gated1, ctx->m_dec1, 512, 512, 256);
-      P.e.act = ACT_RELU;
       P.e.mul = enc;
       P.e.mul_ld = 512;
       P.e.out_f32 = sep + static_cast<size_t>(spk) * M * 512;
       P.e.out_ld = 512;
-      P.e.zero_pad_rows = 1;
-      CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4>>(P, mtiles * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearGeneric<2, 256, 4, EF_MUL | EF_OUT_F32 | EF_ZERO_PAD, ACT_RELU>>(
+          P, mtiles * P.n_tiles, sms, st)));
     }
   }
   STEP(ST_DECODER) decoder_kernel<<<dim3(B * (Sp / DEC_FRAMES), 2), 256, 0, st>>>(sep, W.dec_w, out, B, Sp, S, T);

@@ -127,8 +127,8 @@ def run_step(h, step):
     h.poison()
     zpad_ok = lambda v: bool((v[:, S:] == 0).all())
 
-    def ss_of(x):  # ScaleNorm sums of the two channel halves
-        return torch.stack(((x[..., :256] ** 2).sum(-1), (x[..., 256:] ** 2).sum(-1)), dim=-1)
+    def ss_of(x):  # ScaleNorm partial sums: one per 128 channels
+        return (x ** 2).reshape(*x.shape[:-1], 4, 128).sum(-1)
 
     if step == "ENCODER":
         h.run(k)
@@ -156,7 +156,7 @@ def run_step(h, step):
         xb = h.get("xbf", bf, 512, valid_only=False)
         ok &= _check(m, "xbf", tp["x0"], xb[:, :S], 45)
         ok &= zpad_ok(xb)
-        ok &= _check(m, "ss", ss_of(tp["x0"]), h.get("ss", f32, 2), 55)
+        ok &= _check(m, "ss", ss_of(tp["x0"]), h.get("ss", f32, 4), 55)
     elif step == "FLASH_IN":
         h.put("xbf", tp["x0"], bf)
         h.put("ss", ss_of(tp["x0"]), f32)
@@ -199,11 +199,11 @@ def run_step(h, step):
         h.put_raw(h.lay.kv, tp["kv"].to(bf))
         h.run(k)
         ok &= _check(m, "o", tp["o"], h.get("o", bf, 1024), 38)
-        oss = h.get("o_ss", f32, 8).sum(-1)
+        oss = h.get("o_ss", f32, 16).sum(-1)
         ok &= _check(m, "o_ss", (tp["o"] ** 2).sum(-1), oss, 35)
     elif step == "TO_OUT":
         h.put("o", tp["o"], bf)
-        ss = (tp["o"] ** 2).reshape(B, S, 8, 128).sum(-1)
+        ss = (tp["o"] ** 2).reshape(B, S, 8, 2, 64).sum(-1).reshape(B, S, 16)
         h.put("o_ss", ss, f32)
         h.run(k)
         ok &= _check(m, "y", tp["to_out_pre"], h.get("y", f32, 512), 40)
@@ -275,7 +275,7 @@ def run_step(h, step):
         xb = h.get("xbf", bf, 512, valid_only=False)
         ok &= _check(m, "xbf", tp["layer0"], xb[:, :S], 45)
         ok &= zpad_ok(xb)
-        ok &= _check(m, "ss", ss_of(tp["layer0"]), h.get("ss", f32, 2), 55)
+        ok &= _check(m, "ss", ss_of(tp["layer0"]), h.get("ss", f32, 4), 55)
     elif step == "FINAL_LN":
         h.put("x", tp["layer0"], f32)
         h.run(k)
