@@ -45,6 +45,7 @@ struct EpiGeneric {
   int out_col0;            // column offset added when storing
   __nv_bfloat16* out_bf16;
   int out_bf_ld;
+  int out_bf_col0;         // column offset of the bf16 store
   float* ss_out;           // [Mtot][ss_out_ld], entry = global column / 128
   int ss_out_ld;
 };
@@ -244,7 +245,7 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
         }
       }
       if constexpr ((EF & EF_OUT_BF16) != 0) {
-        uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.out_bf_ld + e.out_col0 + col0);
+        uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.out_bf_ld + e.out_bf_col0 + col0);
         o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         if (full)
           o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),

@@ -265,7 +265,7 @@ def run_step(h, step):
         h.put_raw(h.lay.in_stats, z)
         h.run(k)
         g = h.get("g", f32, 256, valid_only=False)
-        ok &= _check(m, "g", tp["g"], g[:, :S], 90)
+        ok &= _check(m, "g", tp["g"], g[:, :S], 65)  # stored rounded to tf32 (operand of conv2 only)
         ok &= zpad_ok(g)
     elif step == "FSMN_C2":
         h.put("g", tp["g"], f32)
@@ -295,7 +295,7 @@ def run_step(h, step):
         h.put_raw(h.lay.samp + 2 * B * 4, torch.cat((rstd, -rstd * mean)).float())
         h.run(k)
         ab = h.get("uvpre", f32, 512, valid_only=False)
-        ok &= _check(m, "mask_in", tp["mask_in"], ab[:, :S], 100)
+        ok &= _check(m, "mask_in", tp["mask_in"], ab[:, :S], 65)  # stored rounded to tf32
         ok &= zpad_ok(ab)
     elif step == "OUT1":
         h.put("uvpre", tp["mask_in"], f32)
