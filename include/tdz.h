@@ -13,7 +13,7 @@
  *   AudioProcessor.separate_speaker chunk concat               AudioProcessor.py:920-948
  *       -> tdz_stitch_concat()
  *   TargetASR.embedding['eres2netv2_large'](wav, output_emb)   TargetASR.py:102-103,155-163
- *       -> tdz_fbank() + tdz_embed()
+ *       -> tdz_fbank() + tdz_embed()                           (modelscope ERes2NetV2 pipeline)
  *   TargetASR.cosine_similarity                                TargetASR.py:144-152
  *       -> tdz_cosine_scores()
  *
@@ -162,6 +162,46 @@ int64_t tdz_fbank_frames(int64_t T);
 int tdz_set_fbank_tables(tdz_ctx* ctx, const float* window_dev, const float* twiddle_dev, const float* mel_dev,
                          const int32_t* mel_lo_dev, const int32_t* mel_hi_dev);
 int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t T, float* feat_dev, void* stream);
+
+/* ERes2NetV2-Large (modelscope `ERes2NetV2`, m_channels 64, blocks [3,4,6,3], baseWidth 24, scale 4,
+ * expansion 4, TSTP pooling, 192-d embedding).  Every convolution has its eval-mode
+ * BatchNorm folded in by the packer (targetdiarization_b200/weights.py) and is stored as a GEMM operand:
+ * w = bf16 [round_up(N, BN)][round_up(K, 64)], zero padded, K ordered (kh, kw, cin) for 3x3 kernels;
+ * b = fp32 [round_up(N, BN)];  BN = 32 / 64 / 128 / 256 = the smallest of these >= N. */
+#define TDZ_SV_NUM_BLOCKS 16
+#define TDZ_SV_EMBED_DIM 192
+typedef struct tdz_conv {
+  const void* w;
+  const float* b;
+} tdz_conv;
+typedef struct tdz_eres_block {
+  tdz_conv conv1;      /* 1x1, in_planes -> 4*width (stride on this conv) */
+  tdz_conv convs[4];   /* 3x3, width -> width */
+  tdz_conv aff_a[3];   /* AFF blocks only (layers 3-4): 1x1, 2*width -> width/4 */
+  tdz_conv aff_b[3];   /*                               1x1, width/4 -> width */
+  tdz_conv conv3;      /* 1x1, 4*width -> 4*planes */
+  tdz_conv shortcut;   /* 1x1 (stride), in_planes -> 4*planes; w == NULL for identity shortcuts */
+} tdz_eres_block;
+typedef struct tdz_eres2netv2_weights {
+  const float* stem_w; /* fp32 [64][9] conv1 + bn1 folded */
+  const float* stem_b; /* fp32 [64] */
+  tdz_eres_block blocks[TDZ_SV_NUM_BLOCKS];
+  tdz_conv layer3_ds;  /* 3x3 stride 2, 1024 -> 2048, no BN */
+  tdz_conv fuse_a;     /* fuse34 AFF: 4096 -> 512 */
+  tdz_conv fuse_b;     /*             512 -> 2048 */
+  tdz_conv seg1;       /* Linear 40960 -> 192 */
+} tdz_eres2netv2_weights;
+int tdz_set_eres2netv2_weights(tdz_ctx* ctx, const tdz_eres2netv2_weights* w);
+size_t tdz_embed_workspace_bytes(int64_t N, int64_t frames);
+/* feat_dev fp32 [N][frames][80] (output of tdz_fbank) -> emb_dev fp32 [N][192].  Replaces the model call
+ * inside `self.embedding['eres2netv2_large'](wav, output_emb=True)` (TargetASR.py:161). */
+int tdz_embed(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* emb_dev, void* workspace_dev,
+              size_t workspace_bytes, void* stream);
+
+/* Test hook: stops after the stem (stop_block -1), after residual block stop_block (0..15) or after the fuse34
+ * map (16) and copies that fp32 NHWC feature map [N*H*W][C] into out_dev (sized by the caller). */
+int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* out_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream, int stop_block);
 
 /* cosine similarity of N embeddings against one target, TargetASR.cosine_similarity semantics
  * (all-zero vector -> 1.0; result clamped to [0,1]).  emb_dev [N][dim], target_dev [dim] -> scores_dev [N]. */

@@ -34,6 +34,23 @@ class SepLayout(ctypes.Structure):
                    ("kv_nsplit", ctypes.c_int32), ("kv_kb_per_split", ctypes.c_int32)])
 
 
+SV_NUM_BLOCKS = 16
+
+
+class Conv(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("b", ctypes.c_void_p)]
+
+
+class EresBlock(ctypes.Structure):
+    _fields_ = [("conv1", Conv), ("convs", Conv * 4), ("aff_a", Conv * 3), ("aff_b", Conv * 3), ("conv3", Conv),
+                ("shortcut", Conv)]
+
+
+class Eres2NetV2Weights(ctypes.Structure):
+    _fields_ = [("stem_w", ctypes.c_void_p), ("stem_b", ctypes.c_void_p), ("blocks", EresBlock * SV_NUM_BLOCKS),
+                ("layer3_ds", Conv), ("fuse_a", Conv), ("fuse_b", Conv), ("seg1", Conv)]
+
+
 # name -> (restype, argtypes); mirrors include/tdz.h one to one
 _vp, _i64, _sz, _int, _f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
 SIGNATURES = {
@@ -55,6 +72,10 @@ SIGNATURES = {
     "tdz_fbank_frames": (_i64, [_i64]),
     "tdz_set_fbank_tables": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "tdz_fbank": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "tdz_set_eres2netv2_weights": (_int, [_vp, ctypes.POINTER(Eres2NetV2Weights)]),
+    "tdz_embed_workspace_bytes": (_sz, [_i64, _i64]),
+    "tdz_embed": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "tdz_embed_debug": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _int]),
     "tdz_cosine_scores": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
 }
 

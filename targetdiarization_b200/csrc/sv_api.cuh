@@ -217,8 +217,11 @@ static int sv_gemm(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const void* A
 static unsigned sv_grid(int64_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
 // ---------------------------------------------------------------------------------------------- forward
+// stop_block >= -1: test hook, copies the fp32 NHWC output of the stem (-1) or of residual block `stop_block`
+// (0..15), or the fuse34 map (16), into `emb` and returns.  stop_block == SV_RUN_ALL runs the whole model.
+constexpr int SV_RUN_ALL = 1000;
 static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N, int64_t frames, float* emb,
-                    void* ws, size_t ws_bytes, cudaStream_t st) {
+                    void* ws, size_t ws_bytes, cudaStream_t st, int stop_block = SV_RUN_ALL) {
   if (!M.ready) return fail(ctx, "tdz_embed: weights not set");
   if (N <= 0 || frames < 8) return fail(ctx, "tdz_embed: need at least 8 feature frames per utterance");
   SvLayout L;
@@ -236,9 +239,15 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
                 *col = Hh(L.col), *cat4 = Hh(L.cat4), *fcat = Hh(L.fcat), *fmid = Hh(L.fmid), *stats = Hh(L.stats);
   const int n = static_cast<int>(N);
 
+  // columns N..63 of `mid` are never written but are read (against zero weights) by the second AFF conv
+  CUDA_OK(cudaMemsetAsync(mid, 0, static_cast<size_t>(d.Pp[2]) * 64 * 2, st));
   // stem
   sv_stem_kernel<<<sv_grid(d.P[0] * 8), 256, 0, st>>>(feat, M.stem_w, M.stem_b, x_f, x_b, n, static_cast<int>(d.H[0]),
                                                       static_cast<int>(d.W[0]));
+  if (stop_block == -1) {
+    CUDA_OK(cudaMemcpyAsync(emb, x_f, static_cast<size_t>(d.P[0]) * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   int layer = 0;
   for (int k = 0; k < TDZ_SV_NUM_BLOCKS; ++k) {
     const SvBlockSpec& s = M.spec[k];
@@ -313,6 +322,10 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     if (sv_gemm(ctx, st, M.conv3[k], cat4, 4 * wd, P, Pp, SV_RES_HT20_BOTH, e)) return 1;
     std::swap(x_f, y_f);
     std::swap(x_b, y_b);
+    if (k == stop_block) {
+      CUDA_OK(cudaMemcpyAsync(emb, x_f, static_cast<size_t>(P) * 4 * s.planes * 4, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
     if (k == 12) {
       // end of layer3: out3_ds = Conv2d(1024, 2048, 3, stride 2, pad 1)(out3), needed after layer4
       const int64_t P4 = d.P[3], Pp4 = d.Pp[3];
@@ -342,6 +355,10 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     e.out_f32 = fuse;
     e.out_ld = 2048;
     if (sv_gemm(ctx, st, M.fuse_b, fmid, 512, P4, Pp4, SV_AFF_F32, e)) return 1;
+    if (stop_block == TDZ_SV_NUM_BLOCKS) {
+      CUDA_OK(cudaMemcpyAsync(emb, fuse, static_cast<size_t>(P4) * 2048 * 4, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
     // TSTP + embedding Linear
     const int64_t Np = (N + 127) / 128 * 128;
     CUDA_OK(cudaMemsetAsync(stats, 0, static_cast<size_t>(Np) * 40960 * 2, st));

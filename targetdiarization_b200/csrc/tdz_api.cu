@@ -13,6 +13,9 @@
 #include "kernels_fbank.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_sep.cuh"
+#include "kernels_sv.cuh"
+
+#include <algorithm>
 
 using namespace tdz;
 
@@ -36,6 +39,7 @@ struct tdz_ctx {
   CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1;
   bool have_fbank = false;
   FbankTables fb;
+  struct SvModel* sv = nullptr;
 };
 
 static int fail(tdz_ctx* c, const char* fmt, ...) {
@@ -78,7 +82,11 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
   *out = c;
   return 0;
 }
-extern "C" void tdz_destroy(tdz_ctx* ctx) { delete ctx; }
+static void sv_free(tdz_ctx* ctx);
+extern "C" void tdz_destroy(tdz_ctx* ctx) {
+  if (ctx) sv_free(ctx);
+  delete ctx;
+}
 extern "C" const char* tdz_last_error(tdz_ctx* ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
 extern "C" int tdz_num_sms(tdz_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 
@@ -570,4 +578,41 @@ extern "C" int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t 
   fbank_meannorm_kernel<<<static_cast<unsigned>(N), 240, 0, st>>>(feat_dev, frames);
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ embedder
+#include "sv_api.cuh"
+
+static void sv_free(tdz_ctx* ctx) {
+  delete ctx->sv;
+  ctx->sv = nullptr;
+}
+extern "C" int tdz_set_eres2netv2_weights(tdz_ctx* ctx, const tdz_eres2netv2_weights* w) {
+  if (!ctx || !w) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->sv) ctx->sv = new SvModel();
+  ctx->sv->ready = false;
+  return sv_set_weights(ctx, ctx->sv, w);
+}
+extern "C" size_t tdz_embed_workspace_bytes(int64_t N, int64_t frames) {
+  if (N <= 0 || frames < 8) return 0;
+  SvLayout L;
+  sv_layout(N, frames, &L);
+  return L.total;
+}
+extern "C" int tdz_embed(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* emb_dev, void* ws,
+                         size_t ws_bytes, void* stream) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->sv) return fail(ctx, "tdz_embed: weights not set");
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(ctx, "tdz_embed: workspace must be 1024 B aligned");
+  return sv_embed(ctx, *ctx->sv, feat_dev, N, frames, emb_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+extern "C" int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* out_dev, void* ws,
+                               size_t ws_bytes, void* stream, int stop_block) {
+  if (!ctx) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->sv) return fail(ctx, "tdz_embed: weights not set");
+  return sv_embed(ctx, *ctx->sv, feat_dev, N, frames, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream),
+                  stop_block);
 }

@@ -1,0 +1,132 @@
+"""`Embedder`: the callable the reference keeps in `TargetASR.embedding['eres2netv2_large']` (TargetASR.py:102-103)
+and calls as `self.embedding[name](wav, output_emb=True)['embs']` (TargetASR.py:155-163): Kaldi fbank(80) with
+per-utterance mean normalisation, ERes2NetV2-Large, 192-d embedding.  Compute = libtdz.so (tdz_fbank + tdz_embed);
+there is no CPU path.  `embed_many` / `score_many` are the batched forms the per-segment scoring loops of the
+reference (TargetDiarization.py:581-629) collapse into."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, fbank
+from .weights import PackedEres2NetV2
+
+EMBED_DIM = 192
+
+
+class Embedder:
+    sample_rate = 16000
+
+    def __init__(self, state_dict=None, device="cuda:0", max_workspace_bytes=24 << 30, handle=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("tdz.Embedder runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        self._h = handle if handle is not None else _lib.Handle(self.device.index or 0)
+        self._packed = None
+        self._ws = None
+        self.max_workspace_bytes = int(max_workspace_bytes)
+        win, tw = fbank.povey_window(), fbank.twiddles()
+        mel, lo, hi = fbank.mel_banks()
+        self._tables = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in (win, tw, mel, lo, hi)]
+        self._h.check(self._h.lib.tdz_set_fbank_tables(self._h.ptr, *[t.data_ptr() for t in self._tables]),
+                      "tdz_set_fbank_tables")
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def load_state_dict(self, state_dict, strict=True):
+        self._packed = PackedEres2NetV2(state_dict, self.device)
+        self._h.check(self._h.lib.tdz_set_eres2netv2_weights(self._h.ptr, ctypes.byref(self._packed.table)),
+                      "tdz_set_eres2netv2_weights")
+        return self
+
+    # ---- pieces
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def fbank(self, wav):
+        """wav float32 [N,T] on the device -> [N, frames, 80] mean-normalised log-mel features."""
+        wav = wav.to(torch.float32).contiguous()
+        N, T = wav.shape
+        frames = fbank.num_frames(T)
+        if frames < 1:
+            raise ValueError(f"utterance of {T} samples is shorter than one 25 ms fbank window")
+        feat = torch.empty(N, frames, fbank.NMEL, dtype=torch.float32, device=self.device)
+        self._h.check(self._h.lib.tdz_fbank(self._h.ptr, wav.data_ptr(), N, T, feat.data_ptr(), self._stream()),
+                      "tdz_fbank")
+        return feat
+
+    def max_batch(self, frames):
+        """Largest sub-batch whose workspace fits max_workspace_bytes (at least 1)."""
+        lib = self._h.lib
+        per1 = int(lib.tdz_embed_workspace_bytes(1, frames))
+        n = max(1, min(256, self.max_workspace_bytes // max(per1, 1)))
+        while n > 1 and int(lib.tdz_embed_workspace_bytes(n, frames)) > self.max_workspace_bytes:
+            n -= 1
+        return n
+
+    def embed_features(self, feat):
+        """feat float32 [N, frames, 80] -> [N,192] (ERes2NetV2 forward)."""
+        if self._packed is None:
+            raise RuntimeError("Embedder has no weights; call load_state_dict first")
+        N, frames, _ = feat.shape
+        emb = torch.empty(N, EMBED_DIM, dtype=torch.float32, device=self.device)
+        nb = self.max_batch(frames)
+        lib, h = self._h.lib, self._h
+        for i in range(0, N, nb):
+            n = min(nb, N - i)
+            nbytes = int(lib.tdz_embed_workspace_bytes(n, frames))
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = None
+                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            h.check(lib.tdz_embed(h.ptr, feat[i:i + n].data_ptr(), n, frames, emb[i:i + n].data_ptr(),
+                                  self._ws.data_ptr(), nbytes, self._stream()), "tdz_embed")
+        return emb
+
+    def embed_many(self, wavs):
+        """Batched embedding.  wavs: device/host tensor [N,T], ndarray [N,T] or a list of 1-D arrays/tensors of
+        possibly different lengths (grouped by length).  Returns a device tensor [N,192]."""
+        if isinstance(wavs, (list, tuple)):
+            arrs = [self._to_dev(w).reshape(-1) for w in wavs]
+            out = torch.empty(len(arrs), EMBED_DIM, dtype=torch.float32, device=self.device)
+            by_len = {}
+            for i, a in enumerate(arrs):
+                by_len.setdefault(a.numel(), []).append(i)
+            for _, idx in sorted(by_len.items()):
+                out[idx] = self.embed_features(self.fbank(torch.stack([arrs[i] for i in idx])))
+            return out
+        w = self._to_dev(wavs)
+        if w.ndim == 1:
+            w = w.unsqueeze(0)
+        return self.embed_features(self.fbank(w))
+
+    def score_many(self, wavs, target_embedding):
+        """cosine_similarity (TargetASR.py:144-152 semantics) of every utterance against one target: [N]."""
+        return self.cosine_scores(self.embed_many(wavs), target_embedding)
+
+    def cosine_scores(self, emb, target_embedding):
+        emb = emb.to(torch.float32).contiguous()
+        tgt = self._to_dev(target_embedding).reshape(-1).contiguous()
+        N, dim = emb.shape
+        scores = torch.empty(N, dtype=torch.float32, device=self.device)
+        self._h.check(self._h.lib.tdz_cosine_scores(self._h.ptr, emb.data_ptr(), tgt.data_ptr(), N, dim,
+                                                    scores.data_ptr(), self._stream()), "tdz_cosine_scores")
+        return scores
+
+    def _to_dev(self, x):
+        if isinstance(x, np.ndarray):
+            if np.issubdtype(x.dtype, np.integer):  # the modelscope pipeline rescales integer PCM by 2^-15
+                x = x.astype(np.float32) / 32768.0
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return x.to(self.device, torch.float32)
+
+    # ---- the reference call surface (TargetASR.py:161)
+    def __call__(self, wav, output_emb=True):
+        if isinstance(wav, str) or (isinstance(wav, (list, tuple)) and wav and isinstance(wav[0], str)):
+            raise TypeError("tdz.Embedder takes waveforms (ndarray [n,T] / list of arrays); file paths are read by "
+                            "the caller (AudioProcessor.read_audio)")
+        embs = self.embed_many(wav).cpu().numpy()
+        out = {"embs": embs}
+        if len(embs) == 2:  # the pipeline also scores a pair when given two inputs
+            a, b = embs
+            out["outputs"] = {"score": float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-12))}
+        return out

@@ -118,3 +118,79 @@ class PackedMossFormer2:
 
     def _tf32(self, x):
         return self._put(round_tf32(x.contiguous()), torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ ERes2NetV2
+SV_BLOCKS = (3, 4, 6, 3)
+BN_EPS = 1e-5
+
+
+def _sv_block_n(n):
+    return 32 if n <= 32 else 64 if n <= 64 else 128 if n <= 128 else 256
+
+
+class PackedEres2NetV2:
+    """ERes2NetV2-Large state dict (published module names: conv1/bn1, layer{l}.{b}.{conv1,bn1,convs.i,bns.i,
+    fuse_models.i.local_att.{0,1,3,4},conv3,bn3,shortcut.{0,1}}, layer3_ds, fuse34.local_att.*, seg_1) ->
+    include/tdz.h: tdz_eres2netv2_weights.  Eval-mode BatchNorm is folded into the preceding convolution."""
+
+    def __init__(self, state_dict, device):
+        self.device = torch.device(device)
+        self._keep = []
+        sd = {k: v.detach().to(torch.float64).cpu() for k, v in state_dict.items() if v.is_floating_point()}
+        self.table = _lib.Eres2NetV2Weights()
+        t = self.table
+
+        def bn_fold(w, b, bn):
+            scale = sd[bn + ".weight"] / torch.sqrt(sd[bn + ".running_var"] + BN_EPS)
+            w = w * scale.view(-1, *([1] * (w.ndim - 1)))
+            b0 = b if b is not None else torch.zeros_like(scale)
+            return w, (b0 - sd[bn + ".running_mean"]) * scale + sd[bn + ".bias"]
+
+        def conv(dst, name, bn=None):
+            w = sd[name + ".weight"]
+            b = sd.get(name + ".bias")
+            if bn is not None:
+                w, b = bn_fold(w, b, bn)
+            if w.ndim == 4:  # [cout, cin, kh, kw] -> K ordered (kh, kw, cin), matching the im2col kernel
+                w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+            n, k = w.shape
+            bn_tile = _sv_block_n(n)
+            n_p, k_p = -(-n // bn_tile) * bn_tile, -(-k // 64) * 64
+            wp = torch.zeros(n_p, k_p, dtype=torch.float64)
+            wp[:n, :k] = w
+            bp = torch.zeros(n_p, dtype=torch.float64)
+            if b is not None:
+                bp[:n] = b
+            dst.w = self._put(wp, torch.bfloat16)
+            dst.b = self._put(bp, torch.float32)
+
+        w, b = bn_fold(sd["conv1.weight"], None, "bn1")
+        t.stem_w = self._put(w.reshape(64, 9), torch.float32)
+        t.stem_b = self._put(b, torch.float32)
+        k = 0
+        for li, nb in enumerate(SV_BLOCKS):
+            for bi in range(nb):
+                p = f"layer{li + 1}.{bi}"
+                blk = t.blocks[k]
+                conv(blk.conv1, p + ".conv1", p + ".bn1")
+                for i in range(4):
+                    conv(blk.convs[i], f"{p}.convs.{i}", f"{p}.bns.{i}")
+                if li >= 2:
+                    for i in range(3):
+                        a = f"{p}.fuse_models.{i}.local_att"
+                        conv(blk.aff_a[i], a + ".0", a + ".1")
+                        conv(blk.aff_b[i], a + ".3", a + ".4")
+                conv(blk.conv3, p + ".conv3", p + ".bn3")
+                if (p + ".shortcut.0.weight") in sd:
+                    conv(blk.shortcut, p + ".shortcut.0", p + ".shortcut.1")
+                k += 1
+        conv(t.layer3_ds, "layer3_ds")
+        conv(t.fuse_a, "fuse34.local_att.0", "fuse34.local_att.1")
+        conv(t.fuse_b, "fuse34.local_att.3", "fuse34.local_att.4")
+        conv(t.seg1, "seg_1")
+
+    def _put(self, x, dtype):
+        x = x.contiguous().to(dtype).to(self.device)
+        self._keep.append(x)
+        return ctypes.c_void_p(x.data_ptr())

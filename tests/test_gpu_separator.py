@@ -37,6 +37,9 @@ def _full(B, T, seed, min_db=40.0):
         ref = mossformer2_forward(sd, mix)
     snr = snr_db(ref, out)
     print(f"full forward B={B} T={T}: {snr:.2f} dB")
+    import json
+    with open(os.path.join(ROOT, "gpurun_out", "parity.jsonl"), "a") as f:
+        f.write(json.dumps({"test": f"separator_full_B{B}_T{T}_seed{seed}_snr_db", "value": snr}) + "\n")
     assert out.shape == (B, 2, T)
     # north_star tolerance: waveform SNR >= 40 dB versus the reference output
     assert snr >= min_db, f"{snr:.2f} dB"
