@@ -181,9 +181,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle.synth import random_state_dict, synthetic_mixture   # synthetic weights/data generators only
-    from targetdiarization_b200 import Separator
     from targetdiarization_b200.pipeline import SeparationScoringStage
+    from targetdiarization_b200.synth import synthetic_mixture
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -294,7 +293,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * B * T * 4, "d2h_bytes_per_step": world * (B * 2 * T * 4 + B * 2 * 4)},
-            "gpu_launches": stage.launches_per_step() * args.steps,
+            "gpu_launches": stage.launches_per_run(B, T) * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
         }

@@ -38,68 +38,8 @@ def fbank_features(wav):
     return torch.stack(feats)
 
 
-def block_specs():
-    """[(name, in_planes, planes, stride, is_aff)] for the 16 residual blocks."""
-    specs = []
-    in_planes = M_CHANNELS
-    for li, (n, mult, stride, aff) in enumerate(zip(NUM_BLOCKS, (1, 2, 4, 8), (1, 2, 2, 2), (False, False, True, True))):
-        planes = M_CHANNELS * mult
-        for bi in range(n):
-            specs.append((f"layer{li + 1}.{bi}", in_planes, planes, stride if bi == 0 else 1, aff))
-            in_planes = planes * EXPANSION
-    return specs
-
-
-def random_state_dict(seed=0):
-    """Random-init weights with non-trivial BatchNorm running statistics (so BN folding is exercised)."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-
-    def conv(name, cout, cin, k, bias=False):
-        fan_in = cin * k * k
-        bound = 1.0 / math.sqrt(fan_in)
-        # kaiming-uniform(a=sqrt(5)) as nn.Conv2d does
-        sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
-        if bias:
-            sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
-
-    def bn(name, c):
-        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
-        sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
-        sd[name + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
-        sd[name + ".running_var"] = 1.0 + 0.2 * torch.rand(c, generator=g)
-
-    def aff(name, channels, r=4):
-        inter = channels // r
-        conv(name + ".local_att.0", inter, channels * 2, 1, bias=True)
-        bn(name + ".local_att.1", inter)
-        conv(name + ".local_att.3", channels, inter, 1, bias=True)
-        bn(name + ".local_att.4", channels)
-
-    conv("conv1", M_CHANNELS, 1, 3)
-    bn("bn1", M_CHANNELS)
-    for name, in_planes, planes, stride, is_aff in block_specs():
-        width = int(math.floor(planes * (BASE_WIDTH / 64.0)))
-        conv(name + ".conv1", width * SCALE, in_planes, 1)
-        bn(name + ".bn1", width * SCALE)
-        for i in range(SCALE):
-            conv(f"{name}.convs.{i}", width, width, 3)
-            bn(f"{name}.bns.{i}", width)
-        if is_aff:
-            for i in range(SCALE - 1):
-                aff(f"{name}.fuse_models.{i}", width)
-        conv(name + ".conv3", planes * EXPANSION, width * SCALE, 1)
-        bn(name + ".bn3", planes * EXPANSION)
-        if stride != 1 or in_planes != planes * EXPANSION:
-            conv(name + ".shortcut.0", planes * EXPANSION, in_planes, 1)
-            bn(name + ".shortcut.1", planes * EXPANSION)
-    conv("layer3_ds", M_CHANNELS * 8 * EXPANSION, M_CHANNELS * 4 * EXPANSION, 3)
-    aff("fuse34", M_CHANNELS * 8 * EXPANSION)
-    stats_dim = (FEAT_DIM // 8) * M_CHANNELS * 8 * EXPANSION * 2
-    bound = 1.0 / math.sqrt(stats_dim)
-    sd["seg_1.weight"] = (torch.rand(EMBED_DIM, stats_dim, generator=g) * 2 - 1) * bound
-    sd["seg_1.bias"] = (torch.rand(EMBED_DIM, generator=g) * 2 - 1) * bound
-    return sd
+from targetdiarization_b200.synth import block_specs  # noqa: E402  (architecture table shared with the generator)
+from targetdiarization_b200.synth import random_eres2netv2_state_dict as random_state_dict  # noqa: E402,F401
 
 
 def _bn(x, sd, name):

@@ -1,0 +1,175 @@
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE in the build container (where /root/reference exists).
+
+TEST INFRASTRUCTURE ONLY (oracle).  Run:  python -m oracle.make_golden
+The vectors are small (a few hundred KB in total) and are committed together with this script, so that the
+oracle restatements (oracle/mossformer2_port.py, oracle/stage_port.py) and the CUDA path can be checked against
+outputs of the reference itself on the GPU box, where the reference tree does not exist.
+
+  mossformer2_small.npz   reference MossFormer2 module (look2hear/models/mossformer2.py) loaded with the weights of
+                          targetdiarization_b200.synth.random_state_dict(seed, perturb=True): full forward on two
+                          ragged inputs + layer taps (strided samples, to stay small)
+  host_logic.npz          AudioProcessor.separate_speaker (extracted from AudioProcessor.py with `ast`, run with a
+                          recording stand-in for self.separater) -> chunk boundaries for a list of lengths;
+                          look2hear.utils.wav_chunk_inference (imported by path) with a toy model -> stitched output;
+                          TargetASR.cosine_similarity (extracted with `ast`) on fixed vectors
+  fbank.npz               torchaudio.compliance.kaldi.fbank (the function the modelscope pipeline calls) on a fixed
+                          1 s signal, mean-normalised
+"""
+import ast
+import os
+import sys
+import textwrap
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from targetdiarization_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CHUNK_LENGTHS = [1, 15999, 79999, 80000, 80001, 159999, 160000, 160001, 239999, 240000, 240001, 320000, 400000,
+                 400001, 480000, 559999, 1000000, 1680001]
+
+
+def extract_method(path, cls, name):
+    """Source of method `name` of class `cls` in the reference file `path`, dedented."""
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == name:
+                    return textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno]))
+    raise KeyError(f"{cls}.{name} not found in {path}")
+
+
+def reference_separate_speaker():
+    """AudioProcessor.separate_speaker compiled from the reference source; returns a function
+    (audio, separater, loudness) -> (spk1, spk2, [(start, end)...])."""
+    code = extract_method(os.path.join(ref_loader.REF_ROOT, "AudioProcessor.py"), "AudioProcessor", "separate_speaker")
+    ns = {"np": np, "torch": torch}
+    exec(compile(code, "AudioProcessor.separate_speaker", "exec"), ns)
+    fn = ns["separate_speaker"]
+
+    def run(audio, separater, loudness):
+        calls = []
+
+        def rec(x):
+            calls.append(int(x.shape[-1]))
+            return separater(x)
+        fake = types.SimpleNamespace(
+            is_separate_audio=True, verbose_log=False, device="cpu", separater=rec,
+            ndarray_to_torchaudio=lambda a: torch.tensor(a.reshape(1, -1)),   # AudioProcessor.py:1051-1056
+            meter_loudness=lambda audio_data, sampling_rate: loudness(audio_data))
+        s1, s2 = fn(fake, audio, 16000, False)
+        bounds, pos = [], 0
+        for n in calls:
+            bounds.append((pos, pos + n))
+            pos += n
+        return s1, s2, bounds
+    return run
+
+
+def toy_separater(x):
+    """[1,T] -> [1,2,T]: cheap, chunk-position dependent (so boundaries show in the output)."""
+    t = torch.arange(x.shape[-1], dtype=torch.float32) / x.shape[-1]
+    return torch.stack((x * (0.5 + t), -0.25 * x + 0.1 * t), dim=1)
+
+
+def rms_loudness(a):
+    return round(float(10 * np.log10(np.mean(np.square(a.astype(np.float64))) + 1e-12)), 1)
+
+
+def make_host_logic():
+    run = reference_separate_speaker()
+    out = {}
+    bounds_flat, bounds_off = [], [0]
+    for L in CHUNK_LENGTHS:
+        audio = np.zeros(L, dtype=np.float32)
+        _, _, b = run(audio, lambda x: torch.zeros(1, 2, x.shape[-1]), lambda a: 0.0)
+        bounds_flat += [v for se in b for v in se]
+        bounds_off.append(len(bounds_flat))
+    out["chunk_lengths"] = np.array(CHUNK_LENGTHS, dtype=np.int64)
+    out["chunk_bounds_flat"] = np.array(bounds_flat, dtype=np.int64)
+    out["chunk_bounds_off"] = np.array(bounds_off, dtype=np.int64)
+    # full run with a toy separater on 2.6 windows; stream order decided by the stub loudness
+    g = np.random.default_rng(7)
+    audio = (g.standard_normal(416000) * 0.1).astype(np.float32)
+    s1, s2, b = run(audio, toy_separater, rms_loudness)
+    out["sepspk_audio_seed"] = np.array([7, 416000], dtype=np.int64)
+    out["sepspk_spk1_stride"] = s1[::997].copy()
+    out["sepspk_spk2_stride"] = s2[::997].copy()
+    out["sepspk_bounds"] = np.array(b, dtype=np.int64)
+    # wav_chunk_inference with a toy model at sr = 1000 (session 12000, hop 4000)
+    wci = ref_loader.load_reference_wav_chunk_inference()
+    mix = torch.from_numpy((g.standard_normal(30500) * 0.1).astype(np.float32))[None, None, :]
+
+    def toy_model(x):  # [n,1,session] -> [n,2,1,session]
+        t = torch.arange(x.shape[-1], dtype=torch.float32) / x.shape[-1]
+        return torch.stack((x * (0.5 + t), x * x - 0.3 * t), dim=1)
+    y = wci(toy_model, mix, sr=1000, target_length=12.0, hop_length=4.0, batch_size=10, n_tracks=2)
+    out["ola_mix"] = mix[0, 0].numpy()
+    out["ola_out"] = y[:, 0].numpy()
+    # cosine_similarity from TargetASR
+    code = extract_method(os.path.join(ref_loader.REF_ROOT, "TargetASR.py"), "TargetASR", "cosine_similarity")
+    ns = {"np": np}
+    exec(compile(code, "TargetASR.cosine_similarity", "exec"), ns)
+    a = g.standard_normal((6, 192)).astype(np.float32)
+    tgt = g.standard_normal(192).astype(np.float32)
+    a[2] = 0.0
+    a[4] = -tgt
+    a[5] = 3 * tgt
+    out["cos_a"] = a
+    out["cos_target"] = tgt
+    out["cos_scores"] = np.array([ns["cosine_similarity"](None, a[i], tgt) for i in range(6)], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, "host_logic.npz"), **out)
+    print("host_logic.npz:", {k: v.shape for k, v in out.items()})
+
+
+def make_mossformer2():
+    pkg = ref_loader.load_reference_modules()
+    out = {}
+    for tag, seed, B, T in (("a", 0, 1, 4000), ("b", 1, 2, 2413)):
+        sd = synth.random_state_dict(seed=seed, perturb=True)
+        model = pkg.mossformer2.MossFormer2().eval()
+        missing, unexpected = model.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(1234 + seed)
+        mix = torch.randn(B, T, generator=g) * 0.1
+        taps = {}
+        hooks = []
+        blk = model.mask_net.mdl.intra_mdl.mossformerM
+        for i in (0, 11, 23):
+            hooks.append(blk.layers[i].register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"flash{i}", o)))
+            hooks.append(blk.fsmn[i].register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"layer{i}", o)))
+        with torch.no_grad():
+            y = model(mix)
+        for h in hooks:
+            h.remove()
+        out[f"{tag}_cfg"] = np.array([seed, B, T], dtype=np.int64)
+        out[f"{tag}_out"] = y.numpy()
+        for k, v in taps.items():
+            out[f"{tag}_{k}"] = v[:, ::37, ::7].contiguous().numpy()   # strided sample of [B,S,512]
+    np.savez_compressed(os.path.join(GOLDEN, "mossformer2_small.npz"), **out)
+    print("mossformer2_small.npz:", {k: v.shape for k, v in out.items()})
+
+
+def make_fbank():
+    import torchaudio.compliance.kaldi as kaldi
+    wav = synth.synthetic_mixture(1, 16037, seed=5)
+    f = kaldi.fbank(wav, num_mel_bins=80)
+    f = f - f.mean(dim=0, keepdim=True)
+    np.savez_compressed(os.path.join(GOLDEN, "fbank.npz"), cfg=np.array([5, 16037], dtype=np.int64), feat=f.numpy())
+    print("fbank.npz:", tuple(f.shape))
+
+
+if __name__ == "__main__":
+    if not ref_loader.reference_available():
+        sys.exit("the reference tree is not present; golden vectors can only be generated in the build container")
+    os.makedirs(GOLDEN, exist_ok=True)
+    make_host_logic()
+    make_fbank()
+    make_mossformer2()

@@ -9,3 +9,6 @@ Drop-in pieces:
 """
 from ._lib import Handle, load  # noqa: F401
 from .separator import Separator  # noqa: F401
+from .embedder import Embedder  # noqa: F401
+from .pipeline import SeparationScoringStage, meter_loudness  # noqa: F401
+from .plan import chunk_bounds, ola_plan, pick_target  # noqa: F401

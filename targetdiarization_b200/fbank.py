@@ -39,25 +39,23 @@ def _mel(f):
 
 def mel_banks():
     """[80, 257] triangular filters on the mel scale (Kaldi get_mel_banks; last column is the zero pad),
-    plus first/last non-zero bin per filter."""
-    nyquist = 0.5 * SAMPLE_RATE
-    high = nyquist
+    plus first/last non-zero bin per filter.  Evaluated with float32 torch ops in the order torchaudio uses
+    (kaldi.py:436-511), so the table is bit-identical to the one the reference pipeline multiplies by."""
+    import torch
     bin_width = SAMPLE_RATE / NFFT
-    mel_lo, mel_hi = _mel(LOW_FREQ), _mel(high)
+    mel_lo = 1127.0 * math.log(1.0 + LOW_FREQ / 700.0)
+    mel_hi = 1127.0 * math.log(1.0 + 0.5 * SAMPLE_RATE / 700.0)
     delta = (mel_hi - mel_lo) / (NMEL + 1)
-    # torchaudio evaluates the filter edges and the mel scale of the bin centres in float32
-    f32 = np.float32
-    b = np.arange(NMEL, dtype=np.float32)[:, None]
-    left = (f32(mel_lo) + b * f32(delta)).astype(f32)
-    center = (f32(mel_lo) + (b + f32(1.0)) * f32(delta)).astype(f32)
-    right = (f32(mel_lo) + (b + f32(2.0)) * f32(delta)).astype(f32)
-    freqs = (f32(bin_width) * np.arange(NFFT // 2, dtype=np.float32)).astype(f32)
-    mel = (f32(1127.0) * np.log(f32(1.0) + freqs / f32(700.0))).astype(f32)[None, :]
-    up = ((mel - left) / (center - left)).astype(f32)
-    down = ((right - mel) / (right - center)).astype(f32)
-    w = np.maximum(f32(0.0), np.minimum(up, down))
+    b = torch.arange(NMEL).unsqueeze(1)
+    left = mel_lo + b * delta
+    center = mel_lo + (b + 1.0) * delta
+    right = mel_lo + (b + 2.0) * delta
+    mel = (1127.0 * (1.0 + (bin_width * torch.arange(NFFT // 2)) / 700.0).log()).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    w = torch.max(torch.zeros(1), torch.min(up, down)).numpy()
     full = np.zeros((NMEL, NBIN), dtype=np.float32)
-    full[:, :NFFT // 2] = w.astype(np.float32)
+    full[:, :NFFT // 2] = w
     lo = np.zeros(NMEL, dtype=np.int32)
     hi = np.zeros(NMEL, dtype=np.int32)
     for i in range(NMEL):

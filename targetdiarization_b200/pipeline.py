@@ -1,0 +1,331 @@
+"""The target-speaker separation + scoring stage, host side (PyTorch for device memory / streams / NCCL only).
+
+  SeparationScoringStage.separate_speaker     <-> AudioProcessor.separate_speaker            (AudioProcessor.py:885-956)
+  SeparationScoringStage.wav_chunk_inference  <-> look2hear.utils.wav_chunk_inference       (look2hear/utils/separator.py:72-132)
+  SeparationScoringStage.get_speaker_embedding<-> TargetASR.get_speaker_embedding            (TargetASR.py:155-163)
+  SeparationScoringStage.cosine_similarity    <-> TargetASR.cosine_similarity                (TargetASR.py:144-152)
+  SeparationScoringStage.separate_and_score   <-> the core of multi_speakers_separate_asr    (TargetASR.py:609-625)
+  SeparationScoringStage.score_segments       <-> the per-segment loops                      (TargetDiarization.py:581-629)
+
+Every number is produced by libtdz.so kernels; this file only plans chunks (plan.py), moves buffers and, with
+more than one rank, gathers the per-rank spans (one collective at the end)."""
+import numpy as np
+import torch
+
+from . import plan as P
+from .embedder import Embedder
+from .separator import Separator
+
+
+class CudaKernels:
+    """The libtdz.so entry points the stage needs, on device tensors.  (The gloo/CPU tests of the sharding logic
+    substitute a numpy stand-in for this object; the product has no other implementation.)"""
+
+    def __init__(self, separator, max_workspace_bytes=100 << 30):
+        self.sep = separator
+        self.device = separator.device
+        self.max_workspace_bytes = int(max_workspace_bytes)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def to_device(self, audio):
+        if isinstance(audio, np.ndarray):
+            audio = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
+        return audio.to(self.device, torch.float32, non_blocking=True).contiguous()
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def max_batch(self, T):
+        per1 = self.sep.workspace_bytes(1, T)
+        return int(max(1, min(4096, self.max_workspace_bytes // max(per1, 1))))
+
+    def separate(self, chunks):
+        """[n,T] -> [n,2,T], in sub-batches that fit the workspace budget."""
+        n, T = chunks.shape
+        nb = self.max_batch(T)
+        if n <= nb:
+            return self.sep(chunks)
+        out = self.empty(n, 2, T)
+        for i in range(0, n, nb):
+            out[i:i + nb] = self.sep(chunks[i:i + nb])
+        return out
+
+    def gather_segments(self, mix, plan, seg_lo, n_seg):
+        h = self.sep._h
+        seg = self.empty(n_seg, plan.session)
+        h.check(h.lib.tdz_gather_segments(h.ptr, mix.data_ptr(), plan.length, plan.session, plan.hop, seg_lo, n_seg,
+                                          seg.data_ptr(), self._stream()), "tdz_gather_segments")
+        return seg
+
+    def stitch_ola(self, est, plan, seg_lo, out_begin, n_out):
+        h = self.sep._h
+        out = self.empty(2, n_out)
+        h.check(h.lib.tdz_stitch_ola(h.ptr, est.data_ptr(), plan.session, plan.hop, seg_lo, est.shape[0], plan.length,
+                                     out_begin, n_out, float(plan.ratio), out.data_ptr(), self._stream()),
+                "tdz_stitch_ola")
+        return out
+
+    def stitch_concat(self, est, out, start):
+        """est [2,len] (one chunk) -> out[:, start:start+len]."""
+        h = self.sep._h
+        h.check(h.lib.tdz_stitch_concat(h.ptr, est.data_ptr(), est.shape[-1], start, out.shape[-1], out.data_ptr(),
+                                        self._stream()), "tdz_stitch_concat")
+
+
+# ------------------------------------------------------------------------------------------------ span engines
+def concat_span(kern, mix, bounds, span_begin, span_end):
+    """Concat mode over the windows `bounds` (absolute sample indices inside `mix`): equal-length windows share one
+    batched separator call.  Returns [2, span_end - span_begin]."""
+    out = kern.empty(2, span_end - span_begin)
+    by_len = {}
+    for b, e in bounds:
+        by_len.setdefault(e - b, []).append(b)
+    for T, starts in sorted(by_len.items()):
+        nb = kern.max_batch(T)
+        for i in range(0, len(starts), nb):
+            grp = starts[i:i + nb]
+            chunks = torch.stack([mix[s:s + T] for s in grp]) if len(grp) > 1 else mix[grp[0]:grp[0] + T].unsqueeze(0)
+            est = kern.separate(chunks.contiguous())
+            for j, s in enumerate(grp):
+                kern.stitch_concat(est[j], out, s - span_begin)
+    return out
+
+
+def ola_span(kern, mix, plan, out_begin, out_end, seg_lo, seg_hi, batch_size=None):
+    """Overlap-add mode for output samples [out_begin, out_end) from segments [seg_lo, seg_hi).  Returns [2, n]."""
+    n_seg = seg_hi - seg_lo
+    if n_seg <= 0 or out_end <= out_begin:
+        return kern.empty(2, max(out_end - out_begin, 0))
+    seg = kern.gather_segments(mix, plan, seg_lo, n_seg)
+    if batch_size is None:
+        est = kern.separate(seg)
+    else:
+        est = kern.empty(n_seg, 2, plan.session)
+        for i in range(0, n_seg, batch_size):
+            est[i:i + batch_size] = kern.separate(seg[i:i + batch_size])
+    return kern.stitch_ola(est, plan, seg_lo, out_begin, out_end - out_begin)
+
+
+def all_gather_spans(local, span_lens, group=None):
+    """One collective: every rank contributes its [2, n_r] span, everyone receives [2, sum n_r] (rank order).
+    Spans are padded to the longest one for the fixed-size all_gather (NCCL on device tensors, gloo on CPU)."""
+    import torch.distributed as dist
+    world = len(span_lens)
+    n_max = max(max(span_lens), 1)
+    buf = torch.zeros(2, n_max, dtype=local.dtype, device=local.device)
+    buf[:, :local.shape[1]] = local
+    allbuf = torch.empty(world * 2, n_max, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(allbuf, buf, group=group)  # concatenation along dim 0 (NCCL and gloo)
+    allbuf = allbuf.view(world, 2, n_max)
+    return torch.cat([allbuf[r, :, :span_lens[r]] for r in range(world)], dim=1)
+
+
+def _rank_world(group):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def separate_concat(kern, audio, window=P.WINDOW, vad_frames=None, group=None):
+    """The chunk loop of separate_speaker on the device.  audio [L] (device tensor) -> [2, L_out].
+
+    vad_frames=None is the reference's no-VAD path (one frame [0, L)).  With frames given (low_gpu_ram mode,
+    AudioProcessor.py:902-919) the gaps before each frame are zero filled and the output ends at the last frame."""
+    L = int(audio.shape[0])
+    rank, world = _rank_world(group)
+    if vad_frames is None:
+        if world == 1:
+            return concat_span(kern, audio, P.chunk_bounds(L, window), 0, L)
+        spans = [P.concat_shard(L, r, world, window) for r in range(world)]
+        mine, b, e = spans[rank]
+        local = concat_span(kern, audio, mine, b, e)
+        return all_gather_spans(local, [s[2] - s[1] for s in spans], group)
+    pieces = []
+    total = 0
+    for i, (fb, fe) in enumerate(vad_frames):
+        if fb > total:
+            gap = fb if i == 0 else fb - vad_frames[i - 1][1]
+            pieces.append(torch.zeros(2, gap, dtype=torch.float32, device=audio.device))
+            total += gap
+        pieces.append(concat_span(kern, audio, P.chunk_bounds(fe - fb, window, fb), fb, fe))
+        total += fe - fb
+    return torch.cat(pieces, dim=1) if pieces else torch.zeros(2, 0, dtype=torch.float32, device=audio.device)
+
+
+def separate_ola(kern, audio, sr=16000, target_length=12.0, hop_length=4.0, batch_size=None, group=None):
+    """wav_chunk_inference on the device.  audio [L] -> [2, L]."""
+    L = int(audio.shape[0])
+    plan = P.ola_plan(L, sr, target_length, hop_length)
+    rank, world = _rank_world(group)
+    if world == 1:
+        return ola_span(kern, audio, plan, 0, L, 0, plan.num_session, batch_size)
+    shards = [P.ola_shard(plan, r, world) for r in range(world)]
+    ob, oe, lo, hi = shards[rank]
+    local = ola_span(kern, audio, plan, ob, oe, lo, hi, batch_size)
+    return all_gather_spans(local, [s[1] - s[0] for s in shards], group)
+
+
+# ------------------------------------------------------------------------------------------------ loudness
+def meter_loudness(audio, rate=16000):
+    """AudioProcessor.meter_loudness (AudioProcessor.py:1123-1127): BS.1770 integrated loudness, rounded to 0.1.
+    Host numpy like the reference (pyloudnorm, absent here: restated; see DESIGN.md 'next rows').  Only the
+    ordering of the two returned streams depends on it."""
+    from scipy.signal import lfilter
+    x = np.asarray(audio, dtype=np.float64)
+    block = 0.4
+    if x.shape[0] < block * rate:
+        raise ValueError("Audio must have length greater than the block size.")
+    for G, Q, fc, shelf in ((4.0, 1.0 / np.sqrt(2.0), 1500.0, True), (0.0, 0.5, 38.0, False)):
+        A = 10 ** (G / 40.0)
+        w0 = 2.0 * np.pi * (fc / rate)
+        al, c = np.sin(w0) / (2.0 * Q), np.cos(w0)
+        if shelf:
+            sq = 2 * np.sqrt(A) * al
+            b = [A * ((A + 1) + (A - 1) * c + sq), -2 * A * ((A - 1) + (A + 1) * c), A * ((A + 1) + (A - 1) * c - sq)]
+            a = [(A + 1) - (A - 1) * c + sq, 2 * ((A - 1) - (A + 1) * c), (A + 1) - (A - 1) * c - sq]
+        else:
+            b = [(1 + c) / 2, -(1 + c), (1 + c) / 2]
+            a = [1 + al, -2 * c, 1 - al]
+        x = lfilter(np.array(b) / a[0], np.array(a) / a[0], x)
+    T = x.shape[0] / rate
+    nblk = int(np.round((T - block) / (block * 0.25)) + 1)
+    n = int(block * rate)
+    cs = np.concatenate(([0.0], np.cumsum(np.square(x))))
+    lo = (block * 0.25 * rate * np.arange(nblk)).astype(np.int64)
+    hi = np.minimum((block * (0.25 * np.arange(nblk) + 1) * rate).astype(np.int64), x.shape[0])
+    z = (cs[hi] - cs[lo]) / n
+    with np.errstate(divide="ignore", invalid="ignore"):
+        l = -0.691 + 10.0 * np.log10(z)
+        keep = l >= -70.0
+        zg = z[keep].mean() if keep.any() else np.nan
+        gamma_r = -0.691 + 10.0 * np.log10(zg) - 10.0
+        keep = (l > gamma_r) & (l > -70.0)
+        zg = z[keep].mean() if keep.any() else 0.0
+        return round(float(-0.691 + 10.0 * np.log10(zg)), 1)
+
+
+# ------------------------------------------------------------------------------------------------ the stage
+class SeparationScoringStage:
+    """Owns one Separator and one Embedder on one GPU (one process per GPU; `group` = the ranks that share a long
+    input).  Method names and arguments follow the reference methods they stand behind."""
+
+    def __init__(self, separator, embedder, group=None, similarity_threshold=0.0):
+        self.separator = separator
+        self.embedder = embedder
+        self.device = separator.device
+        self.group = group
+        self.kern = CudaKernels(separator)
+        self.similarity_threshold = similarity_threshold
+        self.is_separate_audio = True
+
+    @classmethod
+    def random_init(cls, device="cuda:0", seed=0, **kw):
+        """Random-init weights of the named architectures (no checkpoints are shipped with the reference)."""
+        from . import synth
+        return cls.from_state_dicts(synth.random_state_dict(seed=seed), synth.random_eres2netv2_state_dict(seed=seed),
+                                    device, **kw)
+
+    @classmethod
+    def from_state_dicts(cls, separator_sd, embedder_sd, device="cuda:0", **kw):
+        return cls(Separator(separator_sd, device), Embedder(embedder_sd, device), **kw)
+
+    # ---- AudioProcessor.separate_speaker
+    def separate_speaker(self, audio_data, sampling_rate=16000, low_gpu_ram=False, mode="concat", vad_frames=None,
+                         resample=None, loudness=meter_loudness, return_device=False, **ola_kw):
+        """np.float32 [L] -> (spk1, spk2) np.float32 [L], louder stream first.
+
+        mode="concat" is the reference rule (10 s windows, bit-exact boundaries); mode="ola" stitches 12 s / 4 s-hop
+        segments by overlap-add (wav_chunk_inference).  low_gpu_ram=True uses 1 s windows inside `vad_frames`
+        (which the caller's VAD supplies; the reference runs silero-vad there).  `resample(audio, orig_sr,
+        target_sr) -> audio` is needed only when sampling_rate != 16000 (the reference calls librosa)."""
+        if not self.is_separate_audio:
+            return audio_data, audio_data
+        orig_sr = sampling_rate
+        if sampling_rate != 16000:
+            if resample is None:
+                raise ValueError("separate_speaker: input is not 16 kHz and no `resample` callable was given")
+            audio_data = resample(audio_data, sampling_rate, 16000)
+            sampling_rate = 16000
+        if low_gpu_ram and vad_frames is None:
+            raise ValueError("separate_speaker: low_gpu_ram=True needs `vad_frames` ([[start, end], ...] from the "
+                             "caller's VAD, AudioProcessor.py:902-905)")
+        window = P.WINDOW_LOW_RAM if low_gpu_ram else P.WINDOW
+        mix = self.kern.to_device(audio_data).reshape(-1)
+        if mode == "concat":
+            est = separate_concat(self.kern, mix, window, vad_frames if low_gpu_ram else None, self.group)
+        elif mode == "ola":
+            est = separate_ola(self.kern, mix, sampling_rate, group=self.group, **ola_kw)
+        else:
+            raise ValueError(f"unknown mode {mode!r}")
+        if return_device and loudness is None:
+            return est[0], est[1]
+        host = est.cpu().numpy()
+        spk1, spk2 = host[0], host[1]
+        if loudness is not None and loudness(spk1, sampling_rate) < loudness(spk2, sampling_rate):
+            spk1, spk2 = spk2, spk1
+        if orig_sr != sampling_rate:
+            spk1, spk2 = resample(spk1, sampling_rate, orig_sr), resample(spk2, sampling_rate, orig_sr)
+        return spk1, spk2
+
+    # ---- look2hear.utils.wav_chunk_inference
+    def wav_chunk_inference(self, mixture_tensor, sr=16000, target_length=12.0, hop_length=4.0, batch_size=10,
+                            n_tracks=2):
+        """mixture [1, 1, L] (or [1, L] / [L]) -> [n_tracks=2, 1, L] like the reference with the MossFormer2 adapter
+        `lambda x: model(x).unsqueeze(2)`.  batch_size only bounds the sub-batch, not the result."""
+        if n_tracks != 2:
+            raise ValueError("the separator has 2 output tracks")
+        mix = self.kern.to_device(mixture_tensor).reshape(-1)
+        est = separate_ola(self.kern, mix, sr, target_length, hop_length, None, self.group)
+        return est.unsqueeze(1)
+
+    # ---- TargetASR scoring
+    def get_speaker_embedding(self, wav_file, embedding_model="eres2netv2_large"):
+        if isinstance(wav_file, np.ndarray):
+            wav_file = wav_file.reshape(1, -1)
+        return self.embedder(wav_file, output_emb=True)["embs"].reshape(-1)
+
+    @staticmethod
+    def cosine_similarity(embedding_a, embedding_b):
+        """Scalar form of TargetASR.cosine_similarity for callers that hold host vectors (same rule as the
+        tdz_cosine_scores kernel: zero vector -> 1.0, clamp to [0,1])."""
+        a = np.asarray(embedding_a)
+        b = np.asarray(embedding_b)
+        if np.all(a == 0.0) or np.all(b == 0.0):
+            return 1.0
+        s = np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))
+        return float(max(0.0, min(s, 1.0)))
+
+    def separate_and_score(self, audio_data, target_embedding, threshold=None, **kw):
+        """TargetASR.multi_speakers_separate_asr lines 609-625: separate, embed both streams, cosine vs the target,
+        pick.  Returns dict(target=1|2|None, spk1_score, spk2_score, spk1_audio, spk2_audio)."""
+        threshold = self.similarity_threshold if threshold is None else threshold
+        spk1, spk2 = self.separate_speaker(audio_data, **kw)
+        scores = self.embedder.score_many([spk1, spk2], target_embedding).cpu().tolist()
+        return dict(target=P.pick_target(scores[0], scores[1], threshold), spk1_score=scores[0],
+                    spk2_score=scores[1], spk1_audio=spk1, spk2_audio=spk2)
+
+    def score_segments(self, segments, target_embedding):
+        """Batched form of the per-segment loops (TargetDiarization.py:581-629): [N] cosine scores on the device."""
+        return self.embedder.score_many(segments, target_embedding)
+
+    # ---- the benchmark step: B independent chunks, both streams scored
+    def run(self, mix_dev, target_embedding):
+        """mix_dev [B,T] on the device -> (est [B,2,T], scores [B,2]); target pick = scores[:,0] > scores[:,1]."""
+        est = self.kern.separate(mix_dev)
+        B, _, T = est.shape
+        scores = self.embedder.score_many(est.view(2 * B, T), target_embedding)
+        return est, scores.view(B, 2)
+
+    def embed(self, wav_dev):
+        return self.embedder.embed_many(wav_dev)
+
+    def launches_per_run(self, B, T):
+        """Kernels of libtdz.so launched by one run() (memsets/memcpys not counted)."""
+        from . import fbank
+        n_sep = -(-B // self.kern.max_batch(T))
+        frames = fbank.num_frames(T)
+        n_emb = -(-2 * B // self.embedder.max_batch(frames))
+        return n_sep * Separator.KERNELS_PER_FORWARD + 2 + n_emb * Embedder.KERNELS_PER_FORWARD + 1

@@ -1,0 +1,104 @@
+"""Host-side planning of the separation stage: which windows / segments exist for an input of L samples and
+which of them a rank owns.  Pure integer arithmetic (no torch, no CUDA), so that chunk boundaries are bit-exact
+with the reference and testable everywhere.
+
+  chunk_bounds            <-> AudioProcessor.separate_speaker window rule      (AudioProcessor.py:892-935)
+  ola_plan / OlaPlan      <-> look2hear.utils.wav_chunk_inference segmenting   (look2hear/utils/separator.py:84-112)
+  shard_range, *_shard    <-> new: contiguous spans per rank; the reference is single-device
+"""
+from dataclasses import dataclass
+
+WINDOW = 160000           # AudioProcessor.py:896 (10 s at 16 kHz)
+WINDOW_LOW_RAM = 16000    # AudioProcessor.py:893 (low_gpu_ram=True; the reference then also runs a VAD)
+
+
+def chunk_bounds(length, window=WINDOW, start=0):
+    """[(begin, end)] of the windows fed to the separator for the sample range [start, start+length).
+
+    round_num = length // window; 0 -> one window [start, start+length); else round_num full windows, and the
+    remainder r = length % window is its own window when r > window/2, is appended to the last window when
+    0 < r <= window/2 (so a window holds at most 1.5*window samples)."""
+    length = int(length)
+    n = length // window
+    if n == 0:
+        return [(start, start + length)]
+    bounds = [(start + j * window, start + (j + 1) * window) for j in range(n)]
+    rem = length % window
+    if rem > 0:
+        if rem > window / 2:
+            bounds.append((bounds[-1][1], start + length))
+        else:
+            bounds[-1] = (bounds[-1][0], start + length)
+    return bounds
+
+
+def shard_range(n_units, rank, world):
+    """Contiguous unit range [lo, hi) of rank `rank`: lo = floor(rank*n/world)."""
+    return (rank * n_units) // world, ((rank + 1) * n_units) // world
+
+
+def concat_shard(length, rank, world, window=WINDOW):
+    """Windows owned by `rank` in concat mode and the sample span they cover: (bounds, span_begin, span_end).
+    A rank without windows gets ([], x, x)."""
+    bounds = chunk_bounds(length, window)
+    lo, hi = shard_range(len(bounds), rank, world)
+    mine = bounds[lo:hi]
+    if not mine:
+        edge = bounds[lo - 1][1] if lo > 0 else 0
+        return [], edge, edge
+    return mine, mine[0][0], mine[-1][1]
+
+
+@dataclass(frozen=True)
+class OlaPlan:
+    length: int        # input samples L
+    session: int       # samples per segment (sr * target_length)
+    hop: int           # segment hop (sr * hop_length)
+    pad: int           # zeros on each side = session - hop
+    num_session: int   # (L + 2*pad - session) // hop + 2
+    ratio: float       # target_length / hop_length: every sample is covered `ratio` times
+
+    def segment_range(self, i):
+        """Input sample range [a, b) (may run outside [0, L): zeros) that segment i reads."""
+        a = i * self.hop - self.pad
+        return a, a + self.session
+
+    def segments_covering(self, out_begin, out_end):
+        """Segment index range [lo, hi) whose outputs are summed into samples [out_begin, out_end)."""
+        if out_end <= out_begin:
+            return 0, 0
+        p_lo = out_begin + self.pad
+        p_hi = out_end - 1 + self.pad
+        lo = max(0, -(-(p_lo - self.session + 1) // self.hop))
+        hi = min(self.num_session - 1, p_hi // self.hop)
+        return lo, hi + 1
+
+
+def ola_plan(length, sr=16000, target_length=12.0, hop_length=4.0):
+    session = int(sr * target_length)
+    hop = int(sr * hop_length)
+    if session - hop <= 0:
+        raise ValueError("overlap-add needs target_length > hop_length")
+    pad = session - hop
+    num_session = (int(length) + 2 * pad - session) // hop + 2
+    return OlaPlan(int(length), session, hop, pad, num_session, target_length / hop_length)
+
+
+def ola_shard(plan, rank, world):
+    """Overlap-add mode: rank owns output samples [out_begin, out_end), cut on hop multiples, and recomputes the
+    segments that reach into its span from the neighbours (halo, no communication): returns
+    (out_begin, out_end, seg_lo, seg_hi)."""
+    n_hops = -(-plan.length // plan.hop)
+    lo, hi = shard_range(n_hops, rank, world)
+    out_begin = min(lo * plan.hop, plan.length)
+    out_end = min(hi * plan.hop, plan.length)
+    seg_lo, seg_hi = plan.segments_covering(out_begin, out_end)
+    return out_begin, out_end, seg_lo, seg_hi
+
+
+def pick_target(spk1_score, spk2_score, threshold=0.0):
+    """Target/non-target assignment of one separated pair (TargetASR.py:612-625, 541-553): None when both scores
+    are below `threshold`; 1 iff spk1_score > spk2_score (strict), else 2."""
+    if spk1_score < threshold and spk2_score < threshold:
+        return None
+    return 1 if spk1_score > spk2_score else 2

@@ -1,0 +1,83 @@
+"""CPU tests of the drop-in boundary: libtdz.so loads without a GPU, exports every symbol include/tdz.h declares,
+the ctypes table mirrors the header, and the product path fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tdz.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\*?\s*(tdz_[a-z0-9_]+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from targetdiarization_b200 import _lib
+    return _lib
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("tdz_create", "tdz_separate", "tdz_stitch_ola", "tdz_stitch_concat", "tdz_gather_segments",
+                 "tdz_fbank", "tdz_embed", "tdz_cosine_scores", "tdz_last_error"):
+        assert must in names
+    assert len(names) >= 20
+
+
+def test_library_exports_every_declared_symbol(lib):
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(so, name), f"{name} declared in include/tdz.h but not exported by libtdz.so"
+
+
+def test_ctypes_table_matches_header(lib):
+    assert sorted(lib.SIGNATURES) == declared_functions()
+
+
+def test_layout_helpers_without_gpu(lib):
+    so = lib.load()
+    assert so.tdz_version().startswith(b"tdz")
+    assert so.tdz_num_frames(64000) == 7999 and so.tdz_padded_frames(64000) == 8192
+    assert so.tdz_num_frames(138634) == 17328 and so.tdz_num_frames(15) == 0
+    assert so.tdz_fbank_frames(64000) == 398 and so.tdz_fbank_frames(399) == 0
+    lay = lib.SepLayout()
+    assert so.tdz_separate_layout(64, 64000, 148, ctypes.byref(lay)) == 0
+    assert (lay.S, lay.Sp, lay.Mtot) == (7999, 8192, 64 * 8192)
+    assert lay.total % 1024 == 0 and lay.total > lay.Mtot * 2176 * 4
+
+
+def test_struct_sizes_match_header(lib):
+    # pointer tables only: 29 pointers per layer; 7 + 24*29 + 11 for the model
+    assert ctypes.sizeof(lib.LayerWeights) == 29 * 8
+    assert ctypes.sizeof(lib.MossFormer2Weights) == (7 + 24 * 29 + 11) * 8
+    assert ctypes.sizeof(lib.EresBlock) == (1 + 4 + 3 + 3 + 1 + 1) * 16
+    assert ctypes.sizeof(lib.Eres2NetV2Weights) == 16 + 16 * ctypes.sizeof(lib.EresBlock) + 4 * 16
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    from targetdiarization_b200 import Embedder, Separator
+    with pytest.raises(RuntimeError):
+        Separator(None, "cpu")
+    with pytest.raises(RuntimeError):
+        Embedder(None, "cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            lib.Handle(0)   # tdz_create refuses anything but an sm_100 GPU
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "targetdiarization_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn

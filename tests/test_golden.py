@@ -1,0 +1,119 @@
+"""CPU tests: the oracle restatements and the product's host logic against the golden vectors that
+oracle/make_golden.py produced by executing the reference (tests/golden/*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stage_port
+from oracle.mossformer2_port import mossformer2_forward, snr_db
+from targetdiarization_b200 import plan, synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def host():
+    return np.load(os.path.join(GOLDEN, "host_logic.npz"))
+
+
+@pytest.fixture(scope="module")
+def moss():
+    return np.load(os.path.join(GOLDEN, "mossformer2_small.npz"))
+
+
+def _golden_bounds(host):
+    off = host["chunk_bounds_off"]
+    flat = host["chunk_bounds_flat"]
+    for i, L in enumerate(host["chunk_lengths"]):
+        b = flat[off[i]:off[i + 1]].reshape(-1, 2)
+        yield int(L), [(int(s), int(e)) for s, e in b]
+
+
+def test_chunk_bounds_bit_exact(host):
+    """Chunk boundaries of AudioProcessor.separate_speaker: oracle port and product planner vs the reference run."""
+    n = 0
+    for L, want in _golden_bounds(host):
+        assert stage_port.chunk_bounds(L) == want, L
+        assert plan.chunk_bounds(L) == want, L
+        n += 1
+    assert n == 18
+
+
+def test_separate_speaker_port_matches_reference_run(host):
+    from oracle.make_golden import rms_loudness, toy_separater
+    seed, L = (int(v) for v in host["sepspk_audio_seed"])
+    g = np.random.default_rng(seed)
+    audio = (g.standard_normal(L) * 0.1).astype(np.float32)
+    s1, s2 = stage_port.separate_speaker(audio, toy_separater, rms_loudness)
+    assert s1.shape == (L,) and s2.shape == (L,)
+    assert np.array_equal(s1[::997], host["sepspk_spk1_stride"])
+    assert np.array_equal(s2[::997], host["sepspk_spk2_stride"])
+    assert [tuple(b) for b in host["sepspk_bounds"].tolist()] == stage_port.chunk_bounds(L)
+
+
+def test_wav_chunk_inference_port_matches_reference_run(host):
+    mix = torch.from_numpy(host["ola_mix"])[None, None, :]
+
+    def toy_model(x):
+        t = torch.arange(x.shape[-1], dtype=torch.float32) / x.shape[-1]
+        return torch.stack((x * (0.5 + t), x * x - 0.3 * t), dim=1)
+    y = stage_port.wav_chunk_inference(toy_model, mix, sr=1000, target_length=12.0, hop_length=4.0, batch_size=10)
+    assert np.array_equal(y[:, 0].numpy(), host["ola_out"])
+    # the product's plan agrees on the segment count / geometry
+    p = plan.ola_plan(mix.shape[-1], 1000, 12.0, 4.0)
+    assert (p.session, p.hop, p.pad, p.ratio) == (12000, 4000, 8000, 3.0)
+    assert p.num_session == stage_port.ola_plan(mix.shape[-1], 1000)[3]
+
+
+def test_cosine_similarity_matches_reference_run(host):
+    from targetdiarization_b200 import SeparationScoringStage
+    a, tgt, want = host["cos_a"], host["cos_target"], host["cos_scores"]
+    for i in range(len(a)):
+        assert stage_port.cosine_similarity(a[i], tgt) == pytest.approx(want[i], abs=1e-7)
+        assert SeparationScoringStage.cosine_similarity(a[i], tgt) == pytest.approx(want[i], abs=1e-7)
+    assert want[2] == 1.0 and want[4] == 0.0 and want[5] == pytest.approx(1.0, abs=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mossformer2_port_matches_reference_run(moss, tag):
+    """oracle/mossformer2_port.py vs the reference module's output on the same weights and input (fp32 CPU both;
+    fp32-vs-fp64 noise floor of the model is ~97 dB)."""
+    seed, B, T = (int(v) for v in moss[f"{tag}_cfg"])
+    sd = synth.random_state_dict(seed=seed, perturb=True)
+    g = torch.Generator().manual_seed(1234 + seed)
+    mix = torch.randn(B, T, generator=g) * 0.1
+    taps = {}
+    with torch.no_grad():
+        y = mossformer2_forward(sd, mix, taps=taps)
+    assert y.shape == (B, 2, T)
+    assert snr_db(torch.from_numpy(moss[f"{tag}_out"]), y) >= 90.0
+    for i in (0, 11, 23):
+        for k in (f"flash{i}", f"layer{i}"):
+            assert snr_db(torch.from_numpy(moss[f"{tag}_{k}"]), taps[k][:, ::37, ::7]) >= 90.0, k
+
+
+def test_fbank_tables_match_kaldi():
+    """The host-side tables the fbank kernel reads vs torchaudio's own (torchaudio/compliance/kaldi.py)."""
+    import torchaudio.compliance.kaldi as kaldi
+    from targetdiarization_b200 import fbank
+    win = kaldi._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32)
+    assert np.allclose(fbank.povey_window(), win.numpy(), atol=1e-7)
+    mel, _ = kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    full, lo, hi = fbank.mel_banks()
+    assert full.shape == (80, 257) and np.all(full[:, 256] == 0)
+    assert np.array_equal(full[:, :256], mel.numpy())
+    for i in range(80):
+        assert np.all(full[i, :lo[i]] == 0) and np.all(full[i, hi[i] + 1:] == 0)
+    assert fbank.num_frames(16037) == 98 and fbank.num_frames(399) == 0 and fbank.num_frames(400) == 1
+
+
+def test_fbank_golden_is_kaldi():
+    import torchaudio.compliance.kaldi as kaldi
+    gd = np.load(os.path.join(GOLDEN, "fbank.npz"))
+    seed, T = (int(v) for v in gd["cfg"])
+    wav = synth.synthetic_mixture(1, T, seed=seed)
+    f = kaldi.fbank(wav, num_mel_bins=80)
+    f = f - f.mean(dim=0, keepdim=True)
+    assert np.allclose(f.numpy(), gd["feat"], atol=1e-4)

@@ -1,0 +1,115 @@
+"""GPU tests of the stage's host logic on top of the kernels: chunk loop (concat), overlap-add, scoring and
+assignment, through the public Python surface that mirrors the reference methods."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(name, value):
+    with open(os.path.join(ROOT, "gpurun_out", "parity.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, "value": value}) + "\n")
+
+
+@pytest.fixture(scope="module")
+def stage():
+    import torch
+    from targetdiarization_b200 import SeparationScoringStage
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    return torch, SeparationScoringStage.random_init("cuda:0", seed=0)
+
+
+def test_separate_speaker_concat_is_the_reference_chunk_loop(stage):
+    """L = 400 001 -> windows [0,160000) [160000,320000) [320000,400001): the stitched streams equal, bit for bit,
+    separator calls on exactly those windows; the louder stream comes first (AudioProcessor.py:949-952)."""
+    torch, st = stage
+    from oracle import stage_port
+    from targetdiarization_b200.synth import synthetic_mixture
+    L = 400001
+    audio = synthetic_mixture(1, L, seed=21)[0].numpy()
+    spk1, spk2 = st.separate_speaker(audio)
+    assert spk1.shape == (L,) and spk2.shape == (L,) and spk1.dtype == np.float32
+    bounds = stage_port.chunk_bounds(L)
+    assert bounds == [(0, 160000), (160000, 320000), (320000, 400001)]
+    parts = [st.separator(torch.from_numpy(audio[b:e]).cuda().unsqueeze(0))[0].cpu().numpy() for b, e in bounds]
+    want = np.concatenate(parts, axis=1)
+    l0, l1 = stage_port.meter_loudness(want[0]), stage_port.meter_loudness(want[1])
+    if l0 < l1:
+        want = want[::-1]
+    assert np.array_equal(spk1, want[0]) and np.array_equal(spk2, want[1])
+    assert stage_port.meter_loudness(spk1) >= stage_port.meter_loudness(spk2)
+
+
+def test_separate_speaker_vs_cpu_oracle_low_ram_windows(stage):
+    """1 s windows inside a VAD frame (low_gpu_ram path) against the CPU oracle end to end: >= 40 dB."""
+    torch, st = stage
+    from oracle import stage_port
+    from oracle.mossformer2_port import mossformer2_forward, snr_db
+    from targetdiarization_b200.synth import random_state_dict, synthetic_mixture
+    sd = random_state_dict(seed=0)
+    audio = synthetic_mixture(1, 43000, seed=22)[0].numpy()
+    frames = [[2000, 42000]]
+    s1, s2 = st.separate_speaker(audio, low_gpu_ram=True, vad_frames=frames, loudness=None)
+    assert s1.shape == (42000,)   # the reference output ends at the last VAD frame
+    assert not s1[:2000].any() and not s2[:2000].any()
+    o1, o2 = stage_port.separate_speaker(audio[2000:42000], lambda x: mossformer2_forward(sd, x), lambda a: 0.0,
+                                         window=16000)
+    snr = snr_db(torch.from_numpy(np.stack((o1, o2))), torch.from_numpy(np.stack((s1[2000:], s2[2000:]))))
+    _record("separate_speaker_low_ram_vs_oracle_snr_db", snr)
+    assert snr >= 40.0
+
+
+def test_wav_chunk_inference_is_bit_exact_overlap_add(stage):
+    """The device gather/stitch kernels against the oracle's wav_chunk_inference driven by the same separator:
+    identical segments in, identical sums out (ascending order, divide by 3)."""
+    torch, st = stage
+    from oracle import stage_port
+    from targetdiarization_b200.synth import synthetic_mixture
+    L = 30500
+    mix = synthetic_mixture(1, L, seed=23)
+    got = st.wav_chunk_inference(mix[None].cuda(), sr=1000).cpu()
+    assert got.shape == (2, 1, L)
+
+    def model(x):  # [n,1,session] -> [n,2,1,session]
+        return st.separator(x[:, 0].cuda()).cpu().unsqueeze(2)
+    want = stage_port.wav_chunk_inference(model, mix[None], sr=1000)
+    assert torch.equal(got, want)
+
+
+def test_separate_and_score_assignment(stage):
+    """TargetASR.multi_speakers_separate_asr core: scores of both streams vs the target and the strict-> pick equal
+    the oracle's on the same separated streams."""
+    torch, st = stage
+    from oracle import eres2netv2_port as E
+    from oracle import stage_port
+    from targetdiarization_b200.synth import random_eres2netv2_state_dict, synthetic_mixture
+    esd = random_eres2netv2_state_dict(seed=0)
+    audio = synthetic_mixture(1, 32000, seed=24)[0].numpy()
+    target_wav = synthetic_mixture(1, 24000, seed=25)
+    target = st.get_speaker_embedding(target_wav[0].numpy())
+    assert target.shape == (192,) and target.dtype == np.float32
+    r = st.separate_and_score(audio, target)
+    ref_t = E.embed(esd, target_wav)[0].numpy()
+    ref_e = E.embed(esd, torch.from_numpy(np.stack((r["spk1_audio"], r["spk2_audio"]))))
+    s = [stage_port.cosine_similarity(ref_e[i].numpy(), ref_t) for i in range(2)]
+    _record("score_abs_err_max", max(abs(s[0] - r["spk1_score"]), abs(s[1] - r["spk2_score"])))
+    assert abs(s[0] - r["spk1_score"]) < 2e-3 and abs(s[1] - r["spk2_score"]) < 2e-3
+    assert r["target"] == stage_port.pick_target(s[0], s[1], 0.0)
+    assert st.separate_and_score(audio, target, threshold=1.5)["target"] is None
+
+
+def test_run_batch_step(stage):
+    torch, st = stage
+    from targetdiarization_b200.synth import synthetic_mixture
+    mix = synthetic_mixture(3, 16000, seed=26).cuda()
+    tgt = st.embed(synthetic_mixture(1, 16000, seed=27).cuda())[0]
+    est, scores = st.run(mix, tgt)
+    assert est.shape == (3, 2, 16000) and scores.shape == (3, 2)
+    again = st.score_segments(est.view(6, 16000), tgt).view(3, 2)
+    assert torch.equal(scores, again)
+    assert bool(((scores >= 0) & (scores <= 1)).all())
+    assert st.launches_per_run(3, 16000) == 445 + 2 + 256 + 1
