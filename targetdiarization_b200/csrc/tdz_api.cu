@@ -165,13 +165,12 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->S = S;
   L->Sp = Sp;
   L->Mtot = M;
-  // split the frame axis of the lin_kv GEMM until there are about two work items per SM
+  // lin_kv GEMM: the frame axis is cut into fixed spans of 2048 frames (32 k-blocks) whatever the batch size, so
+  // that the summation order - and with it every output bit - does not depend on how chunks are batched.
+  (void)num_sms;
   const int total_kb = static_cast<int>(Sp / 64);
-  int nsplit = 1;
-  const int64_t want = 2 * static_cast<int64_t>(num_sms > 0 ? num_sms : 148);
-  while (B * 8 * nsplit < want && nsplit * 2 <= total_kb && nsplit < 64) nsplit *= 2;
-  int kbps = (total_kb + nsplit - 1) / nsplit;
-  nsplit = (total_kb + kbps - 1) / kbps;
+  const int kbps = 32;
+  const int nsplit = (total_kb + kbps - 1) / kbps;
   L->kv_nsplit = nsplit;
   L->kv_kb_per_split = kbps;
   size_t off = 0;

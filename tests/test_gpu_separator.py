@@ -56,14 +56,16 @@ def test_full_forward_batch_ragged_tail():
     assert float(out[..., 9608:].abs().max()) == 0.0
 
 
-def test_batch_equals_singles():
-    """Chunks are independent units: a batch of 2 equals two single calls bit for bit."""
+@pytest.mark.parametrize("T", [6000, 140000])
+def test_batch_equals_singles(T):
+    """Chunks are independent units: a batch of 2 equals two single calls bit for bit (T = 140 000 spans several
+    fixed-size splits of the linear-attention sum, whose order must not depend on the batch)."""
     import torch
     from oracle.synth import random_state_dict
     from targetdiarization_b200 import Separator
     sd = random_state_dict(seed=2)
     g = torch.Generator().manual_seed(7)
-    mix = (torch.randn(2, 6000, generator=g) * 0.1).cuda()
+    mix = (torch.randn(2, T, generator=g) * 0.1).cuda()
     sep = Separator(sd, "cuda:0")
     both = sep(mix).clone()
     one0 = sep(mix[0:1]).clone()
