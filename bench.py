@@ -33,17 +33,14 @@ WORKLOAD = "C2: 64 synthetic 4 s 2-speaker mixtures/GPU, MossFormer2 separation 
 STEP_TABLE = {
     "ENCODER": dict(bound="hbm", bytes=32 + 2048),
     "ENC1X1": dict(bound="tensor", flops=524288, bytes=2048 + 2048 + 1024 + 8),
-    "FLASH_IN": dict(bound="tensor", flops=2 * 512 * 2176, bytes=1024 + 2176 * 4),
-    "DW_VU": dict(bound="hbm", bytes=2048 * 4 + 2048 * 2),
-    "DW_QK": dict(bound="hbm", bytes=128 * 4 + 512 * 2),
+    # Linear 512->2176 + SiLU + depthwise k17 + OffsetScale/rotary in one kernel: reads xbf, writes vu + qk4 (bf16)
+    "FLASH_IN": dict(bound="tensor", flops=2 * 512 * 2176, bytes=1024 + 4096 + 1024),
     "SIM": dict(bound="tensor", flops=2 * 256 * 128, bytes=512 + 512),
     "KV": dict(bound="tensor", flops=2 * 128 * 2048, bytes=256 + 4096),
     "ATT_OUT": dict(bound="tensor", flops=2 * 256 * 2048 + 2 * 128 * 2048, bytes=512 + 4096 + 256 + 4096 + 2048),
-    "TO_OUT": dict(bound="tensor", flops=2 * 1024 * 512, bytes=2048 + 2048),
-    "DW_RESX": dict(bound="hbm", bytes=2048 * 3),
+    "TO_OUT": dict(bound="tensor", flops=2 * 1024 * 512, bytes=2048 + 2048 + 2048),
     "FSMN_C1": dict(bound="tensor", flops=2 * 512 * 256, bytes=2048 + 1024 + 512),
-    "FSMN_UV": dict(bound="tensor", flops=2 * 256 * 512, bytes=512 + 2048),
-    "DW_UV": dict(bound="hbm", bytes=2048 + 2048 + 512),
+    "FSMN_UV": dict(bound="tensor", flops=2 * 256 * 512, bytes=512 + 2048 + 512),
     "FSMN_LIN": dict(bound="tensor", flops=2 * 256 * 256, bytes=512 + 512),
     "FSMN_PROJ": dict(bound="tensor", flops=2 * 256 * 256, bytes=512 + 1024),
     "DD1": dict(bound="hbm", bytes=1024 + 1024),
@@ -57,8 +54,8 @@ STEP_TABLE = {
     "DEC1": dict(bound="tensor", flops=2 * 2 * 512 * 512, bytes=4096 + 2048 + 4096),
     "DECODER": dict(bound="hbm", bytes=4096 + 64),
 }
-LAYER_STEPS = ["FLASH_IN", "DW_VU", "DW_QK", "SIM", "KV", "ATT_OUT", "TO_OUT", "DW_RESX", "FSMN_C1", "FSMN_UV",
-               "DW_UV", "FSMN_LIN", "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2"]
+LAYER_STEPS = ["FLASH_IN", "SIM", "KV", "ATT_OUT", "TO_OUT", "FSMN_C1", "FSMN_UV", "FSMN_LIN", "FSMN_PROJ", "DD1",
+               "DD2", "FSMN_TAIL", "FSMN_C2"]
 ALL_STEPS = ["ENCODER", "ENC1X1"] + LAYER_STEPS + ["FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1", "DECODER"]
 
 

@@ -43,12 +43,12 @@ typedef struct tdz_ctx tdz_ctx;
 typedef struct tdz_layer_weights {
   const void* w_in;        /* bf16 [2176][512]: to_hidden (2048 rows, ScaleNorm g folded) | to_qk (128 rows) */
   const float* b_in;       /* [2176] */
-  const float* dw_in;      /* [2176][17] depthwise taps of the two ConvModules */
+  const float* dw_in;      /* [17][2176] depthwise taps of the two ConvModules, tap-major */
   const float* os_gamma;   /* [4][128] OffsetScale */
   const float* os_beta;    /* [4][128] */
   const void* w_out;       /* bf16 [512][1024], ScaleNorm g folded */
   const float* b_out;      /* [512] */
-  const float* dw_out;     /* [512][17] */
+  const float* dw_out;     /* [17][512] tap-major */
   const float* w_c1;       /* fp32 [256][512] fsmn.conv1 (tf32 operand) */
   const float* b_c1;       /* [256] */
   const float* prelu_c1;   /* [1] */
@@ -56,7 +56,7 @@ typedef struct tdz_layer_weights {
   const float* ln1_b;      /* [256] */
   const void* w_uv;        /* bf16 [512][256]: to_u | to_v with their LayerNorm affine folded */
   const float* b_uv;       /* [512] */
-  const float* dw_uv;      /* [512][17] */
+  const float* dw_uv;      /* [17][512] tap-major */
   const void* w_lin;       /* bf16 [256][256] fsmn.linear */
   const float* b_lin;      /* [256] */
   const void* w_proj;      /* bf16 [256][256] fsmn.project (no bias) */
@@ -119,15 +119,15 @@ int tdz_separate(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float
                  size_t workspace_bytes, void* stream);
 
 /* Test hook: run only the first `num_layers` layer pairs, and of the launch sequence only the steps whose
- * index lies in [step_lo, step_hi] (step numbering: enum Step in csrc/tdz_api.cu; 0..24).  The tests write
+ * index lies in [step_lo, step_hi] (step numbering: enum Step in csrc/tdz_api.cu; 0..20).  The tests write
  * oracle intermediates into the workspace, run one step and compare its outputs.  Offsets (bytes) of the
  * named intermediates inside the workspace are returned by tdz_separate_layout(). */
 int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* workspace_dev,
                        size_t workspace_bytes, void* stream, int num_layers, int step_lo, int step_hi);
 
 typedef struct tdz_sep_layout {
-  size_t enc, x0, x, xbf, ss, h, vu, qk4, P, o, o_ss, y, c, nhat, uvpre, xuv, xubf, f1, p, y1, y2, g, kv_part, kv,
-      gn_stats, in_stats, samp, rot, total;
+  size_t enc, x0, x, xbf, ss, vu, qk4, P, o, o_ss, c, nhat, xuv, xubf, f1, p, y1, y2, g, lnb, ab, mb, gated, sep,
+      kv_part, kv, gn_stats, in_stats, in_ss, samp, rot, total;
   int64_t S, Sp, Mtot;
   int32_t kv_nsplit, kv_kb_per_split;
 } tdz_sep_layout;

@@ -50,6 +50,25 @@ struct EpiGeneric {
   int ss_out_ld;
 };
 
+// Outputs of the GEMMs whose epilogue also runs the depthwise k=17 time convolution of the ConvModule that
+// follows the Linear in every FFConvM (mossformer_block.py:89-102, conv_module.py:209-220).
+struct EpiConv {
+  const float* dw_t;   // taps, tap-major [17][ldw]; column index = output column of the GEMM
+  int ldw;
+  // CONV_VUQK: to_hidden|to_qk  -> (v|u) bf16 and the four rotated OffsetScale heads bf16
+  __nv_bfloat16* vu;   // [Mtot][2048]
+  __nv_bfloat16* qk4;  // [Mtot][512]
+  const float* gamma;  // [4][128]
+  const float* beta;   // [4][128]
+  const float2* rot;   // [Sp][16] (cos, sin)
+  // CONV_RESX: to_out -> x_out = x_in + y + dwconv(y)
+  const float* x_in;   // [Mtot][512]
+  float* x_out;
+  // CONV_UV: to_u|to_v -> xuv fp32 [Mtot][512] and bf16 copy of x_u [Mtot][256]
+  float* xuv;
+  __nv_bfloat16* xubf;
+};
+
 struct LinearParams {
   CUtensorMap tmA;  // 3-D {K, Sp, B}, box {KB, 128, 1}
   CUtensorMap tmB;  // 2-D {K, N},     box {KB, BLOCK_N} (split_n: {KB, BLOCK_N/2})
@@ -58,7 +77,9 @@ struct LinearParams {
   int shift_kblocks;  // leading k-blocks read one frame earlier (token shift, mossformer_block.py:204-207)
   int a_k0;           // element offset along K inside A
   int split_n;        // >0: tile columns [0,BN/2) come from W rows n0/2.., [BN/2,BN) from rows split_n+n0/2..
+  int tps;            // LinearConv: 112-row output tiles per sample = ceil(S / 112)
   EpiGeneric e;
+  EpiConv cv;
   // epilogue specific extras
   const float* alpha;  // PReLU slope (LN256 epilogue)
   const float* ln_g1;
@@ -73,6 +94,7 @@ struct LinearBase {
   static constexpr int STAGES = STAGES_;
   static constexpr int A_MN = 0;
   static constexpr int B_MN = 0;
+  static constexpr int PANEL_BYTES = 0;
   static constexpr int KB = (FMT_ == 2) ? 32 : 64;
 
   __device__ static void prefetch(const Params& P) {
@@ -152,7 +174,8 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   static constexpr int EPI_SPLIT = (BLOCK_N_ >= 64) ? 2 : 1;
   static constexpr int COLS = BLOCK_N_ / EPI_SPLIT;  // columns handled by one epilogue warp
 
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
     const bool valid = t < P.S;
@@ -259,6 +282,156 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   }
 };
 
+// Linear + SiLU + ConvModule in one kernel.  An accumulator tile covers 128 consecutive frames of ONE sample,
+// of which the inner 112 are outputs and 8 on each side are the halo of the k=17 depthwise convolution (tiles
+// overlap by 16 rows; TMA zero-fills rows outside the sample).  Epilogue, per 128-column panel:
+//   phase 1  thread = tile row : tcgen05.ld -> row scale (ScaleNorm) + bias + SiLU -> fp32 panel in shared
+//            memory (rows outside [0,S) are written as zeros = the convolution's zero padding)
+//   phase 2  thread = 2 adjacent columns x 28 output rows: register sliding window down the panel column,
+//            y + dwconv(y), then the op-specific tail (bf16 operand copies, OffsetScale + rotary, residual add)
+// so the pre-convolution activation (8.7 KB per frame for to_hidden) never goes to HBM.
+enum ConvMode : int { CONV_VUQK = 0, CONV_RESX = 1, CONV_UV = 2 };
+constexpr int CONV_ROWS = 112;
+constexpr int PANEL_LD = 132;  // floats per panel row: 128 + 4 keeps the row-wise float4 stores conflict free
+
+template <int MODE, int STAGES_>
+struct LinearConv : LinearBase<1, 256, STAGES_> {
+  using Params = LinearParams;
+  static constexpr int EPI_SPLIT = 2;
+  static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4;
+
+  __device__ static int num_tiles(const Params& P) { return P.B * P.tps * P.n_tiles; }
+  __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
+    const int mt = tile / P.n_tiles;
+    const int nt = tile - mt * P.n_tiles;
+    ti.b = mt / P.tps;
+    const int j = mt - ti.b * P.tps;
+    ti.t0 = j * CONV_ROWS - 8;  // frame of tile row 0 (negative for the first tile of a sample)
+    ti.m0 = ti.b * P.Sp;        // first row of the sample in the token space
+    ti.n0 = nt * 256;
+    ti.nkb = P.K / 64;
+    ti.aux = nt;
+  }
+  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
+    const int trow = ti.t0 - (kb < P.shift_kblocks ? 1 : 0);
+    tma_load_3d(sa, &P.tmA, bar, kb * 64, trow, ti.b);
+    tma_load_2d(sb, &P.tmB, bar, kb * 64, ti.n0);
+  }
+
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx& cx) {
+    const EpiGeneric& e = P.e;
+    const EpiConv& cv = P.cv;
+    const int t = ti.t0 + row;
+    const bool valid = t >= 0 && t < P.S;
+    const size_t srow = static_cast<size_t>(ti.m0);
+    float rs = 1.f;
+    if (valid) {
+      if constexpr (MODE == CONV_VUQK) {
+        const size_t grow = srow + t;
+        const float4 cur = *reinterpret_cast<const float4*>(e.ss_in + grow * 4);
+        float ss = cur.z + cur.w;  // channels 256..511 of this frame
+        if (t > 0) {
+          const float4 prv = *reinterpret_cast<const float4*>(e.ss_in + (grow - 1) * 4);
+          ss += prv.x + prv.y;     // channels 0..255 of the previous frame (token shift)
+        }
+        rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
+      }
+      if constexpr (MODE == CONV_RESX) {
+        const size_t grow = srow + t;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(e.ss_in + grow * 16 + 4 * i);
+          ss += (a.x + a.y) + (a.z + a.w);
+        }
+        rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
+      }
+    }
+    float* prow = cx.panel + row * PANEL_LD + half * 64;
+    const int w = cx.tid >> 5, lane = cx.tid & 31;
+    const int cp = (w & 1) * 32 + lane;  // column pair inside the panel
+    const int rg = w >> 1;               // group of 28 output rows
+#pragma unroll 1
+    for (int pn = 0; pn < 2; ++pn) {
+      const int pc0 = ti.n0 + pn * 128;  // first output column of the panel
+      if (pc0 >= P.N) break;
+      // ---- phase 1: accumulator -> activated fp32 panel
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = pn * 128 + half * 64 + cc;
+        float v[16], bias[16];
+        tmem_ld16(tacc + c0, v);
+        ld_f32x16(e.bias + ti.n0 + c0, bias);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = valid ? silu_f(fmaf(v[j], rs, bias[j])) : 0.f;
+        float4* dst = reinterpret_cast<float4*>(prow + cc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      epi_bar_sync<256>();
+      // ---- phase 2: y + depthwise conv over time, then the tail of the op
+      {
+        const int c = pc0 + 2 * cp;
+        float2 wt[17];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(cv.dw_t + k * cv.ldw + c));
+        const float* pcol = cx.panel + 2 * cp;
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+          const int r0 = 28 * rg + 14 * it;
+          float2 buf[30];
+#pragma unroll
+          for (int i = 0; i < 30; ++i) buf[i] = *reinterpret_cast<const float2*>(pcol + (r0 + i) * PANEL_LD);
+#pragma unroll
+          for (int j = 0; j < 14; ++j) {
+            float a0 = buf[j + 8].x, a1 = buf[j + 8].y;
+#pragma unroll
+            for (int k = 0; k < 17; ++k) {
+              a0 = fmaf(wt[k].x, buf[j + k].x, a0);
+              a1 = fmaf(wt[k].y, buf[j + k].y, a1);
+            }
+            const int tt = ti.t0 + r0 + 8 + j;
+            if (tt < P.S) {
+              const size_t grow = srow + tt;
+              if constexpr (MODE == CONV_VUQK) {
+                if (c < 2048) {
+                  *reinterpret_cast<uint32_t*>(cv.vu + grow * 2048 + c) = pack_bf16(a0, a1);
+                } else {
+                  const int qc = c - 2048;
+#pragma unroll
+                  for (int h = 0; h < 4; ++h) {
+                    float x0 = fmaf(a0, __ldg(cv.gamma + h * 128 + qc), __ldg(cv.beta + h * 128 + qc));
+                    float x1 = fmaf(a1, __ldg(cv.gamma + h * 128 + qc + 1), __ldg(cv.beta + h * 128 + qc + 1));
+                    if (qc < 32) {
+                      const float2 cs = cv.rot[tt * 16 + (qc >> 1)];
+                      const float r0v = x0 * cs.x - x1 * cs.y;
+                      const float r1v = x1 * cs.x + x0 * cs.y;
+                      x0 = r0v;
+                      x1 = r1v;
+                    }
+                    *reinterpret_cast<uint32_t*>(cv.qk4 + grow * 512 + h * 128 + qc) = pack_bf16(x0, x1);
+                  }
+                }
+              }
+              if constexpr (MODE == CONV_RESX) {
+                const float2 r = *reinterpret_cast<const float2*>(cv.x_in + grow * 512 + c);
+                *reinterpret_cast<float2*>(cv.x_out + grow * 512 + c) = make_float2(r.x + a0, r.y + a1);
+              }
+              if constexpr (MODE == CONV_UV) {
+                *reinterpret_cast<float2*>(cv.xuv + grow * 512 + c) = make_float2(a0, a1);
+                if (c < 256) *reinterpret_cast<uint32_t*>(cv.xubf + grow * 256 + c) = pack_bf16(a0, a1);
+              }
+            }
+          }
+        }
+      }
+      epi_bar_sync<256>();
+    }
+  }
+};
+
 // FSMN block entry: Conv1d(512->256,k1)+bias -> PReLU(1) -> CLayerNorm(256) -> (to_u|to_v) LayerNorm(256)
 // statistics (mossformer_block.py:405-409,419-421,301-312; layer_norm.py:9-30).  One tile holds the whole
 // 256-wide row, so both LayerNorms run in the epilogue.  Outputs: c = norm1 output (fp32, later residual)
@@ -267,7 +440,7 @@ template <int FMT_, int STAGES_>
 struct LinearLN256 : LinearBase<FMT_, 256, STAGES_> {
   using Params = LinearParams;
   static constexpr int EPI_SPLIT = 1;
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int, const EpiCtx&) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
     const bool valid = t < P.S;
@@ -346,7 +519,8 @@ template <int FMT_, int STAGES_>
 struct LinearTanhSig : LinearBase<FMT_, 256, STAGES_> {
   using Params = LinearParams;
   static constexpr int EPI_SPLIT = 2;
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
     const EpiGeneric& e = P.e;
     const int t = ti.t0 + row;
     const bool valid = t < P.S;  // no early return: tcgen05.ld is warp-collective
@@ -400,6 +574,7 @@ struct AttnParams {
 // sim = quad_q quad_k^T / 256 ; attn = relu(sim)^2    (mossformer_block.py:256-258)
 struct AttnSim {
   using Params = AttnParams;
+  static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 0, EPI_SPLIT = 2;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmQK);
@@ -418,7 +593,8 @@ struct AttnSim {
     tma_load_3d(sa, &P.tmQK, bar, 0 + kb * 64, ti.t0, ti.b);      // quad_q
     tma_load_3d(sb, &P.tmQKb, bar, 256 + kb * 64, ti.aux, ti.b);  // quad_k of the whole group
   }
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
     const size_t grow = static_cast<size_t>(ti.m0) + row;
 #pragma unroll 1
     for (int cc = 0; cc < 128; cc += 32) {
@@ -446,6 +622,7 @@ struct AttnSim {
 // Both operands are read MN-major straight from the token-major buffers.
 struct AttnKV {
   using Params = AttnParams;
+  static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 1, B_MN = 1, EPI_SPLIT = 2;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmQKmn);
@@ -471,7 +648,8 @@ struct AttnKV {
 #pragma unroll
     for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 8192, &P.tmVUmn, bar, ti.n0 + j * 64, trow, ti.b);
   }
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
     float* dst = P.kv_part + ((static_cast<size_t>(ti.b) * P.nsplit + ti.aux) * 128 + row) * 2048 + ti.n0;
 #pragma unroll 1
     for (int cc = 0; cc < 128; cc += 32) {
@@ -492,6 +670,7 @@ struct AttnKV {
 // 128 u-columns, so the gate runs in the epilogue and the [.,2048] attention output never reaches HBM.
 struct AttnOut {
   using Params = AttnParams;
+  static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 1, EPI_SPLIT = 2;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmP);
@@ -530,7 +709,8 @@ struct AttnOut {
     }
   }
   // o_ss holds 16 partial sums per row: index = 2 * n_tile + half (the consumer adds them in index order)
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half) {
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
     const int t = ti.t0 + row;
     const bool valid = t < P.S;
     const size_t grow = static_cast<size_t>(ti.m0) + row;

@@ -26,9 +26,22 @@ struct TileInfo {
   int aux;  // Cfg specific (group index, split index ...)
 };
 
-template <int BLOCK_N, int STAGES>
+// Shared memory of one CTA: operand stages | barriers (256 B) | optional fp32 epilogue panel (Cfg::PANEL_BYTES).
+template <int BLOCK_N, int STAGES, int PANEL_BYTES = 0>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (GEMM_STAGE_A_BYTES + BLOCK_N * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return STAGES * (GEMM_STAGE_A_BYTES + BLOCK_N * 128) + 1024 /*align slack*/ + 256 /*barriers*/ + PANEL_BYTES;
+}
+
+// What the epilogue warps get besides the accumulator address: their index among the epilogue threads and the
+// shared-memory panel (nullptr when the Cfg asks for none).
+struct EpiCtx {
+  float* panel;
+  int tid;  // 0 .. 128*EPI_SPLIT-1
+};
+// Barrier among the epilogue warps only (named barrier 1; producer / MMA warps never join it).
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
 }
 
 template <class Cfg>
@@ -142,6 +155,11 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int half = (warp - 2) >> 2;  // which column half this warp owns (always 0 when EPI_SPLIT == 1)
+    EpiCtx ectx;
+    ectx.tid = threadIdx.x - 64;
+    ectx.panel = Cfg::PANEL_BYTES > 0
+                     ? reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 256)
+                     : nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       TileInfo ti;
@@ -150,7 +168,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
       mbar_wait(tfull_bar(as), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-      Cfg::epilogue(P, ti, tacc, row, half);
+      Cfg::epilogue(P, ti, tacc, row, half, ectx);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
 
 template <class Cfg>
 cudaError_t launch_gemm(const typename Cfg::Params& P, int ntiles, int num_sms, cudaStream_t st) {
-  constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES>();
+  constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES, Cfg::PANEL_BYTES>();
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

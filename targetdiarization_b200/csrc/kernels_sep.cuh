@@ -80,111 +80,6 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
   tab[i] = make_float2(cosf(a), sinf(a));
 }
 
-// ---------------------------------------------------------------- depthwise conv k=17 + residual
-// ConvModule: y = x + depthwise_conv1d(x, k=17, pad=8) over time (conv_module.py:209-220).
-// Thread = 2 adjacent channels x DW_TT consecutive frames per step; block = 128 threads = 256 channels.
-constexpr int DW_TT = 16;
-constexpr int DW_STRIP = 128;
-
-template <class Epi>
-__global__ void __launch_bounds__(128) dwconv17_kernel(const float* __restrict__ in, int ld_in, int c_begin,
-                                                       const float* __restrict__ taps, int C, int Sp, int S,
-                                                       Epi epi) {
-  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
-  if (c >= C) return;
-  const int strips = Sp / DW_STRIP;
-  const int b = blockIdx.y / strips;
-  const int ts = (blockIdx.y - b * strips) * DW_STRIP;
-  if (ts >= S) {
-    // whole strip is padding: the epilogue still has to write zeros where buffers require it
-    for (int t = ts; t < ts + DW_STRIP; ++t) epi(b, t, static_cast<size_t>(b) * Sp + t, c, 0.f, 0.f, false);
-    return;
-  }
-  float2 w[17];
-#pragma unroll
-  for (int k = 0; k < 17; ++k) w[k] = make_float2(taps[c * 17 + k], taps[(c + 1) * 17 + k]);
-  const float* base = in + static_cast<size_t>(b) * Sp * ld_in + c_begin + c;
-  auto ld = [&](int t) -> float2 {
-    if (t < 0 || t >= S) return make_float2(0.f, 0.f);
-    return *reinterpret_cast<const float2*>(base + static_cast<size_t>(t) * ld_in);
-  };
-  float2 buf[DW_TT + 16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) buf[DW_TT + i] = ld(ts - 8 + i);
-#pragma unroll 1
-  for (int t = ts; t < ts + DW_STRIP; t += DW_TT) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) buf[i] = buf[DW_TT + i];
-#pragma unroll
-    for (int i = 0; i < DW_TT; ++i) buf[16 + i] = ld(t + 8 + i);
-#pragma unroll
-    for (int j = 0; j < DW_TT; ++j) {
-      float a0 = buf[j + 8].x, a1 = buf[j + 8].y;
-#pragma unroll
-      for (int k = 0; k < 17; ++k) {
-        a0 = fmaf(w[k].x, buf[j + k].x, a0);
-        a1 = fmaf(w[k].y, buf[j + k].y, a1);
-      }
-      const int tt = t + j;
-      epi(b, tt, static_cast<size_t>(b) * Sp + tt, c, a0, a1, tt < S);
-    }
-  }
-}
-
-// to_hidden tail: (v|u) = h + dwconv(h) -> bf16 operand copy, zero in padded frames
-struct EpiVU {
-  __nv_bfloat16* vu;  // [Mtot][2048]
-  __device__ void operator()(int, int, size_t grow, int c, float a0, float a1, bool valid) const {
-    *reinterpret_cast<uint32_t*>(vu + grow * 2048 + c) = valid ? pack_bf16(a0, a1) : 0u;
-  }
-};
-// to_qk tail: OffsetScale (4 heads) + rotary on dims 0..31 (interleaved pairs) -> qk4 bf16
-// (mossformer_block.py:76-86,214,230-233).  Head order: quad_q, lin_q, quad_k, lin_k.
-struct EpiQK {
-  __nv_bfloat16* qk4;    // [Mtot][512]
-  const float* gamma;    // [4][128]
-  const float* beta;     // [4][128]
-  const float2* rot;     // [Sp][16] (cos, sin)
-  __device__ void operator()(int, int t, size_t grow, int c, float a0, float a1, bool valid) const {
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      uint32_t packed = 0u;
-      if (valid) {
-        float x0 = a0 * gamma[h * 128 + c] + beta[h * 128 + c];
-        float x1 = a1 * gamma[h * 128 + c + 1] + beta[h * 128 + c + 1];
-        if (c < 32) {
-          const float2 cs = rot[t * 16 + (c >> 1)];
-          const float r0 = x0 * cs.x - x1 * cs.y;
-          const float r1 = x1 * cs.x + x0 * cs.y;
-          x0 = r0;
-          x1 = r1;
-        }
-        packed = pack_bf16(x0, x1);
-      }
-      *reinterpret_cast<uint32_t*>(qk4 + grow * 512 + h * 128 + c) = packed;
-    }
-  }
-};
-// to_out tail + FLASH residual: x_out = x_in + y + dwconv(y)   (mossformer_block.py:219)
-struct EpiResX {
-  const float* x_in;  // [Mtot][512]
-  float* x_out;
-  __device__ void operator()(int, int, size_t grow, int c, float a0, float a1, bool valid) const {
-    if (!valid) return;
-    const float2 r = *reinterpret_cast<const float2*>(x_in + grow * 512 + c);
-    *reinterpret_cast<float2*>(x_out + grow * 512 + c) = make_float2(r.x + a0, r.y + a1);
-  }
-};
-// to_u | to_v tail: xuv fp32 (u = cols 0..255, v = 256..511) and bf16 copy of x_u for fsmn.linear
-struct EpiUV {
-  float* xuv;          // [Mtot][512]
-  __nv_bfloat16* xu;   // [Mtot][256]
-  __device__ void operator()(int, int, size_t grow, int c, float a0, float a1, bool valid) const {
-    if (valid) *reinterpret_cast<float2*>(xuv + grow * 512 + c) = make_float2(a0, a1);
-    if (c < 256) *reinterpret_cast<uint32_t*>(xu + grow * 256 + c) = valid ? pack_bf16(a0, a1) : 0u;
-  }
-};
-
 // ---------------------------------------------------------------- DilatedDenseNet  (fsmn.py:76-111)
 // stage 1: y1 = depthwise conv (39 taps, pad 19) of p; statistics for InstanceNorm over all S frames.
 // stage 2: y2[c] = sum_{j<2} conv39_dilation2( cat[2c+j] ), cat = [PReLU(IN(y1)) ; p], pad 38.
@@ -249,18 +144,22 @@ __global__ void __launch_bounds__(128) dd_conv1_kernel(const float* __restrict__
   atomicAdd(st + 3, static_cast<double>(s2y));
 }
 
-// InstanceNorm2d(affine) parameters from the accumulated statistics: biased variance, eps 1e-5.
-__device__ __forceinline__ float2 in_scale_shift(const double* st, double count, float g, float bt) {
-  const double mean = st[0] / count;
-  double var = st[1] / count - mean * mean;
+// InstanceNorm2d(affine) scale / shift per (sample, channel) from the accumulated fp64 sums: biased variance,
+// eps 1e-5 (fsmn.py:93,103).  out[b*256+c] = (rstd*g, beta - mean*rstd*g).
+__global__ void in_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ g,
+                                   const float* __restrict__ bt, float2* __restrict__ out, int n, double count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = i & 255;
+  const double mean = stats[2 * i] / count;
+  double var = stats[2 * i + 1] / count - mean * mean;
   if (var < 0) var = 0;
   const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
-  return make_float2(rstd * g, bt - static_cast<float>(mean) * rstd * g);
+  out[i] = make_float2(rstd * g[c], bt[c] - static_cast<float>(mean) * rstd * g[c]);
 }
 
 __global__ void __launch_bounds__(128) dd_conv2_kernel(const float* __restrict__ y1, const float* __restrict__ p,
-                                                       const double* __restrict__ stats1,
-                                                       const float* __restrict__ in1_g, const float* __restrict__ in1_b,
+                                                       const float2* __restrict__ in1_ss,
                                                        const float* __restrict__ prelu1,
                                                        const float* __restrict__ taps /*[256][2][39]*/,
                                                        float* __restrict__ y2, double* __restrict__ stats2, int Sp,
@@ -278,9 +177,8 @@ __global__ void __launch_bounds__(128) dd_conv2_kernel(const float* __restrict__
   float2 sc0 = make_float2(1.f, 0.f), sc1 = make_float2(1.f, 0.f);
   float a0 = 1.f, a1 = 1.f;
   if (from_y1) {
-    const double* st = stats1 + (static_cast<size_t>(b) * 256 + ic) * 2;
-    sc0 = in_scale_shift(st, static_cast<double>(S), in1_g[ic], in1_b[ic]);
-    sc1 = in_scale_shift(st + 2, static_cast<double>(S), in1_g[ic + 1], in1_b[ic + 1]);
+    sc0 = in1_ss[b * 256 + ic];
+    sc1 = in1_ss[b * 256 + ic + 1];
     a0 = prelu1[ic];
     a1 = prelu1[ic + 1];
   }
@@ -336,9 +234,7 @@ __global__ void __launch_bounds__(128) dd_conv2_kernel(const float* __restrict__
 
 // FSMN tail: o2 = PReLU(IN(y2)); f = x_u + o2 (fsmn.py:144); g = x_v*f + c (mossformer_block.py:324);
 // CLayerNorm(256) (norm2, :423) with its affine folded into conv2 -> bf16 operand.  One warp per frame.
-__global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict__ y2, const double* __restrict__ stats2,
-                                                        const float* __restrict__ in2_g,
-                                                        const float* __restrict__ in2_b,
+__global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict__ y2, const float2* __restrict__ in2_ss,
                                                         const float* __restrict__ prelu2,
                                                         const float* __restrict__ xuv, const float* __restrict__ cres,
                                                         float* __restrict__ gout, int B, int Sp, int S) {
@@ -372,8 +268,7 @@ __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
-    const float2 ss = in_scale_shift(stats2 + (static_cast<size_t>(b) * 256 + c) * 2, static_cast<double>(S),
-                                     in2_g[c], in2_b[c]);
+    const float2 ss = in2_ss[b * 256 + c];
     float o = y[i] * ss.x + ss.y;
     o = o >= 0.f ? o : prelu2[c] * o;
     g[i] = v[i] * (u[i] + o) + cr[i];

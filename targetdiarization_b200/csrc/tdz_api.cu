@@ -185,16 +185,15 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->x = take(m * 512 * 4);
   L->xbf = take(m * 512 * 2);
   L->ss = take(m * 4 * 4);
-  L->h = take(m * 2176 * 4);
+  // one region, two views: the per-layer intermediates, and (after the 24 layers) the mask-head buffers
+  const size_t region = off;
   L->vu = take(m * 2048 * 2);
   L->qk4 = take(m * 512 * 2);
   L->P = take(m * 256 * 2);
   L->o = take(m * 1024 * 2);
   L->o_ss = take(m * 16 * 4);
-  L->y = take(m * 512 * 4);
   L->c = take(m * 256 * 4);
   L->nhat = take(m * 256 * 2);
-  L->uvpre = take(m * 512 * 4);
   L->xuv = take(m * 512 * 4);
   L->xubf = take(m * 256 * 2);
   L->f1 = take(m * 256 * 2);
@@ -202,10 +201,19 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->y1 = take(m * 256 * 4);
   L->y2 = take(m * 256 * 4);
   L->g = take(m * 256 * 4);
+  const size_t layer_end = off;
+  off = region;
+  L->lnb = take(m * 512 * 4);
+  L->ab = take(m * 512 * 4);
+  L->mb = take(m * 1024 * 4);
+  L->gated = take(m * 1024 * 4);
+  L->sep = take(m * 1024 * 4);
+  off = std::max(off, layer_end);
   L->kv_part = take(static_cast<size_t>(B) * nsplit * 128 * 2048 * 4);
   L->kv = take(static_cast<size_t>(B) * 128 * 2048 * 2);
   L->gn_stats = take(static_cast<size_t>(B) * 2 * 8 * 2);       // two GroupNorms
   L->in_stats = take(static_cast<size_t>(B) * 256 * 2 * 8 * 2); // two InstanceNorms (re-zeroed per layer)
+  L->in_ss = take(static_cast<size_t>(B) * 256 * 8 * 2);        // their (scale, shift) tables
   L->samp = take(static_cast<size_t>(B) * 4 * 4);               // A,B for each GroupNorm
   L->rot = take(static_cast<size_t>(Sp) * 16 * 8);
   L->total = off;
@@ -224,9 +232,9 @@ extern "C" size_t tdz_separate_workspace_bytes(int64_t B, int64_t T) {
 
 // Launch steps, selectable through tdz_separate_debug (tests drive single kernels with oracle inputs).
 enum Step : int {
-  ST_ENCODER = 0, ST_ENC1X1, ST_FLASH_IN, ST_DW_VU, ST_DW_QK, ST_SIM, ST_KV, ST_ATT_OUT, ST_TO_OUT, ST_DW_RESX,
-  ST_FSMN_C1, ST_FSMN_UV, ST_DW_UV, ST_FSMN_LIN, ST_FSMN_PROJ, ST_DD1, ST_DD2, ST_FSMN_TAIL, ST_FSMN_C2,
-  ST_FINAL_LN, ST_FINAL_GN, ST_OUT1, ST_TANHSIG, ST_DEC1, ST_DECODER, ST_COUNT
+  ST_ENCODER = 0, ST_ENC1X1, ST_FLASH_IN, ST_SIM, ST_KV, ST_ATT_OUT, ST_TO_OUT, ST_FSMN_C1, ST_FSMN_UV, ST_FSMN_LIN,
+  ST_FSMN_PROJ, ST_DD1, ST_DD2, ST_FSMN_TAIL, ST_FSMN_C2, ST_FINAL_LN, ST_FINAL_GN, ST_OUT1, ST_TANHSIG, ST_DEC1,
+  ST_DECODER, ST_COUNT
 };
 
 static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64, float* out, void* ws, size_t ws_bytes,
@@ -247,20 +255,16 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   uint8_t* base = static_cast<uint8_t*>(ws);
   auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
   auto H = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
-  float *enc = F(L.enc), *x0 = F(L.x0), *x = F(L.x), *ss = F(L.ss), *h = F(L.h), *o_ss = F(L.o_ss), *y = F(L.y),
-        *c = F(L.c), *uvpre = F(L.uvpre), *xuv = F(L.xuv), *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g),
-        *kv_part = F(L.kv_part), *samp = F(L.samp);
+  float *enc = F(L.enc), *x0 = F(L.x0), *x = F(L.x), *ss = F(L.ss), *o_ss = F(L.o_ss), *c = F(L.c), *xuv = F(L.xuv),
+        *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g), *kv_part = F(L.kv_part), *samp = F(L.samp);
   __nv_bfloat16 *xbf = H(L.xbf), *vu = H(L.vu), *qk4 = H(L.qk4), *Pm = H(L.P), *o = H(L.o), *nhat = H(L.nhat),
                 *xubf = H(L.xubf), *f1 = H(L.f1), *kv = H(L.kv);
   double* gn_stats = reinterpret_cast<double*>(base + L.gn_stats);
   double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
+  float2* in_ss = reinterpret_cast<float2*>(base + L.in_ss);
   float2* rot = reinterpret_cast<float2*>(base + L.rot);
-  // aliases used after the layer loop
-  float* lnb = y;                        // [M][512]
-  float* ab = uvpre;                     // [M][512]
-  float* mb = h;                         // [M][1024]
-  float* gated = h + M * 1024;           // [2][M][512]
-  float* sep = reinterpret_cast<float*>(vu);  // [2][M][512]
+  // mask-head buffers (second view of the layer region, used after the layer loop)
+  float *lnb = F(L.lnb), *ab = F(L.ab), *mb = F(L.mb), *gated = F(L.gated), *sep = F(L.sep);
 
   // ---- activation tensor maps (buffers are reused by every layer)
   CUtensorMap m_enc, m_xbf, m_x, m_o, m_nhat, m_xubf, m_f1, m_g, m_ab, m_mb, m_gated0, m_gated1;
@@ -296,6 +300,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   AP.o_ss = o_ss;
 
   const int mtiles = static_cast<int>(M / 128);
+  const int tps = (S + CONV_ROWS - 1) / CONV_ROWS;
   auto lin_base = [&](LinearParams& P, const CUtensorMap& a, const CUtensorMap& w, int N, int K, int block_n) {
     memset(&P, 0, sizeof P);
     P.tmA = a;
@@ -306,12 +311,20 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     P.N = N;
     P.K = K;
     P.n_tiles = (N + block_n - 1) / block_n;
+    P.tps = tps;
   };
 
   // ---- front: encoder -> GroupNorm -> conv1d_encoder (+pos enc)   (mossformer2.py:573,487-496)
   STEP(ST_ENCODER) {
     CUDA_OK(cudaMemsetAsync(gn_stats, 0, static_cast<size_t>(B) * 4 * 8, st));
     if (static_cast<int64_t>(Sp) * 8 < T) CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(B) * 2 * T * 4, st));
+    if (Sp > S) {
+      // padded frames of the attention operands stay zero for the whole forward (nobody writes them later)
+      CUDA_OK(cudaMemset2DAsync(vu + static_cast<size_t>(S) * 2048, static_cast<size_t>(Sp) * 2048 * 2, 0,
+                                static_cast<size_t>(Sp - S) * 2048 * 2, B, st));
+      CUDA_OK(cudaMemset2DAsync(qk4 + static_cast<size_t>(S) * 512, static_cast<size_t>(Sp) * 512 * 2, 0,
+                                static_cast<size_t>(Sp - S) * 512 * 2, B, st));
+    }
     encoder_kernel<<<B * (Sp / ENC_FRAMES), 512, 0, st>>>(mix, T, W.enc_w, enc, gn_stats, B, Sp, S);
     gn_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(gn_stats, samp, samp + B, B, 512.0 * S, 1e-8);
     rotary_table_kernel<<<(Sp * 16 + 255) / 256, 256, 0, st>>>(W.rot_freqs, rot, Sp);
@@ -336,27 +349,27 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
                                        ACT_NONE>>(P, mtiles * P.n_tiles, sms, st)));
   }
 
-  const dim3 dw_grid_y(1, B * (Sp / DW_STRIP));
   for (int li = 0; li < num_layers; ++li) {
     const tdz_layer_weights& LW = W.layers[li];
     const auto& LM = ctx->lm[li];
     const float* x_in = (li == 0) ? x0 : x;
     // ---------------- FLASH_ShareA_FFConvM (mossformer_block.py:191-220)
-    STEP(ST_FLASH_IN) {  // token shift + ScaleNorm + to_hidden|to_qk Linear + SiLU
+    STEP(ST_FLASH_IN) {  // token shift + ScaleNorm + to_hidden|to_qk Linear + SiLU + ConvModule + OffsetScale/rotary
       LinearParams P;
       lin_base(P, m_xbf, LM.w_in, 2176, 512, 256);
       P.shift_kblocks = 4;
       P.e.ss_in = ss;
       P.e.ss_dim_rsqrt = 0.044194173824159216f;  // 512^-0.5
       P.e.bias = LW.b_in;
-      P.e.out_f32 = h;
-      P.e.out_ld = 2176;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_SS_SHIFT | EF_BIAS | EF_OUT_F32, ACT_SILU>>(
-          P, mtiles * P.n_tiles, sms, st)));
+      P.cv.dw_t = LW.dw_in;
+      P.cv.ldw = 2176;
+      P.cv.vu = vu;
+      P.cv.qk4 = qk4;
+      P.cv.gamma = LW.os_gamma;
+      P.cv.beta = LW.os_beta;
+      P.cv.rot = rot;
+      CUDA_OK((launch_gemm<LinearConv<CONV_VUQK, 3>>(P, B * tps * P.n_tiles, sms, st)));
     }
-    STEP(ST_DW_VU) dwconv17_kernel<EpiVU><<<dim3(8, dw_grid_y.y), 128, 0, st>>>(h, 2176, 0, LW.dw_in, 2048, Sp, S, EpiVU{vu});
-    STEP(ST_DW_QK) dwconv17_kernel<EpiQK><<<dim3(1, dw_grid_y.y), 128, 0, st>>>(h, 2176, 2048, LW.dw_in + 2048 * 17, 128, Sp, S,
-                                                                EpiQK{qk4, LW.os_gamma, LW.os_beta, rot});
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {
       CUDA_OK((launch_gemm<AttnKV>(AP, B * AP.nsplit * 8, sms, st)));
@@ -365,18 +378,18 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
           kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
     }
     STEP(ST_ATT_OUT) CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
-    STEP(ST_TO_OUT) {  // ScaleNorm(1024) + to_out Linear + SiLU
+    STEP(ST_TO_OUT) {  // ScaleNorm(1024) + to_out Linear + SiLU + ConvModule + FLASH residual (mossformer_block.py:219)
       LinearParams P;
       lin_base(P, m_o, LM.w_out, 512, 1024, 256);
       P.e.ss_in = o_ss;
       P.e.ss_dim_rsqrt = 0.03125f;  // 1024^-0.5
       P.e.bias = LW.b_out;
-      P.e.out_f32 = y;
-      P.e.out_ld = 512;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_SS_PARTS | EF_BIAS | EF_OUT_F32, ACT_SILU>>(
-          P, mtiles * P.n_tiles, sms, st)));
+      P.cv.dw_t = LW.dw_out;
+      P.cv.ldw = 512;
+      P.cv.x_in = x_in;
+      P.cv.x_out = x;
+      CUDA_OK((launch_gemm<LinearConv<CONV_RESX, 3>>(P, B * tps * P.n_tiles, sms, st)));
     }
-    STEP(ST_DW_RESX) dwconv17_kernel<EpiResX><<<dim3(2, dw_grid_y.y), 128, 0, st>>>(y, 512, 0, LW.dw_out, 512, Sp, S, EpiResX{x_in, x});
     // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
     STEP(ST_FSMN_C1) {  // conv1 + PReLU + norm1 + inner LayerNorm statistics
       LinearParams P;
@@ -389,16 +402,16 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.out_bf16 = nhat;
       CUDA_OK((launch_gemm<LinearLN256<2, 4>>(P, mtiles, sms, st)));
     }
-    STEP(ST_FSMN_UV) {  // to_u | to_v Linear + SiLU
+    STEP(ST_FSMN_UV) {  // to_u | to_v: Linear + SiLU + ConvModule
       LinearParams P;
       lin_base(P, m_nhat, LM.w_uv, 512, 256, 256);
       P.e.bias = LW.b_uv;
-      P.e.out_f32 = uvpre;
-      P.e.out_ld = 512;
-      CUDA_OK((launch_gemm<LinearGeneric<1, 256, 4, EF_BIAS | EF_OUT_F32, ACT_SILU>>(P, mtiles * P.n_tiles, sms,
-                                                                                     st)));
+      P.cv.dw_t = LW.dw_uv;
+      P.cv.ldw = 512;
+      P.cv.xuv = xuv;
+      P.cv.xubf = xubf;
+      CUDA_OK((launch_gemm<LinearConv<CONV_UV, 3>>(P, B * tps * P.n_tiles, sms, st)));
     }
-    STEP(ST_DW_UV) dwconv17_kernel<EpiUV><<<dim3(2, dw_grid_y.y), 128, 0, st>>>(uvpre, 512, 0, LW.dw_uv, 512, Sp, S, EpiUV{xuv, xubf});
     STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;
       lin_base(P, m_xubf, LM.w_lin, 256, 256, 256);
@@ -421,10 +434,17 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       CUDA_OK(cudaMemsetAsync(in_stats, 0, static_cast<size_t>(B) * 256 * 2 * 8 * 2, st));
       dd_conv1_kernel<<<B * (Sp / DD_STRIP), 128, 0, st>>>(p, LW.dd_w1, y1, st1, Sp, S);
     }
-    STEP(ST_DD2) dd_conv2_kernel<<<dim3(B * (Sp / DD_STRIP), 2), 128, 0, st>>>(y1, p, st1, LW.in1_g, LW.in1_b,
-                                                                      LW.dd_prelu1, LW.dd_w2, y2, st2, Sp, S);
-    STEP(ST_FSMN_TAIL) fsmn_tail_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st>>>(y2, st2, LW.in2_g, LW.in2_b,
-                                                                                  LW.dd_prelu2, xuv, c, g, B, Sp, S);
+    float2* in_ss1 = in_ss;
+    float2* in_ss2 = in_ss + static_cast<size_t>(B) * 256;
+    STEP(ST_DD2) {
+      in_finalize_kernel<<<B, 256, 0, st>>>(st1, LW.in1_g, LW.in1_b, in_ss1, B * 256, static_cast<double>(S));
+      dd_conv2_kernel<<<dim3(B * (Sp / DD_STRIP), 2), 128, 0, st>>>(y1, p, in_ss1, LW.dd_prelu1, LW.dd_w2, y2, st2, Sp, S);
+    }
+    STEP(ST_FSMN_TAIL) {
+      in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
+      fsmn_tail_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c, g,
+                                                                                   B, Sp, S);
+    }
     STEP(ST_FSMN_C2) {  // conv2 + residual; also the bf16 copy and ScaleNorm sums the next FLASH layer needs
       LinearParams P;
       lin_base(P, m_g, LM.w_c2, 512, 256, 256);

@@ -53,12 +53,12 @@ class PackedMossFormer2:
             L.w_in = bf16(torch.cat((sd[p + "to_hidden.mdl.1.weight"] * gh, sd[p + "to_qk.mdl.1.weight"] * gq), 0))
             L.b_in = f32(torch.cat((sd[p + "to_hidden.mdl.1.bias"], sd[p + "to_qk.mdl.1.bias"]), 0))
             L.dw_in = f32(torch.cat((sd[p + "to_hidden.mdl.3.sequential.1.conv.weight"][:, 0, :],
-                                     sd[p + "to_qk.mdl.3.sequential.1.conv.weight"][:, 0, :]), 0))
+                                     sd[p + "to_qk.mdl.3.sequential.1.conv.weight"][:, 0, :]), 0).t())  # tap-major
             L.os_gamma = f32(sd[p + "qk_offset_scale.gamma"])
             L.os_beta = f32(sd[p + "qk_offset_scale.beta"])
             L.w_out = bf16(sd[p + "to_out.mdl.1.weight"] * go)
             L.b_out = f32(sd[p + "to_out.mdl.1.bias"])
-            L.dw_out = f32(sd[p + "to_out.mdl.3.sequential.1.conv.weight"][:, 0, :])
+            L.dw_out = f32(sd[p + "to_out.mdl.3.sequential.1.conv.weight"][:, 0, :].t())
             q = FSMN.format(i)
             L.w_c1 = tf32(sd[q + "conv1.0.weight"][:, :, 0])
             L.b_c1 = f32(sd[q + "conv1.0.bias"])
@@ -74,7 +74,7 @@ class PackedMossFormer2:
                 dws.append(sd[q + f"gated_fsmn.{n}.mdl.3.sequential.1.conv.weight"][:, 0, :])
             L.w_uv = bf16(torch.cat(ws, 0))
             L.b_uv = f32(torch.cat(bs, 0))
-            L.dw_uv = f32(torch.cat(dws, 0))
+            L.dw_uv = f32(torch.cat(dws, 0).t())
             L.w_lin = bf16(sd[q + "gated_fsmn.fsmn.linear.weight"])
             L.b_lin = f32(sd[q + "gated_fsmn.fsmn.linear.bias"])
             L.w_proj = bf16(sd[q + "gated_fsmn.fsmn.project.weight"])

@@ -20,9 +20,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-STEPS = ["ENCODER", "ENC1X1", "FLASH_IN", "DW_VU", "DW_QK", "SIM", "KV", "ATT_OUT", "TO_OUT", "DW_RESX", "FSMN_C1",
-         "FSMN_UV", "DW_UV", "FSMN_LIN", "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2", "FINAL_LN", "FINAL_GN",
-         "OUT1", "TANHSIG", "DEC1", "DECODER"]
+STEPS = ["ENCODER", "ENC1X1", "FLASH_IN", "SIM", "KV", "ATT_OUT", "TO_OUT", "FSMN_C1", "FSMN_UV", "FSMN_LIN",
+         "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2", "FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1",
+         "DECODER"]
 B, T = 2, 9613  # S = 1200 frames -> Sp = 1280 (partial last group), two samples
 
 
@@ -158,29 +158,21 @@ def run_step(h, step):
         ok &= zpad_ok(xb)
         ok &= _check(m, "ss", ss_of(tp["x0"]), h.get("ss", f32, 4), 55)
     elif step == "FLASH_IN":
+        # token shift + ScaleNorm + Linear + SiLU + ConvModule (+ OffsetScale / rotary) in one kernel
         h.put("xbf", tp["x0"], bf)
         h.put("ss", ss_of(tp["x0"]), f32)
-        h.run(k)
-        ref = torch.cat((tp["to_hidden_pre"], tp["to_qk_pre"]), -1)
-        ok &= _check(m, "h", ref, h.get("h", f32, 2176), 40)
-        ok &= _check(m, "h_first_frames", ref[:, :2], h.get("h", f32, 2176)[:, :2], 40)
-    elif step == "DW_VU":
-        h.put("h", torch.cat((tp["to_hidden_pre"], tp["to_qk_pre"]), -1), f32)
-        h.run(k)
-        vu = h.get("vu", bf, 2048, valid_only=False)
-        ok &= _check(m, "vu", tp["vu"], vu[:, :S], 45)
-        ok &= zpad_ok(vu)
-    elif step == "DW_QK":
-        h.put("h", torch.cat((tp["to_hidden_pre"], tp["to_qk_pre"]), -1), f32)
         fr = h.sd["mask_net.mdl.intra_mdl.mossformerM.layers.0.rotary_pos_emb.freqs"]
         ang = torch.arange(Sp, dtype=f32)[:, None] * fr[None, :]
         h.put_raw(h.lay.rot, torch.stack((ang.cos(), ang.sin()), -1))
         h.run(k)
-        qk = h.get("qk4", bf, 512, valid_only=False)
-        ok &= _check(m, "qk4", tp["qk4"], qk[:, :S], 45)
+        vu = h.get("vu", bf, 2048)
+        ok &= _check(m, "vu", tp["vu"], vu, 40)
+        ok &= _check(m, "vu_first_frames", tp["vu"][:, :12], vu[:, :12], 40)
+        ok &= _check(m, "vu_last_frames", tp["vu"][:, -12:], vu[:, -12:], 40)
+        qk = h.get("qk4", bf, 512)
+        ok &= _check(m, "qk4", tp["qk4"], qk, 40)
         for i, n in enumerate(("quad_q", "lin_q", "quad_k", "lin_k")):
-            ok &= _check(m, n, tp["qk4"][..., i * 128:(i + 1) * 128], qk[:, :S, i * 128:(i + 1) * 128], 45)
-        ok &= zpad_ok(qk)
+            ok &= _check(m, n, tp["qk4"][..., i * 128:(i + 1) * 128], qk[..., i * 128:(i + 1) * 128], 40)
     elif step == "SIM":
         h.put("qk4", tp["qk4"], bf)
         h.run(k)
@@ -202,16 +194,15 @@ def run_step(h, step):
         oss = h.get("o_ss", f32, 16).sum(-1)
         ok &= _check(m, "o_ss", (tp["o"] ** 2).sum(-1), oss, 35)
     elif step == "TO_OUT":
+        # ScaleNorm + Linear + SiLU + ConvModule + residual: x = x0 + to_out(o)
         h.put("o", tp["o"], bf)
         ss = (tp["o"] ** 2).reshape(B, S, 8, 2, 64).sum(-1).reshape(B, S, 16)
         h.put("o_ss", ss, f32)
-        h.run(k)
-        ok &= _check(m, "y", tp["to_out_pre"], h.get("y", f32, 512), 40)
-    elif step == "DW_RESX":
-        h.put("y", tp["to_out_pre"], f32)
         h.put("x0", tp["x0"], f32)
         h.run(k)
-        ok &= _check(m, "x_flash", tp["flash0"], h.get("x", f32, 512), 100)
+        xf = h.get("x", f32, 512)
+        ok &= _check(m, "x_flash", tp["flash0"], xf, 50)
+        ok &= _check(m, "to_out_branch", tp["flash0"] - tp["x0"], xf - tp["x0"], 40)
     elif step == "FSMN_C1":
         h.put("x", tp["flash0"], f32)
         h.run(k)
@@ -222,14 +213,8 @@ def run_step(h, step):
     elif step == "FSMN_UV":
         h.put("nhat", tp["nhat"], bf)
         h.run(k)
-        ok &= _check(m, "uvpre", torch.cat((tp["u_pre"], tp["v_pre"]), -1), h.get("uvpre", f32, 512), 40)
-    elif step == "DW_UV":
-        h.put("uvpre", torch.cat((tp["u_pre"], tp["v_pre"]), -1), f32)
-        h.run(k)
-        ok &= _check(m, "xuv", tp["xuv"], h.get("xuv", f32, 512), 100)
-        xb = h.get("xubf", bf, 256, valid_only=False)
-        ok &= _check(m, "xubf", tp["xuv"][..., :256], xb[:, :S], 45)
-        ok &= zpad_ok(xb)
+        ok &= _check(m, "xuv", tp["xuv"], h.get("xuv", f32, 512), 40)
+        ok &= _check(m, "xubf", tp["xuv"][..., :256], h.get("xubf", bf, 256), 40)
     elif step == "FSMN_LIN":
         h.put("xubf", tp["xuv"][..., :256], bf)
         h.run(k)
@@ -279,7 +264,7 @@ def run_step(h, step):
     elif step == "FINAL_LN":
         h.put("x", tp["layer0"], f32)
         h.run(k)
-        ok &= _check(m, "final_ln", tp["final_ln"], h.get("y", f32, 512), 100)
+        ok &= _check(m, "final_ln", tp["final_ln"], h.get("lnb", f32, 512), 100)
         samp = h.get_raw(h.lay.samp, f32, 4 * B)
         e = tp["final_ln"].double()
         mean = e.mean(dim=(1, 2))
@@ -287,33 +272,33 @@ def run_step(h, step):
         ok &= _check(m, "gn_rstd", rstd.float(), samp[2 * B:3 * B], 100)
         ok &= _check(m, "gn_shift", (-rstd * mean).float(), samp[3 * B:], 90)
     elif step == "FINAL_GN":
-        h.put("y", tp["final_ln"], f32)
+        h.put("lnb", tp["final_ln"], f32)
         h.put("x0", tp["x0"], f32)
         e = tp["final_ln"].double()
         mean = e.mean(dim=(1, 2))
         rstd = 1 / torch.sqrt(e.var(dim=(1, 2), unbiased=False) + 1e-8)
         h.put_raw(h.lay.samp + 2 * B * 4, torch.cat((rstd, -rstd * mean)).float())
         h.run(k)
-        ab = h.get("uvpre", f32, 512, valid_only=False)
+        ab = h.get("ab", f32, 512, valid_only=False)
         ok &= _check(m, "mask_in", tp["mask_in"], ab[:, :S], 65)  # stored rounded to tf32
         ok &= zpad_ok(ab)
     elif step == "OUT1":
-        h.put("uvpre", tp["mask_in"], f32)
+        h.put("ab", tp["mask_in"], f32)
         h.run(k)
-        ok &= _check(m, "m", tp["m"], h.get("h", f32, 1024), 55)
+        ok &= _check(m, "m", tp["m"], h.get("mb", f32, 1024), 55)
     elif step == "TANHSIG":
-        h.put("h", tp["m"], f32)
+        h.put("mb", tp["m"], f32)
         h.run(k)
-        g = h.get("h", f32, 512, extra_off=M * 1024 * 4, lead=2)
+        g = h.get("gated", f32, 512, lead=2)
         ok &= _check(m, "gated", torch.stack(tp["gated"]), g, 55)
     elif step == "DEC1":
-        h.put("h", torch.stack(tp["gated"]), f32, extra_off=M * 1024 * 4, lead=2)
+        h.put("gated", torch.stack(tp["gated"]), f32, lead=2)
         h.put("enc", tp["enc"], f32)
         h.run(k)
-        sp = h.get("vu", f32, 512, lead=2)
+        sp = h.get("sep", f32, 512, lead=2)
         ok &= _check(m, "sep", torch.stack(tp["sep"]), sp, 55)
     elif step == "DECODER":
-        h.put("vu", torch.stack(tp["sep"]), f32, lead=2)
+        h.put("sep", torch.stack(tp["sep"]), f32, lead=2)
         out = h.run(k)
         ok &= _check(m, "out", h.ref_out, out, 100)
     else:

@@ -52,7 +52,7 @@ def test_layout_helpers_without_gpu(lib):
     lay = lib.SepLayout()
     assert so.tdz_separate_layout(64, 64000, 148, ctypes.byref(lay)) == 0
     assert (lay.S, lay.Sp, lay.Mtot) == (7999, 8192, 64 * 8192)
-    assert lay.total % 1024 == 0 and lay.total > lay.Mtot * 2176 * 4
+    assert lay.total % 1024 == 0 and lay.total > lay.Mtot * 16384
 
 
 def test_struct_sizes_match_header(lib):

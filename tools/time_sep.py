@@ -26,7 +26,7 @@ ms = e0.elapsed_time(e1) / reps
 print(json.dumps(dict(B=B, T=T, ms=ms, xrt=B * T / 16000 / (ms / 1e3), ws_gb=sep.workspace_bytes(B, T) / 1e9)))
 if os.environ.get("TDZ_STEPS", "1") == "1":
     tab = sep.time_steps(mix, reps=3)
-    layer = [n for n in sep.STEP_NAMES[2:19]]
+    layer = list(sep.LAYER_STEPS)
     tot = sum(v * (24 if n in layer else 1) for n, v in tab.items())
     for n, v in sorted(tab.items(), key=lambda kv: -kv[1] * (24 if kv[0] in layer else 1)):
         m = 24 if n in layer else 1
