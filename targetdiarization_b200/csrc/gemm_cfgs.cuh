@@ -356,22 +356,24 @@ struct LinearConv : LinearBase<1, 256, STAGES_> {
     for (int pn = 0; pn < 2; ++pn) {
       const int pc0 = ti.n0 + pn * 128;  // first output column of the panel
       if (pc0 >= P.N) break;
-      // ---- phase 1: accumulator -> activated fp32 panel
+      // ---- phase 1: accumulator -> activated fp32 panel (32 columns per TMEM round trip)
 #pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 16) {
+      for (int cc = 0; cc < 64; cc += 32) {
         const int c0 = pn * 128 + half * 64 + cc;
-        float v[16], bias[16];
+        float v[32], bias[32];
         tmem_ld16(tacc + c0, v);
+        tmem_ld16(tacc + c0 + 16, v + 16);
         ld_f32x16(e.bias + ti.n0 + c0, bias);
+        ld_f32x16(e.bias + ti.n0 + c0 + 16, bias + 16);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = valid ? silu_f(fmaf(v[j], rs, bias[j])) : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = valid ? silu_fast(fmaf(v[j], rs, bias[j])) : 0.f;
         float4* dst = reinterpret_cast<float4*>(prow + cc);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
       epi_bar_sync<256>();
-      // ---- phase 2: y + depthwise conv over time, then the tail of the op
+      // ---- phase 2: y + depthwise conv over time (28 independent accumulator chains per thread), then the tail
       {
         const int c = pc0 + 2 * cp;
         float2 wt[17];
@@ -384,45 +386,71 @@ struct LinearConv : LinearBase<1, 256, STAGES_> {
           float2 buf[30];
 #pragma unroll
           for (int i = 0; i < 30; ++i) buf[i] = *reinterpret_cast<const float2*>(pcol + (r0 + i) * PANEL_LD);
+          float2 acc[14];
 #pragma unroll
-          for (int j = 0; j < 14; ++j) {
-            float a0 = buf[j + 8].x, a1 = buf[j + 8].y;
+          for (int j = 0; j < 14; ++j) acc[j] = buf[j + 8];
 #pragma unroll
-            for (int k = 0; k < 17; ++k) {
-              a0 = fmaf(wt[k].x, buf[j + k].x, a0);
-              a1 = fmaf(wt[k].y, buf[j + k].y, a1);
+          for (int k = 0; k < 17; ++k) {
+#pragma unroll
+            for (int j = 0; j < 14; ++j) {
+              acc[j].x = fmaf(wt[k].x, buf[j + k].x, acc[j].x);
+              acc[j].y = fmaf(wt[k].y, buf[j + k].y, acc[j].y);
             }
-            const int tt = ti.t0 + r0 + 8 + j;
-            if (tt < P.S) {
-              const size_t grow = srow + tt;
-              if constexpr (MODE == CONV_VUQK) {
-                if (c < 2048) {
-                  *reinterpret_cast<uint32_t*>(cv.vu + grow * 2048 + c) = pack_bf16(a0, a1);
-                } else {
-                  const int qc = c - 2048;
+          }
+          const int tt0 = ti.t0 + r0 + 8;       // frame of acc[0]
+          const int nrow = P.S - tt0;           // rows j < nrow are inside the sample
+          const size_t grow0 = srow + tt0;
+          if constexpr (MODE == CONV_VUQK) {
+            if (c < 2048) {
+              __nv_bfloat16* dst = cv.vu + grow0 * 2048 + c;
 #pragma unroll
-                  for (int h = 0; h < 4; ++h) {
-                    float x0 = fmaf(a0, __ldg(cv.gamma + h * 128 + qc), __ldg(cv.beta + h * 128 + qc));
-                    float x1 = fmaf(a1, __ldg(cv.gamma + h * 128 + qc + 1), __ldg(cv.beta + h * 128 + qc + 1));
-                    if (qc < 32) {
-                      const float2 cs = cv.rot[tt * 16 + (qc >> 1)];
-                      const float r0v = x0 * cs.x - x1 * cs.y;
-                      const float r1v = x1 * cs.x + x0 * cs.y;
-                      x0 = r0v;
-                      x1 = r1v;
-                    }
-                    *reinterpret_cast<uint32_t*>(cv.qk4 + grow * 512 + h * 128 + qc) = pack_bf16(x0, x1);
-                  }
+              for (int j = 0; j < 14; ++j)
+                if (j < nrow) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(j) * 2048) = pack_bf16(acc[j].x, acc[j].y);
+            } else {
+              const int qc = c - 2048;
+              __nv_bfloat16* dst = cv.qk4 + grow0 * 512 + qc;
+              float2 cs[14];
+#pragma unroll
+              for (int j = 0; j < 14; ++j)
+                cs[j] = (qc < 32 && j < nrow) ? cv.rot[(tt0 + j) * 16 + (qc >> 1)] : make_float2(1.f, 0.f);
+#pragma unroll 1
+              for (int h = 0; h < 4; ++h) {
+                const float g0 = __ldg(cv.gamma + h * 128 + qc), g1 = __ldg(cv.gamma + h * 128 + qc + 1);
+                const float b0 = __ldg(cv.beta + h * 128 + qc), b1 = __ldg(cv.beta + h * 128 + qc + 1);
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                  const float x0 = fmaf(acc[j].x, g0, b0), x1 = fmaf(acc[j].y, g1, b1);
+                  // rotary on interleaved pairs of dims 0..31 (identity rotation elsewhere)
+                  const float r0v = x0 * cs[j].x - x1 * cs[j].y;
+                  const float r1v = x1 * cs[j].x + x0 * cs[j].y;
+                  if (j < nrow)
+                    *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(j) * 512 + h * 128) = pack_bf16(r0v, r1v);
                 }
               }
-              if constexpr (MODE == CONV_RESX) {
-                const float2 r = *reinterpret_cast<const float2*>(cv.x_in + grow * 512 + c);
-                *reinterpret_cast<float2*>(cv.x_out + grow * 512 + c) = make_float2(r.x + a0, r.y + a1);
-              }
-              if constexpr (MODE == CONV_UV) {
-                *reinterpret_cast<float2*>(cv.xuv + grow * 512 + c) = make_float2(a0, a1);
-                if (c < 256) *reinterpret_cast<uint32_t*>(cv.xubf + grow * 256 + c) = pack_bf16(a0, a1);
-              }
+            }
+          }
+          if constexpr (MODE == CONV_RESX) {
+            const float* src = cv.x_in + grow0 * 512 + c;
+            float* dst = cv.x_out + grow0 * 512 + c;
+            float2 r[14];
+#pragma unroll
+            for (int j = 0; j < 14; ++j)
+              r[j] = (j < nrow) ? *reinterpret_cast<const float2*>(src + static_cast<size_t>(j) * 512) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 14; ++j)
+              if (j < nrow)
+                *reinterpret_cast<float2*>(dst + static_cast<size_t>(j) * 512) = make_float2(r[j].x + acc[j].x, r[j].y + acc[j].y);
+          }
+          if constexpr (MODE == CONV_UV) {
+            float* dst = cv.xuv + grow0 * 512 + c;
+#pragma unroll
+            for (int j = 0; j < 14; ++j)
+              if (j < nrow) *reinterpret_cast<float2*>(dst + static_cast<size_t>(j) * 512) = acc[j];
+            if (c < 256) {
+              __nv_bfloat16* db = cv.xubf + grow0 * 256 + c;
+#pragma unroll
+              for (int j = 0; j < 14; ++j)
+                if (j < nrow) *reinterpret_cast<uint32_t*>(db + static_cast<size_t>(j) * 256) = pack_bf16(acc[j].x, acc[j].y);
             }
           }
         }

@@ -160,8 +160,22 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint
 }
 
 // ---------------------------------------------------------------- misc math
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+// exp / reciprocal on the special-function unit (MUFU.EX2 / MUFU.RCP, <= 2 ulp), flush-to-zero, no slow paths:
+// in the GEMM epilogues the issue slots of the few epilogue warps are the critical resource, and IEEE division
+// (a subroutine with a fix-up branch per element) costs more than the rest of the epilogue together.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+__device__ __forceinline__ float silu_fast(float x) { return silu_f(x); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
