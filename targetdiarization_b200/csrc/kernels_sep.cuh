@@ -83,65 +83,231 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
 // ---------------------------------------------------------------- DilatedDenseNet  (fsmn.py:76-111)
 // stage 1: y1 = depthwise conv (39 taps, pad 19) of p; statistics for InstanceNorm over all S frames.
 // stage 2: y2[c] = sum_{j<2} conv39_dilation2( cat[2c+j] ), cat = [PReLU(IN(y1)) ; p], pad 38.
-// A thread owns 2 adjacent channels (stage 1) or one output channel = 2 adjacent input channels (stage 2)
-// and DD_TT frames of one parity, with the taps in shared memory (conflict-free: lanes = channels).
-constexpr int DD_TT = 16;
-constexpr int DD_STRIP = 256;
+//
+// Streaming kernel: a CTA owns (sample, group of 128 input channels, time segment) and walks along time.
+// Thread 0 keeps TMA loads of 64-row x 512 B chunks two steps ahead in a 5-slot shared-memory ring, so every
+// input element is read from HBM once and the loads overlap the FMAs; a fix-up pass applies InstanceNorm +
+// PReLU (stage 2, y1 half) and the zero padding in place in shared memory, after which the inner loop is pure
+// FMA: thread = one channel (pair) x 16 outputs, 54-deep register window, taps from shared memory.
+constexpr int DD_CHUNK = 64;                 // rows per ring slot / outputs per step
+constexpr int DD_SLOTS = 5;
+constexpr int DD_RING_ROWS = DD_CHUNK * DD_SLOTS;
+constexpr int DD_ROW_BYTES = 512;            // 128 fp32 channels
+constexpr int DD_SMEM_BYTES = DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8 + 64 /*barriers*/ + 1024 * 8 /*stats*/ + 128;
 
-__global__ void __launch_bounds__(128) dd_conv1_kernel(const float* __restrict__ p, const float* __restrict__ taps,
-                                                       float* __restrict__ y1, double* __restrict__ stats, int Sp,
-                                                       int S) {
-  __shared__ float2 ws[39][128];
-  const int c = threadIdx.x * 2;
-  const int strips = Sp / DD_STRIP;
-  const int b = blockIdx.x / strips;
-  const int ts = (blockIdx.x - b * strips) * DD_STRIP;
-  if (ts >= S) return;
-  for (int k = 0; k < 39; ++k) ws[k][threadIdx.x] = make_float2(taps[c * 39 + k], taps[(c + 1) * 39 + k]);
-  const float* base = p + static_cast<size_t>(b) * Sp * 256 + c;
-  auto ld = [&](int t) -> float2 {
-    if (t < 0 || t >= S) return make_float2(0.f, 0.f);
-    return *reinterpret_cast<const float2*>(base + static_cast<size_t>(t) * 256);
-  };
-  float2 buf[DD_TT + 38];
-#pragma unroll
-  for (int i = 0; i < 38; ++i) buf[DD_TT + i] = ld(ts - 19 + i);
-  float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
-#pragma unroll 1
-  for (int t = ts; t < ts + DD_STRIP && t < S; t += DD_TT) {
-#pragma unroll
-    for (int i = 0; i < 38; ++i) buf[i] = buf[DD_TT + i];
-#pragma unroll
-    for (int i = 0; i < DD_TT; ++i) buf[38 + i] = ld(t + 19 + i);
-    float2 acc[DD_TT];
-#pragma unroll
-    for (int j = 0; j < DD_TT; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 39; ++k) {
-      const float2 wk = ws[k][threadIdx.x];
-#pragma unroll
-      for (int j = 0; j < DD_TT; ++j) {
-        acc[j].x = fmaf(wk.x, buf[j + k].x, acc[j].x);
-        acc[j].y = fmaf(wk.y, buf[j + k].y, acc[j].y);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < DD_TT; ++j) {
-      const int tt = t + j;
-      if (tt < S) {
-        *reinterpret_cast<float2*>(y1 + (static_cast<size_t>(b) * Sp + tt) * 256 + c) = acc[j];
-        s1x += acc[j].x;
-        s1y += acc[j].y;
-        s2x += acc[j].x * acc[j].x;
-        s2y += acc[j].y * acc[j].y;
+struct DdParams {
+  CUtensorMap tmA;       // stage 1: p;  stage 2: y1          3-D {256, Sp, B}, box {128, 64, 1}, no swizzle
+  CUtensorMap tmB;       // stage 2: p
+  const float* taps;     // stage 1: [256][39];  stage 2: [256][2][39]
+  const float2* in_ss;   // stage 2: InstanceNorm-1 (scale, shift) [B][256]
+  const float* prelu;    // stage 2: PReLU-1 slopes [256]
+  float* out;            // y1 / y2 [Mtot][256]
+  double* stats;         // [B][256][2] sum, sum of squares of the outputs
+  int B, Sp, S, nseg, seg_len;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant__ DdParams P) {
+  constexpr int NCG = STAGE == 1 ? 2 : 4;
+  constexpr int HALO = STAGE == 1 ? 19 : 38;
+  constexpr int STEP = STAGE == 1 ? 1 : 2;   // dilation
+  extern __shared__ uint8_t dd_smem_raw[];
+  uint8_t* sm = dd_smem_raw + ((128u - (smem_u32(dd_smem_raw) & 127u)) & 127u);
+  float* ring = reinterpret_cast<float*>(sm);
+  float2* ws = reinterpret_cast<float2*>(sm + DD_RING_ROWS * DD_ROW_BYTES);
+  const uint32_t bar0 = smem_u32(sm + DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8);
+  double* red = reinterpret_cast<double*>(sm + DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8 + 64);
+
+  const int tid = threadIdx.x;
+  int bid = blockIdx.x;
+  const int cg = bid % NCG;
+  bid /= NCG;
+  const int seg = bid % P.nseg;
+  const int b = bid / P.nseg;
+  const int seg_lo = seg * P.seg_len;
+  if (seg_lo >= P.S) return;
+  const int seg_hi = min(seg_lo + P.seg_len, P.S);
+  const int nsteps = (seg_hi - seg_lo + DD_CHUNK - 1) / DD_CHUNK;
+  const bool from_y1 = (STAGE == 2) && cg < 2;
+  const int cin0 = (STAGE == 1) ? cg * 128 : (cg & 1) * 128;
+  const CUtensorMap* map = (STAGE == 2 && !from_y1) ? &P.tmB : &P.tmA;
+
+  const int cp = tid & 63;   // channel pair (stage 1) / output channel (stage 2) inside the group
+  const int q = tid >> 6;    // which 16 outputs of the step
+  for (int k = 0; k < 39; ++k) {
+    if (tid < 64) {
+      if (STAGE == 1) {
+        const int c = cg * 128 + 2 * cp;
+        ws[k * 64 + cp] = make_float2(P.taps[c * 39 + k], P.taps[(c + 1) * 39 + k]);
+      } else {
+        const int oc = cg * 64 + cp;
+        ws[k * 64 + cp] = make_float2(P.taps[(oc * 2 + 0) * 39 + k], P.taps[(oc * 2 + 1) * 39 + k]);
       }
     }
   }
-  double* st = stats + (static_cast<size_t>(b) * 256 + c) * 2;
-  atomicAdd(st + 0, static_cast<double>(s1x));
-  atomicAdd(st + 1, static_cast<double>(s2x));
-  atomicAdd(st + 2, static_cast<double>(s1y));
-  atomicAdd(st + 3, static_cast<double>(s2y));
+  if (tid == 0) {
+    tma_prefetch_desc(map);
+    for (int s = 0; s < DD_SLOTS; ++s) mbar_init(bar0 + 8u * s, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int m) {  // chunk m = rows [seg_lo + 64 m, +64) of the 128 channels -> slot (m+1) % 5
+    const int slot = (m + 1) % DD_SLOTS;
+    const uint32_t bar = bar0 + 8u * slot;
+    mbar_arrive_expect_tx(bar, DD_CHUNK * DD_ROW_BYTES);
+    tma_load_3d(smem_u32(ring) + slot * DD_CHUNK * DD_ROW_BYTES, map, bar, cin0, seg_lo + DD_CHUNK * m, b);
+  };
+  auto wait_chunk = [&](int m) { mbar_wait(bar0 + 8u * ((m + 1) % DD_SLOTS), ((m + 1) / DD_SLOTS) & 1); };
+  if (tid == 0) {
+    for (int m = -1; m <= 2 && m <= nsteps; ++m) issue(m);
+  }
+
+  // fix-up pass constants: this thread touches 4 fixed channels
+  const int fc4 = (tid & 31) * 4;
+  float fsc[4] = {1.f, 1.f, 1.f, 1.f}, fsh[4] = {0.f, 0.f, 0.f, 0.f}, fal[4] = {1.f, 1.f, 1.f, 1.f};
+  if (from_y1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 ss = P.in_ss[b * 256 + cin0 + fc4 + i];
+      fsc[i] = ss.x;
+      fsh[i] = ss.y;
+      fal[i] = P.prelu[cin0 + fc4 + i];
+    }
+  }
+  auto fixup = [&](int m) {  // InstanceNorm + PReLU (y1 half) and zero padding outside [0, S), in place
+    const int t0 = seg_lo + DD_CHUNK * m;
+    const bool all_valid = t0 >= 0 && t0 + DD_CHUNK <= P.S;
+    if (!from_y1 && all_valid) return;
+    float* base = ring + ((m + 1) % DD_SLOTS) * DD_CHUNK * 128 + fc4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = (tid >> 5) + 8 * i;
+      const int t = t0 + rr;
+      float4* ptr = reinterpret_cast<float4*>(base + rr * 128);
+      float4 v = *ptr;
+      if (t < 0 || t >= P.S) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (from_y1) {
+        v.x = fmaf(v.x, fsc[0], fsh[0]); v.x = v.x >= 0.f ? v.x : fal[0] * v.x;
+        v.y = fmaf(v.y, fsc[1], fsh[1]); v.y = v.y >= 0.f ? v.y : fal[1] * v.y;
+        v.z = fmaf(v.z, fsc[2], fsh[2]); v.z = v.z >= 0.f ? v.z : fal[2] * v.z;
+        v.w = fmaf(v.w, fsc[3], fsh[3]); v.w = v.w >= 0.f ? v.w : fal[3] * v.w;
+      }
+      *ptr = v;
+    }
+  };
+
+  float s1x = 0.f, s2x = 0.f, s1y = 0.f, s2y = 0.f;
+  for (int n = 0; n < nsteps; ++n) {
+    if (n == 0) {
+      wait_chunk(-1);
+      fixup(-1);
+      wait_chunk(0);
+      fixup(0);
+    }
+    wait_chunk(n + 1);
+    fixup(n + 1);
+    __syncthreads();  // fix-ups visible; everybody is done with step n-1, so the slot of chunk n-2 is free
+    if (tid == 0 && n + 3 <= nsteps) {
+      fence_proxy_async();
+      issue(n + 3);
+    }
+    // first input row of this thread's window, relative to the ring origin (row -64 of the segment = ring row 0)
+    int r_out0, r_in0;
+    if (STAGE == 1) {
+      r_out0 = DD_CHUNK * n + 16 * q;
+      r_in0 = r_out0 - HALO;
+    } else {
+      r_out0 = DD_CHUNK * n + (q & 1) + 32 * (q >> 1);
+      r_in0 = r_out0 - HALO;
+    }
+    int R = (r_in0 + DD_CHUNK) % DD_RING_ROWS;
+    float2 buf[54];
+    const float* col = ring + 2 * cp;
+#pragma unroll
+    for (int i = 0; i < 54; ++i) {
+      buf[i] = *reinterpret_cast<const float2*>(col + R * 128);
+      R += STEP;
+      if (R >= DD_RING_ROWS) R -= DD_RING_ROWS;
+    }
+    if (STAGE == 1) {
+      float2 acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 39; ++k) {
+        const float2 wk = ws[k * 64 + cp];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          acc[j].x = fmaf(wk.x, buf[j + k].x, acc[j].x);
+          acc[j].y = fmaf(wk.y, buf[j + k].y, acc[j].y);
+        }
+      }
+      const int t0 = seg_lo + r_out0;
+      float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 128 + 2 * cp;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (t0 + j < seg_hi) {
+          *reinterpret_cast<float2*>(dst + static_cast<size_t>(j) * 256) = acc[j];
+          s1x += acc[j].x;
+          s2x = fmaf(acc[j].x, acc[j].x, s2x);
+          s1y += acc[j].y;
+          s2y = fmaf(acc[j].y, acc[j].y, s2y);
+        }
+      }
+    } else {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 39; ++k) {
+        const float2 wk = ws[k * 64 + cp];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(wk.x, buf[j + k].x, fmaf(wk.y, buf[j + k].y, acc[j]));
+      }
+      const int t0 = seg_lo + r_out0;
+      float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 64 + cp;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (t0 + 2 * j < seg_hi) {
+          dst[static_cast<size_t>(2 * j) * 256] = acc[j];
+          s1x += acc[j];
+          s2x = fmaf(acc[j], acc[j], s2x);
+        }
+      }
+    }
+  }
+  // statistics: reduce the four time groups of a channel, then one fp64 atomic pair per channel
+  red[(q * 64 + cp) * 2 + 0] = static_cast<double>(s1x);
+  red[(q * 64 + cp) * 2 + 1] = static_cast<double>(s2x);
+  if (STAGE == 1) {
+    red[512 + (q * 64 + cp) * 2 + 0] = static_cast<double>(s1y);
+    red[512 + (q * 64 + cp) * 2 + 1] = static_cast<double>(s2y);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    double a = 0, c2 = 0, ay = 0, cy = 0;
+    for (int g = 0; g < 4; ++g) {
+      a += red[(g * 64 + tid) * 2];
+      c2 += red[(g * 64 + tid) * 2 + 1];
+      if (STAGE == 1) {
+        ay += red[512 + (g * 64 + tid) * 2];
+        cy += red[512 + (g * 64 + tid) * 2 + 1];
+      }
+    }
+    if (STAGE == 1) {
+      double* st = P.stats + (static_cast<size_t>(b) * 256 + cg * 128 + 2 * tid) * 2;
+      atomicAdd(st + 0, a);
+      atomicAdd(st + 1, c2);
+      atomicAdd(st + 2, ay);
+      atomicAdd(st + 3, cy);
+    } else {
+      double* st = P.stats + (static_cast<size_t>(b) * 256 + cg * 64 + tid) * 2;
+      atomicAdd(st + 0, a);
+      atomicAdd(st + 1, c2);
+    }
+  }
 }
 
 // InstanceNorm2d(affine) scale / shift per (sample, channel) from the accumulated fp64 sums: biased variance,
@@ -156,80 +322,6 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
   if (var < 0) var = 0;
   const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
   out[i] = make_float2(rstd * g[c], bt[c] - static_cast<float>(mean) * rstd * g[c]);
-}
-
-__global__ void __launch_bounds__(128) dd_conv2_kernel(const float* __restrict__ y1, const float* __restrict__ p,
-                                                       const float2* __restrict__ in1_ss,
-                                                       const float* __restrict__ prelu1,
-                                                       const float* __restrict__ taps /*[256][2][39]*/,
-                                                       float* __restrict__ y2, double* __restrict__ stats2, int Sp,
-                                                       int S) {
-  __shared__ float2 ws[39][128];
-  const int c = blockIdx.y * 128 + threadIdx.x;  // output channel
-  const int strips = Sp / DD_STRIP;
-  const int b = blockIdx.x / strips;
-  const int ts = (blockIdx.x - b * strips) * DD_STRIP;
-  if (ts >= S) return;
-  for (int k = 0; k < 39; ++k)
-    ws[k][threadIdx.x] = make_float2(taps[(c * 2 + 0) * 39 + k], taps[(c * 2 + 1) * 39 + k]);
-  const bool from_y1 = c < 128;
-  const int ic = from_y1 ? 2 * c : 2 * (c - 128);  // first of the two adjacent input channels
-  float2 sc0 = make_float2(1.f, 0.f), sc1 = make_float2(1.f, 0.f);
-  float a0 = 1.f, a1 = 1.f;
-  if (from_y1) {
-    sc0 = in1_ss[b * 256 + ic];
-    sc1 = in1_ss[b * 256 + ic + 1];
-    a0 = prelu1[ic];
-    a1 = prelu1[ic + 1];
-  }
-  const float* base = (from_y1 ? y1 : p) + static_cast<size_t>(b) * Sp * 256 + ic;
-  auto ld = [&](int t) -> float2 {
-    if (t < 0 || t >= S) return make_float2(0.f, 0.f);
-    float2 v = *reinterpret_cast<const float2*>(base + static_cast<size_t>(t) * 256);
-    if (from_y1) {
-      v.x = v.x * sc0.x + sc0.y;
-      v.y = v.y * sc1.x + sc1.y;
-      v.x = v.x >= 0.f ? v.x : a0 * v.x;
-      v.y = v.y >= 0.f ? v.y : a1 * v.y;
-    }
-    return v;
-  };
-  float s1 = 0.f, s2 = 0.f;
-  // two passes over the strip, one per frame parity (dilation 2 keeps parities independent)
-#pragma unroll 1
-  for (int par = 0; par < 2; ++par) {
-    float2 buf[DD_TT + 38];
-#pragma unroll
-    for (int i = 0; i < 38; ++i) buf[DD_TT + i] = ld(ts + par - 38 + 2 * i);
-#pragma unroll 1
-    for (int t = ts + par; t < ts + DD_STRIP && t < S; t += 2 * DD_TT) {
-#pragma unroll
-      for (int i = 0; i < 38; ++i) buf[i] = buf[DD_TT + i];
-#pragma unroll
-      for (int i = 0; i < DD_TT; ++i) buf[38 + i] = ld(t + 38 + 2 * i);
-      float acc[DD_TT];
-#pragma unroll
-      for (int j = 0; j < DD_TT; ++j) acc[j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 39; ++k) {
-        const float2 wk = ws[k][threadIdx.x];
-#pragma unroll
-        for (int j = 0; j < DD_TT; ++j) acc[j] = fmaf(wk.x, buf[j + k].x, fmaf(wk.y, buf[j + k].y, acc[j]));
-      }
-#pragma unroll
-      for (int j = 0; j < DD_TT; ++j) {
-        const int tt = t + 2 * j;
-        if (tt < S) {
-          y2[(static_cast<size_t>(b) * Sp + tt) * 256 + c] = acc[j];
-          s1 += acc[j];
-          s2 += acc[j] * acc[j];
-        }
-      }
-    }
-  }
-  double* st = stats2 + (static_cast<size_t>(b) * 256 + c) * 2;
-  atomicAdd(st + 0, static_cast<double>(s1));
-  atomicAdd(st + 1, static_cast<double>(s2));
 }
 
 // FSMN tail: o2 = PReLU(IN(y2)); f = x_u + o2 (fsmn.py:144); g = x_v*f + c (mossformer_block.py:324);

@@ -93,7 +93,7 @@ extern "C" int tdz_num_sms(tdz_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 // ------------------------------------------------------------------------------------------------ tensor maps
 // rank-2/3 row-major tensor, innermost dimension contiguous, 128 B swizzle.
 static int make_tmap(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int rank, const uint64_t* dims,
-                     const uint32_t* box) {
+                     const uint32_t* box, bool swizzle = true) {
   const uint64_t es = f32 ? 4 : 2;
   cuuint64_t gdim[3] = {1, 1, 1};
   cuuint64_t gstr[2] = {0, 0};
@@ -106,10 +106,11 @@ static int make_tmap(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, in
     stride *= dims[i];
     if (i < rank - 1) gstr[i] = stride;
   }
-  if (bx[0] * es > 128) return fail(ctx, "tensor map inner box exceeds the 128 B swizzle span");
+  if (swizzle && bx[0] * es > 128) return fail(ctx, "tensor map inner box exceeds the 128 B swizzle span");
   CUresult r = ctx->encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
                            const_cast<void*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return 0;
@@ -120,6 +121,12 @@ static int act_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int 
   const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Sp), static_cast<uint64_t>(B)};
   const uint32_t box[3] = {box_c, box_rows, 1};
   return make_tmap(ctx, m, ptr, f32, 3, dims, box);
+}
+// fp32 activation [B][Sp][256] read in un-swizzled {128 channels, 64 rows} chunks (DilatedDenseNet ring)
+static int dd_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, int64_t Sp, int64_t B) {
+  const uint64_t dims[3] = {256, static_cast<uint64_t>(Sp), static_cast<uint64_t>(B)};
+  const uint32_t box[3] = {128, DD_CHUNK, 1};
+  return make_tmap(ctx, m, ptr, true, 3, dims, box, false);
 }
 // weight [N][K] -> 2-D map {K, N}
 static int w_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int N, int K, uint32_t box_rows) {
@@ -298,6 +305,27 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   AP.vu = vu;
   AP.o = o;
   AP.o_ss = o_ss;
+  // DilatedDenseNet streaming kernels: time segments long enough to amortise the 76-row halo, short enough to
+  // give every SM a few CTAs
+  CUtensorMap m_p, m_y1;
+  if (dd_map(ctx, &m_p, p, Sp, B)) return 1;
+  if (dd_map(ctx, &m_y1, y1, Sp, B)) return 1;
+  DdParams dd;
+  memset(&dd, 0, sizeof dd);
+  dd.B = B;
+  dd.Sp = Sp;
+  dd.S = S;
+  dd.seg_len = 2048;
+  while (dd.seg_len > 256 && static_cast<int64_t>(B) * 4 * ((S + dd.seg_len - 1) / dd.seg_len) < 4 * sms) dd.seg_len /= 2;
+  dd.nseg = (S + dd.seg_len - 1) / dd.seg_len;
+  {
+    static bool dd_configured = false;
+    if (!dd_configured) {
+      CUDA_OK(cudaFuncSetAttribute(dd_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM_BYTES));
+      CUDA_OK(cudaFuncSetAttribute(dd_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM_BYTES));
+      dd_configured = true;
+    }
+  }
 
   const int mtiles = static_cast<int>(M / 128);
   const int tps = (S + CONV_ROWS - 1) / CONV_ROWS;
@@ -432,13 +460,26 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     double* st2 = in_stats + static_cast<size_t>(B) * 512;
     STEP(ST_DD1) {
       CUDA_OK(cudaMemsetAsync(in_stats, 0, static_cast<size_t>(B) * 256 * 2 * 8 * 2, st));
-      dd_conv1_kernel<<<B * (Sp / DD_STRIP), 128, 0, st>>>(p, LW.dd_w1, y1, st1, Sp, S);
+      DdParams D = dd;
+      D.taps = LW.dd_w1;
+      D.out = y1;
+      D.stats = st1;
+      D.tmA = m_p;
+      dd_stream_kernel<1><<<B * dd.nseg * 2, 256, DD_SMEM_BYTES, st>>>(D);
     }
     float2* in_ss1 = in_ss;
     float2* in_ss2 = in_ss + static_cast<size_t>(B) * 256;
     STEP(ST_DD2) {
       in_finalize_kernel<<<B, 256, 0, st>>>(st1, LW.in1_g, LW.in1_b, in_ss1, B * 256, static_cast<double>(S));
-      dd_conv2_kernel<<<dim3(B * (Sp / DD_STRIP), 2), 128, 0, st>>>(y1, p, in_ss1, LW.dd_prelu1, LW.dd_w2, y2, st2, Sp, S);
+      DdParams D = dd;
+      D.taps = LW.dd_w2;
+      D.in_ss = in_ss1;
+      D.prelu = LW.dd_prelu1;
+      D.out = y2;
+      D.stats = st2;
+      D.tmA = m_y1;
+      D.tmB = m_p;
+      dd_stream_kernel<2><<<B * dd.nseg * 4, 256, DD_SMEM_BYTES, st>>>(D);
     }
     STEP(ST_FSMN_TAIL) {
       in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
