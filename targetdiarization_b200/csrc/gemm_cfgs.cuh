@@ -282,183 +282,9 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   }
 };
 
-// Linear + SiLU + ConvModule in one kernel.  An accumulator tile covers 128 consecutive frames of ONE sample,
-// of which the inner 112 are outputs and 8 on each side are the halo of the k=17 depthwise convolution (tiles
-// overlap by 16 rows; TMA zero-fills rows outside the sample).  Epilogue, per 128-column panel:
-//   phase 1  thread = tile row : tcgen05.ld -> row scale (ScaleNorm) + bias + SiLU -> fp32 panel in shared
-//            memory (rows outside [0,S) are written as zeros = the convolution's zero padding)
-//   phase 2  thread = 2 adjacent columns x 28 output rows: register sliding window down the panel column,
-//            y + dwconv(y), then the op-specific tail (bf16 operand copies, OffsetScale + rotary, residual add)
-// so the pre-convolution activation (8.7 KB per frame for to_hidden) never goes to HBM.
+// Linear + SiLU + ConvModule in one kernel: see gemm_conv.cuh.  Modes of its tail:
 enum ConvMode : int { CONV_VUQK = 0, CONV_RESX = 1, CONV_UV = 2 };
-constexpr int CONV_ROWS = 112;
-constexpr int PANEL_LD = 132;  // floats per panel row: 128 + 4 keeps the row-wise float4 stores conflict free
-
-template <int MODE, int STAGES_>
-struct LinearConv : LinearBase<1, 256, STAGES_> {
-  using Params = LinearParams;
-  static constexpr int EPI_SPLIT = 2;
-  static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4;
-
-  __device__ static int num_tiles(const Params& P) { return P.B * P.tps * P.n_tiles; }
-  __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
-    const int mt = tile / P.n_tiles;
-    const int nt = tile - mt * P.n_tiles;
-    ti.b = mt / P.tps;
-    const int j = mt - ti.b * P.tps;
-    ti.t0 = j * CONV_ROWS - 8;  // frame of tile row 0 (negative for the first tile of a sample)
-    ti.m0 = ti.b * P.Sp;        // first row of the sample in the token space
-    ti.n0 = nt * 256;
-    ti.nkb = P.K / 64;
-    ti.aux = nt;
-  }
-  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
-    const int trow = ti.t0 - (kb < P.shift_kblocks ? 1 : 0);
-    tma_load_3d(sa, &P.tmA, bar, kb * 64, trow, ti.b);
-    tma_load_2d(sb, &P.tmB, bar, kb * 64, ti.n0);
-  }
-
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
-                                  const EpiCtx& cx) {
-    const EpiGeneric& e = P.e;
-    const EpiConv& cv = P.cv;
-    const int t = ti.t0 + row;
-    const bool valid = t >= 0 && t < P.S;
-    const size_t srow = static_cast<size_t>(ti.m0);
-    float rs = 1.f;
-    if (valid) {
-      if constexpr (MODE == CONV_VUQK) {
-        const size_t grow = srow + t;
-        const float4 cur = *reinterpret_cast<const float4*>(e.ss_in + grow * 4);
-        float ss = cur.z + cur.w;  // channels 256..511 of this frame
-        if (t > 0) {
-          const float4 prv = *reinterpret_cast<const float4*>(e.ss_in + (grow - 1) * 4);
-          ss += prv.x + prv.y;     // channels 0..255 of the previous frame (token shift)
-        }
-        rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
-      }
-      if constexpr (MODE == CONV_RESX) {
-        const size_t grow = srow + t;
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 a = *reinterpret_cast<const float4*>(e.ss_in + grow * 16 + 4 * i);
-          ss += (a.x + a.y) + (a.z + a.w);
-        }
-        rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
-      }
-    }
-    float* prow = cx.panel + row * PANEL_LD + half * 64;
-    const int w = cx.tid >> 5, lane = cx.tid & 31;
-    const int cp = (w & 1) * 32 + lane;  // column pair inside the panel
-    const int rg = w >> 1;               // group of 28 output rows
-#pragma unroll 1
-    for (int pn = 0; pn < 2; ++pn) {
-      const int pc0 = ti.n0 + pn * 128;  // first output column of the panel
-      if (pc0 >= P.N) break;
-      // ---- phase 1: accumulator -> activated fp32 panel (32 columns per TMEM round trip)
-#pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 32) {
-        const int c0 = pn * 128 + half * 64 + cc;
-        float v[32], bias[32];
-        tmem_ld16(tacc + c0, v);
-        tmem_ld16(tacc + c0 + 16, v + 16);
-        ld_f32x16(e.bias + ti.n0 + c0, bias);
-        ld_f32x16(e.bias + ti.n0 + c0 + 16, bias + 16);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = valid ? silu_fast(fmaf(v[j], rs, bias[j])) : 0.f;
-        float4* dst = reinterpret_cast<float4*>(prow + cc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      epi_bar_sync<256>();
-      // ---- phase 2: y + depthwise conv over time (28 independent accumulator chains per thread), then the tail
-      {
-        const int c = pc0 + 2 * cp;
-        float2 wt[17];
-#pragma unroll
-        for (int k = 0; k < 17; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(cv.dw_t + k * cv.ldw + c));
-        const float* pcol = cx.panel + 2 * cp;
-#pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
-          const int r0 = 28 * rg + 14 * it;
-          float2 buf[30];
-#pragma unroll
-          for (int i = 0; i < 30; ++i) buf[i] = *reinterpret_cast<const float2*>(pcol + (r0 + i) * PANEL_LD);
-          float2 acc[14];
-#pragma unroll
-          for (int j = 0; j < 14; ++j) acc[j] = buf[j + 8];
-#pragma unroll
-          for (int k = 0; k < 17; ++k) {
-#pragma unroll
-            for (int j = 0; j < 14; ++j) {
-              acc[j].x = fmaf(wt[k].x, buf[j + k].x, acc[j].x);
-              acc[j].y = fmaf(wt[k].y, buf[j + k].y, acc[j].y);
-            }
-          }
-          const int tt0 = ti.t0 + r0 + 8;       // frame of acc[0]
-          const int nrow = P.S - tt0;           // rows j < nrow are inside the sample
-          const size_t grow0 = srow + tt0;
-          if constexpr (MODE == CONV_VUQK) {
-            if (c < 2048) {
-              __nv_bfloat16* dst = cv.vu + grow0 * 2048 + c;
-#pragma unroll
-              for (int j = 0; j < 14; ++j)
-                if (j < nrow) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(j) * 2048) = pack_bf16(acc[j].x, acc[j].y);
-            } else {
-              const int qc = c - 2048;
-              __nv_bfloat16* dst = cv.qk4 + grow0 * 512 + qc;
-              float2 cs[14];
-#pragma unroll
-              for (int j = 0; j < 14; ++j)
-                cs[j] = (qc < 32 && j < nrow) ? cv.rot[(tt0 + j) * 16 + (qc >> 1)] : make_float2(1.f, 0.f);
-#pragma unroll 1
-              for (int h = 0; h < 4; ++h) {
-                const float g0 = __ldg(cv.gamma + h * 128 + qc), g1 = __ldg(cv.gamma + h * 128 + qc + 1);
-                const float b0 = __ldg(cv.beta + h * 128 + qc), b1 = __ldg(cv.beta + h * 128 + qc + 1);
-#pragma unroll
-                for (int j = 0; j < 14; ++j) {
-                  const float x0 = fmaf(acc[j].x, g0, b0), x1 = fmaf(acc[j].y, g1, b1);
-                  // rotary on interleaved pairs of dims 0..31 (identity rotation elsewhere)
-                  const float r0v = x0 * cs[j].x - x1 * cs[j].y;
-                  const float r1v = x1 * cs[j].x + x0 * cs[j].y;
-                  if (j < nrow)
-                    *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(j) * 512 + h * 128) = pack_bf16(r0v, r1v);
-                }
-              }
-            }
-          }
-          if constexpr (MODE == CONV_RESX) {
-            const float* src = cv.x_in + grow0 * 512 + c;
-            float* dst = cv.x_out + grow0 * 512 + c;
-            float2 r[14];
-#pragma unroll
-            for (int j = 0; j < 14; ++j)
-              r[j] = (j < nrow) ? *reinterpret_cast<const float2*>(src + static_cast<size_t>(j) * 512) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 14; ++j)
-              if (j < nrow)
-                *reinterpret_cast<float2*>(dst + static_cast<size_t>(j) * 512) = make_float2(r[j].x + acc[j].x, r[j].y + acc[j].y);
-          }
-          if constexpr (MODE == CONV_UV) {
-            float* dst = cv.xuv + grow0 * 512 + c;
-#pragma unroll
-            for (int j = 0; j < 14; ++j)
-              if (j < nrow) *reinterpret_cast<float2*>(dst + static_cast<size_t>(j) * 512) = acc[j];
-            if (c < 256) {
-              __nv_bfloat16* db = cv.xubf + grow0 * 256 + c;
-#pragma unroll
-              for (int j = 0; j < 14; ++j)
-                if (j < nrow) *reinterpret_cast<uint32_t*>(db + static_cast<size_t>(j) * 256) = pack_bf16(acc[j].x, acc[j].y);
-            }
-          }
-        }
-      }
-      epi_bar_sync<256>();
-    }
-  }
-};
+constexpr int CONV_ROWS = 112;  // output frames per 128-row accumulator tile (8-row halo on each side)
 
 // FSMN block entry: Conv1d(512->256,k1)+bias -> PReLU(1) -> CLayerNorm(256) -> (to_u|to_v) LayerNorm(256)
 // statistics (mossformer_block.py:405-409,419-421,301-312; layer_norm.py:9-30).  One tile holds the whole

@@ -47,18 +47,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Spin on a phase parity. With TDZ_HANG_GUARD the kernel traps instead of hanging the GPU if a
-// barrier is never satisfied (a protocol bug), so a bad launch surfaces as a CUDA error.
+// Wait on a phase parity.  After a first failed probe the thread backs off with nanosleep between probes: the
+// producer / MMA / epilogue warps share four issue ports, and a tight spin (probe + clock read + compare) of the
+// two single-thread warps takes issue slots away from the epilogue warps.  With TDZ_HANG_GUARD the kernel traps
+// instead of hanging the GPU if a barrier is never satisfied (a protocol bug), so a bad launch surfaces as a
+// CUDA error.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#if TDZ_HANG_GUARD
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+#if TDZ_HANG_GUARD
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz: far beyond any legitimate wait
+    __nanosleep(32);
+    if (++spins > 40000000u) __trap();  // > 1 s: far beyond any legitimate wait
   }
 #else
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 #endif
 }
 

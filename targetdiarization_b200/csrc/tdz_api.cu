@@ -10,6 +10,7 @@
 #include <string>
 
 #include "gemm_cfgs.cuh"
+#include "gemm_conv.cuh"
 #include "kernels_fbank.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_sep.cuh"
@@ -396,7 +397,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.gamma = LW.os_gamma;
       P.cv.beta = LW.os_beta;
       P.cv.rot = rot;
-      CUDA_OK((launch_gemm<LinearConv<CONV_VUQK, 3>>(P, B * tps * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm_conv<CONV_VUQK>(P, B * tps * P.n_tiles, sms, st)));
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {
@@ -416,7 +417,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.x_in = x_in;
       P.cv.x_out = x;
-      CUDA_OK((launch_gemm<LinearConv<CONV_RESX, 3>>(P, B * tps * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm_conv<CONV_RESX>(P, B * tps * P.n_tiles, sms, st)));
     }
     // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
     STEP(ST_FSMN_C1) {  // conv1 + PReLU + norm1 + inner LayerNorm statistics
@@ -438,7 +439,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.xuv = xuv;
       P.cv.xubf = xubf;
-      CUDA_OK((launch_gemm<LinearConv<CONV_UV, 3>>(P, B * tps * P.n_tiles, sms, st)));
+      CUDA_OK((launch_gemm_conv<CONV_UV>(P, B * tps * P.n_tiles, sms, st)));
     }
     STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;
