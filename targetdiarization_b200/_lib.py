@@ -29,7 +29,7 @@ class MossFormer2Weights(ctypes.Structure):
 class SepLayout(ctypes.Structure):
     _names = ("enc", "x0", "x", "xbf", "ss", "vu", "qk4", "P", "o", "o_ss", "c", "nhat", "xuv", "xubf", "f1", "p", "y1",
               "y2", "g", "lnb", "ab", "mb", "gated", "sep", "kv_part", "kv", "gn_stats", "in_stats", "in_ss", "samp",
-              "rot", "total")
+              "rot", "hrs", "total")
     _fields_ = ([(n, ctypes.c_size_t) for n in _names]
                 + [("S", ctypes.c_int64), ("Sp", ctypes.c_int64), ("Mtot", ctypes.c_int64),
                    ("kv_nsplit", ctypes.c_int32), ("kv_kb_per_split", ctypes.c_int32)])

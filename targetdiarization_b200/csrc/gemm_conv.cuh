@@ -306,10 +306,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) gemm_conv_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 17; ++k) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-              acc[j].x = fmaf(wt[k].x, win[j + k].x, acc[j].x);
-              acc[j].y = fmaf(wt[k].y, win[j + k].y, acc[j].y);
-            }
+            for (int j = 0; j < 7; ++j) acc[j] = fma2(wt[k], win[j + k], acc[j]);
           }
           if (it == 1) nbar_arrive(3 + buf);  // last read of the panel is done: hand the buffer back early
           const int tt0 = ti.t0 + r0 + 8;     // frame of acc[0]

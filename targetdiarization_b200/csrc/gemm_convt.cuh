@@ -1,0 +1,365 @@
+// Linear + SiLU + ConvModule (depthwise k=17 over time + residual) in one kernel, channel-major accumulator
+// (mossformer_block.py:89-102, conv_module.py:209-220).
+//
+// The product is computed transposed, D[channel][frame] = sum_k W[channel][k] X[frame][k]: the weight tile is the
+// M=128 operand, 256 consecutive frames of ONE sample are the N operand.  In TMEM a lane is then an output channel
+// and the columns are time, so an epilogue thread reads "its" channel's frames straight into a register sliding
+// window with tcgen05.ld and runs the time convolution there: the pre-convolution activation (8.7 KB per frame
+// for to_hidden|to_qk) goes neither to HBM nor to shared memory, bias / taps / OffsetScale are per-thread
+// constants, and shared memory bandwidth is left to the MMA operands (4-stage ring).
+//
+//   warp 0        TMA producer          {W 128 x 64, X 256 x 64} bf16 k-blocks, token shift = X row offset -1
+//   warp 1        tcgen05.mma issuer    fp32 accumulators in TMEM, two accumulator stages
+//   warps 2..13   epilogue              lane quarter (32 channels) x time third (80 output frames + 16 halo)
+//
+// A tile covers frames [240 j - 8, 240 j + 248) of a sample, of which the inner 240 are outputs (TMA zero-fills
+// rows outside the sample; activations of frames outside [0,S) are forced to zero = the convolution's padding).
+#pragma once
+#include <type_traits>
+
+#include "gemm_cfgs.cuh"
+
+namespace tdz {
+
+constexpr int CT_STAGES = 4;
+constexpr int CT_STAGE_BYTES = GEMM_STAGE_A_BYTES + 256 * 128;  // W tile 16 KB + X tile 32 KB
+constexpr int CT_ROWS = 240;                                     // output frames per tile
+constexpr int CT_EPI_WARPS = 12;                                 // 4 lane quarters x 3 time thirds
+constexpr int CT_THREADS = 64 + 32 * CT_EPI_WARPS;
+constexpr int CT_SCR = 96;                                       // frames per epilogue warp (80 outputs + 16 halo)
+constexpr int CT_CONST_FLOATS = 18 * 128;                        // per channel of the tile: 17 taps + bias
+// Both scratch tables are written (cp.async) one tile ahead into the other of two buffers.  Warps share table
+// entries, and the two TMEM stages would let a fast warp run two tiles ahead of a slow one, so the epilogue warps
+// meet at a named barrier at the top of every tile: nobody overwrites a buffer that a straggler has yet to read.
+constexpr int CT_NBUF = 2;
+constexpr int CT_HRS_FLOATS = 3 * CT_SCR;                        // one row of scales per time third
+// operand ring | barriers | frame scales [2 buffers] | per-channel constants [2 buffers]
+constexpr int CT_SMEM_BYTES =
+    CT_STAGES * CT_STAGE_BYTES + 256 + CT_NBUF * CT_HRS_FLOATS * 4 + CT_NBUF * CT_CONST_FLOATS * 4 + 1024;
+
+// 4-byte asynchronous global -> shared copy (the per-tile constants of the NEXT tile are fetched this way while
+// the current tile is being processed, so no global-load latency sits on the per-tile critical path)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + 16, v + 16);
+}
+
+// SiLU through one MUFU.TANH: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx: relative error 2^-11 on the
+// tanh, i.e. an absolute error below 5e-4*|h| - smaller than the bf16 rounding of the operand copy that follows).
+__device__ __forceinline__ float silu_half(float h) { return fmaf(h, tanh_approx(h), h); }
+
+struct ConvTTile {
+  int b, j, ct, t0, srow;
+};
+__device__ __forceinline__ void convt_tile(const LinearParams& P, int tile, ConvTTile& ti) {
+  const int mt = tile / P.n_tiles;      // (sample, time tile)
+  ti.ct = tile - mt * P.n_tiles;        // channel tile: fastest, so concurrent CTAs share the X tile in L2
+  ti.b = mt / P.tps;
+  ti.j = mt - ti.b * P.tps;
+  ti.t0 = ti.j * CT_ROWS - 8;           // frame of accumulator column 0
+  ti.srow = ti.b * P.Sp;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_constant__ LinearParams P) {
+  constexpr int LDW = (MODE == CONV_VUQK) ? 2176 : 512;  // leading dimension of the tap-major tap table
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + CT_STAGES * CT_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (CT_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * CT_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * CT_STAGES + 2 + s); };
+  float* scratch = reinterpret_cast<float*>(smem_al + CT_STAGES * CT_STAGE_BYTES + 256);
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmA);
+    tma_prefetch_desc(&P.tmB);
+    for (int s = 0; s < CT_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), CT_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const int ntiles = P.B * P.tps * P.n_tiles;
+  const int nkb = P.K / 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        ConvTTile ti;
+        convt_tile(P, tile, ti);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), CT_STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * CT_STAGE_BYTES;
+          const int trow = ti.t0 - (kb < P.shift_kblocks ? 1 : 0);  // token shift (mossformer_block.py:204-207)
+          tma_load_2d(sa, &P.tmB, full_bar(stage), kb * 64, ti.ct * 128);                 // weights: M operand
+          tma_load_3d(sa + GEMM_STAGE_A_BYTES, &P.tmA, full_bar(stage), kb * 64, trow, ti.b);  // frames: N operand
+          if (++stage == CT_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc(1, GEMM_BLOCK_M, 256, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * 256;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * CT_STAGE_BYTES;
+          const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32u, 16u, 1024u);
+            const uint64_t db = umma_smem_desc(sb + k * 32u, 16u, 1024u);
+            umma_f16(tacc, da, db, IDESC, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == nkb - 1) umma_commit(tfull_bar(as));
+          if (++stage == CT_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread = one output channel, 80 output frames (5 x 16) + 16 halo frames
+    const int q = warp & 3;           // TMEM lane quarter -> 32 channels
+    const int tq = (warp - 2) >> 2;   // time third
+    const int col0 = 80 * tq;         // first accumulator column this warp reads
+    // shared scratch: the 96 per-frame scales of this warp's time third (0.5 / ScaleNorm denominator, precomputed
+    // per frame by rowscale_kernel) and the per-channel constants of the tile (taps, bias); warps that share an
+    // entry copy the same values (benign)
+    float* hrs_buf = scratch + tq * CT_SCR;                                // + buf * CT_HRS_FLOATS
+    float* cst_buf = scratch + CT_NBUF * CT_HRS_FLOATS + q * 32 + lane;    // + buf * CT_CONST_FLOATS + k * 128
+    const EpiGeneric& e = P.e;
+    const EpiConv& cv = P.cv;
+    auto prefetch = [&](int tile, int buf) {  // asynchronous: completes before the tile that uses `buf` starts
+      ConvTTile tn;
+      convt_tile(P, tile, tn);
+      const int c = tn.ct * 128 + q * 32 + lane;
+      float* cs = cst_buf + buf * CT_CONST_FLOATS;
+#pragma unroll
+      for (int k = 0; k < 17; ++k) cp_async4(cs + k * 128, cv.dw_t + k * LDW + c);
+      cp_async4(cs + 17 * 128, e.bias + c);
+      if constexpr (MODE != CONV_UV) {
+        float* hs = hrs_buf + buf * CT_HRS_FLOATS;
+        const int tb = tn.t0 + col0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int i = lane + 32 * r;
+          const int t = min(max(tb + i, 0), P.S - 1);  // frames outside [0,S) are masked later; any valid address
+          cp_async4(hs + i, e.ss_in + static_cast<size_t>(tn.srow) + t);
+        }
+      }
+    };
+    int it = 0;
+    if (blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      ConvTTile ti;
+      convt_tile(P, tile, ti);
+      const int c = ti.ct * 128 + q * 32 + lane;  // output channel of this thread
+      const int buf = it % CT_NBUF;
+      cp_async_wait_all();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * CT_EPI_WARPS) : "memory");  // epilogue warps only
+      float wt[17];
+#pragma unroll
+      for (int k = 0; k < 17; ++k) wt[k] = cst_buf[buf * CT_CONST_FLOATS + k * 128];
+      const float hb = 0.5f * cst_buf[buf * CT_CONST_FLOATS + 17 * 128];
+      const float* hrs_s = hrs_buf + buf * CT_HRS_FLOATS;
+      if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, (it + 1) % CT_NBUF);
+      const int tbase = ti.t0 + col0;  // frame of accumulator column col0
+      const bool all_valid = tbase >= 0 && tbase + 96 <= P.S;
+
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * 256 + (static_cast<uint32_t>(q * 32) << 16) + col0;
+
+      // SiLU(scale * acc + bias) of N freshly loaded accumulator columns, in place; sidx = index of the first one
+      // in the per-frame scratch (a multiple of 4)
+      float win[36];
+      auto activate = [&](float* w, int sidx, auto n_tag) {
+        constexpr int N = decltype(n_tag)::value;
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {  // four frames at a time keeps the scale / mask operands short-lived
+          float4 hs = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+          if constexpr (MODE != CONV_UV) hs = *reinterpret_cast<const float4*>(hrs_s + sidx + i);
+          // frames outside [0,S) are SELECTED to zero (their accumulators may hold anything, also NaN: the rows of
+          // the N operand beyond S are never written by the producer kernels)
+          const float a0 = silu_half(fmaf(w[i + 0], hs.x, hb)), a1 = silu_half(fmaf(w[i + 1], hs.y, hb));
+          const float a2 = silu_half(fmaf(w[i + 2], hs.z, hb)), a3 = silu_half(fmaf(w[i + 3], hs.w, hb));
+          const unsigned t = static_cast<unsigned>(tbase + sidx + i);  // negative frames wrap to huge values
+          const unsigned Su = static_cast<unsigned>(P.S);
+          w[i + 0] = (all_valid || t + 0u < Su) ? a0 : 0.f;
+          w[i + 1] = (all_valid || t + 1u < Su) ? a1 : 0.f;
+          w[i + 2] = (all_valid || t + 2u < Su) ? a2 : 0.f;
+          w[i + 3] = (all_valid || t + 3u < Su) ? a3 : 0.f;
+        }
+      };
+      tmem_ld32(tacc, win);
+      tmem_ld_wait();
+      activate(win, 0, std::integral_constant<int, 32>{});
+#pragma unroll 1
+      for (int itn = 0; itn < 5; ++itn) {
+        [[maybe_unused]] float rin[16];
+        if constexpr (MODE == CONV_RESX) {  // residual stream of these 16 frames: in flight during the FMAs
+          const int tt0r = tbase + 8 + 16 * itn;
+          const float* src = cv.x_in + (static_cast<size_t>(ti.srow) + tt0r) * 512 + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rin[j] = (tt0r + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
+        }
+        [[maybe_unused]] float2 rcs[16];
+        if constexpr (MODE == CONV_VUQK) {  // rotary (cos, sin) of these 16 frames: in flight during the FMAs
+          if (c >= 2048 && c < 2048 + 32) {  // warp-uniform: lane quarter 0 of the qk channel tile
+            const int tt0r = tbase + 8 + 16 * itn;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              rcs[j] = (tt0r + j < P.S) ? __ldg(cv.rot + (tt0r + j) * 16 + ((c - 2048) >> 1)) : make_float2(1.f, 0.f);
+          }
+        }
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = win[j + 8];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(wt[k], win[j + k], acc[j]);
+        }
+        if (itn < 4) {  // slide the window: the next 16 accumulator columns
+#pragma unroll
+          for (int i = 0; i < 16; ++i) win[i] = win[16 + i];
+          tmem_ld16(tacc + 32 + 16 * itn, win + 16);
+          tmem_ld_wait();
+          if (itn == 3) {  // last TMEM read of this tile is done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
+          activate(win + 16, 32 + 16 * itn, std::integral_constant<int, 16>{});
+        }
+        const int tt0 = tbase + 8 + 16 * itn;  // frame of acc[0]
+        const int nrow = min(P.S - tt0, 16);   // rows j < nrow are inside the sample (may be <= 0)
+        const size_t grow0 = static_cast<size_t>(ti.srow) + tt0;
+        if constexpr (MODE == CONV_VUQK) {
+          if (c < 2048) {  // warp-uniform (the qk channels are one whole channel tile)
+            __nv_bfloat16* dst = cv.vu + grow0 * 2048 + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nrow) dst[static_cast<size_t>(j) * 2048] = __float2bfloat16(acc[j]);
+          } else {
+            const int qc = c - 2048;
+            __nv_bfloat16* dst = cv.qk4 + grow0 * 512 + qc;
+            if (qc < 32) {  // warp-uniform: rotary on interleaved pairs of dims 0..31; the partner is the next lane
+              const float sgn = (qc & 1) ? 1.f : -1.f;
+#pragma unroll 1
+              for (int h = 0; h < 4; ++h) {
+                const float g = __ldg(cv.gamma + h * 128 + qc), bt = __ldg(cv.beta + h * 128 + qc);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float x = fmaf(acc[j], g, bt);
+                  const float other = __shfl_xor_sync(0xffffffffu, x, 1);
+                  const float r = fmaf(sgn * other, rcs[j].y, x * rcs[j].x);  // even: x cos - x' sin; odd: x cos + x' sin
+                  if (j < nrow) dst[static_cast<size_t>(j) * 512 + h * 128] = __float2bfloat16(r);
+                }
+              }
+            } else {
+#pragma unroll 1
+              for (int h = 0; h < 4; ++h) {
+                const float g = __ldg(cv.gamma + h * 128 + qc), bt = __ldg(cv.beta + h * 128 + qc);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < nrow) dst[static_cast<size_t>(j) * 512 + h * 128] = __float2bfloat16(fmaf(acc[j], g, bt));
+              }
+            }
+          }
+        }
+        if constexpr (MODE == CONV_RESX) {
+          float* dst = cv.x_out + grow0 * 512 + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nrow) dst[static_cast<size_t>(j) * 512] = rin[j] + acc[j];
+        }
+        if constexpr (MODE == CONV_UV) {
+          float* dst = cv.xuv + grow0 * 512 + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nrow) dst[static_cast<size_t>(j) * 512] = acc[j];
+          if (c < 256) {
+            __nv_bfloat16* db = cv.xubf + grow0 * 256 + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nrow) db[static_cast<size_t>(j) * 256] = __float2bfloat16(acc[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int MODE>
+cudaError_t launch_gemm_convt(const LinearParams& P, int ntiles, int num_sms, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_convt_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (ntiles <= 0) return cudaSuccess;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  gemm_convt_kernel<MODE><<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace tdz

@@ -80,6 +80,37 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
   tab[i] = make_float2(cosf(a), sinf(a));
 }
 
+// ScaleNorm (mossformer_block.py:44-54) as one scale per frame: out[row] = 0.5 / clamp(||x_row|| dim^-0.5, 1e-5),
+// from the partial sums of squares the producing GEMM epilogue left behind.  The factor 0.5 belongs to the
+// tanh form of SiLU the consumer uses.  SHIFT: the row is the token-shifted frame (channels 0..255 of the
+// previous frame | channels 256..511 of this frame, :204-207) and `parts` holds 4 sums of 128 channels per frame;
+// otherwise `parts` holds 16 sums per frame.
+template <bool SHIFT>
+__global__ void rowscale_kernel(const float* __restrict__ parts, float* __restrict__ out, int Sp, int S, size_t rows,
+                                float dim_rsqrt) {
+  const size_t row = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int t = static_cast<int>(row % Sp);
+  if (t >= S) return;
+  float ss;
+  if (SHIFT) {
+    const float4 cur = *reinterpret_cast<const float4*>(parts + row * 4);
+    ss = cur.z + cur.w;
+    if (t > 0) {
+      const float4 prv = *reinterpret_cast<const float4*>(parts + (row - 1) * 4);
+      ss += prv.x + prv.y;
+    }
+  } else {
+    ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(parts + row * 16 + 4 * i);
+      ss += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  out[row] = 0.5f / fmaxf(sqrtf(ss) * dim_rsqrt, 1e-5f);
+}
+
 // ---------------------------------------------------------------- DilatedDenseNet  (fsmn.py:76-111)
 // stage 1: y1 = depthwise conv (39 taps, pad 19) of p; statistics for InstanceNorm over all S frames.
 // stage 2: y2[c] = sum_{j<2} conv39_dilation2( cat[2c+j] ), cat = [PReLU(IN(y1)) ; p], pad 38.
@@ -239,10 +270,7 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
       for (int k = 0; k < 39; ++k) {
         const float2 wk = ws[k * 64 + cp];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          acc[j].x = fmaf(wk.x, buf[j + k].x, acc[j].x);
-          acc[j].y = fmaf(wk.y, buf[j + k].y, acc[j].y);
-        }
+        for (int j = 0; j < 16; ++j) acc[j] = fma2(wk, buf[j + k], acc[j]);
       }
       const int t0 = seg_lo + r_out0;
       float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 128 + 2 * cp;
@@ -257,15 +285,19 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
         }
       }
     } else {
-      float acc[16];
+      // the two input channels of an output accumulate side by side (packed FMA) and are added at the end
+      float2 acc2[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 16; ++j) acc2[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 39; ++k) {
         const float2 wk = ws[k * 64 + cp];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fmaf(wk.x, buf[j + k].x, fmaf(wk.y, buf[j + k].y, acc[j]));
+        for (int j = 0; j < 16; ++j) acc2[j] = fma2(wk, buf[j + k], acc2[j]);
       }
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = acc2[j].x + acc2[j].y;
       const int t0 = seg_lo + r_out0;
       float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 64 + cp;
 #pragma unroll

@@ -34,34 +34,34 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One probe of a phase parity.  The suspend-time hint lets the hardware park the thread until the phase completes
+// (or the hint expires) instead of returning at once, so a waiting warp does not burn issue slots that the
+// epilogue warps of the same SM need.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(done)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return done != 0;
 }
-// Wait on a phase parity.  After a first failed probe the thread backs off with nanosleep between probes: the
-// producer / MMA / epilogue warps share four issue ports, and a tight spin (probe + clock read + compare) of the
-// two single-thread warps takes issue slots away from the epilogue warps.  With TDZ_HANG_GUARD the kernel traps
-// instead of hanging the GPU if a barrier is never satisfied (a protocol bug), so a bad launch surfaces as a
-// CUDA error.
+// Wait on a phase parity.  With TDZ_HANG_GUARD the kernel traps instead of hanging the GPU if a barrier is never
+// satisfied (a protocol bug), so a bad launch surfaces as a CUDA error.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
 #if TDZ_HANG_GUARD
-  uint32_t spins = 0;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(32);
-    if (++spins > 40000000u) __trap();  // > 1 s: far beyond any legitimate wait
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: far beyond any legitimate wait
   }
 #else
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+  while (!mbar_try_wait(bar, parity)) {
+  }
 #endif
 }
 
@@ -179,6 +179,28 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float silu_fast(float x) { return silu_f(x); }
+// Packed fp32 pair arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 - two fp32 operations per issue slot).  The time
+// convolutions and the epilogue activations are issue-bound, and their data is laid out as channel pairs anyway.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return reinterpret_cast<float2&>(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(r)
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return reinterpret_cast<float2&>(r);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,11 +6,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
 #include "gemm_cfgs.cuh"
 #include "gemm_conv.cuh"
+#include "gemm_convt.cuh"
 #include "kernels_fbank.cuh"
 #include "kernels_misc.cuh"
 #include "kernels_sep.cuh"
@@ -36,6 +38,7 @@ struct tdz_ctx {
   // weight tensor maps (built once per tdz_set_mossformer2_weights)
   struct LayerMaps {
     CUtensorMap w_in, w_out, w_c1, w_uv, w_lin, w_proj, w_c2;
+    CUtensorMap w_in128, w_out128, w_uv128;  // 128-row boxes: M operand of the channel-major conv GEMMs
   } lm[TDZ_NUM_LAYERS];
   CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1;
   bool have_fbank = false;
@@ -150,6 +153,9 @@ extern "C" int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_w
     if (w_map(ctx, &M.w_lin, L.w_lin, false, 256, 256, 256)) return 1;
     if (w_map(ctx, &M.w_proj, L.w_proj, false, 256, 256, 256)) return 1;
     if (w_map(ctx, &M.w_c2, L.w_c2, true, 512, 256, 256)) return 1;
+    if (w_map(ctx, &M.w_in128, L.w_in, false, 2176, 512, 128)) return 1;
+    if (w_map(ctx, &M.w_out128, L.w_out, false, 512, 1024, 128)) return 1;
+    if (w_map(ctx, &M.w_uv128, L.w_uv, false, 512, 256, 128)) return 1;
   }
   if (w_map(ctx, &ctx->m_enc1x1, w->w_enc1x1, true, 512, 512, 256)) return 1;
   if (w_map(ctx, &ctx->m_out1, w->w_out1, true, 1024, 512, 256)) return 1;
@@ -224,6 +230,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->in_ss = take(static_cast<size_t>(B) * 256 * 8 * 2);        // their (scale, shift) tables
   L->samp = take(static_cast<size_t>(B) * 4 * 4);               // A,B for each GroupNorm
   L->rot = take(static_cast<size_t>(Sp) * 16 * 8);
+  L->hrs = take(m * 4);                                         // per-frame ScaleNorm scale of the next conv GEMM
   L->total = off;
   return 0;
 }
@@ -271,11 +278,18 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
   float2* in_ss = reinterpret_cast<float2*>(base + L.in_ss);
   float2* rot = reinterpret_cast<float2*>(base + L.rot);
+  float* hrs = F(L.hrs);
   // mask-head buffers (second view of the layer region, used after the layer loop)
   float *lnb = F(L.lnb), *ab = F(L.ab), *mb = F(L.mb), *gated = F(L.gated), *sep = F(L.sep);
 
   // ---- activation tensor maps (buffers are reused by every layer)
   CUtensorMap m_enc, m_xbf, m_x, m_o, m_nhat, m_xubf, m_f1, m_g, m_ab, m_mb, m_gated0, m_gated1;
+  CUtensorMap m_xbf256, m_o256, m_nhat256;  // 256-frame boxes: N operand of the channel-major conv GEMMs
+  if (act_map(ctx, &m_xbf256, xbf, false, 512, Sp, B, 64, 256)) return 1;
+  if (act_map(ctx, &m_o256, o, false, 1024, Sp, B, 64, 256)) return 1;
+  if (act_map(ctx, &m_nhat256, nhat, false, 256, Sp, B, 64, 256)) return 1;
+  const bool conv_t = getenv("TDZ_CONV_ROWMAJOR") == nullptr;  // development switch: old row-major conv kernel
+  const int tps_t = (S + CT_ROWS - 1) / CT_ROWS;
   if (act_map(ctx, &m_enc, enc, true, 512, Sp, B, 32, 128)) return 1;
   if (act_map(ctx, &m_xbf, xbf, false, 512, Sp, B, 64, 128)) return 1;
   if (act_map(ctx, &m_x, x, true, 512, Sp, B, 32, 128)) return 1;
@@ -397,7 +411,18 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.gamma = LW.os_gamma;
       P.cv.beta = LW.os_beta;
       P.cv.rot = rot;
-      CUDA_OK((launch_gemm_conv<CONV_VUQK>(P, B * tps * P.n_tiles, sms, st)));
+      if (conv_t) {
+        rowscale_kernel<true><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(ss, hrs, Sp, S, M,
+                                                                                     0.044194173824159216f);
+        P.e.ss_in = hrs;
+        P.tmA = m_xbf256;
+        P.tmB = LM.w_in128;
+        P.n_tiles = getenv("TDZ_NOQK") ? 16 : 17;
+        P.tps = tps_t;
+        CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_conv<CONV_VUQK>(P, B * tps * P.n_tiles, sms, st)));
+      }
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {
@@ -417,7 +442,17 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.x_in = x_in;
       P.cv.x_out = x;
-      CUDA_OK((launch_gemm_conv<CONV_RESX>(P, B * tps * P.n_tiles, sms, st)));
+      if (conv_t) {
+        rowscale_kernel<false><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(o_ss, hrs, Sp, S, M, 0.03125f);
+        P.e.ss_in = hrs;
+        P.tmA = m_o256;
+        P.tmB = LM.w_out128;
+        P.n_tiles = 4;
+        P.tps = tps_t;
+        CUDA_OK((launch_gemm_convt<CONV_RESX>(P, B * tps_t * 4, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_conv<CONV_RESX>(P, B * tps * P.n_tiles, sms, st)));
+      }
     }
     // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
     STEP(ST_FSMN_C1) {  // conv1 + PReLU + norm1 + inner LayerNorm statistics
@@ -439,7 +474,15 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.xuv = xuv;
       P.cv.xubf = xubf;
-      CUDA_OK((launch_gemm_conv<CONV_UV>(P, B * tps * P.n_tiles, sms, st)));
+      if (conv_t) {
+        P.tmA = m_nhat256;
+        P.tmB = LM.w_uv128;
+        P.n_tiles = 4;
+        P.tps = tps_t;
+        CUDA_OK((launch_gemm_convt<CONV_UV>(P, B * tps_t * 4, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_conv<CONV_UV>(P, B * tps * P.n_tiles, sms, st)));
+      }
     }
     STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;

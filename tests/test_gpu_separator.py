@@ -50,6 +50,12 @@ def test_full_forward_small():
     _full(1, 8000, 0)
 
 
+def test_full_forward_production_window():
+    """The window AudioProcessor.separate_speaker actually feeds (160 000 samples = 10 s, S = 19 999 frames, 79 attention
+    groups, 10 fixed-size linear-attention splits): the precision budget is tightest here."""
+    _full(1, 160000, 3)
+
+
 def test_full_forward_batch_ragged_tail():
     # T = 9613 -> S = 1200, T' = 9608: the last 5 samples are the zero pad of mossformer2.py:585-586
     out = _full(2, 9613, 1)
