@@ -12,6 +12,8 @@ outputs of the reference itself on the GPU box, where the reference tree does no
                           recording stand-in for self.separater) -> chunk boundaries for a list of lengths;
                           look2hear.utils.wav_chunk_inference (imported by path) with a toy model -> stitched output;
                           TargetASR.cosine_similarity (extracted with `ast`) on fixed vectors
+  chat_mix_excerpt.npz    1.5 s of assets/chat_mix.wav (the reference's demo input, config C1) through the reference
+                          MossFormer2 module with the seed-0 synthetic weights
   fbank.npz               torchaudio.compliance.kaldi.fbank (the function the modelscope pipeline calls) on a fixed
                           1 s signal, mean-normalised
 """
@@ -157,6 +159,23 @@ def make_mossformer2():
     print("mossformer2_small.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_chat_mix_excerpt():
+    """1.5 s of the reference's demo mixture assets/chat_mix.wav (config C1 input; int16 PCM, samples 32000..55999)
+    through the reference MossFormer2 module with the seed-0 synthetic weights: real speech statistics."""
+    from scipy.io import wavfile
+    sr, wav = wavfile.read(os.path.join(ref_loader.REF_ROOT, "assets", "chat_mix.wav"))
+    assert sr == 16000 and wav.dtype == np.int16
+    ex = wav[32000:32000 + 24000].copy()
+    pkg = ref_loader.load_reference_modules()
+    model = pkg.mossformer2.MossFormer2().eval()
+    model.load_state_dict(synth.random_state_dict(seed=0, perturb=True), strict=True)
+    x = torch.from_numpy(ex.astype(np.float32) / 32768.0)[None]   # AudioProcessor.int16_to_float32 (:1043-1048)
+    with torch.no_grad():
+        y = model(x)
+    np.savez_compressed(os.path.join(GOLDEN, "chat_mix_excerpt.npz"), pcm=ex, offset=np.array([32000]), out=y.numpy())
+    print("chat_mix_excerpt.npz:", tuple(y.shape))
+
+
 def make_fbank():
     import torchaudio.compliance.kaldi as kaldi
     wav = synth.synthetic_mixture(1, 16037, seed=5)
@@ -173,3 +192,4 @@ if __name__ == "__main__":
     make_host_logic()
     make_fbank()
     make_mossformer2()
+    make_chat_mix_excerpt()

@@ -117,3 +117,13 @@ def test_fbank_golden_is_kaldi():
     f = kaldi.fbank(wav, num_mel_bins=80)
     f = f - f.mean(dim=0, keepdim=True)
     assert np.allclose(f.numpy(), gd["feat"], atol=1e-4)
+
+
+def test_mossformer2_port_on_real_speech_excerpt():
+    """Config C1 input (1.5 s of the reference's assets/chat_mix.wav) through the port vs the reference module."""
+    gd = np.load(os.path.join(GOLDEN, "chat_mix_excerpt.npz"))
+    sd = synth.random_state_dict(seed=0, perturb=True)
+    x = torch.from_numpy(gd["pcm"].astype(np.float32) / 32768.0)[None]
+    with torch.no_grad():
+        y = mossformer2_forward(sd, x)
+    assert snr_db(torch.from_numpy(gd["out"]), y) >= 90.0

@@ -77,3 +77,22 @@ def test_batch_equals_singles(T):
     one0 = sep(mix[0:1]).clone()
     one1 = sep(mix[1:2]).clone()
     assert torch.equal(both[0], one0[0]) and torch.equal(both[1], one1[0])
+
+
+def test_real_speech_excerpt_against_reference_run():
+    """CUDA path vs the output of the reference module itself (tests/golden/chat_mix_excerpt.npz, generated in the
+    build container from assets/chat_mix.wav, config C1): waveform SNR >= 40 dB."""
+    import json
+    import numpy as np
+    import torch
+    from oracle.mossformer2_port import snr_db
+    from oracle.synth import random_state_dict
+    from targetdiarization_b200 import Separator
+    gd = np.load(os.path.join(ROOT, "tests", "golden", "chat_mix_excerpt.npz"))
+    sep = Separator(random_state_dict(seed=0, perturb=True), "cuda:0")
+    x = torch.from_numpy(gd["pcm"].astype(np.float32) / 32768.0)[None]
+    y = sep(x.cuda()).cpu()
+    snr = snr_db(torch.from_numpy(gd["out"]), y)
+    with open(os.path.join(ROOT, "gpurun_out", "parity.jsonl"), "a") as f:
+        f.write(json.dumps({"test": "separator_chat_mix_excerpt_vs_reference_run_snr_db", "value": snr}) + "\n")
+    assert snr >= 40.0, snr
