@@ -58,6 +58,7 @@ struct EpiConv {
   // CONV_VUQK: to_hidden|to_qk  -> (v|u) bf16 and the four rotated OffsetScale heads bf16
   __nv_bfloat16* vu;   // [Mtot][2048]
   __nv_bfloat16* qk4;  // [Mtot][512]
+  __nv_bfloat16* lq_lo;  // [Mtot][128] lin_q minus its bf16 value (second term of the split)
   const float* gamma;  // [4][128]
   const float* beta;   // [4][128]
   const float2* rot;   // [Sp][16] (cos, sin)
@@ -414,7 +415,9 @@ struct AttnParams {
   CUtensorMap tmQKmn;  // 3-D {512, Sp, B}  box {64, 64, 1}   MN-major atoms (A of kv: lin_k^T)
   CUtensorMap tmVUmn;  // 3-D {2048, Sp, B} box {64, 64, 1}   MN-major atoms (B of quad*VU and of kv)
   CUtensorMap tmP;     // 3-D {256, Sp, B}  box {64, 128, 1}  relu^2 attention weights
-  CUtensorMap tmKVmn;  // 3-D {2048, 128, B} box {64, 64, 1}  MN-major atoms of lin_kv | lin_ku
+  CUtensorMap tmKVmn;  // 3-D {2048, 256, B} box {64, 64, 1}  MN-major atoms of lin_kv | lin_ku: rows 0..127 the bf16
+                       //     value, rows 128..255 the bf16 of the rounding residual (two-term split)
+  CUtensorMap tmLQlo;  // 3-D {128, Sp, B}  box {64, 128, 1}  rounding residual of lin_q (two-term split)
   int B, Sp, S;
   int nsplit;          // kv: splits of the frame axis
   int kb_per_split;
@@ -531,6 +534,7 @@ struct AttnOut {
     tma_prefetch_desc(&P.tmVUmn);
     tma_prefetch_desc(&P.tmQK);
     tma_prefetch_desc(&P.tmKVmn);
+    tma_prefetch_desc(&P.tmLQlo);
   }
   __device__ static int num_tiles(const Params& P) { return (P.B * P.Sp / GEMM_BLOCK_M) * 8; }
   __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
@@ -540,7 +544,7 @@ struct AttnOut {
     ti.n0 = nt * 128;  // first v channel; the u channel is 1024 + n0
     ti.b = ti.m0 / P.Sp;
     ti.t0 = ti.m0 - ti.b * P.Sp;
-    ti.nkb = 6;
+    ti.nkb = 10;  // 4 quadratic (256 keys) + 6 linear: q_hi kv_hi, q_hi kv_lo, q_lo kv_hi (128 each)
     ti.aux = nt;
   }
   __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
@@ -553,12 +557,21 @@ struct AttnOut {
         tma_load_3d(sb + j * 8192, &P.tmVUmn, bar, ch, g0 + kb * 64, ti.b);
       }
     } else {
-      const int k0 = (kb - 4) * 64;
-      tma_load_3d(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);  // lin_q
+      // The linear-attention product lin_q @ lin_kv carries the largest rounding error of the whole network when
+      // both operands are single bf16 values (measured: +4.8 dB of output SNR without it), so it runs as a
+      // three-term split: (q_hi + q_lo)(kv_hi + kv_lo) ~ q_hi kv_hi + q_hi kv_lo + q_lo kv_hi.
+      const int kk = kb - 4;               // 0,1: q_hi kv_hi   2,3: q_hi kv_lo   4,5: q_lo kv_hi
+      const int k0 = (kk & 1) * 64;
+      if (kk < 4) {
+        tma_load_3d(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);  // lin_q
+      } else {
+        tma_load_3d(sa, &P.tmLQlo, bar, k0, ti.t0, ti.b);      // lin_q - bf16(lin_q)
+      }
+      const int kvrow = ((kk >> 1) == 1 ? 128 : 0) + k0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
-        tma_load_3d(sb + j * 8192, &P.tmKVmn, bar, ch, k0, ti.b);
+        tma_load_3d(sb + j * 8192, &P.tmKVmn, bar, ch, kvrow, ti.b);
       }
     }
   }

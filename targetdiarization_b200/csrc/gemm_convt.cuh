@@ -303,7 +303,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
                   const float x = fmaf(acc[j], g, bt);
                   const float other = __shfl_xor_sync(0xffffffffu, x, 1);
                   const float r = fmaf(sgn * other, rcs[j].y, x * rcs[j].x);  // even: x cos - x' sin; odd: x cos + x' sin
-                  if (j < nrow) dst[static_cast<size_t>(j) * 512 + h * 128] = __float2bfloat16(r);
+                  if (j < nrow) {
+                    const __nv_bfloat16 rb = __float2bfloat16(r);
+                    dst[static_cast<size_t>(j) * 512 + h * 128] = rb;
+                    if (h == 1)  // lin_q: second term of the two-term split
+                      cv.lq_lo[(grow0 + j) * 128 + qc] = __float2bfloat16(r - __bfloat162float(rb));
+                  }
                 }
               }
             } else {
@@ -311,8 +316,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
               for (int h = 0; h < 4; ++h) {
                 const float g = __ldg(cv.gamma + h * 128 + qc), bt = __ldg(cv.beta + h * 128 + qc);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (j < nrow) dst[static_cast<size_t>(j) * 512 + h * 128] = __float2bfloat16(fmaf(acc[j], g, bt));
+                for (int j = 0; j < 16; ++j) {
+                  if (j < nrow) {
+                    const float r = fmaf(acc[j], g, bt);
+                    const __nv_bfloat16 rb = __float2bfloat16(r);
+                    dst[static_cast<size_t>(j) * 512 + h * 128] = rb;
+                    if (h == 1) cv.lq_lo[(grow0 + j) * 128 + qc] = __float2bfloat16(r - __bfloat162float(rb));
+                  }
+                }
               }
             }
           }

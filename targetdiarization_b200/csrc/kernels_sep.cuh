@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict_
   op[1] = make_float4(g[4], g[5], g[6], g[7]);
 }
 
-// lin_kv reduce: KV[b][d][e] = (sum_s part[b][s][d][e]) / S  -> bf16  (mossformer_block.py:286,289)
+// lin_kv reduce: KV[b][d][e] = (sum_s part[b][s][d][e]) / S  (mossformer_block.py:286,289), stored as a two-term
+// bf16 split: kv[b][d][e] = bf16(KV), kv[b][128+d][e] = bf16(KV - bf16(KV)).
 __global__ void kv_reduce_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ kv, int nsplit,
                                  float inv_n, size_t per_sample /*128*2048*/, size_t total4) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -431,8 +432,15 @@ __global__ void kv_reduce_kernel(const float* __restrict__ part, __nv_bfloat16* 
     acc.z += v.z;
     acc.w += v.w;
   }
-  uint2 o = make_uint2(pack_bf16(acc.x * inv_n, acc.y * inv_n), pack_bf16(acc.z * inv_n, acc.w * inv_n));
-  *reinterpret_cast<uint2*>(kv + e) = o;
+  const float x0 = acc.x * inv_n, x1 = acc.y * inv_n, x2 = acc.z * inv_n, x3 = acc.w * inv_n;
+  const __nv_bfloat16 h0 = __float2bfloat16(x0), h1 = __float2bfloat16(x1), h2 = __float2bfloat16(x2),
+                      h3 = __float2bfloat16(x3);
+  __nv_bfloat16* hi = kv + b * 2 * per_sample + r;
+  __nv_bfloat16* lo = hi + per_sample;
+  *reinterpret_cast<uint2*>(hi) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+  *reinterpret_cast<uint2*>(lo) =
+      make_uint2(pack_bf16(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1)),
+                 pack_bf16(x2 - __bfloat162float(h2), x3 - __bfloat162float(h3)));
 }
 
 // ---------------------------------------------------------------- after the 24 layers

@@ -11,7 +11,6 @@
 #include <string>
 
 #include "gemm_cfgs.cuh"
-#include "gemm_conv.cuh"
 #include "gemm_convt.cuh"
 #include "kernels_fbank.cuh"
 #include "kernels_misc.cuh"
@@ -203,6 +202,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   const size_t region = off;
   L->vu = take(m * 2048 * 2);
   L->qk4 = take(m * 512 * 2);
+  L->lq_lo = take(m * 128 * 2);
   L->P = take(m * 256 * 2);
   L->o = take(m * 1024 * 2);
   L->o_ss = take(m * 16 * 4);
@@ -224,7 +224,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->sep = take(m * 1024 * 4);
   off = std::max(off, layer_end);
   L->kv_part = take(static_cast<size_t>(B) * nsplit * 128 * 2048 * 4);
-  L->kv = take(static_cast<size_t>(B) * 128 * 2048 * 2);
+  L->kv = take(static_cast<size_t>(B) * 256 * 2048 * 2);           // two-term bf16 split: value | residual
   L->gn_stats = take(static_cast<size_t>(B) * 2 * 8 * 2);       // two GroupNorms
   L->in_stats = take(static_cast<size_t>(B) * 256 * 2 * 8 * 2); // two InstanceNorms (re-zeroed per layer)
   L->in_ss = take(static_cast<size_t>(B) * 256 * 8 * 2);        // their (scale, shift) tables
@@ -273,7 +273,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   float *enc = F(L.enc), *x0 = F(L.x0), *x = F(L.x), *ss = F(L.ss), *o_ss = F(L.o_ss), *c = F(L.c), *xuv = F(L.xuv),
         *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g), *kv_part = F(L.kv_part), *samp = F(L.samp);
   __nv_bfloat16 *xbf = H(L.xbf), *vu = H(L.vu), *qk4 = H(L.qk4), *Pm = H(L.P), *o = H(L.o), *nhat = H(L.nhat),
-                *xubf = H(L.xubf), *f1 = H(L.f1), *kv = H(L.kv);
+                *xubf = H(L.xubf), *f1 = H(L.f1), *kv = H(L.kv), *lq_lo = H(L.lq_lo);
   double* gn_stats = reinterpret_cast<double*>(base + L.gn_stats);
   double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
   float2* in_ss = reinterpret_cast<float2*>(base + L.in_ss);
@@ -288,7 +288,6 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   if (act_map(ctx, &m_xbf256, xbf, false, 512, Sp, B, 64, 256)) return 1;
   if (act_map(ctx, &m_o256, o, false, 1024, Sp, B, 64, 256)) return 1;
   if (act_map(ctx, &m_nhat256, nhat, false, 256, Sp, B, 64, 256)) return 1;
-  const bool conv_t = getenv("TDZ_CONV_ROWMAJOR") == nullptr;  // development switch: old row-major conv kernel
   const int tps_t = (S + CT_ROWS - 1) / CT_ROWS;
   if (act_map(ctx, &m_enc, enc, true, 512, Sp, B, 32, 128)) return 1;
   if (act_map(ctx, &m_xbf, xbf, false, 512, Sp, B, 64, 128)) return 1;
@@ -309,7 +308,8 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   if (act_map(ctx, &AP.tmQKmn, qk4, false, 512, Sp, B, 64, 64)) return 1;
   if (act_map(ctx, &AP.tmVUmn, vu, false, 2048, Sp, B, 64, 64)) return 1;
   if (act_map(ctx, &AP.tmP, Pm, false, 256, Sp, B, 64, 128)) return 1;
-  if (act_map(ctx, &AP.tmKVmn, kv, false, 2048, 128, B, 64, 64)) return 1;
+  if (act_map(ctx, &AP.tmKVmn, kv, false, 2048, 256, B, 64, 64)) return 1;
+  if (act_map(ctx, &AP.tmLQlo, lq_lo, false, 128, Sp, B, 64, 128)) return 1;
   AP.B = B;
   AP.Sp = Sp;
   AP.S = S;
@@ -407,21 +407,18 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 2176;
       P.cv.vu = vu;
       P.cv.qk4 = qk4;
+      P.cv.lq_lo = lq_lo;
       P.cv.gamma = LW.os_gamma;
       P.cv.beta = LW.os_beta;
       P.cv.rot = rot;
-      if (conv_t) {
-        rowscale_kernel<true><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(ss, hrs, Sp, S, M,
-                                                                                     0.044194173824159216f);
-        P.e.ss_in = hrs;
-        P.tmA = m_xbf256;
-        P.tmB = LM.w_in128;
-        P.n_tiles = getenv("TDZ_NOQK") ? 16 : 17;
-        P.tps = tps_t;
-        CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
-      } else {
-        CUDA_OK((launch_gemm_conv<CONV_VUQK>(P, B * tps * P.n_tiles, sms, st)));
-      }
+      rowscale_kernel<true><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(ss, hrs, Sp, S, M,
+                                                                                   0.044194173824159216f);
+      P.e.ss_in = hrs;
+      P.tmA = m_xbf256;
+      P.tmB = LM.w_in128;
+      P.n_tiles = 17;
+      P.tps = tps_t;
+      CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {
@@ -441,17 +438,13 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.x_in = x_in;
       P.cv.x_out = x;
-      if (conv_t) {
-        rowscale_kernel<false><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(o_ss, hrs, Sp, S, M, 0.03125f);
-        P.e.ss_in = hrs;
-        P.tmA = m_o256;
-        P.tmB = LM.w_out128;
-        P.n_tiles = 4;
-        P.tps = tps_t;
-        CUDA_OK((launch_gemm_convt<CONV_RESX>(P, B * tps_t * 4, sms, st)));
-      } else {
-        CUDA_OK((launch_gemm_conv<CONV_RESX>(P, B * tps * P.n_tiles, sms, st)));
-      }
+      rowscale_kernel<false><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(o_ss, hrs, Sp, S, M, 0.03125f);
+      P.e.ss_in = hrs;
+      P.tmA = m_o256;
+      P.tmB = LM.w_out128;
+      P.n_tiles = 4;
+      P.tps = tps_t;
+      CUDA_OK((launch_gemm_convt<CONV_RESX>(P, B * tps_t * 4, sms, st)));
     }
     // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
     STEP(ST_FSMN_C1) {  // conv1 + PReLU + norm1 + inner LayerNorm statistics
@@ -473,15 +466,11 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.xuv = xuv;
       P.cv.xubf = xubf;
-      if (conv_t) {
-        P.tmA = m_nhat256;
-        P.tmB = LM.w_uv128;
-        P.n_tiles = 4;
-        P.tps = tps_t;
-        CUDA_OK((launch_gemm_convt<CONV_UV>(P, B * tps_t * 4, sms, st)));
-      } else {
-        CUDA_OK((launch_gemm_conv<CONV_UV>(P, B * tps * P.n_tiles, sms, st)));
-      }
+      P.tmA = m_nhat256;
+      P.tmB = LM.w_uv128;
+      P.n_tiles = 4;
+      P.tps = tps_t;
+      CUDA_OK((launch_gemm_convt<CONV_UV>(P, B * tps_t * 4, sms, st)));
     }
     STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;

@@ -173,6 +173,8 @@ def run_step(h, step):
         ok &= _check(m, "qk4", tp["qk4"], qk, 40)
         for i, n in enumerate(("quad_q", "lin_q", "quad_k", "lin_k")):
             ok &= _check(m, n, tp["qk4"][..., i * 128:(i + 1) * 128], qk[..., i * 128:(i + 1) * 128], 40)
+        # two-term split of lin_q: value + residual
+        ok &= _check(m, "lin_q_split", tp["qk4"][..., 128:256], qk[..., 128:256] + h.get("lq_lo", bf, 128), 50)
     elif step == "SIM":
         h.put("qk4", tp["qk4"], bf)
         h.run(k)
@@ -182,13 +184,18 @@ def run_step(h, step):
         h.put("qk4", tp["qk4"], bf)
         h.put("vu", tp["vu"], bf)
         h.run(k)
-        kv = h.get_raw(h.lay.kv, bf, B * 128 * 2048).float().view(B, 128, 2048)
-        ok &= _check(m, "kv", tp["kv"], kv, 40)
+        kv = h.get_raw(h.lay.kv, bf, B * 256 * 2048).float().view(B, 2, 128, 2048)
+        ok &= _check(m, "kv", tp["kv"], kv[:, 0], 40)
+        ok &= _check(m, "kv_split", tp["kv"], kv[:, 0] + kv[:, 1], 50)
     elif step == "ATT_OUT":
         h.put("qk4", tp["qk4"], bf)
         h.put("vu", tp["vu"], bf)
         h.put("P", tp["P"], bf)
-        h.put_raw(h.lay.kv, tp["kv"].to(bf))
+        kv_hi = tp["kv"].to(bf)
+        kv_lo = (tp["kv"] - kv_hi.float()).to(bf)
+        h.put_raw(h.lay.kv, torch.stack((kv_hi, kv_lo), dim=1))   # [B][2][128][2048]: value | residual
+        lq = tp["qk4"][..., 128:256]
+        h.put("lq_lo", lq - lq.to(bf).float(), bf)
         h.run(k)
         ok &= _check(m, "o", tp["o"], h.get("o", bf, 1024), 38)
         oss = h.get("o_ss", f32, 16).sum(-1)
