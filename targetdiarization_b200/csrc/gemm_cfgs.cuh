@@ -283,6 +283,162 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   }
 };
 
+constexpr int PANEL_LD = 132;  // floats per panel row: 128 + 4 keeps the row-wise float4 stores conflict free
+
+// LinearGeneric with a coalescing epilogue for BLOCK_N = 128 / 256.  With tcgen05.ld a thread owns a tile ROW, so
+// the direct epilogue above reads / writes global memory in 64 B pieces that are a whole row pitch apart (32
+// different lines per warp instruction): measured 13 % tensor-pipe activity and L2 at 65 % for the FSMN conv2
+// GEMM.  Here the accumulator goes through a 128 x 128 fp32 shared-memory panel:
+//   phase 1  thread = row : tcgen05.ld -> row scale / GroupNorm fold / bias -> panel
+//   phase 2  warp = row, lane = 4 consecutive columns: residual / gate operands are read and all outputs written
+//            as 512 B (fp32) or 256 B (bf16) contiguous row segments; activation, AFF gate, positional encoding,
+//            tf32 rounding and the ScaleNorm partial sums (one warp reduction per row) happen here.
+template <int FMT_, int BLOCK_N_, int STAGES_, unsigned EF, int ACT>
+struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
+  using Params = LinearParams;
+  static_assert(BLOCK_N_ == 128 || BLOCK_N_ == 256, "panel epilogue handles 128-column panels");
+  static constexpr int BLOCK_N = BLOCK_N_;
+  static constexpr int EPI_SPLIT = 2;
+  static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4;
+
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx& cx) {
+    const EpiGeneric& e = P.e;
+    const size_t grow_t = static_cast<size_t>(ti.m0) + row;  // this thread's row (phase 1)
+    float rs = 1.f;
+    if constexpr ((EF & EF_SS_SHIFT) != 0) {
+      const int t = ti.t0 + row;
+      const float4 cur = *reinterpret_cast<const float4*>(e.ss_in + grow_t * 4);
+      float ss = cur.z + cur.w;
+      if (t > 0) {
+        const float4 prv = *reinterpret_cast<const float4*>(e.ss_in + (grow_t - 1) * 4);
+        ss += prv.x + prv.y;
+      }
+      rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
+    }
+    if constexpr ((EF & EF_SS_PARTS) != 0) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(e.ss_in + grow_t * 16 + 4 * i);
+        ss += (a.x + a.y) + (a.z + a.w);
+      }
+      rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
+    }
+    float sA = 1.f, sB = 0.f;
+    if constexpr ((EF & EF_SAMP) != 0) {
+      sA = e.sampA[ti.b];
+      sB = e.sampB[ti.b];
+    }
+    const int w = cx.tid >> 5, lane = cx.tid & 31;
+    float* prow = cx.panel + row * PANEL_LD + half * 64;
+#pragma unroll 1
+    for (int pn = 0; pn < BLOCK_N / 128; ++pn) {
+      const int pc0 = ti.n0 + pn * 128;  // first output column of the panel
+      if (pc0 >= P.N) break;             // warp-uniform
+      // ---- phase 1
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = pn * 128 + half * 64 + cc;
+        if (ti.n0 + c0 >= P.N) break;
+        float v[16], bias[16], cs[16];
+        tmem_ld16(tacc + c0, v);
+        if constexpr ((EF & EF_BIAS) != 0) ld_f32x16(e.bias + ti.n0 + c0, bias);
+        if constexpr ((EF & EF_SAMP) != 0) ld_f32x16(e.colsum + ti.n0 + c0, cs);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = v[j] * rs;
+          if constexpr ((EF & EF_SAMP) != 0) x = x * sA + sB * cs[j];
+          if constexpr ((EF & EF_BIAS) != 0) x += bias[j];
+          v[j] = x;
+        }
+        float4* dst = reinterpret_cast<float4*>(prow + cc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      epi_bar_sync<256>();
+      // ---- phase 2
+      {
+        const int col = pc0 + 4 * lane;
+        const bool col_ok = col < P.N;  // N is a multiple of 4
+        float pf[4] = {0.f, 0.f, 0.f, 0.f};
+        float pscale = 0.f;
+        if constexpr ((EF & EF_POS) != 0) {
+          pscale = e.pos_scale[0];
+          const int hlf = P.N >> 1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pf[i] = __ldg(e.pos_inv_freq + ((col + i) < hlf ? (col + i) : (col + i) - hlf));
+        }
+#pragma unroll 1
+        for (int r0 = w * 16; r0 < w * 16 + 16; r0 += 4) {
+          float4 x4[4], rsd[4], ml[4];
+          bool valid[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i;
+            valid[i] = (ti.t0 + r) < P.S;
+            x4[i] = *reinterpret_cast<const float4*>(cx.panel + r * PANEL_LD + 4 * lane);
+            const size_t grow = static_cast<size_t>(ti.m0) + r;
+            rsd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ml[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[i] && col_ok) {
+              if constexpr ((EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF)
+                rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + col);
+              if constexpr ((EF & EF_MUL) != 0 || ACT == ACT_AFF)
+                ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + col);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i;
+            const int t = ti.t0 + r;
+            const size_t grow = static_cast<size_t>(ti.m0) + r;
+            float xv[4] = {x4[i].x, x4[i].y, x4[i].z, x4[i].w};
+            const float rv[4] = {rsd[i].x, rsd[i].y, rsd[i].z, rsd[i].w};
+            const float mv[4] = {ml[i].x, ml[i].y, ml[i].z, ml[i].w};
+            float ssq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x = xv[j];
+              if constexpr (ACT == ACT_AFF) {
+                const float att = 1.f + tanhf(x);
+                x = mv[j] * att + rv[j] * (2.f - att);
+              } else {
+                if constexpr ((EF & EF_RESID_PRE) != 0) x += rv[j];
+                x = act_apply<ACT>(x);
+                if constexpr ((EF & EF_RESID) != 0) x += rv[j];
+                if constexpr ((EF & EF_MUL) != 0) x *= mv[j];
+              }
+              if constexpr ((EF & EF_POS) != 0) {
+                const float a = static_cast<float>(t) * pf[j];
+                x += pscale * ((col + j) < (P.N >> 1) ? sinf(a) : cosf(a));
+              }
+              if (!valid[i]) x = 0.f;
+              if constexpr ((EF & EF_SS_OUT) != 0) ssq += x * x;
+              if constexpr ((EF & EF_ROUND_TF32) != 0) x = round_tf32_rn(x);
+              xv[j] = x;
+            }
+            if constexpr ((EF & EF_SS_OUT) != 0) {
+              ssq = warp_sum(ssq);
+              if (lane == 0) e.ss_out[grow * e.ss_out_ld + pc0 / 128] = ssq;
+            }
+            if ((valid[i] || (EF & EF_ZERO_PAD) != 0) && col_ok) {
+              if constexpr ((EF & EF_OUT_F32) != 0)
+                *reinterpret_cast<float4*>(e.out_f32 + grow * e.out_ld + e.out_col0 + col) =
+                    make_float4(xv[0], xv[1], xv[2], xv[3]);
+              if constexpr ((EF & EF_OUT_BF16) != 0)
+                *reinterpret_cast<uint2*>(e.out_bf16 + grow * e.out_bf_ld + e.out_bf_col0 + col) =
+                    make_uint2(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]));
+            }
+          }
+        }
+      }
+      epi_bar_sync<256>();
+    }
+  }
+};
+
 // Linear + SiLU + ConvModule in one kernel: see gemm_conv.cuh.  Modes of its tail:
 enum ConvMode : int { CONV_VUQK = 0, CONV_RESX = 1, CONV_UV = 2 };
 constexpr int CONV_ROWS = 112;  // output frames per 128-row accumulator tile (8-row halo on each side)

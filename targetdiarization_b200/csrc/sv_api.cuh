@@ -159,8 +159,12 @@ enum SvEpi { SV_HT20_F32, SV_HT20_BOTH, SV_SILU_BF16, SV_AFF_F32, SV_RES_HT20_BO
 
 template <int BN, unsigned EF, int ACT>
 static cudaError_t sv_launch(const LinearParams& P, int sms, cudaStream_t st) {
-  constexpr int STAGES = BN == 256 ? 4 : 6;
-  return launch_gemm<LinearGeneric<1, BN, STAGES, EF, ACT>>(P, (P.B * P.Sp / 128) * P.n_tiles, sms, st);
+  if constexpr (BN >= 128) {  // wide outputs go through the coalescing panel epilogue
+    constexpr int STAGES = BN == 256 ? 3 : 4;
+    return launch_gemm<LinearPanel<1, BN, STAGES, EF, ACT>>(P, (P.B * P.Sp / 128) * P.n_tiles, sms, st);
+  } else {
+    return launch_gemm<LinearGeneric<1, BN, 6, EF, ACT>>(P, (P.B * P.Sp / 128) * P.n_tiles, sms, st);
+  }
 }
 
 // out = epilogue(A[P][K] @ W^T): A bf16 with leading dimension lda (>= K), P pixels in a Pp-row buffer.
