@@ -33,8 +33,9 @@ WORKLOAD = "C2: 64 synthetic 4 s 2-speaker mixtures/GPU, MossFormer2 separation 
 STEP_TABLE = {
     "ENCODER": dict(bound="hbm", bytes=32 + 2048),
     "ENC1X1": dict(bound="tensor", flops=524288, bytes=2048 + 2048 + 1024 + 8),
-    # Linear 512->2176 + SiLU + depthwise k17 + OffsetScale/rotary in one kernel: reads xbf, writes vu + qk4 (bf16)
-    "FLASH_IN": dict(bound="tensor", flops=2 * 512 * 2176, bytes=1024 + 4096 + 1024),
+    # Linear 512->2176 + SiLU + depthwise k17 (one kernel) + OffsetScale/rotary (small kernel): reads xbf, writes
+    # vu + qk4 + lin_q residual (bf16)
+    "FLASH_IN": dict(bound="tensor", flops=2 * 512 * 2176, bytes=1024 + 4096 + 1024 + 256),
     "SIM": dict(bound="tensor", flops=2 * 256 * 128, bytes=512 + 512),
     "KV": dict(bound="tensor", flops=2 * 128 * 2048, bytes=256 + 4096),
     "ATT_OUT": dict(bound="tensor", flops=2 * 256 * 2048 + 2 * 128 * 2048, bytes=512 + 4096 + 256 + 4096 + 2048),
@@ -265,8 +266,13 @@ def main():
             rows.append(row)
         rows.sort(key=lambda r: -r["ms_per_forward"])
         top = rows[0]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+        if os.path.isfile(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            with open(tp) as f:
+                traffic = json.load(f).get(top["step"])
         roof = dict(kernel=top["step"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"],
-                    unit=top["unit"], frac=top["frac"], traffic=None, peak_source=peaks["source"],
+                    unit=top["unit"], frac=top["frac"], traffic=traffic, peak_source=peaks["source"],
                     share_of_separator=top["ms_per_forward"] / sum(r["ms_per_forward"] for r in rows))
         if args.breakdown:
             os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)

@@ -126,7 +126,7 @@ int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T,
                        size_t workspace_bytes, void* stream, int num_layers, int step_lo, int step_hi);
 
 typedef struct tdz_sep_layout {
-  size_t enc, x0, x, xbf, ss, vu, qk4, lq_lo, P, o, o_ss, c, nhat, xuv, xubf, f1, p, y1, y2, g, lnb, ab, mb, gated, sep,
+  size_t enc, x0, x, xbf, ss, vu, qk4, lq_lo, qkf, P, o, o_ss, c, nhat, xuv, xubf, f1, p, y1, y2, g, lnb, ab, mb, gated, sep,
       kv_part, kv, gn_stats, in_stats, in_ss, samp, rot, hrs, total;
   int64_t S, Sp, Mtot;
   int32_t kv_nsplit, kv_kb_per_split;

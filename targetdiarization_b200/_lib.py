@@ -27,7 +27,7 @@ class MossFormer2Weights(ctypes.Structure):
 
 
 class SepLayout(ctypes.Structure):
-    _names = ("enc", "x0", "x", "xbf", "ss", "vu", "qk4", "lq_lo", "P", "o", "o_ss", "c", "nhat", "xuv", "xubf", "f1", "p", "y1",
+    _names = ("enc", "x0", "x", "xbf", "ss", "vu", "qk4", "lq_lo", "qkf", "P", "o", "o_ss", "c", "nhat", "xuv", "xubf", "f1", "p", "y1",
               "y2", "g", "lnb", "ab", "mb", "gated", "sep", "kv_part", "kv", "gn_stats", "in_stats", "in_ss", "samp",
               "rot", "hrs", "total")
     _fields_ = ([(n, ctypes.c_size_t) for n in _names]

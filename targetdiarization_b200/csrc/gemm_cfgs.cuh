@@ -55,13 +55,9 @@ struct EpiGeneric {
 struct EpiConv {
   const float* dw_t;   // taps, tap-major [17][ldw]; column index = output column of the GEMM
   int ldw;
-  // CONV_VUQK: to_hidden|to_qk  -> (v|u) bf16 and the four rotated OffsetScale heads bf16
+  // CONV_VUQK: to_hidden|to_qk  -> (v|u) bf16 and the to_qk activations fp32
   __nv_bfloat16* vu;   // [Mtot][2048]
-  __nv_bfloat16* qk4;  // [Mtot][512]
-  __nv_bfloat16* lq_lo;  // [Mtot][128] lin_q minus its bf16 value (second term of the split)
-  const float* gamma;  // [4][128]
-  const float* beta;   // [4][128]
-  const float2* rot;   // [Sp][16] (cos, sin)
+  float* qkf;          // [Mtot][128] to_qk output (fp32; the four heads are made by qk_heads_kernel)
   // CONV_RESX: to_out -> x_out = x_in + y + dwconv(y)
   const float* x_in;   // [Mtot][512]
   float* x_out;

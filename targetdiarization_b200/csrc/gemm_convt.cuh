@@ -252,15 +252,6 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) rin[j] = (tt0r + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
         }
-        [[maybe_unused]] float2 rcs[16];
-        if constexpr (MODE == CONV_VUQK) {  // rotary (cos, sin) of these 16 frames: in flight during the FMAs
-          if (c >= 2048 && c < 2048 + 32) {  // warp-uniform: lane quarter 0 of the qk channel tile
-            const int tt0r = tbase + 8 + 16 * itn;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              rcs[j] = (tt0r + j < P.S) ? __ldg(cv.rot + (tt0r + j) * 16 + ((c - 2048) >> 1)) : make_float2(1.f, 0.f);
-          }
-        }
         float acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = win[j + 8];
@@ -291,41 +282,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
             for (int j = 0; j < 16; ++j)
               if (j < nrow) dst[static_cast<size_t>(j) * 2048] = __float2bfloat16(acc[j]);
           } else {
-            const int qc = c - 2048;
-            __nv_bfloat16* dst = cv.qk4 + grow0 * 512 + qc;
-            if (qc < 32) {  // warp-uniform: rotary on interleaved pairs of dims 0..31; the partner is the next lane
-              const float sgn = (qc & 1) ? 1.f : -1.f;
-#pragma unroll 1
-              for (int h = 0; h < 4; ++h) {
-                const float g = __ldg(cv.gamma + h * 128 + qc), bt = __ldg(cv.beta + h * 128 + qc);
+            // to_qk channels: fp32, OffsetScale + rotary + bf16 split happen in qk_heads_kernel (the 32 rotary
+            // channels all sit in one TMEM lane quarter, i.e. on one scheduler: doing that work here serialises it)
+            float* dst = cv.qkf + grow0 * 128 + (c - 2048);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float x = fmaf(acc[j], g, bt);
-                  const float other = __shfl_xor_sync(0xffffffffu, x, 1);
-                  const float r = fmaf(sgn * other, rcs[j].y, x * rcs[j].x);  // even: x cos - x' sin; odd: x cos + x' sin
-                  if (j < nrow) {
-                    const __nv_bfloat16 rb = __float2bfloat16(r);
-                    dst[static_cast<size_t>(j) * 512 + h * 128] = rb;
-                    if (h == 1)  // lin_q: second term of the two-term split
-                      cv.lq_lo[(grow0 + j) * 128 + qc] = __float2bfloat16(r - __bfloat162float(rb));
-                  }
-                }
-              }
-            } else {
-#pragma unroll 1
-              for (int h = 0; h < 4; ++h) {
-                const float g = __ldg(cv.gamma + h * 128 + qc), bt = __ldg(cv.beta + h * 128 + qc);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  if (j < nrow) {
-                    const float r = fmaf(acc[j], g, bt);
-                    const __nv_bfloat16 rb = __float2bfloat16(r);
-                    dst[static_cast<size_t>(j) * 512 + h * 128] = rb;
-                    if (h == 1) cv.lq_lo[(grow0 + j) * 128 + qc] = __float2bfloat16(r - __bfloat162float(rb));
-                  }
-                }
-              }
-            }
+            for (int j = 0; j < 16; ++j)
+              if (j < nrow) dst[static_cast<size_t>(j) * 128] = acc[j];
           }
         }
         if constexpr (MODE == CONV_RESX) {

@@ -80,6 +80,39 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
   tab[i] = make_float2(cosf(a), sinf(a));
 }
 
+// OffsetScale (4 heads) + rotary on dims 0..31 (interleaved pairs, rotary_embedding_torch) of the to_qk output
+// (mossformer_block.py:76-86,214,230-233) -> qk4 bf16 [Mtot][512] = quad_q | lin_q | quad_k | lin_k, plus the bf16
+// rounding residual of lin_q (second term of the split used by the linear-attention output product).
+// Thread = one frame x 2 adjacent channels; block = 4 frames.
+__global__ void __launch_bounds__(256) qk_heads_kernel(const float* __restrict__ qkf, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float2* __restrict__ rot,
+                                                       __nv_bfloat16* __restrict__ qk4, __nv_bfloat16* __restrict__ lq_lo,
+                                                       int Sp, int S, size_t rows) {
+  const size_t row = static_cast<size_t>(blockIdx.x) * 4 + (threadIdx.x >> 6);
+  if (row >= rows) return;
+  const int t = static_cast<int>(row % Sp);
+  if (t >= S) return;  // padded frames stay zero (zeroed once per forward)
+  const int c = (threadIdx.x & 63) * 2;
+  const float2 v = *reinterpret_cast<const float2*>(qkf + row * 128 + c);
+  float2 cs = make_float2(1.f, 0.f);
+  if (c < 32) cs = rot[t * 16 + (c >> 1)];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float2 g = *reinterpret_cast<const float2*>(gamma + h * 128 + c);
+    const float2 b = *reinterpret_cast<const float2*>(beta + h * 128 + c);
+    const float x0 = fmaf(v.x, g.x, b.x), x1 = fmaf(v.y, g.y, b.y);
+    const float r0 = x0 * cs.x - x1 * cs.y;
+    const float r1 = x1 * cs.x + x0 * cs.y;
+    const uint32_t packed = pack_bf16(r0, r1);
+    *reinterpret_cast<uint32_t*>(qk4 + row * 512 + h * 128 + c) = packed;
+    if (h == 1) {
+      const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&packed);
+      *reinterpret_cast<uint32_t*>(lq_lo + row * 128 + c) =
+          pack_bf16(r0 - __bfloat162float(hb.x), r1 - __bfloat162float(hb.y));
+    }
+  }
+}
+
 // ScaleNorm (mossformer_block.py:44-54) as one scale per frame: out[row] = 0.5 / clamp(||x_row|| dim^-0.5, 1e-5),
 // from the partial sums of squares the producing GEMM epilogue left behind.  The factor 0.5 belongs to the
 // tanh form of SiLU the consumer uses.  SHIFT: the row is the token-shifted frame (channels 0..255 of the

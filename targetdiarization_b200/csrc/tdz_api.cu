@@ -203,6 +203,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->vu = take(m * 2048 * 2);
   L->qk4 = take(m * 512 * 2);
   L->lq_lo = take(m * 128 * 2);
+  L->qkf = take(m * 128 * 4);
   L->P = take(m * 256 * 2);
   L->o = take(m * 1024 * 2);
   L->o_ss = take(m * 16 * 4);
@@ -271,7 +272,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
   auto H = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
   float *enc = F(L.enc), *x0 = F(L.x0), *x = F(L.x), *ss = F(L.ss), *o_ss = F(L.o_ss), *c = F(L.c), *xuv = F(L.xuv),
-        *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g), *kv_part = F(L.kv_part), *samp = F(L.samp);
+        *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g), *kv_part = F(L.kv_part), *samp = F(L.samp), *qkf = F(L.qkf);
   __nv_bfloat16 *xbf = H(L.xbf), *vu = H(L.vu), *qk4 = H(L.qk4), *Pm = H(L.P), *o = H(L.o), *nhat = H(L.nhat),
                 *xubf = H(L.xubf), *f1 = H(L.f1), *kv = H(L.kv), *lq_lo = H(L.lq_lo);
   double* gn_stats = reinterpret_cast<double*>(base + L.gn_stats);
@@ -406,11 +407,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.dw_t = LW.dw_in;
       P.cv.ldw = 2176;
       P.cv.vu = vu;
-      P.cv.qk4 = qk4;
-      P.cv.lq_lo = lq_lo;
-      P.cv.gamma = LW.os_gamma;
-      P.cv.beta = LW.os_beta;
-      P.cv.rot = rot;
+      P.cv.qkf = qkf;
       rowscale_kernel<true><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(ss, hrs, Sp, S, M,
                                                                                    0.044194173824159216f);
       P.e.ss_in = hrs;
@@ -419,6 +416,8 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.n_tiles = 17;
       P.tps = tps_t;
       CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
+      qk_heads_kernel<<<static_cast<unsigned>((M + 3) / 4), 256, 0, st>>>(qkf, LW.os_gamma, LW.os_beta, rot, qk4, lq_lo,
+                                                                           Sp, S, M);
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {

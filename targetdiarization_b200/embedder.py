@@ -80,7 +80,10 @@ class Embedder:
             nbytes = int(lib.tdz_embed_workspace_bytes(n, frames))
             if self._ws is None or self._ws.numel() < nbytes:
                 self._ws = None
-                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                self._ws_raw = None
+                self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+                off = (-self._ws_raw.data_ptr()) % 1024   # the C ABI wants 1024 B alignment; the allocator gives 512
+                self._ws = self._ws_raw[off:off + nbytes]
             h.check(lib.tdz_embed(h.ptr, feat[i:i + n].data_ptr(), n, frames, emb[i:i + n].data_ptr(),
                                   self._ws.data_ptr(), nbytes, self._stream()), "tdz_embed")
         return emb

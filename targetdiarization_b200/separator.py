@@ -56,9 +56,14 @@ class Separator:
         return int(self._h.lib.tdz_separate_workspace_bytes(B, T))
 
     def _workspace(self, nbytes):
+        """Caller-owned scratch, grown on demand; 1024 B aligned (TMA / swizzle atoms), which the caching allocator
+        alone does not guarantee (512 B)."""
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_raw = None
+            self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-self._ws_raw.data_ptr()) % 1024
+            self._ws = self._ws_raw[off:off + nbytes]
         return self._ws
 
     def layout(self, B, T):
@@ -99,7 +104,7 @@ class Separator:
                   "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2", "FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1",
                   "DECODER")
     LAYER_STEPS = STEP_NAMES[2:15]
-    KERNELS_PER_FORWARD = 4 + 24 * 18 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
+    KERNELS_PER_FORWARD = 4 + 24 * 19 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
 
     def time_steps(self, mix, reps=5):
         """CUDA-event time (ms) of every launch step of the forward run alone (layer 0 instance), after a

@@ -74,8 +74,9 @@ def test_block_parity(setup, stop):
     N, frames, _ = feat.shape
     lib, h = emb._h.lib, emb._h
     nbytes = int(lib.tdz_embed_workspace_bytes(N, frames))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    ws.fill_(0xFF)
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device="cuda")
+    raw.fill_(0xFF)
+    ws = raw[(-raw.data_ptr()) % 1024:][:nbytes]   # the C ABI wants a 1024 B aligned workspace
     f = feat.cuda().contiguous()
     h.check(lib.tdz_embed_debug(h.ptr, f.data_ptr(), N, frames, out.data_ptr(), ws.data_ptr(), nbytes,
                                 torch.cuda.current_stream().cuda_stream, stop), "tdz_embed_debug")

@@ -112,4 +112,4 @@ def test_run_batch_step(stage):
     again = st.score_segments(est.view(6, 16000), tgt).view(3, 2)
     assert torch.equal(scores, again)
     assert bool(((scores >= 0) & (scores <= 1)).all())
-    assert st.launches_per_run(3, 16000) == 445 + 2 + 256 + 1
+    assert st.launches_per_run(3, 16000) == 469 + 2 + 256 + 1
