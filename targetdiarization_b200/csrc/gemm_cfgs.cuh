@@ -296,6 +296,8 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   static constexpr int BLOCK_N = BLOCK_N_;
   static constexpr int EPI_SPLIT = 2;
   static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4;
+  // rows a warp has in flight in phase 2: the global operand loads of RB rows (512 B each) are issued together
+  static constexpr int RB = ((EF & EF_MUL) != 0 || ACT == ACT_AFF) ? 4 : 8;
 
   __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
                                   const EpiCtx& cx) {
@@ -367,11 +369,11 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
           for (int i = 0; i < 4; ++i) pf[i] = __ldg(e.pos_inv_freq + ((col + i) < hlf ? (col + i) : (col + i) - hlf));
         }
 #pragma unroll 1
-        for (int r0 = w * 16; r0 < w * 16 + 16; r0 += 4) {
-          float4 x4[4], rsd[4], ml[4];
-          bool valid[4];
+        for (int r0 = w * 16; r0 < w * 16 + 16; r0 += RB) {
+          float4 x4[RB], rsd[RB], ml[RB];
+          bool valid[RB];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < RB; ++i) {
             const int r = r0 + i;
             valid[i] = (ti.t0 + r) < P.S;
             x4[i] = *reinterpret_cast<const float4*>(cx.panel + r * PANEL_LD + 4 * lane);
@@ -386,7 +388,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < RB; ++i) {
             const int r = r0 + i;
             const int t = ti.t0 + r;
             const size_t grow = static_cast<size_t>(ti.m0) + r;
