@@ -199,7 +199,8 @@ int tdz_embed(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, fl
               size_t workspace_bytes, void* stream);
 
 /* Test hook: stops after the stem (stop_block -1), after residual block stop_block (0..15) or after the fuse34
- * map (16) and copies that fp32 NHWC feature map [N*H*W][C] into out_dev (sized by the caller). */
+ * map (16) and copies that NHWC feature map [N*H*W][C] into out_dev (sized by the caller): bf16 for the stem and
+ * the blocks (feature maps are stored in bf16), fp32 for fuse34. */
 int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* out_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream, int stop_block);
 

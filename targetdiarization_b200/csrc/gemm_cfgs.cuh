@@ -25,6 +25,7 @@ enum EpiFlags : unsigned {
   EF_SS_OUT = 1u << 10,     // per-row sum of squares of the stored values, one partial per 128 columns
   EF_ZERO_PAD = 1u << 11,   // padded frames (t >= S) are written as zeros instead of skipped
   EF_ROUND_TF32 = 1u << 12, // fp32 output rounded to nearest tf32 (buffer is only a tf32 MMA operand)
+  EF_OPS_BF16 = 1u << 13,   // resid / mul point to bf16 data (LinearPanel only)
 };
 
 struct EpiGeneric {
@@ -144,6 +145,12 @@ __device__ __forceinline__ void ld_f32x16(const float* p, float* v) {
     v[4 * j + 2] = t.z;
     v[4 * j + 3] = t.w;
   }
+}
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x), __bfloat162float(b.y));
 }
 // same for data written earlier in the same stream (plain loads, no read-only path assumption needed)
 __device__ __forceinline__ void ld_f32x16_rw(const float* p, float* v, bool full) {
@@ -381,10 +388,18 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
             rsd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             ml[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid[i] && col_ok) {
-              if constexpr ((EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF)
-                rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + col);
-              if constexpr ((EF & EF_MUL) != 0 || ACT == ACT_AFF)
-                ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + col);
+              if constexpr ((EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF) {
+                if constexpr ((EF & EF_OPS_BF16) != 0)
+                  rsd[i] = ld_bf16x4(reinterpret_cast<const __nv_bfloat16*>(e.resid) + grow * e.resid_ld + col);
+                else
+                  rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + col);
+              }
+              if constexpr ((EF & EF_MUL) != 0 || ACT == ACT_AFF) {
+                if constexpr ((EF & EF_OPS_BF16) != 0)
+                  ml[i] = ld_bf16x4(reinterpret_cast<const __nv_bfloat16*>(e.mul) + grow * e.mul_ld + col);
+                else
+                  ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + col);
+              }
             }
           }
 #pragma unroll

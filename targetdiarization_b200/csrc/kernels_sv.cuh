@@ -1,16 +1,27 @@
 // Memory-bound kernels of the ERes2NetV2 speaker embedder (architecture restated in
-// oracle/eres2netv2_port.py).  Feature maps are NHWC "pixel-major": [N*H*W][C], H = mel axis, W = time axis,
+// oracle/eres2netv2_port.py).  Feature maps are NHWC "pixel-major" bf16: [N*H*W][C], H = mel axis, W = time axis,
 // so every 1x1 convolution is a plain GEMM over pixels and every 3x3 convolution is a GEMM over an im2col
-// matrix that is written here in bf16 (9 shifted copies of the - usually 24..192 channel wide - input).
+// matrix that is written here (9 shifted copies of the - usually 24..192 channel wide - input).  All maps are
+// tensor-core operands of the next convolution anyway, so they are stored once, in bf16 (accumulation, BN, gates
+// and the residual add happen in fp32 inside the GEMM epilogues).
 #pragma once
 #include "ptx.cuh"
 
 namespace tdz {
 
-// Stem: Conv2d(1,64,3,pad 1) + BN (folded) + ReLU on feat [N][frames][80] -> [N][80][frames][64] fp32 + bf16.
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __bfloat162float(h[i].x);
+    v[2 * i + 1] = __bfloat162float(h[i].y);
+  }
+}
+
+// Stem: Conv2d(1,64,3,pad 1) + BN (folded) + ReLU on feat [N][frames][80] -> [N][80][frames][64] bf16.
 // Thread = one pixel x 8 channels.
 __global__ void __launch_bounds__(256) sv_stem_kernel(const float* __restrict__ feat, const float* __restrict__ w,
-                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                      const float* __restrict__ bias,
                                                       __nv_bfloat16* __restrict__ out_bf, int N, int H, int W) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(N) * H * W * 8;
@@ -40,16 +51,14 @@ __global__ void __launch_bounds__(256) sv_stem_kernel(const float* __restrict__ 
     for (int k = 0; k < 9; ++k) a = fmaf(w[ch * 9 + k], x[k], a);
     o[c] = fmaxf(a, 0.f);
   }
-  float4* dst = reinterpret_cast<float4*>(out + pix * 64 + cg * 8);
-  dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-  dst[1] = make_float4(o[4], o[5], o[6], o[7]);
   *reinterpret_cast<uint4*>(out_bf + pix * 64 + cg * 8) =
       make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
 }
 
-// Stride-2 pixel subsampling (the stride of a 1x1 conv): out[n,h,w,:] = in[n,2h,2w,:], fp32 -> bf16.
-__global__ void __launch_bounds__(256) sv_subsample_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                           int N, int Hin, int Win, int Hout, int Wout, int C) {
+// Stride-2 pixel subsampling (the stride of a 1x1 conv): out[n,h,w,:] = in[n,2h,2w,:].
+__global__ void __launch_bounds__(256) sv_subsample_kernel(const __nv_bfloat16* __restrict__ in,
+                                                           __nv_bfloat16* __restrict__ out, int N, int Hin, int Win,
+                                                           int Hout, int Wout, int C) {
   const int c8 = C / 8;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(N) * Hout * Wout * c8;
@@ -59,19 +68,16 @@ __global__ void __launch_bounds__(256) sv_subsample_kernel(const float* __restri
   const int wq = static_cast<int>(pix % Wout);
   const int hq = static_cast<int>((pix / Wout) % Hout);
   const int n = static_cast<int>(pix / (static_cast<int64_t>(Wout) * Hout));
-  const float4* src =
-      reinterpret_cast<const float4*>(in + ((static_cast<int64_t>(n) * Hin + 2 * hq) * Win + 2 * wq) * C + cg * 8);
-  const float4 a = src[0], b = src[1];
-  *reinterpret_cast<uint4*>(out + pix * C + cg * 8) =
-      make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  *reinterpret_cast<uint4*>(out + pix * C + cg * 8) = *reinterpret_cast<const uint4*>(
+      in + ((static_cast<int64_t>(n) * Hin + 2 * hq) * Win + 2 * wq) * C + cg * 8);
 }
 
 // im2col for a 3x3 convolution (pad 1, stride s): col[p][tap*C + c] = (a + b)[pixel(h*s+dh-1, w*s+dw-1)][c]
-// with zeros outside the image; a, b fp32 with their own leading dimension / channel offset (b optional:
-// the Res2Net hierarchical add sp_{i-1} + x_i, ERes2NetV2 block forward).  Output bf16, K = 9*C.
+// with zeros outside the image; a, b bf16 with their own leading dimension / channel offset (b optional:
+// the Res2Net hierarchical add sp_{i-1} + x_i, ERes2NetV2 block forward; the sum is formed in fp32).  K = 9*C.
 // Thread = one output pixel x one tap x 8 channels.
-__global__ void __launch_bounds__(256) sv_im2col_kernel(const float* __restrict__ a, int lda, int offa,
-                                                        const float* __restrict__ b, int ldb, int offb,
+__global__ void __launch_bounds__(256) sv_im2col_kernel(const __nv_bfloat16* __restrict__ a, int lda, int offa,
+                                                        const __nv_bfloat16* __restrict__ b, int ldb, int offb,
                                                         __nv_bfloat16* __restrict__ col, int N, int Hin, int Win,
                                                         int Hout, int Wout, int C, int stride) {
   const int c8 = C / 8;
@@ -88,36 +94,34 @@ __global__ void __launch_bounds__(256) sv_im2col_kernel(const float* __restrict_
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (hh >= 0 && hh < Hin && ww >= 0 && ww < Win) {
     const int64_t sp = (static_cast<int64_t>(n) * Hin + hh) * Win + ww;
-    const float4* pa = reinterpret_cast<const float4*>(a + sp * lda + offa + cg * 8);
-    float4 x0 = pa[0], x1 = pa[1];
+    o = *reinterpret_cast<const uint4*>(a + sp * lda + offa + cg * 8);
     if (b != nullptr) {
-      const float4* pb = reinterpret_cast<const float4*>(b + sp * ldb + offb + cg * 8);
-      const float4 y0 = pb[0], y1 = pb[1];
-      x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
-      x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+      const uint4 y = *reinterpret_cast<const uint4*>(b + sp * ldb + offb + cg * 8);
+      float xa[8], xb[8];
+      bf16x8_to_f32(o, xa);
+      bf16x8_to_f32(y, xb);
+      o = make_uint4(pack_bf16(xa[0] + xb[0], xa[1] + xb[1]), pack_bf16(xa[2] + xb[2], xa[3] + xb[3]),
+                     pack_bf16(xa[4] + xb[4], xa[5] + xb[5]), pack_bf16(xa[6] + xb[6], xa[7] + xb[7]));
     }
-    o = make_uint4(pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w));
   }
   *reinterpret_cast<uint4*>(col + pix * (9 * C) + tap * C + cg * 8) = o;
 }
 
-// AFF input: cat(x, y) along channels, fp32 -> bf16 [P][2C].
-__global__ void __launch_bounds__(256) sv_cat2_kernel(const float* __restrict__ a, int lda, int offa,
-                                                      const float* __restrict__ b, int ldb, int offb,
+// AFF input: cat(x, y) along channels -> [P][2C].
+__global__ void __launch_bounds__(256) sv_cat2_kernel(const __nv_bfloat16* __restrict__ a, int lda, int offa,
+                                                      const __nv_bfloat16* __restrict__ b, int ldb, int offb,
                                                       __nv_bfloat16* __restrict__ out, int64_t P, int C) {
   const int c8 = C / 8;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= P * 2 * c8) return;
   const int cg = static_cast<int>(idx % (2 * c8));
   const int64_t pix = idx / (2 * c8);
-  const float* src = cg < c8 ? a + pix * lda + offa + cg * 8 : b + pix * ldb + offb + (cg - c8) * 8;
-  const float4 x0 = reinterpret_cast<const float4*>(src)[0], x1 = reinterpret_cast<const float4*>(src)[1];
-  *reinterpret_cast<uint4*>(out + pix * (2 * C) + cg * 8) =
-      make_uint4(pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w));
+  const __nv_bfloat16* src = cg < c8 ? a + pix * lda + offa + cg * 8 : b + pix * ldb + offb + (cg - c8) * 8;
+  *reinterpret_cast<uint4*>(out + pix * (2 * C) + cg * 8) = *reinterpret_cast<const uint4*>(src);
 }
 
 // TSTP pooling: mean and sqrt(unbiased var + 1e-8) over time for every (channel, mel) pair of
-// fuse [N][H][W][C]; output stats[n][c*H + h] (mean block) and stats[n][C*H + c*H + h] (std block) as bf16
+// fuse [N][H][W][C] (fp32); output stats[n][c*H + h] (mean block) and stats[n][C*H + c*H + h] (std block) as bf16
 // operand of the embedding Linear, matching reshape(N, C*F, T) of an NCHW tensor.  Thread = (n, h, c).
 __global__ void __launch_bounds__(256) sv_tstp_kernel(const float* __restrict__ fuse, __nv_bfloat16* __restrict__ stats,
                                                       int N, int H, int W, int C, int ld_stats) {

@@ -107,7 +107,7 @@ static void sv_dims(int64_t N, int64_t frames, SvDims* d) {
 }
 
 struct SvLayout {
-  size_t xa_f, xa_b, xb_f, xb_b, xs, c1, sp, fused, cat2, mid, col, cat4, res, ds, fcat, fmid, fuse, stats, total;
+  size_t xa, xb, xs, c1, fused, cat2, mid, col, cat4, res, ds, fcat, fmid, fuse, stats, total;
 };
 static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
   SvDims d;
@@ -133,20 +133,17 @@ static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
     off += (bytes + 1023) / 1024 * 1024;
     return o;
   };
-  L->xa_f = take(act * 4);
-  L->xa_b = take(act * 2);
-  L->xb_f = take(act * 4);
-  L->xb_b = take(act * 2);
-  L->xs = take(xs * 2);
-  L->c1 = take(c1 * 4);
-  L->sp = take(sp * 4);
-  L->fused = take(sp * 4);
+  L->xa = take(act * 2);     // block input / output (bf16, ping-pong)
+  L->xb = take(act * 2);
+  L->xs = take(xs * 2);      // stride-2 subsampled block input
+  L->c1 = take(c1 * 2);      // conv1 output, 4 groups of `width` channels
+  L->fused = take(sp * 2);   // AFF(sp_{i-1}, x_i)
   L->cat2 = take(cat2 * 2);
   L->mid = take(static_cast<size_t>(d.Pp[2]) * 64 * 2);
-  L->col = take(col * 2);
-  L->cat4 = take(cat4 * 2);
-  L->res = take(act * 4);
-  L->ds = take(static_cast<size_t>(d.Pp[3]) * 2048 * 4);
+  L->col = take(col * 2);    // im2col matrix
+  L->cat4 = take(cat4 * 2);  // the four 3x3 conv outputs, concatenated (input of conv3)
+  L->res = take(act * 2);    // shortcut conv output
+  L->ds = take(static_cast<size_t>(d.Pp[3]) * 2048 * 2);
   L->fcat = take(static_cast<size_t>(d.Pp[3]) * 4096 * 2);
   L->fmid = take(static_cast<size_t>(d.Pp[3]) * 512 * 2);
   L->fuse = take(static_cast<size_t>(d.Pp[3]) * 2048 * 4);
@@ -155,7 +152,9 @@ static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM dispatch
-enum SvEpi { SV_HT20_F32, SV_HT20_BOTH, SV_SILU_BF16, SV_AFF_F32, SV_RES_HT20_BOTH, SV_LINEAR_F32 };
+// epilogue kinds: Hardtanh(0,20) -> bf16; SiLU -> bf16; AFF gate -> bf16 / fp32; + residual, Hardtanh -> bf16;
+// plain linear -> bf16 / fp32
+enum SvEpi { SV_HT20, SV_SILU, SV_AFF, SV_AFF_F32, SV_RES_HT20, SV_LINEAR, SV_LINEAR_F32 };
 
 template <int BN, unsigned EF, int ACT>
 static cudaError_t sv_launch(const LinearParams& P, int sms, cudaStream_t st) {
@@ -184,30 +183,31 @@ static int sv_gemm(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const void* A
   L.e.bias = c.bias;
   const int sms = ctx->num_sms;
   cudaError_t r = cudaErrorInvalidValue;
-  constexpr unsigned F32 = EF_BIAS | EF_OUT_F32, BOTH = EF_BIAS | EF_OUT_F32 | EF_OUT_BF16,
-                     BF = EF_BIAS | EF_OUT_BF16;
+  constexpr unsigned BF = EF_BIAS | EF_OUT_BF16, F32 = EF_BIAS | EF_OUT_F32, OPS = EF_OPS_BF16;
   switch (kind) {
-    case SV_HT20_F32:
-      if (c.BN == 128) r = sv_launch<128, F32, ACT_HARDTANH20>(L, sms, st);
-      else if (c.BN == 256) r = sv_launch<256, F32, ACT_HARDTANH20>(L, sms, st);
+    case SV_HT20:
+      if (c.BN == 32) r = sv_launch<32, BF, ACT_HARDTANH20>(L, sms, st);
+      else if (c.BN == 64) r = sv_launch<64, BF, ACT_HARDTANH20>(L, sms, st);
+      else if (c.BN == 128) r = sv_launch<128, BF, ACT_HARDTANH20>(L, sms, st);
+      else r = sv_launch<256, BF, ACT_HARDTANH20>(L, sms, st);
       break;
-    case SV_HT20_BOTH:
-      if (c.BN == 32) r = sv_launch<32, BOTH, ACT_HARDTANH20>(L, sms, st);
-      else if (c.BN == 64) r = sv_launch<64, BOTH, ACT_HARDTANH20>(L, sms, st);
-      else if (c.BN == 128) r = sv_launch<128, BOTH, ACT_HARDTANH20>(L, sms, st);
-      else r = sv_launch<256, BOTH, ACT_HARDTANH20>(L, sms, st);
-      break;
-    case SV_SILU_BF16:
+    case SV_SILU:
       if (c.BN == 32) r = sv_launch<32, BF, ACT_SILU>(L, sms, st);
       else if (c.BN == 64) r = sv_launch<64, BF, ACT_SILU>(L, sms, st);
       else if (c.BN == 256) r = sv_launch<256, BF, ACT_SILU>(L, sms, st);
       break;
-    case SV_AFF_F32:
-      if (c.BN == 128) r = sv_launch<128, F32, ACT_AFF>(L, sms, st);
-      else if (c.BN == 256) r = sv_launch<256, F32, ACT_AFF>(L, sms, st);
+    case SV_AFF:
+      if (c.BN == 128) r = sv_launch<128, BF | OPS, ACT_AFF>(L, sms, st);
+      else if (c.BN == 256) r = sv_launch<256, BF | OPS, ACT_AFF>(L, sms, st);
       break;
-    case SV_RES_HT20_BOTH:
-      if (c.BN == 256) r = sv_launch<256, BOTH | EF_RESID_PRE, ACT_HARDTANH20>(L, sms, st);
+    case SV_AFF_F32:
+      if (c.BN == 256) r = sv_launch<256, F32 | OPS, ACT_AFF>(L, sms, st);
+      break;
+    case SV_RES_HT20:
+      if (c.BN == 256) r = sv_launch<256, BF | OPS | EF_RESID_PRE, ACT_HARDTANH20>(L, sms, st);
+      break;
+    case SV_LINEAR:
+      if (c.BN == 256) r = sv_launch<256, BF, ACT_NONE>(L, sms, st);
       break;
     case SV_LINEAR_F32:
       if (c.BN == 256) r = sv_launch<256, F32, ACT_NONE>(L, sms, st);
@@ -221,8 +221,8 @@ static int sv_gemm(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const void* A
 static unsigned sv_grid(int64_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
 // ---------------------------------------------------------------------------------------------- forward
-// stop_block >= -1: test hook, copies the fp32 NHWC output of the stem (-1) or of residual block `stop_block`
-// (0..15), or the fuse34 map (16), into `emb` and returns.  stop_block == SV_RUN_ALL runs the whole model.
+// stop_block >= -1: test hook, copies the bf16 NHWC output of the stem (-1) or of residual block `stop_block`
+// (0..15), or the fp32 fuse34 map (16), into `emb` and returns.  stop_block == SV_RUN_ALL runs the whole model.
 constexpr int SV_RUN_ALL = 1000;
 static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N, int64_t frames, float* emb,
                     void* ws, size_t ws_bytes, cudaStream_t st, int stop_block = SV_RUN_ALL) {
@@ -235,21 +235,22 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
   sv_dims(N, frames, &d);
   if (d.Pp[0] * 256 > 0x7fffffffll) return fail(ctx, "tdz_embed: batch too large for one call");
   uint8_t* base = static_cast<uint8_t*>(ws);
-  auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
   auto Hh = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };
-  float *x_f = F(L.xa_f), *y_f = F(L.xb_f), *c1 = F(L.c1), *sp = F(L.sp), *fused = F(L.fused), *res = F(L.res),
-        *ds = F(L.ds), *fuse = F(L.fuse);
-  __nv_bfloat16 *x_b = Hh(L.xa_b), *y_b = Hh(L.xb_b), *xs = Hh(L.xs), *cat2 = Hh(L.cat2), *mid = Hh(L.mid),
-                *col = Hh(L.col), *cat4 = Hh(L.cat4), *fcat = Hh(L.fcat), *fmid = Hh(L.fmid), *stats = Hh(L.stats);
+  __nv_bfloat16 *x = Hh(L.xa), *y = Hh(L.xb), *xs = Hh(L.xs), *c1 = Hh(L.c1), *fused = Hh(L.fused),
+                *cat2 = Hh(L.cat2), *mid = Hh(L.mid), *col = Hh(L.col), *cat4 = Hh(L.cat4), *res = Hh(L.res),
+                *ds = Hh(L.ds), *fcat = Hh(L.fcat), *fmid = Hh(L.fmid), *stats = Hh(L.stats);
+  float* fuse = reinterpret_cast<float*>(base + L.fuse);
   const int n = static_cast<int>(N);
+  // epilogue operands that are bf16 travel through the float* fields of EpiGeneric (EF_OPS_BF16)
+  auto as_f = [](const __nv_bfloat16* p) { return reinterpret_cast<const float*>(p); };
 
   // columns N..63 of `mid` are never written but are read (against zero weights) by the second AFF conv
   CUDA_OK(cudaMemsetAsync(mid, 0, static_cast<size_t>(d.Pp[2]) * 64 * 2, st));
   // stem
-  sv_stem_kernel<<<sv_grid(d.P[0] * 8), 256, 0, st>>>(feat, M.stem_w, M.stem_b, x_f, x_b, n, static_cast<int>(d.H[0]),
+  sv_stem_kernel<<<sv_grid(d.P[0] * 8), 256, 0, st>>>(feat, M.stem_w, M.stem_b, x, n, static_cast<int>(d.H[0]),
                                                       static_cast<int>(d.W[0]));
   if (stop_block == -1) {
-    CUDA_OK(cudaMemcpyAsync(emb, x_f, static_cast<size_t>(d.P[0]) * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(emb, x, static_cast<size_t>(d.P[0]) * 64 * 2, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
   int layer = 0;
@@ -260,101 +261,97 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     if (s.stride == 2) ++layer;
     const int64_t P = d.P[layer], Pp = d.Pp[layer];
     const int Hc = static_cast<int>(d.H[layer]), Wc = static_cast<int>(d.W[layer]);
-    const __nv_bfloat16* a_in = x_b;
+    const __nv_bfloat16* a_in = x;
     if (s.stride == 2) {
       sv_subsample_kernel<<<sv_grid(P * (s.in_planes / 8)), 256, 0, st>>>(
-          x_f, xs, n, static_cast<int>(d.H[lin]), static_cast<int>(d.W[lin]), Hc, Wc, s.in_planes);
+          x, xs, n, static_cast<int>(d.H[lin]), static_cast<int>(d.W[lin]), Hc, Wc, s.in_planes);
       a_in = xs;
     }
     EpiGeneric e;
     // conv1 (1x1) + BN + Hardtanh(0,20)
     memset(&e, 0, sizeof e);
-    e.out_f32 = c1;
-    e.out_ld = 4 * wd;
-    if (sv_gemm(ctx, st, M.conv1[k], a_in, s.in_planes, P, Pp, SV_HT20_F32, e)) return 1;
+    e.out_bf16 = c1;
+    e.out_bf_ld = 4 * wd;
+    if (sv_gemm(ctx, st, M.conv1[k], a_in, s.in_planes, P, Pp, SV_HT20, e)) return 1;
     // shortcut
-    const float* resid = x_f;  // identity
+    const __nv_bfloat16* resid = a_in;  // identity (never strided: stride-2 blocks always have a shortcut conv)
     if (M.has_shortcut[k]) {
       memset(&e, 0, sizeof e);
-      e.out_f32 = res;
-      e.out_ld = 4 * s.planes;
-      if (sv_gemm(ctx, st, M.shortcut[k], a_in, s.in_planes, P, Pp, SV_LINEAR_F32, e)) return 1;
+      e.out_bf16 = res;
+      e.out_bf_ld = 4 * s.planes;
+      if (sv_gemm(ctx, st, M.shortcut[k], a_in, s.in_planes, P, Pp, SV_LINEAR, e)) return 1;
       resid = res;
     }
-    // four chained 3x3 convs over the channel groups
+    // four chained 3x3 convs over the channel groups; conv i writes block i of cat4, which is also sp_i
     for (int i = 0; i < 4; ++i) {
       if (i == 0) {
         sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(c1, 4 * wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
                                                                    Wc, wd, 1);
       } else if (!s.aff) {
-        sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(sp, wd, 0, c1, 4 * wd, i * wd, col, n, Hc, Wc,
-                                                                   Hc, Wc, wd, 1);
+        sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, col,
+                                                                   n, Hc, Wc, Hc, Wc, wd, 1);
       } else {
         // AFF(sp, x_i): two 1x1 convs on cat(sp, x_i), then the gate in the second epilogue
-        sv_cat2_kernel<<<sv_grid(P * 2 * (wd / 8)), 256, 0, st>>>(sp, wd, 0, c1, 4 * wd, i * wd, cat2, P, wd);
+        sv_cat2_kernel<<<sv_grid(P * 2 * (wd / 8)), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, cat2,
+                                                                 P, wd);
         memset(&e, 0, sizeof e);
         e.out_bf16 = mid;
         e.out_bf_ld = 64;
-        if (sv_gemm(ctx, st, M.aff_a[k][i - 1], cat2, 2 * wd, P, Pp, SV_SILU_BF16, e)) return 1;
+        if (sv_gemm(ctx, st, M.aff_a[k][i - 1], cat2, 2 * wd, P, Pp, SV_SILU, e)) return 1;
         memset(&e, 0, sizeof e);
-        e.mul = sp;
-        e.mul_ld = wd;
-        e.resid = c1 + i * wd;
+        e.mul = as_f(cat4 + (i - 1) * wd);
+        e.mul_ld = 4 * wd;
+        e.resid = as_f(c1 + i * wd);
         e.resid_ld = 4 * wd;
-        e.out_f32 = fused;
-        e.out_ld = wd;
-        if (sv_gemm(ctx, st, M.aff_b[k][i - 1], mid, 64, P, Pp, SV_AFF_F32, e)) return 1;
+        e.out_bf16 = fused;
+        e.out_bf_ld = wd;
+        if (sv_gemm(ctx, st, M.aff_b[k][i - 1], mid, 64, P, Pp, SV_AFF, e)) return 1;
         sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(fused, wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
                                                                    Wc, wd, 1);
       }
       memset(&e, 0, sizeof e);
-      e.out_f32 = sp;
-      e.out_ld = wd;
       e.out_bf16 = cat4;
       e.out_bf_ld = 4 * wd;
       e.out_bf_col0 = i * wd;
-      if (sv_gemm(ctx, st, M.convs[k][i], col, 9 * wd, P, Pp, SV_HT20_BOTH, e)) return 1;
+      if (sv_gemm(ctx, st, M.convs[k][i], col, 9 * wd, P, Pp, SV_HT20, e)) return 1;
     }
     // conv3 (1x1) + BN + shortcut + Hardtanh
     memset(&e, 0, sizeof e);
-    e.resid = resid;
+    e.resid = as_f(resid);
     e.resid_ld = 4 * s.planes;
-    e.out_f32 = y_f;
-    e.out_ld = 4 * s.planes;
-    e.out_bf16 = y_b;
+    e.out_bf16 = y;
     e.out_bf_ld = 4 * s.planes;
-    if (sv_gemm(ctx, st, M.conv3[k], cat4, 4 * wd, P, Pp, SV_RES_HT20_BOTH, e)) return 1;
-    std::swap(x_f, y_f);
-    std::swap(x_b, y_b);
+    if (sv_gemm(ctx, st, M.conv3[k], cat4, 4 * wd, P, Pp, SV_RES_HT20, e)) return 1;
+    std::swap(x, y);
     if (k == stop_block) {
-      CUDA_OK(cudaMemcpyAsync(emb, x_f, static_cast<size_t>(P) * 4 * s.planes * 4, cudaMemcpyDeviceToDevice, st));
+      CUDA_OK(cudaMemcpyAsync(emb, x, static_cast<size_t>(P) * 4 * s.planes * 2, cudaMemcpyDeviceToDevice, st));
       return 0;
     }
     if (k == 12) {
       // end of layer3: out3_ds = Conv2d(1024, 2048, 3, stride 2, pad 1)(out3), needed after layer4
       const int64_t P4 = d.P[3], Pp4 = d.Pp[3];
-      sv_im2col_kernel<<<sv_grid(P4 * 9 * (1024 / 8)), 256, 0, st>>>(x_f, 1024, 0, nullptr, 0, 0, col, n, Hc, Wc,
+      sv_im2col_kernel<<<sv_grid(P4 * 9 * (1024 / 8)), 256, 0, st>>>(x, 1024, 0, nullptr, 0, 0, col, n, Hc, Wc,
                                                                     static_cast<int>(d.H[3]),
                                                                     static_cast<int>(d.W[3]), 1024, 2);
       memset(&e, 0, sizeof e);
-      e.out_f32 = ds;
-      e.out_ld = 2048;
-      if (sv_gemm(ctx, st, M.layer3_ds, col, 9216, P4, Pp4, SV_LINEAR_F32, e)) return 1;
+      e.out_bf16 = ds;
+      e.out_bf_ld = 2048;
+      if (sv_gemm(ctx, st, M.layer3_ds, col, 9216, P4, Pp4, SV_LINEAR, e)) return 1;
     }
   }
   // fuse34 = AFF(out4, out3_ds)
   {
     const int64_t P4 = d.P[3], Pp4 = d.Pp[3];
     EpiGeneric e;
-    sv_cat2_kernel<<<sv_grid(P4 * 2 * (2048 / 8)), 256, 0, st>>>(x_f, 2048, 0, ds, 2048, 0, fcat, P4, 2048);
+    sv_cat2_kernel<<<sv_grid(P4 * 2 * (2048 / 8)), 256, 0, st>>>(x, 2048, 0, ds, 2048, 0, fcat, P4, 2048);
     memset(&e, 0, sizeof e);
     e.out_bf16 = fmid;
     e.out_bf_ld = 512;
-    if (sv_gemm(ctx, st, M.fuse_a, fcat, 4096, P4, Pp4, SV_SILU_BF16, e)) return 1;
+    if (sv_gemm(ctx, st, M.fuse_a, fcat, 4096, P4, Pp4, SV_SILU, e)) return 1;
     memset(&e, 0, sizeof e);
-    e.mul = x_f;
+    e.mul = as_f(x);
     e.mul_ld = 2048;
-    e.resid = ds;
+    e.resid = as_f(ds);
     e.resid_ld = 2048;
     e.out_f32 = fuse;
     e.out_ld = 2048;
