@@ -75,25 +75,27 @@ __global__ void __launch_bounds__(256) sv_subsample_kernel(const __nv_bfloat16* 
 // im2col for a 3x3 convolution (pad 1, stride s): col[p][tap*C + c] = (a + b)[pixel(h*s+dh-1, w*s+dw-1)][c]
 // with zeros outside the image; a, b bf16 with their own leading dimension / channel offset (b optional:
 // the Res2Net hierarchical add sp_{i-1} + x_i, ERes2NetV2 block forward; the sum is formed in fp32).  K = 9*C.
-// Thread = one output pixel x one tap x 8 channels.
+// Grid y = output image row (n, h); thread = one output pixel of the row x one tap x 8 channels, so consecutive
+// threads write consecutive 16 B pieces of the col row (all index arithmetic is 32-bit).
 __global__ void __launch_bounds__(256) sv_im2col_kernel(const __nv_bfloat16* __restrict__ a, int lda, int offa,
                                                         const __nv_bfloat16* __restrict__ b, int ldb, int offb,
                                                         __nv_bfloat16* __restrict__ col, int N, int Hin, int Win,
                                                         int Hout, int Wout, int C, int stride) {
-  const int c8 = C / 8;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t total = static_cast<int64_t>(N) * Hout * Wout * 9 * c8;
-  if (idx >= total) return;
-  const int cg = static_cast<int>(idx % c8);
-  const int tap = static_cast<int>((idx / c8) % 9);
-  const int64_t pix = idx / (9 * c8);
-  const int wq = static_cast<int>(pix % Wout);
-  const int hq = static_cast<int>((pix / Wout) % Hout);
-  const int n = static_cast<int>(pix / (static_cast<int64_t>(Wout) * Hout));
-  const int hh = hq * stride + tap / 3 - 1, ww = wq * stride + tap % 3 - 1;
+  const int c8 = C >> 3;
+  const int per_pix = 9 * c8;
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;  // position inside the output row
+  if (j >= static_cast<unsigned>(Wout * per_pix)) return;
+  const int wq = j / per_pix;
+  const int r = j - wq * per_pix;
+  const int tap = r / c8;
+  const int cg = r - tap * c8;
+  const int n = blockIdx.y / Hout;
+  const int hq = blockIdx.y - n * Hout;
+  const int dh = tap / 3;
+  const int hh = hq * stride + dh - 1, ww = wq * stride + (tap - 3 * dh) - 1;
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (hh >= 0 && hh < Hin && ww >= 0 && ww < Win) {
-    const int64_t sp = (static_cast<int64_t>(n) * Hin + hh) * Win + ww;
+    const size_t sp = (static_cast<size_t>(n) * Hin + hh) * Win + ww;
     o = *reinterpret_cast<const uint4*>(a + sp * lda + offa + cg * 8);
     if (b != nullptr) {
       const uint4 y = *reinterpret_cast<const uint4*>(b + sp * ldb + offb + cg * 8);
@@ -104,7 +106,8 @@ __global__ void __launch_bounds__(256) sv_im2col_kernel(const __nv_bfloat16* __r
                      pack_bf16(xa[4] + xb[4], xa[5] + xb[5]), pack_bf16(xa[6] + xb[6], xa[7] + xb[7]));
     }
   }
-  *reinterpret_cast<uint4*>(col + pix * (9 * C) + tap * C + cg * 8) = o;
+  const size_t pix = (static_cast<size_t>(n) * Hout + hq) * Wout + wq;
+  *reinterpret_cast<uint4*>(col + pix * (9 * C) + r * 8) = o;
 }
 
 // AFF input: cat(x, y) along channels -> [P][2C].

@@ -285,10 +285,10 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     // four chained 3x3 convs over the channel groups; conv i writes block i of cat4, which is also sp_i
     for (int i = 0; i < 4; ++i) {
       if (i == 0) {
-        sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(c1, 4 * wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
+        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(c1, 4 * wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
                                                                    Wc, wd, 1);
       } else if (!s.aff) {
-        sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, col,
+        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, col,
                                                                    n, Hc, Wc, Hc, Wc, wd, 1);
       } else {
         // AFF(sp, x_i): two 1x1 convs on cat(sp, x_i), then the gate in the second epilogue
@@ -306,7 +306,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
         e.out_bf16 = fused;
         e.out_bf_ld = wd;
         if (sv_gemm(ctx, st, M.aff_b[k][i - 1], mid, 64, P, Pp, SV_AFF, e)) return 1;
-        sv_im2col_kernel<<<sv_grid(P * 9 * (wd / 8)), 256, 0, st>>>(fused, wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
+        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(fused, wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
                                                                    Wc, wd, 1);
       }
       memset(&e, 0, sizeof e);
@@ -330,7 +330,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     if (k == 12) {
       // end of layer3: out3_ds = Conv2d(1024, 2048, 3, stride 2, pad 1)(out3), needed after layer4
       const int64_t P4 = d.P[3], Pp4 = d.Pp[3];
-      sv_im2col_kernel<<<sv_grid(P4 * 9 * (1024 / 8)), 256, 0, st>>>(x, 1024, 0, nullptr, 0, 0, col, n, Hc, Wc,
+      sv_im2col_kernel<<<dim3(sv_grid(d.W[3] * 9 * (1024 / 8)), n * static_cast<int>(d.H[3])), 256, 0, st>>>(x, 1024, 0, nullptr, 0, 0, col, n, Hc, Wc,
                                                                     static_cast<int>(d.H[3]),
                                                                     static_cast<int>(d.W[3]), 1024, 2);
       memset(&e, 0, sizeof e);
