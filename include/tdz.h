@@ -151,6 +151,16 @@ int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t session, int64_t 
 int tdz_stitch_concat(tdz_ctx* ctx, const float* est_dev, int64_t len, int64_t start, int64_t L, float* out_dev,
                       void* stream);
 
+/* ---- loudness -------------------------------------------------------------------------------- */
+/* The heavy part of AudioProcessor.meter_loudness (AudioProcessor.py:1123-1127; pyloudnorm integrated loudness,
+ * BS.1770): K-weighting of n_streams signals x_dev fp32 [n_streams][L] in fp64 (coef = for each of the two biquads
+ * b0 b1 b2 a0 a1 a2, a0 == 1) and the mean square of every 400 ms block [lo[j], hi[j]) -> z_dev fp64
+ * [n_streams][nblk] (= sum * inv_len).  ysq_dev is fp64 scratch [n_streams][L].  The two gates over the block
+ * values (a few thousand numbers) are applied by the caller. */
+int tdz_loudness_blocks(tdz_ctx* ctx, const float* x_dev, int64_t n_streams, int64_t L, const double* coef,
+                        const int64_t* lo_dev, const int64_t* hi_dev, int64_t nblk, double inv_len, double* ysq_dev,
+                        double* z_dev, void* stream);
+
 /* ---- speaker scoring ------------------------------------------------------------------------- */
 /* Kaldi fbank (80 mel bins, 25 ms / 10 ms, povey window, pre-emphasis 0.97, DC removal, power, log,
  * snip_edges) + per-utterance mean normalisation, as the modelscope ERes2NetV2 pipeline computes it

@@ -70,6 +70,8 @@ SIGNATURES = {
     "tdz_gather_segments": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "tdz_stitch_ola": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _vp, _vp]),
     "tdz_stitch_concat": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "tdz_loudness_blocks": (_int, [_vp, _vp, _i64, _i64, ctypes.POINTER(ctypes.c_double), _vp, _vp, _i64,
+                                   ctypes.c_double, _vp, _vp, _vp]),
     "tdz_fbank_frames": (_i64, [_i64]),
     "tdz_set_fbank_tables": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "tdz_fbank": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),

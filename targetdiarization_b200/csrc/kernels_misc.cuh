@@ -77,3 +77,60 @@ __global__ void cosine_scores_kernel(const float* __restrict__ emb, const float*
 }
 
 }  // namespace tdz
+
+namespace tdz {
+
+// ---------------------------------------------------------------- BS.1770 loudness (AudioProcessor.meter_loudness)
+// K-weighting = two cascaded biquads (pyloudnorm: high shelf + high pass), evaluated in fp64 like scipy.lfilter on
+// the host.  The recursion is cut into segments of LK_SEG samples that each start LK_WARM samples early from a
+// zero state: the slowest pole pair of the 38 Hz high pass decays by < 1e-13 over the warm-up, so the segments are
+// independent to fp64 round-off.  Output: squared filtered samples (fp64), input of the gated block means.
+constexpr int LK_SEG = 2048, LK_WARM = 2048;
+struct KWeight {
+  double b[2][3];
+  double a[2][3];  // a[.][0] == 1
+};
+__global__ void __launch_bounds__(128) kweight_sq_kernel(const float* __restrict__ x, int64_t L, int64_t n_streams,
+                                                         KWeight kw, double* __restrict__ ysq) {
+  const int64_t seg = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t segs_per_stream = (L + LK_SEG - 1) / LK_SEG;
+  if (seg >= segs_per_stream * n_streams) return;
+  const int64_t s = seg / segs_per_stream;
+  const int64_t n0 = (seg - s * segs_per_stream) * LK_SEG;
+  const float* xs = x + s * L;
+  double* ys = ysq + s * L;
+  double z1a = 0, z2a = 0, z1b = 0, z2b = 0;
+  const int64_t start = n0 - LK_WARM < 0 ? 0 : n0 - LK_WARM;
+  const int64_t end = n0 + LK_SEG < L ? n0 + LK_SEG : L;
+  for (int64_t n = start; n < end; ++n) {
+    const double v = static_cast<double>(xs[n]);
+    const double y1 = kw.b[0][0] * v + z1a;           // direct form II transposed, as scipy.signal.lfilter
+    z1a = kw.b[0][1] * v - kw.a[0][1] * y1 + z2a;
+    z2a = kw.b[0][2] * v - kw.a[0][2] * y1;
+    const double y2 = kw.b[1][0] * y1 + z1b;
+    z1b = kw.b[1][1] * y1 - kw.a[1][1] * y2 + z2b;
+    z2b = kw.b[1][2] * y1 - kw.a[1][2] * y2;
+    if (n >= n0) ys[n] = y2 * y2;
+  }
+}
+
+// z[s][j] = sum(ysq[s][lo[j] : hi[j]]) * inv_len   (400 ms blocks; the bounds come from the host so that they are
+// the same integers pyloudnorm's float arithmetic produces).  One warp per block.
+__global__ void __launch_bounds__(256) loudness_blocks_kernel(const double* __restrict__ ysq, int64_t L,
+                                                              const int64_t* __restrict__ lo,
+                                                              const int64_t* __restrict__ hi, int64_t nblk,
+                                                              int64_t n_streams, double inv_len,
+                                                              double* __restrict__ z) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nblk * n_streams) return;
+  const int64_t s = w / nblk, j = w - s * nblk;
+  const double* ys = ysq + s * L;
+  double acc = 0;
+  for (int64_t n = lo[j] + lane; n < hi[j]; n += 32) acc += ys[n];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) z[w] = acc * inv_len;
+}
+
+}  // namespace tdz

@@ -265,7 +265,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   const int B = static_cast<int>(B64), T = static_cast<int>(T64);
   const int S = static_cast<int>(L.S), Sp = static_cast<int>(L.Sp);
   const size_t M = static_cast<size_t>(L.Mtot);
-  if (M * 2176 > 0x7fffffffull * 4) return fail(ctx, "tdz_separate: batch too large for one call");
+  if (M > (1ull << 24)) return fail(ctx, "tdz_separate: batch too large for one call (more than 2^24 padded frames)");
   const int sms = ctx->num_sms;
   const tdz_mossformer2_weights& W = ctx->sep;
   uint8_t* base = static_cast<uint8_t*>(ws);
@@ -639,6 +639,27 @@ extern "C" int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float
   if (N <= 0) return 0;
   cosine_scores_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       emb_dev, target_dev, static_cast<int>(N), static_cast<int>(dim), scores_dev);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ loudness
+extern "C" int tdz_loudness_blocks(tdz_ctx* ctx, const float* x_dev, int64_t n_streams, int64_t L, const double* coef,
+                                   const int64_t* lo_dev, const int64_t* hi_dev, int64_t nblk, double inv_len,
+                                   double* ysq_dev, double* z_dev, void* stream) {
+  if (!ctx) return 1;
+  if (n_streams <= 0 || L <= 0 || nblk <= 0) return fail(ctx, "tdz_loudness_blocks: empty input");
+  KWeight kw;
+  for (int f = 0; f < 2; ++f)
+    for (int i = 0; i < 3; ++i) {
+      kw.b[f][i] = coef[f * 6 + i];
+      kw.a[f][i] = coef[f * 6 + 3 + i];
+    }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t segs = (L + LK_SEG - 1) / LK_SEG * n_streams;
+  kweight_sq_kernel<<<static_cast<unsigned>((segs + 127) / 128), 128, 0, st>>>(x_dev, L, n_streams, kw, ysq_dev);
+  loudness_blocks_kernel<<<static_cast<unsigned>((nblk * n_streams * 32 + 255) / 256), 256, 0, st>>>(
+      ysq_dev, L, lo_dev, hi_dev, nblk, n_streams, inv_len, z_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

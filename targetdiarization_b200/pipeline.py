@@ -39,7 +39,8 @@ class CudaKernels:
 
     def max_batch(self, T):
         per1 = self.sep.workspace_bytes(1, T)
-        return int(max(1, min(4096, self.max_workspace_bytes // max(per1, 1))))
+        frames = -(-max(T // 8, 1) // 256) * 256
+        return int(max(1, min(4096, self.max_workspace_bytes // max(per1, 1), (1 << 23) // frames)))
 
     def separate(self, chunks):
         """[n,T] -> [n,2,T], in sub-batches that fit the workspace budget."""
@@ -169,15 +170,10 @@ def separate_ola(kern, audio, sr=16000, target_length=12.0, hop_length=4.0, batc
 
 
 # ------------------------------------------------------------------------------------------------ loudness
-def meter_loudness(audio, rate=16000):
-    """AudioProcessor.meter_loudness (AudioProcessor.py:1123-1127): BS.1770 integrated loudness, rounded to 0.1.
-    Host numpy like the reference (pyloudnorm, absent here: restated; see DESIGN.md 'next rows').  Only the
-    ordering of the two returned streams depends on it."""
-    from scipy.signal import lfilter
-    x = np.asarray(audio, dtype=np.float64)
-    block = 0.4
-    if x.shape[0] < block * rate:
-        raise ValueError("Audio must have length greater than the block size.")
+def _k_weighting(rate):
+    """The two K-weighting biquads as pyloudnorm builds them (high shelf +4 dB / 1500 Hz / Q 1/sqrt2, high pass
+    38 Hz / Q 0.5; RBJ forms normalised by a0): [(b, a), (b, a)] in float64."""
+    out = []
     for G, Q, fc, shelf in ((4.0, 1.0 / np.sqrt(2.0), 1500.0, True), (0.0, 0.5, 38.0, False)):
         A = 10 ** (G / 40.0)
         w0 = 2.0 * np.pi * (fc / rate)
@@ -189,14 +185,22 @@ def meter_loudness(audio, rate=16000):
         else:
             b = [(1 + c) / 2, -(1 + c), (1 + c) / 2]
             a = [1 + al, -2 * c, 1 - al]
-        x = lfilter(np.array(b) / a[0], np.array(a) / a[0], x)
-    T = x.shape[0] / rate
+        out.append((np.array(b) / a[0], np.array(a) / a[0]))
+    return out
+
+
+def _block_bounds(n_samples, rate, block=0.4):
+    """[lo, hi) of the 400 ms / 75 %-overlap blocks with pyloudnorm's float arithmetic (so the integers agree)."""
+    T = n_samples / rate
     nblk = int(np.round((T - block) / (block * 0.25)) + 1)
-    n = int(block * rate)
-    cs = np.concatenate(([0.0], np.cumsum(np.square(x))))
-    lo = (block * 0.25 * rate * np.arange(nblk)).astype(np.int64)
-    hi = np.minimum((block * (0.25 * np.arange(nblk) + 1) * rate).astype(np.int64), x.shape[0])
-    z = (cs[hi] - cs[lo]) / n
+    j = np.arange(nblk)
+    lo = np.array([int(block * (k * 0.25) * rate) for k in j], dtype=np.int64)
+    hi = np.minimum(np.array([int(block * (k * 0.25 + 1) * rate) for k in j], dtype=np.int64), n_samples)
+    return lo, hi
+
+
+def _gate(z):
+    """The two gates of BS.1770 over the block mean squares (absolute -70 LUFS, relative -10 LU) -> LUFS."""
     with np.errstate(divide="ignore", invalid="ignore"):
         l = -0.691 + 10.0 * np.log10(z)
         keep = l >= -70.0
@@ -204,7 +208,24 @@ def meter_loudness(audio, rate=16000):
         gamma_r = -0.691 + 10.0 * np.log10(zg) - 10.0
         keep = (l > gamma_r) & (l > -70.0)
         zg = z[keep].mean() if keep.any() else 0.0
-        return round(float(-0.691 + 10.0 * np.log10(zg)), 1)
+        return float(-0.691 + 10.0 * np.log10(zg))
+
+
+def meter_loudness(audio, rate=16000):
+    """AudioProcessor.meter_loudness (AudioProcessor.py:1123-1127): BS.1770 integrated loudness, rounded to 0.1.
+    Host numpy like the reference's pyloudnorm call (absent here: restated).  For streams that already live on the
+    device use SeparationScoringStage.meter_loudness_device."""
+    from scipy.signal import lfilter
+    x = np.asarray(audio, dtype=np.float64)
+    block = 0.4
+    if x.shape[0] < block * rate:
+        raise ValueError("Audio must have length greater than the block size.")
+    for b, a in _k_weighting(rate):
+        x = lfilter(b, a, x)
+    lo, hi = _block_bounds(x.shape[0], rate, block)
+    cs = np.concatenate(([0.0], np.cumsum(np.square(x))))
+    z = (cs[hi] - cs[lo]) / (block * rate)
+    return round(_gate(z), 1)
 
 
 # ------------------------------------------------------------------------------------------------ the stage
@@ -234,11 +255,12 @@ class SeparationScoringStage:
 
     # ---- AudioProcessor.separate_speaker
     def separate_speaker(self, audio_data, sampling_rate=16000, low_gpu_ram=False, mode="concat", vad_frames=None,
-                         resample=None, loudness=meter_loudness, return_device=False, **ola_kw):
+                         resample=None, loudness="device", return_device=False, **ola_kw):
         """np.float32 [L] -> (spk1, spk2) np.float32 [L], louder stream first.
 
         mode="concat" is the reference rule (10 s windows, bit-exact boundaries); mode="ola" stitches 12 s / 4 s-hop
-        segments by overlap-add (wav_chunk_inference).  low_gpu_ram=True uses 1 s windows inside `vad_frames`
+        segments by overlap-add (wav_chunk_inference).  loudness: "device" (BS.1770 meter on the GPU), a callable
+        (audio, rate) -> LUFS such as AudioProcessor.meter_loudness, or None (keep the separator's order).  low_gpu_ram=True uses 1 s windows inside `vad_frames`
         (which the caller's VAD supplies; the reference runs silero-vad there).  `resample(audio, orig_sr,
         target_sr) -> audio` is needed only when sampling_rate != 16000 (the reference calls librosa)."""
         if not self.is_separate_audio:
@@ -262,13 +284,42 @@ class SeparationScoringStage:
             raise ValueError(f"unknown mode {mode!r}")
         if return_device and loudness is None:
             return est[0], est[1]
+        swap = False
+        if isinstance(loudness, str):  # "device": BS.1770 meter on the GPU, before the streams leave it
+            if loudness != "device":
+                raise ValueError(f"unknown loudness meter {loudness!r}")
+            l1, l2 = self.meter_loudness_device(est, sampling_rate)
+            swap = l1 < l2
         host = est.cpu().numpy()
         spk1, spk2 = host[0], host[1]
-        if loudness is not None and loudness(spk1, sampling_rate) < loudness(spk2, sampling_rate):
+        if callable(loudness):
+            swap = loudness(spk1, sampling_rate) < loudness(spk2, sampling_rate)
+        if swap:
             spk1, spk2 = spk2, spk1
         if orig_sr != sampling_rate:
             spk1, spk2 = resample(spk1, sampling_rate, orig_sr), resample(spk2, sampling_rate, orig_sr)
         return spk1, spk2
+
+    def meter_loudness_device(self, streams, rate=16000):
+        """meter_loudness of n device streams [n, L] at once: K-weighting (fp64) and block mean squares on the GPU
+        (tdz_loudness_blocks), the two gates over the few thousand block values on the host.  Returns n floats."""
+        import ctypes
+        x = streams.to(torch.float32).contiguous()
+        n, L = x.shape
+        block = 0.4
+        if L < block * rate:
+            raise ValueError("Audio must have length greater than the block size.")
+        lo, hi = _block_bounds(L, rate, block)
+        coef = np.concatenate([np.concatenate((b, a)) for b, a in _k_weighting(rate)]).astype(np.float64)
+        lo_d, hi_d = torch.from_numpy(lo).to(self.device), torch.from_numpy(hi).to(self.device)
+        ysq = torch.empty(n, L, dtype=torch.float64, device=self.device)
+        z = torch.empty(n, len(lo), dtype=torch.float64, device=self.device)
+        h = self.separator._h
+        h.check(h.lib.tdz_loudness_blocks(h.ptr, x.data_ptr(), n, L, coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                          lo_d.data_ptr(), hi_d.data_ptr(), len(lo), 1.0 / (block * rate),
+                                          ysq.data_ptr(), z.data_ptr(), self.kern._stream()), "tdz_loudness_blocks")
+        zh = z.cpu().numpy()
+        return [round(_gate(zh[i]), 1) for i in range(n)]
 
     # ---- look2hear.utils.wav_chunk_inference
     def wav_chunk_inference(self, mixture_tensor, sr=16000, target_length=12.0, hop_length=4.0, batch_size=10,

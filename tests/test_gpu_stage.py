@@ -113,3 +113,27 @@ def test_run_batch_step(stage):
     assert torch.equal(scores, again)
     assert bool(((scores >= 0) & (scores <= 1)).all())
     assert st.launches_per_run(3, 16000) == 469 + 2 + 256 + 1
+
+
+def test_device_loudness_meter(stage):
+    """BS.1770 integrated loudness on the device (fp64 K-weighting in independent warm-started segments + block
+    means) against the oracle's pyloudnorm restatement: same value to 1e-6 dB, same 0.1-rounded value, on signals
+    with silences (gating) and at several lengths incl. one just above the 400 ms minimum."""
+    torch, st = stage
+    import math
+    from oracle import stage_port
+    from targetdiarization_b200.pipeline import _block_bounds, _gate, _k_weighting
+    from targetdiarization_b200.synth import synthetic_mixture
+    for L, seed in ((6400 + 3, 1), (48000, 2), (160000 + 777, 3), (16000 * 70 + 5, 4)):
+        x = synthetic_mixture(2, L, seed=seed)
+        x[1] *= 0.05
+        x[1, L // 3: L // 2] = 0.0     # silence: exercises the absolute gate
+        got = st.meter_loudness_device(x.cuda())
+        for i in range(2):
+            want = stage_port.integrated_loudness(x[i].numpy())
+            assert got[i] == round(want, 1), (L, i, got[i], want)
+    with pytest.raises(ValueError):
+        st.meter_loudness_device(torch.zeros(1, 3000).cuda())
+    # known answer: full-scale 997 Hz sine = -3.0 LUFS (16 kHz RBJ filters: -3.06)
+    t = torch.arange(48000) / 16000.0
+    assert st.meter_loudness_device(torch.sin(2 * math.pi * 997.0 * t)[None].cuda())[0] == pytest.approx(-3.0, abs=0.15)

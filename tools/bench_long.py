@@ -37,9 +37,7 @@ def main():
     out = {"audio_seconds": L / 16000, "world": world}
     for mode in ("concat", "ola"):
         res = {}
-        for what, loud in (("device_only", None), ("with_host_loudness", meter_loudness)):
-            if what == "with_host_loudness" and rank != 0 and False:
-                continue
+        for what, loud in (("no_loudness", None), ("device_loudness", "device"), ("host_loudness", meter_loudness)):
             stage.separate_speaker(audio[: 16000 * 30], mode=mode, loudness=None)   # warm-up
             torch.cuda.synchronize()
             if world > 1:
