@@ -137,3 +137,26 @@ def test_device_loudness_meter(stage):
     # known answer: full-scale 997 Hz sine = -3.0 LUFS (16 kHz RBJ filters: -3.06)
     t = torch.arange(48000) / 16000.0
     assert st.meter_loudness_device(torch.sin(2 * math.pi * 997.0 * t)[None].cuda())[0] == pytest.approx(-3.0, abs=0.15)
+
+
+def test_full_size_c2_batch_properties(stage):
+    """BASELINE config 2 at full size (64 mixtures x 4 s): size-independent properties instead of a CPU oracle run -
+    every item of the batch equals, bit for bit, the same mixture separated on its own; scores are reproducible from
+    the separated streams and lie in [0, 1]; nothing is NaN; the louder-first swap is a pure permutation."""
+    torch, st = stage
+    from targetdiarization_b200.synth import synthetic_mixture
+    mix = synthetic_mixture(64, 64000, seed=31).cuda()
+    tgt = st.embed(synthetic_mixture(1, 64000, seed=32).cuda())[0]
+    est, scores = st.run(mix, tgt)
+    assert est.shape == (64, 2, 64000) and scores.shape == (64, 2)
+    assert bool(torch.isfinite(est).all()) and bool(torch.isfinite(scores).all())
+    assert bool(((scores >= 0) & (scores <= 1)).all())
+    for i in (0, 17, 63):
+        single = st.separator(mix[i:i + 1])
+        assert torch.equal(single[0], est[i]), f"item {i} depends on its batch"
+    again = st.score_segments(est.view(128, 64000), tgt).view(64, 2)
+    assert torch.equal(scores, again)
+    # separate_speaker on one item returns the two streams of run(), louder first
+    s1, s2 = st.separate_speaker(mix[5].cpu().numpy())
+    a, b = est[5, 0].cpu().numpy(), est[5, 1].cpu().numpy()
+    assert (np.array_equal(s1, a) and np.array_equal(s2, b)) or (np.array_equal(s1, b) and np.array_equal(s2, a))
