@@ -102,3 +102,55 @@ def pick_target(spk1_score, spk2_score, threshold=0.0):
     if spk1_score < threshold and spk2_score < threshold:
         return None
     return 1 if spk1_score > spk2_score else 2
+
+
+# ---------------------------------------------------------------------------------------------- per-segment rules
+# The scalar rules the reference applies to per-segment cosine scores.  The scores come from one batched
+# Embedder.score_many call; the rules stay on the host exactly as in the reference.
+def target_spk_from_scores(speakers, scores):
+    """TargetDiarization.target_embedding_to_target_spk (TargetDiarization.py:581-600): mean score per speaker in
+    first-appearance order, stable sort descending, first wins; '' when there are no segments."""
+    sums, counts, order = {}, {}, []
+    for spk, sc in zip(speakers, scores):
+        if spk not in sums:
+            sums[spk], counts[spk] = 0.0, 0
+            order.append(spk)
+        sums[spk] += float(sc)
+        counts[spk] += 1
+    score_map = [[spk, sums[spk] / counts[spk]] for spk in order]
+    if not score_map:
+        return ""
+    score_map.sort(key=lambda x: x[1], reverse=True)
+    return score_map[0][0]
+
+
+def recheck_target_speaker(result, scores, target_spk, threshold, method="recheck_target"):
+    """TargetDiarization.recheck_target_speaker (TargetDiarization.py:603-629) given the batched scores of the
+    clips (scores[i] for result[i]; None where the clip has no audio): relabels in place and returns `result`."""
+    if not result:
+        return []
+    for r in result:
+        r["score"] = -1.0
+    if not threshold or threshold == 0.0:
+        return result
+    for r, sc in zip(result, scores):
+        if method == "recheck_target" and r["speaker"] != target_spk:
+            continue
+        if method == "recheck_others" and r["speaker"] == target_spk:
+            continue
+        if sc is None:
+            continue
+        r["score"] = round(float(sc), 3)
+        if sc >= threshold:
+            if r["speaker"] != target_spk:
+                r["speaker"] = target_spk
+        elif r["speaker"] == target_spk:
+            r["speaker"] = "-1"
+    return result
+
+
+def is_same_person(similarity, threshold=0.4, verbose_result=False):
+    """Decision part of TargetASR.is_same_person (TargetASR.py:491-505); `similarity` is the cosine between the mean
+    of the existing embeddings and the target embedding."""
+    same = similarity >= threshold
+    return {"is_same": bool(same), "score": round(float(similarity), 3)} if verbose_result else bool(same)

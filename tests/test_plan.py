@@ -96,3 +96,44 @@ def test_meter_loudness_known_answers():
     assert meter_loudness(y, sr) == stage_port.meter_loudness(y, sr)
     with pytest.raises(ValueError):
         meter_loudness(x[:6000], sr)   # pyloudnorm raises under one 400 ms block
+
+
+def test_per_segment_rules_match_reference_source():
+    """target_embedding_to_target_spk / recheck_target_speaker / is_same_person: the product's score rules against the
+    reference functions themselves (extracted from the reference source with `ast` in the build container) on random
+    scores; everywhere: fixed known answers."""
+    import random
+    from tests.conftest import has_reference
+    assert plan.target_spk_from_scores(["a", "b", "a", "c"], [0.2, 0.5, 0.9, 0.55]) == "a"     # means .55 .5 .55: first of the tie
+    assert plan.target_spk_from_scores([], []) == ""
+    res = [{"speaker": "a", "audio": 1}, {"speaker": "b", "audio": 1}, {"speaker": "a", "audio": None}]
+    out = plan.recheck_target_speaker([dict(r) for r in res], [0.1, 0.9, None], "a", 0.2)
+    assert [r["speaker"] for r in out] == ["-1", "b", "a"] and [r["score"] for r in out] == [0.1, -1.0, -1.0]
+    out = plan.recheck_target_speaker([dict(r) for r in res], [0.1, 0.9, None], "a", 0.2, method="recheck_both")
+    assert [r["speaker"] for r in out] == ["-1", "a", "a"]
+    assert plan.is_same_person(0.4) is True and plan.is_same_person(0.39999) is False
+    assert plan.is_same_person(0.1234567, verbose_result=True) == {"is_same": False, "score": 0.123}
+    if not has_reference():
+        return
+    import types
+    from oracle.make_golden import extract_method
+    ns = {"np": np, "Literal": __import__("typing").Literal, "Union": __import__("typing").Union}
+    code = extract_method("/root/reference/TargetDiarization.py", "TargetDiarization", "recheck_target_speaker")
+    exec(compile(code, "ref", "exec"), ns)
+    ref_recheck = ns["recheck_target_speaker"]
+    rng = random.Random(3)
+    for trial in range(50):
+        n = rng.randint(1, 8)
+        result = [{"speaker": rng.choice(["a", "b", "c"]), "audio": (None if rng.random() < 0.2 else i)} for i in range(n)]
+        scores = [rng.random() for _ in range(n)]
+        thr = rng.choice([0.0, 0.2, 0.5])
+        method = rng.choice(["recheck_target", "recheck_others", "recheck_both"])
+        fake = types.SimpleNamespace(
+            target_similarity_threshold=thr,
+            tasr=types.SimpleNamespace(get_speaker_embedding=lambda wav_file: wav_file,
+                                       cosine_similarity=lambda embedding_a, embedding_b: scores[embedding_b]))
+        want = ref_recheck(fake, [dict(r) for r in result], "a", "tgt", method)
+        got = plan.recheck_target_speaker([dict(r) for r in result],
+                                          [None if r["audio"] is None else scores[r["audio"]] for r in result], "a", thr,
+                                          method)
+        assert got == want, (trial, got, want)
