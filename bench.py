@@ -291,7 +291,7 @@ def main():
             "dtype": "bf16 tensor-core operands (tf32 for the FSMN 1x1 and mask-net convs), fp32 accumulate/activations",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "items_per_gpu": B, "samples_per_item": T, "weights": "random-init",
-                       "l2": "per-step working set ~19 GB >> 126 MB L2 (inputs 16 MB); no explicit flush needed",
+                       "l2": "per-step working set ~13 GB of intermediates >> 126 MB L2 (inputs 16 MB); no explicit flush needed",
                        "parallelism": f"dp{world} (independent chunks, no data-path collective)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
