@@ -83,32 +83,42 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
 // OffsetScale (4 heads) + rotary on dims 0..31 (interleaved pairs, rotary_embedding_torch) of the to_qk output
 // (mossformer_block.py:76-86,214,230-233) -> qk4 bf16 [Mtot][512] = quad_q | lin_q | quad_k | lin_k, plus the bf16
 // rounding residual of lin_q (second term of the split used by the linear-attention output product).
-// Thread = one frame x 2 adjacent channels; block = 4 frames.
+// Thread = 2 adjacent channels x QKH_FRAMES frames (the OffsetScale constants of its channels stay in registers);
+// block = 4 x QKH_FRAMES consecutive frames.
+constexpr int QKH_FRAMES = 8;
 __global__ void __launch_bounds__(256) qk_heads_kernel(const float* __restrict__ qkf, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float2* __restrict__ rot,
                                                        __nv_bfloat16* __restrict__ qk4, __nv_bfloat16* __restrict__ lq_lo,
                                                        int Sp, int S, size_t rows) {
-  const size_t row = static_cast<size_t>(blockIdx.x) * 4 + (threadIdx.x >> 6);
-  if (row >= rows) return;
-  const int t = static_cast<int>(row % Sp);
-  if (t >= S) return;  // padded frames stay zero (zeroed once per forward)
   const int c = (threadIdx.x & 63) * 2;
-  const float2 v = *reinterpret_cast<const float2*>(qkf + row * 128 + c);
-  float2 cs = make_float2(1.f, 0.f);
-  if (c < 32) cs = rot[t * 16 + (c >> 1)];
+  float2 g[4], bt[4];
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
-    const float2 g = *reinterpret_cast<const float2*>(gamma + h * 128 + c);
-    const float2 b = *reinterpret_cast<const float2*>(beta + h * 128 + c);
-    const float x0 = fmaf(v.x, g.x, b.x), x1 = fmaf(v.y, g.y, b.y);
-    const float r0 = x0 * cs.x - x1 * cs.y;
-    const float r1 = x1 * cs.x + x0 * cs.y;
-    const uint32_t packed = pack_bf16(r0, r1);
-    *reinterpret_cast<uint32_t*>(qk4 + row * 512 + h * 128 + c) = packed;
-    if (h == 1) {
-      const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&packed);
-      *reinterpret_cast<uint32_t*>(lq_lo + row * 128 + c) =
-          pack_bf16(r0 - __bfloat162float(hb.x), r1 - __bfloat162float(hb.y));
+    g[h] = *reinterpret_cast<const float2*>(gamma + h * 128 + c);
+    bt[h] = *reinterpret_cast<const float2*>(beta + h * 128 + c);
+  }
+  const size_t row0 = static_cast<size_t>(blockIdx.x) * (4 * QKH_FRAMES) + (threadIdx.x >> 6);
+#pragma unroll 2
+  for (int f = 0; f < QKH_FRAMES; ++f) {
+    const size_t row = row0 + 4 * f;
+    if (row >= rows) return;
+    const int t = static_cast<int>(row % Sp);
+    if (t >= S) continue;  // padded frames stay zero (zeroed once per forward)
+    const float2 v = *reinterpret_cast<const float2*>(qkf + row * 128 + c);
+    float2 cs = make_float2(1.f, 0.f);
+    if (c < 32) cs = rot[t * 16 + (c >> 1)];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float x0 = fmaf(v.x, g[h].x, bt[h].x), x1 = fmaf(v.y, g[h].y, bt[h].y);
+      const float r0 = x0 * cs.x - x1 * cs.y;
+      const float r1 = x1 * cs.x + x0 * cs.y;
+      const uint32_t packed = pack_bf16(r0, r1);
+      *reinterpret_cast<uint32_t*>(qk4 + row * 512 + h * 128 + c) = packed;
+      if (h == 1) {
+        const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&packed);
+        *reinterpret_cast<uint32_t*>(lq_lo + row * 128 + c) =
+            pack_bf16(r0 - __bfloat162float(hb.x), r1 - __bfloat162float(hb.y));
+      }
     }
   }
 }
@@ -390,61 +400,80 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 }
 
 // FSMN tail: o2 = PReLU(IN(y2)); f = x_u + o2 (fsmn.py:144); g = x_v*f + c (mossformer_block.py:324);
-// CLayerNorm(256) (norm2, :423) with its affine folded into conv2 -> bf16 operand.  One warp per frame.
+// CLayerNorm(256) (norm2, :423) with its affine folded into conv2 -> tf32 operand.  One warp per group of
+// TAIL_FRAMES consecutive frames of one sample (the per-channel InstanceNorm / PReLU constants of the lane's 8
+// channels are loaded once per group, as vectors).
+constexpr int TAIL_FRAMES = 8;
 __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict__ y2, const float2* __restrict__ in2_ss,
                                                         const float* __restrict__ prelu2,
                                                         const float* __restrict__ xuv, const float* __restrict__ cres,
                                                         float* __restrict__ gout, int B, int Sp, int S) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= B * Sp) return;
-  const int b = warp / Sp;
-  const int t = warp - b * Sp;
-  const size_t grow = warp;
-  float g[8];
-  if (t >= S) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) gout[grow * 256 + lane * 8 + i] = 0.f;
-    return;
-  }
+  const int groups = Sp / TAIL_FRAMES;  // Sp is a multiple of 256
+  if (warp >= B * groups) return;
+  const int b = warp / groups;
+  const int t0 = (warp - b * groups) * TAIL_FRAMES;
   const int c0 = lane * 8;
-  const float4* yp = reinterpret_cast<const float4*>(y2 + grow * 256 + c0);
-  const float4* up = reinterpret_cast<const float4*>(xuv + grow * 512 + c0);
-  const float4* vp = reinterpret_cast<const float4*>(xuv + grow * 512 + 256 + c0);
-  const float4* cp = reinterpret_cast<const float4*>(cres + grow * 256 + c0);
-  float y[8], u[8], v[8], cr[8];
-  *reinterpret_cast<float4*>(y) = yp[0];
-  *reinterpret_cast<float4*>(y + 4) = yp[1];
-  *reinterpret_cast<float4*>(u) = up[0];
-  *reinterpret_cast<float4*>(u + 4) = up[1];
-  *reinterpret_cast<float4*>(v) = vp[0];
-  *reinterpret_cast<float4*>(v + 4) = vp[1];
-  *reinterpret_cast<float4*>(cr) = cp[0];
-  *reinterpret_cast<float4*>(cr + 4) = cp[1];
-  float s1 = 0.f;
+  float sc[8], sh[8], al[8];
+  {
+    const float4* sp = reinterpret_cast<const float4*>(in2_ss + static_cast<size_t>(b) * 256 + c0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    const float2 ss = in2_ss[b * 256 + c];
-    float o = y[i] * ss.x + ss.y;
-    o = o >= 0.f ? o : prelu2[c] * o;
-    g[i] = v[i] * (u[i] + o) + cr[i];
-    s1 += g[i];
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = sp[i];
+      sc[2 * i] = v.x;
+      sh[2 * i] = v.y;
+      sc[2 * i + 1] = v.z;
+      sh[2 * i + 1] = v.w;
+    }
+    *reinterpret_cast<float4*>(al) = *reinterpret_cast<const float4*>(prelu2 + c0);
+    *reinterpret_cast<float4*>(al + 4) = *reinterpret_cast<const float4*>(prelu2 + c0 + 4);
   }
-  const float mean = warp_sum(s1) * (1.f / 256.f);
-  float s2 = 0.f;
+#pragma unroll 2
+  for (int f = 0; f < TAIL_FRAMES; ++f) {
+    const int t = t0 + f;
+    const size_t grow = static_cast<size_t>(b) * Sp + t;
+    float4* op = reinterpret_cast<float4*>(gout + grow * 256 + c0);
+    if (t >= S) {  // warp-uniform
+      op[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      op[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float4* yp = reinterpret_cast<const float4*>(y2 + grow * 256 + c0);
+    const float4* up = reinterpret_cast<const float4*>(xuv + grow * 512 + c0);
+    const float4* vp = reinterpret_cast<const float4*>(xuv + grow * 512 + 256 + c0);
+    const float4* cp = reinterpret_cast<const float4*>(cres + grow * 256 + c0);
+    float y[8], u[8], v[8], cr[8], g[8];
+    *reinterpret_cast<float4*>(y) = yp[0];
+    *reinterpret_cast<float4*>(y + 4) = yp[1];
+    *reinterpret_cast<float4*>(u) = up[0];
+    *reinterpret_cast<float4*>(u + 4) = up[1];
+    *reinterpret_cast<float4*>(v) = vp[0];
+    *reinterpret_cast<float4*>(v + 4) = vp[1];
+    *reinterpret_cast<float4*>(cr) = cp[0];
+    *reinterpret_cast<float4*>(cr + 4) = cp[1];
+    float s1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float d = g[i] - mean;
-    s2 += d * d;
+    for (int i = 0; i < 8; ++i) {
+      float o = fmaf(y[i], sc[i], sh[i]);
+      o = o >= 0.f ? o : al[i] * o;
+      g[i] = fmaf(v[i], u[i] + o, cr[i]);
+      s1 += g[i];
+    }
+    const float mean = warp_sum(s1) * (1.f / 256.f);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = g[i] - mean;
+      s2 += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(s2) * (1.f / 256.f) + 1e-5f);
+    // g is only the tf32 operand of conv2: round to nearest here (the MMA would truncate)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = round_tf32_rn((g[i] - mean) * rstd);
+    op[0] = make_float4(g[0], g[1], g[2], g[3]);
+    op[1] = make_float4(g[4], g[5], g[6], g[7]);
   }
-  const float rstd = rsqrtf(warp_sum(s2) * (1.f / 256.f) + 1e-5f);
-  float4* op = reinterpret_cast<float4*>(gout + grow * 256 + c0);
-  // g is only the tf32 operand of conv2: round to nearest here (the MMA would truncate)
-#pragma unroll
-  for (int i = 0; i < 8; ++i) g[i] = round_tf32_rn((g[i] - mean) * rstd);
-  op[0] = make_float4(g[0], g[1], g[2], g[3]);
-  op[1] = make_float4(g[4], g[5], g[6], g[7]);
 }
 
 // lin_kv reduce: KV[b][d][e] = (sum_s part[b][s][d][e]) / S  (mossformer_block.py:286,289), stored as a two-term

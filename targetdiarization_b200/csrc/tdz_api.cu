@@ -416,7 +416,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.n_tiles = 17;
       P.tps = tps_t;
       CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
-      qk_heads_kernel<<<static_cast<unsigned>((M + 3) / 4), 256, 0, st>>>(qkf, LW.os_gamma, LW.os_beta, rot, qk4, lq_lo,
+      qk_heads_kernel<<<static_cast<unsigned>((M + 4 * QKH_FRAMES - 1) / (4 * QKH_FRAMES)), 256, 0, st>>>(qkf, LW.os_gamma, LW.os_beta, rot, qk4, lq_lo,
                                                                            Sp, S, M);
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
@@ -514,7 +514,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     }
     STEP(ST_FSMN_TAIL) {
       in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
-      fsmn_tail_kernel<<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c, g,
+      fsmn_tail_kernel<<<static_cast<unsigned>((M / TAIL_FRAMES * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c, g,
                                                                                    B, Sp, S);
     }
     STEP(ST_FSMN_C2) {  // conv2 + residual; also the bf16 copy and ScaleNorm sums the next FLASH layer needs
