@@ -744,6 +744,90 @@ struct AttnOut {
       }
     }
   }
+  // ---- paired launch: the two query tiles of one 256-frame group share the whole B operand (keys / kv rows)
+  __device__ static int num_pair_tiles(const Params& P) { return (P.B * P.Sp / 256) * 8; }
+  __device__ static void pair_tile_info(const Params& P, int w, uint32_t rank, TileInfo& ti) {
+    tile_info(P, ((w >> 3) * 2 + static_cast<int>(rank)) * 8 + (w & 7), ti);
+  }
+  __device__ static void load_pair(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar,
+                                   uint32_t rank) {
+    const int j0 = 2 * static_cast<int>(rank);  // this CTA multicasts B boxes j0, j0+1 (of 4) to both CTAs
+    if (kb < 4) {
+      const int g0 = (ti.t0 / 256) * 256;
+      tma_load_3d(sa, &P.tmP, bar, kb * 64, ti.t0, ti.b);
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = j0 + jj;
+        const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
+        tma_load_3d_mc(sb + j * 8192, &P.tmVUmn, bar, ch, g0 + kb * 64, ti.b, 0x3);
+      }
+    } else {
+      const int kk = kb - 4;
+      const int k0 = (kk & 1) * 64;
+      if (kk < 4) {
+        tma_load_3d(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);
+      } else {
+        tma_load_3d(sa, &P.tmLQlo, bar, k0, ti.t0, ti.b);
+      }
+      const int kvrow = ((kk >> 1) == 1 ? 128 : 0) + k0;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = j0 + jj;
+        const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
+        tma_load_3d_mc(sb + j * 8192, &P.tmKVmn, bar, ch, kvrow, ti.b, 0x3);
+      }
+    }
+  }
+  // v / u of this thread's row and 64 columns (bf16), fetched ahead of the accumulator
+  struct EpiPrefetch {
+    uint4 v[8], u[8];
+  };
+  __device__ static void epi_prefetch(const Params& P, const TileInfo& ti, int row, int half, EpiPrefetch& pre) {
+    const int t = ti.t0 + row;
+    if (t < P.S) {
+      const size_t grow = static_cast<size_t>(ti.m0) + row;
+      const uint4* vp = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + ti.n0 + half * 64);
+      const uint4* up = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + 1024 + ti.n0 + half * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pre.v[i] = vp[i];
+        pre.u[i] = up[i];
+      }
+    }
+  }
+  __device__ static void epilogue_pre(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                      const EpiPrefetch& pre) {
+    const int t = ti.t0 + row;
+    const bool valid = t < P.S;
+    const size_t grow = static_cast<size_t>(ti.m0) + row;
+    float ssq = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 16) {
+      const int c0 = half * 64 + cc;
+      float av[16], au[16];
+      tmem_ld16(tacc + c0, av);
+      tmem_ld16(tacc + 128 + c0, au);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&pre.v[cc / 8]);
+      const __nv_bfloat16* ub = reinterpret_cast<const __nv_bfloat16*>(&pre.u[cc / 8]);
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float v = __bfloat162float(vb[j]);
+        const float u = __bfloat162float(ub[j]);
+        const float x = (au[j] * v) * sigmoid_f(av[j] * u);
+        o[j] = x;
+        ssq += x * x;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(P.o + grow * 1024 + ti.n0 + c0);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                            pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+    }
+    P.o_ss[grow * 16 + ti.aux * 2 + half] = valid ? ssq : 0.f;
+  }
   // o_ss holds 16 partial sums per row: index = 2 * n_tile + half (the consumer adds them in index order)
   __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
                                   const EpiCtx&) {

@@ -426,7 +426,13 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       kv_reduce_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
           kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
     }
-    STEP(ST_ATT_OUT) CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
+    STEP(ST_ATT_OUT) {
+      if (getenv("TDZ_ATT_SINGLE")) {  // development switch: un-paired launch
+        CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_pair<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
+      }
+    }
     STEP(ST_TO_OUT) {  // ScaleNorm(1024) + to_out Linear + SiLU + ConvModule + FLASH residual (mossformer_block.py:219)
       LinearParams P;
       lin_base(P, m_o, LM.w_out, 512, 1024, 256);
