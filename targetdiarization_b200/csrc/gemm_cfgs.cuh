@@ -296,12 +296,15 @@ constexpr int PANEL_LD = 132;  // floats per panel row: 128 + 4 keeps the row-wi
 //   phase 2  warp = row, lane = 4 consecutive columns: residual / gate operands are read and all outputs written
 //            as 512 B (fp32) or 256 B (bf16) contiguous row segments; activation, AFF gate, positional encoding,
 //            tf32 rounding and the ScaleNorm partial sums (one warp reduction per row) happen here.
-template <int FMT_, int BLOCK_N_, int STAGES_, unsigned EF, int ACT>
+template <int FMT_, int BLOCK_N_, int STAGES_, unsigned EF, int ACT, int ES = 2>
 struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   using Params = LinearParams;
   static_assert(BLOCK_N_ == 128 || BLOCK_N_ == 256, "panel epilogue handles 128-column panels");
+  static_assert(ES == 2 || ES == 4, "8 or 16 epilogue warps");
   static constexpr int BLOCK_N = BLOCK_N_;
-  static constexpr int EPI_SPLIT = 2;
+  static constexpr int EPI_SPLIT = ES;      // ES = 4: 16 epilogue warps, twice the rows (global loads) in flight
+  static constexpr int PCOLS = 128 / ES;    // panel columns per thread in phase 1
+  static constexpr int PROWS = 128 / (4 * ES);  // panel rows per warp in phase 2
   static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4;
   // rows a warp has in flight in phase 2: the global operand loads of RB rows (512 B each) are issued together
   static constexpr int RB = ((EF & EF_MUL) != 0 || ACT == ACT_AFF) ? 4 : 8;
@@ -336,15 +339,15 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
       sB = e.sampB[ti.b];
     }
     const int w = cx.tid >> 5, lane = cx.tid & 31;
-    float* prow = cx.panel + row * PANEL_LD + half * 64;
+    float* prow = cx.panel + row * PANEL_LD + half * PCOLS;
 #pragma unroll 1
     for (int pn = 0; pn < BLOCK_N / 128; ++pn) {
       const int pc0 = ti.n0 + pn * 128;  // first output column of the panel
       if (pc0 >= P.N) break;             // warp-uniform
       // ---- phase 1
 #pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 16) {
-        const int c0 = pn * 128 + half * 64 + cc;
+      for (int cc = 0; cc < PCOLS; cc += 16) {
+        const int c0 = pn * 128 + half * PCOLS + cc;
         if (ti.n0 + c0 >= P.N) break;
         float v[16], bias[16], cs[16];
         tmem_ld16(tacc + c0, v);
@@ -362,7 +365,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-      epi_bar_sync<256>();
+      epi_bar_sync<128 * ES>();
       // ---- phase 2
       {
         const int col = pc0 + 4 * lane;
@@ -376,7 +379,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
           for (int i = 0; i < 4; ++i) pf[i] = __ldg(e.pos_inv_freq + ((col + i) < hlf ? (col + i) : (col + i) - hlf));
         }
 #pragma unroll 1
-        for (int r0 = w * 16; r0 < w * 16 + 16; r0 += RB) {
+        for (int r0 = w * PROWS; r0 < w * PROWS + PROWS; r0 += RB) {
           float4 x4[RB], rsd[RB], ml[RB];
           bool valid[RB];
 #pragma unroll
@@ -447,7 +450,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
           }
         }
       }
-      epi_bar_sync<256>();
+      epi_bar_sync<128 * ES>();
     }
   }
 };

@@ -160,7 +160,7 @@ template <int BN, unsigned EF, int ACT>
 static cudaError_t sv_launch(const LinearParams& P, int sms, cudaStream_t st) {
   if constexpr (BN >= 128) {  // wide outputs go through the coalescing panel epilogue
     constexpr int STAGES = BN == 256 ? 3 : 4;
-    return launch_gemm<LinearPanel<1, BN, STAGES, EF, ACT>>(P, (P.B * P.Sp / 128) * P.n_tiles, sms, st);
+    return launch_gemm<LinearPanel<1, BN, STAGES, EF, ACT, 4>>(P, (P.B * P.Sp / 128) * P.n_tiles, sms, st);
   } else {
     return launch_gemm<LinearGeneric<1, BN, 6, EF, ACT>>(P, (P.B * P.Sp / 128) * P.n_tiles, sms, st);
   }

@@ -389,7 +389,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     P.e.ss_out_ld = 4;
     CUDA_OK((launch_gemm<LinearPanel<2, 256, 3,
                                        EF_SAMP | EF_BIAS | EF_POS | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT | EF_ZERO_PAD,
-                                       ACT_NONE>>(P, mtiles * P.n_tiles, sms, st)));
+                                       ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));
   }
 
   for (int li = 0; li < num_layers; ++li) {
@@ -483,7 +483,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.bias = LW.b_lin;
       P.e.out_bf16 = f1;
       P.e.out_bf_ld = 256;
-      CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_BIAS | EF_OUT_BF16 | EF_ZERO_PAD, ACT_RELU>>(P, mtiles, sms,
+      CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_BIAS | EF_OUT_BF16 | EF_ZERO_PAD, ACT_RELU, 4>>(P, mtiles, sms,
                                                                                                     st)));
     }
     STEP(ST_FSMN_PROJ) {  // fsmn.project
@@ -491,7 +491,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       lin_base(P, m_f1, LM.w_proj, 256, 256, 256);
       P.e.out_f32 = p;
       P.e.out_ld = 256;
-      CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_OUT_F32, ACT_NONE>>(P, mtiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_OUT_F32, ACT_NONE, 4>>(P, mtiles, sms, st)));
     }
     double* st1 = in_stats;
     double* st2 = in_stats + static_cast<size_t>(B) * 512;
@@ -537,7 +537,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.ss_out_ld = 4;
       CUDA_OK((launch_gemm<LinearPanel<2, 256, 3,
                                          EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT | EF_ZERO_PAD,
-                                         ACT_NONE>>(P, mtiles * P.n_tiles, sms, st)));
+                                         ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));
     }
     CUDA_OK(cudaGetLastError());
   }
@@ -562,7 +562,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     P.e.out_f32 = mb;
     P.e.out_ld = 1024;
     // m is only the tf32 operand of the two gate convs: rounded to nearest tf32 on store
-    CUDA_OK((launch_gemm<LinearPanel<2, 256, 3, EF_BIAS | EF_OUT_F32 | EF_ZERO_PAD | EF_ROUND_TF32, ACT_NONE>>(
+    CUDA_OK((launch_gemm<LinearPanel<2, 256, 3, EF_BIAS | EF_OUT_F32 | EF_ZERO_PAD | EF_ROUND_TF32, ACT_NONE, 4>>(
         P, mtiles * P.n_tiles, sms, st)));
   }
   for (int spk = 0; spk < 2; ++spk) {
@@ -583,7 +583,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.mul_ld = 512;
       P.e.out_f32 = sep + static_cast<size_t>(spk) * M * 512;
       P.e.out_ld = 512;
-      CUDA_OK((launch_gemm<LinearPanel<2, 256, 3, EF_MUL | EF_OUT_F32 | EF_ZERO_PAD, ACT_RELU>>(
+      CUDA_OK((launch_gemm<LinearPanel<2, 256, 3, EF_MUL | EF_OUT_F32 | EF_ZERO_PAD, ACT_RELU, 4>>(
           P, mtiles * P.n_tiles, sms, st)));
     }
   }
