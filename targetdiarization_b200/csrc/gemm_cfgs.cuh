@@ -463,79 +463,130 @@ constexpr int CONV_ROWS = 112;  // output frames per 128-row accumulator tile (8
 // statistics (mossformer_block.py:405-409,419-421,301-312; layer_norm.py:9-30).  One tile holds the whole
 // 256-wide row, so both LayerNorms run in the epilogue.  Outputs: c = norm1 output (fp32, later residual)
 // and nhat = (c-mean(c))*rstd(c) in bf16 (the affine of the two inner LayerNorms is folded into W_u|W_v).
+// 16 epilogue warps: thread = (tile row, quarter of the 256 columns); the two LayerNorm statistics are combined
+// across the four threads of a row through shared memory (two-pass: mean, then centred sum of squares), then
+// the values go through the 128-column panel so that c (fp32) and nhat (bf16) are written as whole row segments.
 template <int FMT_, int STAGES_>
 struct LinearLN256 : LinearBase<FMT_, 256, STAGES_> {
   using Params = LinearParams;
-  static constexpr int EPI_SPLIT = 1;
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int, const EpiCtx&) {
+  static constexpr int EPI_SPLIT = 4;
+  static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4 + 128 * 8 * 4;  // panel + per-row scratch [128][8]
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int cq,
+                                  const EpiCtx& cx) {
     const EpiGeneric& e = P.e;
-    const int t = ti.t0 + row;
-    const bool valid = t < P.S;
-    const size_t grow = static_cast<size_t>(ti.m0) + row;
+    float* rowst = cx.panel + 128 * PANEL_LD;  // [128][8]: 4 partials | results
     const float alpha = P.alpha[0];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 16) {
-      float v[16], bias[16];
+    const int w = cx.tid >> 5, lane = cx.tid & 31;
+    const int cb = cq * 64;  // this thread's columns
+    // activation of the accumulator: bias + PReLU
+    auto act = [&](int c0, float* v) {
+      float bias[16];
       tmem_ld16(tacc + c0, v);
       ld_f32x16(e.bias + c0, bias);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x = v[j] + bias[j];
-        x = x >= 0.f ? x : alpha * x;
-        s1 += x;
-        s2 += x * x;
+        const float x = v[j] + bias[j];
+        v[j] = x >= 0.f ? x : alpha * x;
+      }
+    };
+    // ---- statistics of norm1 (two-pass over the row: mean, then centred second moment)
+    float v[16];
+    float s = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 64; cc += 16) {
+      act(cb + cc, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];
+    }
+    rowst[row * 8 + cq] = s;
+    epi_bar_sync<512>();
+    const float mean1 = (rowst[row * 8] + rowst[row * 8 + 1] + rowst[row * 8 + 2] + rowst[row * 8 + 3]) * (1.f / 256.f);
+    s = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 64; cc += 16) {
+      act(cb + cc, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float d = v[j] - mean1;
+        s = fmaf(d, d, s);
       }
     }
-    const float mean1 = s1 * (1.f / 256.f);
-    const float rstd1 = rsqrtf(fmaxf(s2 * (1.f / 256.f) - mean1 * mean1, 0.f) + 1e-5f);
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 16) {
-      float v[16], bias[16], g1[16], b1[16];
-      tmem_ld16(tacc + c0, v);
-      ld_f32x16(e.bias + c0, bias);
+    rowst[row * 8 + 4 + cq] = s;
+    epi_bar_sync<512>();
+    const float rstd1 =
+        rsqrtf((rowst[row * 8 + 4] + rowst[row * 8 + 5] + rowst[row * 8 + 6] + rowst[row * 8 + 7]) * (1.f / 256.f) + 1e-5f);
+    epi_bar_sync<512>();  // everybody has read the partials before they are reused
+    // ---- statistics of the inner LayerNorms on c = norm1 output
+    auto norm1 = [&](int c0, float* x) {  // x: activated values in, c out
+      float g1[16], b1[16];
       ld_f32x16(P.ln_g1 + c0, g1);
       ld_f32x16(P.ln_b1 + c0, b1);
-      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = fmaf((x[j] - mean1) * rstd1, g1[j], b1[j]);
+    };
+    s = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 64; cc += 16) {
+      act(cb + cc, v);
+      norm1(cb + cc, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];
+    }
+    rowst[row * 8 + cq] = s;
+    epi_bar_sync<512>();
+    const float mean2 = (rowst[row * 8] + rowst[row * 8 + 1] + rowst[row * 8 + 2] + rowst[row * 8 + 3]) * (1.f / 256.f);
+    s = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 64; cc += 16) {
+      act(cb + cc, v);
+      norm1(cb + cc, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x = v[j] + bias[j];
-        x = x >= 0.f ? x : alpha * x;
-        x = (x - mean1) * rstd1 * g1[j] + b1[j];
-        v[j] = x;
-        c1 += x;
-        c2 += x * x;
-      }
-      if (valid) {
-        float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * 256 + c0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        const float d = v[j] - mean2;
+        s = fmaf(d, d, s);
       }
     }
-    const float mean2 = c1 * (1.f / 256.f);
-    const float rstd2 = rsqrtf(fmaxf(c2 * (1.f / 256.f) - mean2 * mean2, 0.f) + 1e-5f);
+    rowst[row * 8 + 4 + cq] = s;
+    epi_bar_sync<512>();
+    const float rstd2 =
+        rsqrtf((rowst[row * 8 + 4] + rowst[row * 8 + 5] + rowst[row * 8 + 6] + rowst[row * 8 + 7]) * (1.f / 256.f) + 1e-5f);
+    epi_bar_sync<512>();
+    if (cq == 0) {  // results for phase 2
+      rowst[row * 8] = mean2;
+      rowst[row * 8 + 1] = rstd2;
+    }
+    // ---- values through the panel, 128 columns at a time
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 16) {
-      float v[16], bias[16], g1[16], b1[16];
-      tmem_ld16(tacc + c0, v);
-      ld_f32x16(e.bias + c0, bias);
-      ld_f32x16(P.ln_g1 + c0, g1);
-      ld_f32x16(P.ln_b1 + c0, b1);
-      tmem_ld_wait();
+    for (int pn = 0; pn < 2; ++pn) {
+      if ((cq >> 1) == pn) {
+        float* prow = cx.panel + row * PANEL_LD + (cq & 1) * 64;
+#pragma unroll 1
+        for (int cc = 0; cc < 64; cc += 16) {
+          act(cb + cc, v);
+          norm1(cb + cc, v);
+          float4* dst = reinterpret_cast<float4*>(prow + cc);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = v[j] + bias[j];
-        x = x >= 0.f ? x : alpha * x;
-        x = (x - mean1) * rstd1 * g1[j] + b1[j];
-        v[j] = valid ? (x - mean2) * rstd2 : 0.f;
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
       }
-      uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * 256 + c0);
+      epi_bar_sync<512>();
+      // phase 2: warp = 8 rows, lane = 4 columns
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        o[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      for (int i = 0; i < 8; ++i) {
+        const int r = w * 8 + i;
+        const bool valid = (ti.t0 + r) < P.S;
+        const size_t grow = static_cast<size_t>(ti.m0) + r;
+        const float4 c4 = *reinterpret_cast<const float4*>(cx.panel + r * PANEL_LD + 4 * lane);
+        const float m2 = rowst[r * 8], r2 = rowst[r * 8 + 1];
+        const int col = pn * 128 + 4 * lane;
+        if (valid) *reinterpret_cast<float4*>(e.out_f32 + grow * 256 + col) = c4;
+        const uint2 nb = valid ? make_uint2(pack_bf16((c4.x - m2) * r2, (c4.y - m2) * r2),
+                                            pack_bf16((c4.z - m2) * r2, (c4.w - m2) * r2))
+                               : make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(e.out_bf16 + grow * 256 + col) = nb;
+      }
+      epi_bar_sync<512>();
     }
   }
 };

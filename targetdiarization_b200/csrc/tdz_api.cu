@@ -461,7 +461,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.ln_b1 = LW.ln1_b;
       P.e.out_f32 = c;
       P.e.out_bf16 = nhat;
-      CUDA_OK((launch_gemm<LinearLN256<2, 4>>(P, mtiles, sms, st)));
+      CUDA_OK((launch_gemm<LinearLN256<2, 3>>(P, mtiles, sms, st)));
     }
     STEP(ST_FSMN_UV) {  // to_u | to_v: Linear + SiLU + ConvModule
       LinearParams P;
