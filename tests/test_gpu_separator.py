@@ -96,3 +96,22 @@ def test_real_speech_excerpt_against_reference_run():
     with open(os.path.join(ROOT, "gpurun_out", "parity.jsonl"), "a") as f:
         f.write(json.dumps({"test": "separator_chat_mix_excerpt_vs_reference_run_snr_db", "value": snr}) + "\n")
     assert snr >= 40.0, snr
+
+
+@pytest.mark.parametrize("T", [16, 23, 100, 2055])
+def test_tiny_inputs(T):
+    """Shortest inputs the encoder accepts (T = 16 -> one frame) up to just over one attention group.  With a handful
+    of frames the per-chunk statistics (GroupNorm over frames, InstanceNorm over time) are degenerate and amplify
+    rounding differences, and the reference's own chunk loop cannot process such inputs (pyloudnorm needs 0.4 s), so
+    the three shortest cases are a robustness check with a 35 dB floor (measured 40.8 / 47.9 / 41.4 dB); from one
+    attention group on the 40 dB contract applies."""
+    _full(1, T, 4, min_db=40.0 if T >= 2048 else 35.0)
+
+
+def test_too_short_input_is_an_error():
+    import torch
+    from oracle.synth import random_state_dict
+    from targetdiarization_b200 import Separator
+    sep = Separator(random_state_dict(seed=0), "cuda:0")
+    with pytest.raises(RuntimeError):
+        sep(torch.zeros(1, 15).cuda())
