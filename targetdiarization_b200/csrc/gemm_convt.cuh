@@ -205,9 +205,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
       const int buf = it % CT_NBUF;
       cp_async_wait_all();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * CT_EPI_WARPS) : "memory");  // epilogue warps only
-      float wt[17];
+      float2 wt[17];  // (w_k, w_k): operand of the packed FMA
 #pragma unroll
-      for (int k = 0; k < 17; ++k) wt[k] = cst_buf[buf * CT_CONST_FLOATS + k * 128];
+      for (int k = 0; k < 17; ++k) {
+        const float wk = cst_buf[buf * CT_CONST_FLOATS + k * 128];
+        wt[k] = make_float2(wk, wk);
+      }
       const float hb = 0.5f * cst_buf[buf * CT_CONST_FLOATS + 17 * 128];
       const float* hrs_s = hrs_buf + buf * CT_HRS_FLOATS;
       if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, (it + 1) % CT_NBUF);
@@ -221,7 +224,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
 
       // SiLU(scale * acc + bias) of N freshly loaded accumulator columns, in place; sidx = index of the first one
       // in the per-frame scratch (a multiple of 4)
-      float win[36];
+      // window of 32 consecutive frames as 16 register pairs (frames 2m, 2m+1): the operand form of FFMA2
+      float2 P0[16];
+      float* win = reinterpret_cast<float*>(P0);
       auto activate = [&](float* w, int sidx, auto n_tag) {
         constexpr int N = decltype(n_tag)::value;
 #pragma unroll
@@ -252,13 +257,28 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) rin[j] = (tt0r + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
         }
+        // y + dwconv17(y) for 16 frames with packed FMAs (two fp32 FMAs per issue slot).  Even taps accumulate
+        // into pairs (out[2m], out[2m+1]), odd taps into pairs (out[2m-1], out[2m]): both then read ALIGNED window
+        // pairs P0[m+q], so no shifted copy of the window is needed; the two partial sums are added at the end.
+        float2 accA[8], accB[9];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) accA[m] = P0[m + 4];
+#pragma unroll
+        for (int m = 0; m < 9; ++m) accB[m] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) accA[m] = fma2(wt[2 * q], P0[m + q], accA[m]);
+          if (q < 8) {
+#pragma unroll
+            for (int m = 0; m < 9; ++m) accB[m] = fma2(wt[2 * q + 1], P0[m + q], accB[m]);
+          }
+        }
         float acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = win[j + 8];
-#pragma unroll
-        for (int k = 0; k < 17; ++k) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fmaf(wt[k], win[j + k], acc[j]);
+        for (int m = 0; m < 8; ++m) {
+          acc[2 * m] = accA[m].x + accB[m].y;
+          acc[2 * m + 1] = accA[m].y + accB[m + 1].x;
         }
         if (itn < 4) {  // slide the window: the next 16 accumulator columns
 #pragma unroll
