@@ -648,7 +648,7 @@ struct AttnParams {
   float* kv_part;          // [B][nsplit][128][2048]
   const __nv_bfloat16* vu; // [Mtot][2048]
   __nv_bfloat16* o;        // [Mtot][1024] gated output
-  float* o_ss;             // [Mtot][16]  partial sums of squares of o (ScaleNorm(1024) of to_out)
+  float* o_ss;             // [32][Mtot]  partial sums of squares of o (ScaleNorm(1024) of to_out)
 };
 
 // sim = quad_q quad_k^T / 256 ; attn = relu(sim)^2    (mossformer_block.py:256-258)
@@ -832,6 +832,76 @@ struct AttnOut {
       }
     }
   }
+  // ---- cta_group::2 launch: rank 0 stages the 128 v columns of B, rank 1 the 128 u columns; each its own A rows
+  static constexpr int CG2_STAGES = 6;
+  __device__ static void load_cg2(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar,
+                                  uint32_t rank) {
+    const int ch0 = (rank == 0 ? 0 : 1024) + ti.n0;
+    if (kb < 4) {
+      const int g0 = (ti.t0 / 256) * 256;
+      tma_load_3d_cg2(sa, &P.tmP, bar, kb * 64, ti.t0, ti.b);
+      tma_load_3d_cg2(sb, &P.tmVUmn, bar, ch0, g0 + kb * 64, ti.b);
+      tma_load_3d_cg2(sb + 8192, &P.tmVUmn, bar, ch0 + 64, g0 + kb * 64, ti.b);
+    } else {
+      const int kk = kb - 4;
+      const int k0 = (kk & 1) * 64;
+      if (kk < 4) {
+        tma_load_3d_cg2(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);
+      } else {
+        tma_load_3d_cg2(sa, &P.tmLQlo, bar, k0, ti.t0, ti.b);
+      }
+      const int kvrow = ((kk >> 1) == 1 ? 128 : 0) + k0;
+      tma_load_3d_cg2(sb, &P.tmKVmn, bar, ch0, kvrow, ti.b);
+      tma_load_3d_cg2(sb + 8192, &P.tmKVmn, bar, ch0 + 64, kvrow, ti.b);
+    }
+  }
+  // ---- epilogue of the cta_group::2 launch: 16 warps, thread = one row x 32 v/u columns; v / u are fetched one
+  //      tile ahead with 256-bit loads and the gated output leaves with 256-bit stores (the 128-bit row-per-thread
+  //      form kept the LSU busy for longer than the tile's MMAs take: ncu, stall_lg / long scoreboard on LDTM)
+  static constexpr int CG2_EPI_SPLIT = 4;
+  struct EpiPre4 {
+    U8 v[2], u[2];
+  };
+  __device__ static void epi_prefetch4(const Params& P, const TileInfo& ti, int row, int part, int cc, EpiPre4& pre) {
+    if (ti.t0 + row < P.S) {
+      const __nv_bfloat16* vp = P.vu + (static_cast<size_t>(ti.m0) + row) * 2048 + ti.n0 + part * 32 + cc * 16;
+      pre.v[cc] = ld_global_256(vp);
+      pre.u[cc] = ld_global_256(vp + 1024);
+    }
+  }
+  // `pre` holds v / u of this tile on entry and of tile `nx` (if has_next) on exit: each half is re-requested as
+  // soon as it has been consumed, so the loads of the next tile fly during the rest of this tile's epilogue.
+  __device__ static void epilogue4(const Params& P, const TileInfo& ti, const TileInfo& nx, bool has_next,
+                                   uint32_t tacc, int row, int part, EpiPre4& pre) {
+    const bool valid = ti.t0 + row < P.S;
+    const size_t grow = static_cast<size_t>(ti.m0) + row;
+    float ssq = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = part * 32 + cc * 16;
+      float av[16], au[16];
+      tmem_ld16(tacc + c0, av);
+      tmem_ld16(tacc + 128 + c0, au);
+      tmem_ld_wait();
+      U8 o;
+      if (valid) {
+        const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&pre.v[cc]);
+        const __nv_bfloat16* ub = reinterpret_cast<const __nv_bfloat16*>(&pre.u[cc]);
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float x0 = (au[j] * __bfloat162float(vb[j])) * sigmoid_f(av[j] * __bfloat162float(ub[j]));
+          const float x1 =
+              (au[j + 1] * __bfloat162float(vb[j + 1])) * sigmoid_f(av[j + 1] * __bfloat162float(ub[j + 1]));
+          ssq = fmaf(x0, x0, ssq);
+          ssq = fmaf(x1, x1, ssq);
+          o.r[j / 2] = pack_bf16(x0, x1);
+        }
+      }
+      if (has_next) epi_prefetch4(P, nx, row, part, cc, pre);
+      if (valid) st_global_256(P.o + grow * 1024 + ti.n0 + c0, o);
+    }
+    P.o_ss[(ti.aux * 4 + part) * (static_cast<size_t>(P.B) * P.Sp) + grow] = valid ? ssq : 0.f;
+  }
   // v / u of this thread's row and 64 columns (bf16), fetched ahead of the accumulator
   struct EpiPrefetch {
     uint4 v[8], u[8];
@@ -880,9 +950,12 @@ struct AttnOut {
         dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
                             pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
     }
-    P.o_ss[grow * 16 + ti.aux * 2 + half] = valid ? ssq : 0.f;
+    const size_t mtot = static_cast<size_t>(P.B) * P.Sp;
+    P.o_ss[(ti.aux * 4 + half * 2) * mtot + grow] = valid ? ssq : 0.f;
+    P.o_ss[(ti.aux * 4 + half * 2 + 1) * mtot + grow] = 0.f;
   }
-  // o_ss holds 16 partial sums per row: index = 2 * n_tile + half (the consumer adds them in index order)
+  // o_ss holds 32 partial sums per row, part-major ([32][Mtot]: a warp stores 128 contiguous bytes): index =
+  // 4 * n_tile + column quarter (the consumer adds them in index order)
   __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
                                   const EpiCtx&) {
     const int t = ti.t0 + row;
@@ -923,7 +996,9 @@ struct AttnOut {
         dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
                             pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
     }
-    P.o_ss[grow * 16 + ti.aux * 2 + half] = valid ? ssq : 0.f;
+    const size_t mtot = static_cast<size_t>(P.B) * P.Sp;
+    P.o_ss[(ti.aux * 4 + half * 2) * mtot + grow] = valid ? ssq : 0.f;
+    P.o_ss[(ti.aux * 4 + half * 2 + 1) * mtot + grow] = 0.f;
   }
 };
 

@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
         wt[k] = make_float2(wk, wk);
       }
       const float hb = 0.5f * cst_buf[buf * CT_CONST_FLOATS + 17 * 128];
+      const float2 hb2 = make_float2(hb, hb);
       const float* hrs_s = hrs_buf + buf * CT_HRS_FLOATS;
       if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, (it + 1) % CT_NBUF);
       const int tbase = ti.t0 + col0;  // frame of accumulator column col0
@@ -227,22 +228,40 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
       // window of 32 consecutive frames as 16 register pairs (frames 2m, 2m+1): the operand form of FFMA2
       float2 P0[16];
       float* win = reinterpret_cast<float*>(P0);
-      auto activate = [&](float* w, int sidx, auto n_tag) {
+      auto activate_t = [&](float* w, int sidx, auto n_tag, auto masked_tag) {
         constexpr int N = decltype(n_tag)::value;
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
         for (int i = 0; i < N; i += 4) {  // four frames at a time keeps the scale / mask operands short-lived
           float4 hs = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
           if constexpr (MODE != CONV_UV) hs = *reinterpret_cast<const float4*>(hrs_s + sidx + i);
-          // frames outside [0,S) are SELECTED to zero (their accumulators may hold anything, also NaN: the rows of
-          // the N operand beyond S are never written by the producer kernels)
-          const float a0 = silu_half(fmaf(w[i + 0], hs.x, hb)), a1 = silu_half(fmaf(w[i + 1], hs.y, hb));
-          const float a2 = silu_half(fmaf(w[i + 2], hs.z, hb)), a3 = silu_half(fmaf(w[i + 3], hs.w, hb));
-          const unsigned t = static_cast<unsigned>(tbase + sidx + i);  // negative frames wrap to huge values
-          const unsigned Su = static_cast<unsigned>(P.S);
-          w[i + 0] = (all_valid || t + 0u < Su) ? a0 : 0.f;
-          w[i + 1] = (all_valid || t + 1u < Su) ? a1 : 0.f;
-          w[i + 2] = (all_valid || t + 2u < Su) ? a2 : 0.f;
-          w[i + 3] = (all_valid || t + 3u < Su) ? a3 : 0.f;
+          // h = scale * acc + bias/2 and h + h tanh(h) as packed FMAs on frame pairs
+          const float2 h01 = fma2(make_float2(w[i + 0], w[i + 1]), make_float2(hs.x, hs.y), hb2);
+          const float2 h23 = fma2(make_float2(w[i + 2], w[i + 3]), make_float2(hs.z, hs.w), hb2);
+          const float2 a01 = fma2(h01, make_float2(tanh_approx(h01.x), tanh_approx(h01.y)), h01);
+          const float2 a23 = fma2(h23, make_float2(tanh_approx(h23.x), tanh_approx(h23.y)), h23);
+          if constexpr (!MASKED) {
+            w[i + 0] = a01.x;
+            w[i + 1] = a01.y;
+            w[i + 2] = a23.x;
+            w[i + 3] = a23.y;
+          } else {
+            // frames outside [0,S) are SELECTED to zero (their accumulators may hold anything, also NaN: the rows
+            // of the N operand beyond S are never written by the producer kernels)
+            const unsigned t = static_cast<unsigned>(tbase + sidx + i);  // negative frames wrap to huge values
+            const unsigned Su = static_cast<unsigned>(P.S);
+            w[i + 0] = (t + 0u < Su) ? a01.x : 0.f;
+            w[i + 1] = (t + 1u < Su) ? a01.y : 0.f;
+            w[i + 2] = (t + 2u < Su) ? a23.x : 0.f;
+            w[i + 3] = (t + 3u < Su) ? a23.y : 0.f;
+          }
+        }
+      };
+      auto activate = [&](float* w, int sidx, auto n_tag) {  // warp-uniform: interior tiles carry no masks
+        if (all_valid) {
+          activate_t(w, sidx, n_tag, std::false_type{});
+        } else {
+          activate_t(w, sidx, n_tag, std::true_type{});
         }
       };
       tmem_ld32(tacc, win);
@@ -254,8 +273,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
         if constexpr (MODE == CONV_RESX) {  // residual stream of these 16 frames: in flight during the FMAs
           const int tt0r = tbase + 8 + 16 * itn;
           const float* src = cv.x_in + (static_cast<size_t>(ti.srow) + tt0r) * 512 + c;
+          if (tt0r + 16 <= P.S) {  // warp-uniform fast path: no per-row predicates
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rin[j] = (tt0r + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
+            for (int j = 0; j < 16; ++j) rin[j] = src[static_cast<size_t>(j) * 512];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rin[j] = (tt0r + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
+          }
         }
         // y + dwconv17(y) for 16 frames with packed FMAs (two fp32 FMAs per issue slot).  Even taps accumulate
         // into pairs (out[2m], out[2m+1]), odd taps into pairs (out[2m-1], out[2m]): both then read ALIGNED window
@@ -295,38 +319,32 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
         const int tt0 = tbase + 8 + 16 * itn;  // frame of acc[0]
         const int nrow = min(P.S - tt0, 16);   // rows j < nrow are inside the sample (may be <= 0)
         const size_t grow0 = static_cast<size_t>(ti.srow) + tt0;
-        if constexpr (MODE == CONV_VUQK) {
-          if (c < 2048) {  // warp-uniform (the qk channels are one whole channel tile)
-            __nv_bfloat16* dst = cv.vu + grow0 * 2048 + c;
+        // rows j < nrow are stored; interior tiles (nrow == 16, warp-uniform) take the unpredicated form
+        auto store_rows = [&](auto* dst, size_t ld, auto conv) {
+          if (nrow >= 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[static_cast<size_t>(j) * ld] = conv(j);
+          } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (j < nrow) dst[static_cast<size_t>(j) * 2048] = __float2bfloat16(acc[j]);
+              if (j < nrow) dst[static_cast<size_t>(j) * ld] = conv(j);
+          }
+        };
+        if constexpr (MODE == CONV_VUQK) {
+          if (c < 2048) {  // warp-uniform (the qk channels are one whole channel tile)
+            store_rows(cv.vu + grow0 * 2048 + c, 2048, [&](int j) { return __float2bfloat16(acc[j]); });
           } else {
             // to_qk channels: fp32, OffsetScale + rotary + bf16 split happen in qk_heads_kernel (the 32 rotary
             // channels all sit in one TMEM lane quarter, i.e. on one scheduler: doing that work here serialises it)
-            float* dst = cv.qkf + grow0 * 128 + (c - 2048);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nrow) dst[static_cast<size_t>(j) * 128] = acc[j];
+            store_rows(cv.qkf + grow0 * 128 + (c - 2048), 128, [&](int j) { return acc[j]; });
           }
         }
         if constexpr (MODE == CONV_RESX) {
-          float* dst = cv.x_out + grow0 * 512 + c;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nrow) dst[static_cast<size_t>(j) * 512] = rin[j] + acc[j];
+          store_rows(cv.x_out + grow0 * 512 + c, 512, [&](int j) { return rin[j] + acc[j]; });
         }
         if constexpr (MODE == CONV_UV) {
-          float* dst = cv.xuv + grow0 * 512 + c;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nrow) dst[static_cast<size_t>(j) * 512] = acc[j];
-          if (c < 256) {
-            __nv_bfloat16* db = cv.xubf + grow0 * 256 + c;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nrow) db[static_cast<size_t>(j) * 256] = __float2bfloat16(acc[j]);
-          }
+          store_rows(cv.xuv + grow0 * 512 + c, 512, [&](int j) { return acc[j]; });
+          if (c < 256) store_rows(cv.xubf + grow0 * 256 + c, 256, [&](int j) { return __float2bfloat16(acc[j]); });
         }
       }
     }

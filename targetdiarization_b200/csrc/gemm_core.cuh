@@ -325,6 +325,173 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::EP
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// cta_group::2 variant: the CTA pair executes ONE 256 x 256 MMA per k-step.  Each CTA stages its own 128 rows of A
+// and only its own 128 of the 256 B columns (32 KB per k-block instead of 48), and its tensor core receives the
+// other half of B from the partner, so the shared-memory port of an SM carries 2/3 of the bytes per MMA that the
+// cta_group::1 form needs (operand reads + TMA fills exceed 128 B/clk there, which is what held the 128 x 256
+// single-CTA mainloop at ~2/3 of the MMA rate).  Only the leader (cluster rank 0) issues MMAs:
+//   full[s]    (leader)  <- the leader's expect_tx of both CTAs' bytes + the TMA completions of both CTAs
+//   empty[s]   (each)    <- tcgen05.commit multicast by the leader
+//   tfull[a]   (each)    <- tcgen05.commit multicast by the leader after the last k-block of a tile
+//   tempty[a]  (leader)  <- every epilogue warp of both CTAs (remote mbarrier arrive)
+template <class Cfg>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG2_EPI_SPLIT), 1)
+    gemm_cg2_kernel(const __grid_constant__ typename Cfg::Params P) {
+  constexpr int BLOCK_N = Cfg::BLOCK_N;
+  constexpr int STAGES = Cfg::CG2_STAGES;
+  constexpr int STAGE_B_BYTES = (BLOCK_N / 2) * 128;
+  constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
+  constexpr uint32_t TMEM_COLS = 512;
+  static_assert(BLOCK_N == 256, "cta_group::2 kernel is written for 256-column tiles");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    Cfg::prefetch(P);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * 4 * Cfg::CG2_EPI_SPLIT);  // epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(smem_u32(&s_tmem_base), TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int nwork = Cfg::num_pair_tiles(P);
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t leader_bars = mapa_shared(bar_base, 0);  // full[s] of the leader = leader_bars + 8 s
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < nwork; w += nclusters) {
+        TileInfo ti;
+        Cfg::pair_tile_info(P, w, rank, ti);
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          Cfg::load_cg2(P, ti, kb, sa, sa + GEMM_STAGE_A_BYTES, leader_bars + 8u * stage, rank);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t IDESC = umma_idesc(Cfg::FMT, 2 * GEMM_BLOCK_M, BLOCK_N, Cfg::A_MN, Cfg::B_MN);
+      constexpr uint32_t A_STEP = Cfg::A_MN ? 2048u : 32u;
+      constexpr uint32_t B_STEP = Cfg::B_MN ? 2048u : 32u;
+      constexpr uint32_t A_LBO = Cfg::A_MN ? 8192u : 16u;
+      constexpr uint32_t B_LBO = Cfg::B_MN ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = cluster_id; w < nwork; w += nclusters, ++it) {
+        TileInfo ti;
+        Cfg::pair_tile_info(P, w, 0, ti);
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < ti.nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * A_STEP, A_LBO, 1024u);
+            const uint64_t db = umma_smem_desc(sb + k * B_STEP, B_LBO, 1024u);
+            umma_f16_cg2(tacc, da, db, IDESC, (kb | k) != 0);
+          }
+          umma_commit_cg2_mc(empty_bar(stage), 0x3);
+          if (kb == ti.nkb - 1) umma_commit_cg2_mc(tfull_bar(as), 0x3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int part = (warp - 2) >> 2;
+    const uint32_t leader_tempty = mapa_shared(tempty_bar(0), 0);
+    // The epilogue's global operands (v, u of the thread's row) are requested one tile ahead: each half of the
+    // register set is re-loaded for the next tile right after its last use in the current one.
+    typename Cfg::EpiPre4 pre;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    TileInfo ti, nx;
+    int w = cluster_id;
+    if (w < nwork) {
+      Cfg::pair_tile_info(P, w, rank, ti);
+      Cfg::epi_prefetch4(P, ti, row, part, 0, pre);
+      Cfg::epi_prefetch4(P, ti, row, part, 1, pre);
+    }
+    for (int it = 0; w < nwork; w += nclusters, ++it) {
+      const bool has_next = w + nclusters < nwork;
+      if (has_next) Cfg::pair_tile_info(P, w + nclusters, rank, nx);
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1);
+      tc_fence_after();
+      Cfg::epilogue4(P, ti, nx, has_next, lane_taddr + as * BLOCK_N, row, part, pre);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tempty + 8u * as);
+      ti = nx;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+  }
+}
+
+template <class Cfg>
+cudaError_t launch_gemm_cg2(const typename Cfg::Params& P, int nwork, int num_sms, cudaStream_t st) {
+  constexpr int smem = Cfg::CG2_STAGES * (GEMM_STAGE_A_BYTES + (Cfg::BLOCK_N / 2) * 128) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_cg2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (nwork <= 0) return cudaSuccess;
+  int grid = 2 * nwork < num_sms ? 2 * nwork : (num_sms & ~1);
+  gemm_cg2_kernel<Cfg><<<grid, gemm_threads(Cfg::CG2_EPI_SPLIT), smem, st>>>(P);
+  return cudaGetLastError();
+}
+
 template <class Cfg>
 cudaError_t launch_gemm_pair(const typename Cfg::Params& P, int nwork, int num_sms, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES, 0>();

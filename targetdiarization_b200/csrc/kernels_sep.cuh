@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) qk_heads_kernel(const float* __restrict__
 // from the partial sums of squares the producing GEMM epilogue left behind.  The factor 0.5 belongs to the
 // tanh form of SiLU the consumer uses.  SHIFT: the row is the token-shifted frame (channels 0..255 of the
 // previous frame | channels 256..511 of this frame, :204-207) and `parts` holds 4 sums of 128 channels per frame;
-// otherwise `parts` holds 16 sums per frame.
+// otherwise `parts` holds 32 sums per frame, part-major ([32][rows]).
 template <bool SHIFT>
 __global__ void rowscale_kernel(const float* __restrict__ parts, float* __restrict__ out, int Sp, int S, size_t rows,
                                 float dim_rsqrt) {
@@ -146,10 +146,9 @@ __global__ void rowscale_kernel(const float* __restrict__ parts, float* __restri
   } else {
     ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(parts + row * 16 + 4 * i);
-      ss += (a.x + a.y) + (a.z + a.w);
-    }
+    for (int i = 0; i < 32; i += 4)
+      ss += (parts[i * rows + row] + parts[(i + 1) * rows + row]) +
+            (parts[(i + 2) * rows + row] + parts[(i + 3) * rows + row]);
   }
   out[row] = 0.5f / fmaxf(sqrtf(ss) * dim_rsqrt, 1e-5f);
 }

@@ -206,7 +206,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->qkf = take(m * 128 * 4);
   L->P = take(m * 256 * 2);
   L->o = take(m * 1024 * 2);
-  L->o_ss = take(m * 16 * 4);
+  L->o_ss = take(m * 32 * 4);
   L->c = take(m * 256 * 4);
   L->nhat = take(m * 256 * 2);
   L->xuv = take(m * 512 * 4);
@@ -427,10 +427,13 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
           kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
     }
     STEP(ST_ATT_OUT) {
-      if (getenv("TDZ_ATT_SINGLE")) {  // development switch: un-paired launch
+      // default: one cta_group::2 MMA per CTA pair (M = 256); the env switches select the earlier forms (development)
+      if (getenv("TDZ_ATT_SINGLE")) {
         CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
-      } else {
+      } else if (getenv("TDZ_ATT_PAIR")) {
         CUDA_OK((launch_gemm_pair<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_cg2<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
       }
     }
     STEP(ST_TO_OUT) {  // ScaleNorm(1024) + to_out Linear + SiLU + ConvModule + FLASH residual (mossformer_block.py:219)

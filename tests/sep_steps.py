@@ -198,13 +198,15 @@ def run_step(h, step):
         h.put("lq_lo", lq - lq.to(bf).float(), bf)
         h.run(k)
         ok &= _check(m, "o", tp["o"], h.get("o", bf, 1024), 38)
-        oss = h.get("o_ss", f32, 16).sum(-1)
+        oss = h.get_raw(h.lay.o_ss, f32, 32 * B * h.Sp).view(32, B, h.Sp)[:, :, :S].sum(0)   # part-major [32][Mtot]
         ok &= _check(m, "o_ss", (tp["o"] ** 2).sum(-1), oss, 35)
     elif step == "TO_OUT":
         # ScaleNorm + Linear + SiLU + ConvModule + residual: x = x0 + to_out(o)
         h.put("o", tp["o"], bf)
-        ss = (tp["o"] ** 2).reshape(B, S, 8, 2, 64).sum(-1).reshape(B, S, 16)
-        h.put("o_ss", ss, f32)
+        ss = (tp["o"] ** 2).reshape(B, S, 8, 4, 32).sum(-1).reshape(B, S, 32)
+        ssp = torch.zeros(32, B, h.Sp)
+        ssp[:, :, :S] = ss.permute(2, 0, 1)
+        h.put_raw(h.lay.o_ss, ssp)                                                           # part-major [32][Mtot]
         h.put("x0", tp["x0"], f32)
         h.run(k)
         xf = h.get("x", f32, 512)
