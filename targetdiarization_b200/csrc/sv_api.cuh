@@ -5,6 +5,7 @@
 // BatchNorm (eval) is folded into every convolution by the packer; all convolutions run as tcgen05 GEMMs over
 // NHWC pixel-major activations (3x3 via a bf16 im2col matrix).
 #pragma once
+#include "gemm_conv3.cuh"
 
 struct SvConv {
   CUtensorMap map;
@@ -218,6 +219,46 @@ static int sv_gemm(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const void* A
   return 0;
 }
 
+// 3x3 convolution (stride 1, pad 1) + BN + Hardtanh(0,20) as an implicit GEMM (gemm_conv3.cuh) for the narrow widths
+// (N <= 64: layers 1 and 2, where the im2col matrix was 70 % of the col traffic); input = a (+ b), output in e.
+static bool sv_conv3_supported(const SvConv& c) { return c.BN <= 64; }
+static int sv_conv3(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const __nv_bfloat16* a, int lda, int offa, int H,
+                    int W, int C, int64_t P, int64_t Pp, __nv_bfloat16* out, int out_ld, int out_col0,
+                    const __nv_bfloat16* nx, int nx_ld, int nx_off, __nv_bfloat16* out2, int out2_ld) {
+  Conv3Params CP;
+  memset(&CP, 0, sizeof CP);
+  LinearParams& L = CP.L;
+  L.tmB = c.map;
+  L.B = 1;
+  L.Sp = static_cast<int>(Pp);
+  L.S = static_cast<int>(P);
+  L.N = c.N;
+  L.K = c.K;
+  L.n_tiles = (c.N + c.BN - 1) / c.BN;
+  L.e.bias = c.bias;
+  CP.a = a;
+  CP.lda = lda;
+  CP.offa = offa;
+  CP.H = H;
+  CP.W = W;
+  CP.C = C;
+  CP.out = out;
+  CP.out_ld = out_ld;
+  CP.out_col0 = out_col0;
+  CP.nx = nx;
+  CP.nx_ld = nx_ld;
+  CP.nx_off = nx_off;
+  CP.out2 = out2;
+  CP.out2_ld = out2_ld;
+  if (c.K != 9 * C || (C & 7) != 0 || c.K / 8 > C3_MAX_KCHUNKS) return fail(ctx, "tdz_embed: conv3 shape K=%d C=%d", c.K, C);
+  const int ntiles = static_cast<int>(Pp / 128) * L.n_tiles;
+  cudaError_t r;
+  if (c.BN == 32) r = launch_gemm_conv3<LinearGeneric<1, 32, 6, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
+  else r = launch_gemm_conv3<LinearGeneric<1, 64, 6, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
+  if (r != cudaSuccess) return fail(ctx, "tdz_embed: conv3 launch failed (%s), N=%d K=%d", cudaGetErrorString(r), c.N, c.K);
+  return 0;
+}
+
 static unsigned sv_grid(int64_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -283,14 +324,18 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
       resid = res;
     }
     // four chained 3x3 convs over the channel groups; conv i writes block i of cat4, which is also sp_i
+    const bool implicit = sv_conv3_supported(M.convs[k][0]);
     for (int i = 0; i < 4; ++i) {
-      if (i == 0) {
-        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(c1, 4 * wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
-                                                                   Wc, wd, 1);
-      } else if (!s.aff) {
-        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, col,
-                                                                   n, Hc, Wc, Hc, Wc, wd, 1);
-      } else {
+      // input of conv i: x_0 | sp_{i-1} + x_i | AFF(sp_{i-1}, x_i)
+      const __nv_bfloat16 *ia = c1, *ib = nullptr;
+      int ilda = 4 * wd, ioffa = 0, ildb = 0, ioffb = 0;
+      if (i > 0 && !s.aff) {
+        ia = cat4;
+        ioffa = (i - 1) * wd;
+        ib = c1;
+        ildb = 4 * wd;
+        ioffb = i * wd;
+      } else if (i > 0) {
         // AFF(sp, x_i): two 1x1 convs on cat(sp, x_i), then the gate in the second epilogue
         sv_cat2_kernel<<<sv_grid(P * 2 * (wd / 8)), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, cat2,
                                                                  P, wd);
@@ -306,14 +351,32 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
         e.out_bf16 = fused;
         e.out_bf_ld = wd;
         if (sv_gemm(ctx, st, M.aff_b[k][i - 1], mid, 64, P, Pp, SV_AFF, e)) return 1;
-        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(fused, wd, 0, nullptr, 0, 0, col, n, Hc, Wc, Hc,
-                                                                   Wc, wd, 1);
+        ia = fused;
+        ilda = wd;
       }
       memset(&e, 0, sizeof e);
       e.out_bf16 = cat4;
       e.out_bf_ld = 4 * wd;
       e.out_bf_col0 = i * wd;
-      if (sv_gemm(ctx, st, M.convs[k][i], col, 9 * wd, P, Pp, SV_HT20, e)) return 1;
+      if (implicit) {
+        // the conv gathers ONE map: x_0, the AFF output, or the sum sp_{i-1} + x_i that conv i-1 left in `fused`
+        const bool chain = !s.aff && i < 3;  // this conv also writes sp_i + x_{i+1} for the next one
+        // (ping-pong between `fused` and `cat2`, both unused otherwise in a block without AFF: a conv must not
+        // overwrite the map its neighbours' halos are still being gathered from)
+        __nv_bfloat16* sum_buf[2] = {fused, cat2};
+        if (i > 0 && !s.aff) {
+          ia = sum_buf[(i - 1) & 1];
+          ilda = wd;
+          ioffa = 0;
+        }
+        if (sv_conv3(ctx, st, M.convs[k][i], ia, ilda, ioffa, Hc, Wc, wd, P, Pp, cat4, 4 * wd, i * wd,
+                     chain ? c1 : nullptr, 4 * wd, (i + 1) * wd, chain ? sum_buf[i & 1] : nullptr, wd))
+          return 1;
+      } else {
+        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(
+            ia, ilda, ioffa, ib, ildb, ioffb, col, n, Hc, Wc, Hc, Wc, wd, 1);
+        if (sv_gemm(ctx, st, M.convs[k][i], col, 9 * wd, P, Pp, SV_HT20, e)) return 1;
+      }
     }
     // conv3 (1x1) + BN + shortcut + Hardtanh
     memset(&e, 0, sizeof e);
