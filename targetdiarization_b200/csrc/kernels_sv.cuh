@@ -1,7 +1,7 @@
 // Memory-bound kernels of the ERes2NetV2 speaker embedder (architecture restated in
 // oracle/eres2netv2_port.py).  Feature maps are NHWC "pixel-major" bf16: [N*H*W][C], H = mel axis, W = time axis,
-// so every 1x1 convolution is a plain GEMM over pixels and every 3x3 convolution is a GEMM over an im2col
-// matrix that is written here (9 shifted copies of the - usually 24..192 channel wide - input).  All maps are
+// so every 1x1 convolution is a plain GEMM over pixels and every stride-1 3x3 convolution an implicit GEMM
+// (gemm_conv3.cuh); only the stride-2 layer3_ds convolution goes through the im2col matrix written here.  All maps are
 // tensor-core operands of the next convolution anyway, so they are stored once, in bf16 (accumulation, BN, gates
 // and the residual add happen in fp32 inside the GEMM epilogues).
 #pragma once

@@ -3,7 +3,7 @@
 // blocks (1x1 conv, four chained 3x3 convs on channel groups - joined by addition in layers 1-2 and by the
 // AFF gate in layers 3-4 -, 1x1 conv, shortcut) -> layer3 downsample + AFF fusion -> TSTP pooling -> Linear.
 // BatchNorm (eval) is folded into every convolution by the packer; all convolutions run as tcgen05 GEMMs over
-// NHWC pixel-major activations (3x3 via a bf16 im2col matrix).
+// NHWC pixel-major activations (3x3 convolutions as implicit GEMMs, gemm_conv3.cuh).
 #pragma once
 #include "gemm_conv3.cuh"
 
@@ -121,13 +121,12 @@ static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
     act = std::max(act, pp * planes[l] * 4);
     c1 = std::max(c1, pp * wd * 4);
     sp = std::max(sp, pp * wd);
-    col = std::max(col, pp * wd * 9);
     cat4 = std::max(cat4, pp * wd * 4);
     xs = std::max(xs, pp * (l == 0 ? 64 : planes[l - 1] * 4));
     cat2 = std::max(cat2, pp * wd * 2);
   }
   act = std::max(act, static_cast<size_t>(d.Pp[0]) * 64);
-  col = std::max(col, static_cast<size_t>(d.Pp[3]) * 9216);
+  col = static_cast<size_t>(d.Pp[3]) * 9216;  // only the stride-2 layer3_ds convolution uses an im2col matrix
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -141,7 +140,7 @@ static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
   L->fused = take(sp * 2);   // AFF(sp_{i-1}, x_i)
   L->cat2 = take(cat2 * 2);
   L->mid = take(static_cast<size_t>(d.Pp[2]) * 64 * 2);
-  L->col = take(col * 2);    // im2col matrix
+  L->col = take(col * 2);    // im2col matrix of layer3_ds
   L->cat4 = take(cat4 * 2);  // the four 3x3 conv outputs, concatenated (input of conv3)
   L->res = take(act * 2);    // shortcut conv output
   L->ds = take(static_cast<size_t>(d.Pp[3]) * 2048 * 2);
@@ -219,9 +218,9 @@ static int sv_gemm(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const void* A
   return 0;
 }
 
-// 3x3 convolution (stride 1, pad 1) + BN + Hardtanh(0,20) as an implicit GEMM (gemm_conv3.cuh) for the narrow widths
-// (N <= 64: layers 1 and 2, where the im2col matrix was 70 % of the col traffic); input = a (+ b), output in e.
-static bool sv_conv3_supported(const SvConv& c) { return c.BN <= 64; }
+// 3x3 convolution (stride 1, pad 1) + BN + Hardtanh(0,20) as an implicit GEMM (gemm_conv3.cuh); only the stride-2
+// layer3_ds convolution still goes through the im2col matrix.
+static bool sv_conv3_supported(const SvConv& c) { return c.BN <= 256; }
 static int sv_conv3(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const __nv_bfloat16* a, int lda, int offa, int H,
                     int W, int C, int64_t P, int64_t Pp, __nv_bfloat16* out, int out_ld, int out_col0,
                     const __nv_bfloat16* nx, int nx_ld, int nx_off, __nv_bfloat16* out2, int out2_ld) {
@@ -254,7 +253,9 @@ static int sv_conv3(tdz_ctx* ctx, cudaStream_t st, const SvConv& c, const __nv_b
   const int ntiles = static_cast<int>(Pp / 128) * L.n_tiles;
   cudaError_t r;
   if (c.BN == 32) r = launch_gemm_conv3<LinearGeneric<1, 32, 6, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
-  else r = launch_gemm_conv3<LinearGeneric<1, 64, 6, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
+  else if (c.BN == 64) r = launch_gemm_conv3<LinearGeneric<1, 64, 6, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
+  else if (c.BN == 128) r = launch_gemm_conv3<LinearGeneric<1, 128, 6, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
+  else r = launch_gemm_conv3<LinearGeneric<1, 256, 4, 0u, ACT_NONE>>(CP, ntiles, ctx->num_sms, st);
   if (r != cudaSuccess) return fail(ctx, "tdz_embed: conv3 launch failed (%s), N=%d K=%d", cudaGetErrorString(r), c.N, c.K);
   return 0;
 }

@@ -17,8 +17,9 @@ EMBED_DIM = 192
 class Embedder:
     sample_rate = 16000
     # launches of one tdz_embed call (csrc/sv_api.cuh): stem 1; per block conv1 + [subsample] + [shortcut] +
-    # 4 x (im2col + conv) + [AFF: 3 x (cat + 2 convs)] + conv3 = 31 + 42 + 116 + 59; layer3_ds 2; fuse34/TSTP/Linear 5
-    KERNELS_PER_FORWARD = 1 + 31 + 42 + 116 + 2 + 59 + 5
+    # 4 x implicit-GEMM 3x3 conv + [AFF: 3 x (cat + 2 convs)] + conv3 = 19 + 26 + 92 + 47; layer3_ds 2 (im2col +
+    # GEMM); fuse34/TSTP/Linear 5
+    KERNELS_PER_FORWARD = 1 + 19 + 26 + 92 + 2 + 47 + 5
 
     def __init__(self, state_dict=None, device="cuda:0", max_workspace_bytes=24 << 30, handle=None):
         self.device = torch.device(device)
