@@ -380,39 +380,59 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
         }
 #pragma unroll 1
         for (int r0 = w * PROWS; r0 < w * PROWS + PROWS; r0 += RB) {
-          float4 x4[RB], rsd[RB], ml[RB];
+          // The global operands of all RB rows are requested by UNCONDITIONAL loads issued back to back (padded
+          // rows / columns read an allocated, ignored location; bf16 data stays raw until the compute loop).  With
+          // the loads inside `if (valid)` blocks next to their conversion the compiler serialised them - each row
+          // then paid its own DRAM latency (ncu: 42 % of the epilogue's samples on the first use of a load).
+          float4 x4[RB];
           bool valid[RB];
+          constexpr bool HAS_R = (EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF;
+          constexpr bool HAS_M = (EF & EF_MUL) != 0 || ACT == ACT_AFF;
+          constexpr bool OPS16 = (EF & EF_OPS_BF16) != 0;
+          [[maybe_unused]] float4 rsd[OPS16 ? 1 : RB], ml[OPS16 ? 1 : RB];
+          [[maybe_unused]] uint2 rraw[OPS16 ? RB : 1], mraw[OPS16 ? RB : 1];
+          const int colc = col_ok ? col : 0;
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
-            const int r = r0 + i;
-            valid[i] = (ti.t0 + r) < P.S;
-            x4[i] = *reinterpret_cast<const float4*>(cx.panel + r * PANEL_LD + 4 * lane);
-            const size_t grow = static_cast<size_t>(ti.m0) + r;
-            rsd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ml[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid[i] && col_ok) {
-              if constexpr ((EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF) {
-                if constexpr ((EF & EF_OPS_BF16) != 0)
-                  rsd[i] = ld_bf16x4(reinterpret_cast<const __nv_bfloat16*>(e.resid) + grow * e.resid_ld + col);
-                else
-                  rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + col);
-              }
-              if constexpr ((EF & EF_MUL) != 0 || ACT == ACT_AFF) {
-                if constexpr ((EF & EF_OPS_BF16) != 0)
-                  ml[i] = ld_bf16x4(reinterpret_cast<const __nv_bfloat16*>(e.mul) + grow * e.mul_ld + col);
-                else
-                  ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + col);
-              }
+            const size_t grow = static_cast<size_t>(ti.m0) + r0 + i;
+            if constexpr (HAS_R) {
+              if constexpr (OPS16)
+                rraw[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
+                                                          grow * e.resid_ld + colc);
+              else
+                rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + colc);
+            }
+            if constexpr (HAS_M) {
+              if constexpr (OPS16)
+                mraw[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.mul) +
+                                                          grow * e.mul_ld + colc);
+              else
+                ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + colc);
             }
           }
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
             const int r = r0 + i;
+            valid[i] = (ti.t0 + r) < P.S;
+            x4[i] = *reinterpret_cast<const float4*>(cx.panel + r * PANEL_LD + 4 * lane);
+          }
+          auto bf4 = [](const uint2& u) {
+            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+            const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+            return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x),
+                               __bfloat162float(b.y));
+          };
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int r = r0 + i;
             const int t = ti.t0 + r;
             const size_t grow = static_cast<size_t>(ti.m0) + r;
+            float4 rq = make_float4(0.f, 0.f, 0.f, 0.f), mq = rq;
+            if constexpr (HAS_R) rq = OPS16 ? bf4(rraw[OPS16 ? i : 0]) : rsd[OPS16 ? 0 : i];
+            if constexpr (HAS_M) mq = OPS16 ? bf4(mraw[OPS16 ? i : 0]) : ml[OPS16 ? 0 : i];
             float xv[4] = {x4[i].x, x4[i].y, x4[i].z, x4[i].w};
-            const float rv[4] = {rsd[i].x, rsd[i].y, rsd[i].z, rsd[i].w};
-            const float mv[4] = {ml[i].x, ml[i].y, ml[i].z, ml[i].w};
+            const float rv[4] = {rq.x, rq.y, rq.z, rq.w};
+            const float mv[4] = {mq.x, mq.y, mq.z, mq.w};
             float ssq = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
