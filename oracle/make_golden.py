@@ -18,10 +18,12 @@ outputs of the reference itself on the GPU box, where the reference tree does no
                           1 s signal, mean-normalised
 """
 import ast
+import io
 import os
 import sys
 import textwrap
 import types
+import typing
 
 import numpy as np
 import torch
@@ -132,6 +134,81 @@ def make_host_logic():
     print("host_logic.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_enrolment():
+    """TargetASR.get_target_embedding (is_preprocess=False path) and TargetASR.is_same_person, executed from the
+    reference source with stubs: the embedding of a piece is a deterministic function of its samples, the
+    clusterer labels a fixed pattern, so only the reference's own selection / truncation / reduction rules act."""
+    path = os.path.join(ref_loader.REF_ROOT, "TargetASR.py")
+    ns = {"np": np, "Union": typing.Union, "Literal": typing.Literal, "io": io}
+    labels_for = {}
+
+    class _Clusterer:
+        def __init__(self, **kw):
+            assert kw == {"min_cluster_size": 2, "metric": "euclidean"}, kw
+
+        def fit_predict(self, emb):
+            return labels_for["labels"][:len(emb)]
+    ns["hdbscan"] = types.SimpleNamespace(HDBSCAN=_Clusterer)
+    for name in ("get_target_embedding", "is_same_person", "cosine_similarity"):
+        exec(compile(extract_method(path, "TargetASR", name), "TargetASR." + name, "exec"), ns)
+
+    def toy_embedding(wav_file, embedding_model="eres2netv2_large"):
+        a = np.asarray(wav_file, dtype=np.float64).reshape(-1)
+        e = np.array([a.size, a.sum(), a[:7].sum(), a[-5:].sum()] + [np.sin(a.size * (k + 1) * 1e-3) for k in range(188)])
+        if a.size == 7777:          # one piece yields a NaN embedding (must be skipped)
+            e[3] = np.nan
+        return e.astype(np.float32)
+    fake = types.SimpleNamespace(
+        verbose_log=False, get_speaker_embedding=toy_embedding,
+        ap=types.SimpleNamespace(combine_audio_chunks=lambda audio_data_list: audio_data_list[0]
+                                 if len(audio_data_list) == 1 else np.concatenate(audio_data_list)))
+    fake.cosine_similarity = lambda embedding_a, embedding_b: ns["cosine_similarity"](fake, embedding_a, embedding_b)
+    g = np.random.default_rng(11)
+    cases = [
+        ([3000, 9000, 20000, 399, 6400, 7777], "separate"),
+        ([3000, 9000, 20000, 399, 6400, 7777], "auto"),
+        ([3000, 5000], "auto"),
+        ([50000, 3000, 50000, 100], "auto"),
+        ([500000, 3000], "longest"),
+        ([300000, 300000, 3000], "merge"),
+        ([100, 200, 399], "separate"),
+        ([100, 200], "merge"),
+        ([6400, 6401, 6402, 6403, 6404], "separate"),
+    ]
+    label_sets = [[0, 0, -1, 1, 1, -1], [-1, -1, -1, -1, -1, -1], [0, 0, 0, 0, 0, 0]]
+    out = {"n_cases": np.array([len(cases), len(label_sets)], dtype=np.int64), "seed": np.array([11], dtype=np.int64)}
+    for ci, (lengths, mode) in enumerate(cases):
+        pieces = [(g.standard_normal(n) * 0.1).astype(np.float32) for n in lengths]
+        out[f"c{ci}_lengths"] = np.array(lengths, dtype=np.int64)
+        out[f"c{ci}_mode"] = np.array([["auto", "separate", "merge", "longest"].index(mode)], dtype=np.int64)
+        for li, labels in enumerate(label_sets):
+            labels_for["labels"] = np.array(labels)
+            for cluster in (False, True):
+                # the method takes file paths in a list: the stub's read_audio / audio_resample hand back the prepared
+                # arrays, so the pieces reach the selection rules exactly as after the reference's own reading step
+                fake.ap.read_audio = lambda file_path: (pieces[int(file_path)], 16000)
+                fake.ap.audio_resample = lambda audio_data, orig_sr, target_sr: (audio_data, None)
+                lst = ns["get_target_embedding"](fake, [str(i) for i in range(len(pieces))], False, cluster,
+                                                 "eres2netv2_large", mode, True)
+                one = ns["get_target_embedding"](fake, [str(i) for i in range(len(pieces))], False, cluster,
+                                                 "eres2netv2_large", mode, False)
+                key = f"c{ci}_l{li}_k{int(cluster)}"
+                out[key + "_list"] = np.stack(lst) if len(lst) else np.zeros((0, 192), np.float32)
+                out[key + "_mean"] = np.asarray(one, dtype=np.float32)
+    # is_same_person
+    a = g.standard_normal((4, 192)).astype(np.float32)
+    t = (a.mean(0) + 0.8 * g.standard_normal(192)).astype(np.float32)
+    res = []
+    for thr in (0.2, 0.4, 0.9):
+        r = ns["is_same_person"](fake, [a[i] for i in range(4)], t, thr, True)
+        res.append([float(r["is_same"]), r["score"], float(ns["is_same_person"](fake, a[0], t, thr, False))])
+    out["same_a"] = a
+    out["same_t"] = t
+    out["same_res"] = np.array(res, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, "enrolment.npz"), **out)
+    print("enrolment.npz:", len(out), "arrays")
+
+
 def make_mossformer2():
     pkg = ref_loader.load_reference_modules()
     out = {}
@@ -190,6 +267,7 @@ if __name__ == "__main__":
         sys.exit("the reference tree is not present; golden vectors can only be generated in the build container")
     os.makedirs(GOLDEN, exist_ok=True)
     make_host_logic()
+    make_enrolment()
     make_fbank()
     make_mossformer2()
     make_chat_mix_excerpt()

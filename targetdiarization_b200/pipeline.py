@@ -4,6 +4,8 @@
   SeparationScoringStage.wav_chunk_inference  <-> look2hear.utils.wav_chunk_inference       (look2hear/utils/separator.py:72-132)
   SeparationScoringStage.get_speaker_embedding<-> TargetASR.get_speaker_embedding            (TargetASR.py:155-163)
   SeparationScoringStage.cosine_similarity    <-> TargetASR.cosine_similarity                (TargetASR.py:144-152)
+  SeparationScoringStage.get_target_embedding <-> TargetASR.get_target_embedding             (TargetASR.py:166-258)
+  SeparationScoringStage.same_speaker_batch   <-> TargetDiarizationStream rule 4, batched    (TargetDiarizationStream.py:156-168)
   SeparationScoringStage.separate_and_score   <-> the core of multi_speakers_separate_asr    (TargetASR.py:609-625)
   SeparationScoringStage.score_segments       <-> the per-segment loops                      (TargetDiarization.py:581-629)
 
@@ -229,6 +231,16 @@ def meter_loudness(audio, rate=16000):
 
 
 # ------------------------------------------------------------------------------------------------ the stage
+def _default_hdbscan_labels(emb):
+    """Cluster labels (-1 = noise) as the reference computes them (TargetASR.py:241-242)."""
+    try:
+        import hdbscan  # the reference's dependency
+        return hdbscan.HDBSCAN(min_cluster_size=2, metric="euclidean").fit_predict(emb)
+    except ImportError:
+        from sklearn.cluster import HDBSCAN
+        return HDBSCAN(min_cluster_size=2, metric="euclidean").fit_predict(emb)
+
+
 class SeparationScoringStage:
     """Owns one Separator and one Embedder on one GPU (one process per GPU; `group` = the ranks that share a long
     input).  Method names and arguments follow the reference methods they stand behind."""
@@ -361,6 +373,63 @@ class SeparationScoringStage:
     def score_segments(self, segments, target_embedding):
         """Batched form of the per-segment loops (TargetDiarization.py:581-629): [N] cosine scores on the device."""
         return self.embedder.score_many(segments, target_embedding)
+
+    # ---- SURVEY.md 8f-2: enrolment (TargetASR.get_target_embedding, TargetASR.py:166-258)
+    def get_target_embedding(self, target_audio, is_preprocess=True, is_cluster=True, audio_input_type="separate",
+                             output_embedding_list=True, sampling_rate=16000, vad=None, loudness_control=None,
+                             cluster_labels=None):
+        """Same arguments and return as the reference method for array input (one ndarray or a list of ndarrays at
+        16 kHz; reading / resampling files is the caller's AudioProcessor).  The reference's own models stay
+        callables: `vad(audio) -> [[start_s, end_s], ...]` (FSMN-VAD, ASRProcessor.vad_detection) and
+        `loudness_control(audio, sr) -> audio` (AudioProcessor.audio_loudness_control); with is_preprocess=True both
+        are required.  All selected pieces are embedded by ONE batched embed_many call (grouped by length) instead
+        of one model call per piece.  `cluster_labels` defaults to HDBSCAN(min_cluster_size=2, euclidean) from the
+        `hdbscan` package if installed, else scikit-learn's."""
+        pieces = [np.array(a, dtype=np.float32, copy=True).reshape(-1) for a in
+                  (target_audio if isinstance(target_audio, (list, tuple)) else [target_audio])]
+        if is_preprocess:
+            if vad is None or loudness_control is None:
+                raise ValueError("is_preprocess=True needs the reference's vad and loudness_control callables")
+            done = []
+            for a in pieces:
+                spans = vad(a)
+                if not spans:
+                    continue
+                clips = [a[int(s0 * sampling_rate):int(s1 * sampling_rate)] for s0, s1 in spans]
+                clips = [c for c in clips if c.size]
+                if clips:
+                    a = np.concatenate(clips)
+                done.append(np.asarray(loudness_control(a, sampling_rate), dtype=np.float32).reshape(-1))
+            pieces = done
+        if not pieces:
+            return np.zeros([192], dtype=np.float32)
+        _, picks = P.enrolment_select([p.shape[0] for p in pieces], sampling_rate, audio_input_type)
+        merged = None
+        wavs = []
+        for src, n in picks:
+            if src < 0:
+                merged = np.concatenate(pieces) if merged is None else merged
+                wavs.append(merged[:n])
+            else:
+                wavs.append(pieces[src][:n])
+        embs = self.embedder.embed_many(wavs).cpu().numpy() if wavs else np.zeros((0, 192), np.float32)
+        if is_cluster and len(wavs) > 2 and cluster_labels is None:
+            cluster_labels = _default_hdbscan_labels
+        return P.enrolment_reduce(list(embs), is_cluster, cluster_labels, output_embedding_list)
+
+    # ---- SURVEY.md 8f-3: rule 4 of the streaming gate for many concurrent streams
+    def same_speaker_batch(self, prev_audio, current_chunk, threshold=0.4, verbose_result=False):
+        """TargetDiarizationStream rule 4 (TargetDiarizationStream.py:156-168) for S streams at once: prev_audio[i] =
+        the concatenated earlier chunks of stream i, current_chunk[i] = its newest chunk.  The 2 S clips are
+        embedded in one batched call; the decision is TargetASR.is_same_person per stream."""
+        S = len(prev_audio)
+        if S != len(current_chunk):
+            raise ValueError("one current chunk per stream")
+        if S == 0:
+            return []
+        embs = self.embedder.embed_many(list(prev_audio) + list(current_chunk)).cpu().numpy()
+        return [P.is_same_person(self.cosine_similarity(embs[i], embs[S + i]), threshold, verbose_result)
+                for i in range(S)]
 
     # ---- the benchmark step: B independent chunks, both streams scored
     def run(self, mix_dev, target_embedding):

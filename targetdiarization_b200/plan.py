@@ -5,6 +5,7 @@ with the reference and testable everywhere.
   chunk_bounds            <-> AudioProcessor.separate_speaker window rule      (AudioProcessor.py:892-935)
   ola_plan / OlaPlan      <-> look2hear.utils.wav_chunk_inference segmenting   (look2hear/utils/separator.py:84-112)
   shard_range, *_shard    <-> new: contiguous spans per rank; the reference is single-device
+  enrolment_select / enrolment_reduce <-> the scalar rules of TargetASR.get_target_embedding (TargetASR.py:166-258)
 """
 from dataclasses import dataclass
 
@@ -154,3 +155,57 @@ def is_same_person(similarity, threshold=0.4, verbose_result=False):
     of the existing embeddings and the target embedding."""
     same = similarity >= threshold
     return {"is_same": bool(same), "score": round(float(similarity), 3)} if verbose_result else bool(same)
+
+
+# ---------------------------------------------------------------------------------------------- enrolment rules
+# TargetASR.get_target_embedding (TargetASR.py:166-258) without its model calls: which pieces of the (already
+# VAD-cut, loudness-normalised) enrolment audio are embedded, and how the embeddings are reduced.  The embeddings
+# themselves come from ONE batched Embedder.embed_many call (pipeline.SeparationScoringStage.get_target_embedding).
+def enrolment_select(lengths, sampling_rate=16000, audio_input_type="separate"):
+    """Which pieces are embedded (TargetASR.py:207-227).  `lengths[i]` = samples of piece i.  Returns
+    (mode, [(source, n_samples)]) with source = piece index, or -1 for the concatenation of ALL pieces (mode
+    "merge"); n_samples is the 30 s truncation.  Pieces shorter than 400 samples are dropped (:232-233)."""
+    lengths = [int(n) for n in lengths]
+    if not lengths:
+        return audio_input_type, []
+    longest = max(range(len(lengths)), key=lambda i: lengths[i])   # first maximum, as max(key=...) does
+    normal = [i for i, n in enumerate(lengths) if n >= int(sampling_rate * 0.4)]
+    mode = audio_input_type
+    if mode == "auto":
+        if lengths[longest] >= 3.0 * sampling_rate:
+            mode = "longest"
+        elif len(normal) <= 2:
+            mode = "merge"
+        else:
+            mode = "separate"
+    if mode == "merge":
+        picks = [(-1, sum(lengths))]
+    elif mode == "longest":
+        picks = [(longest, lengths[longest])]
+    else:
+        picks = [(i, lengths[i]) for i in normal]
+    cap = 30 * sampling_rate
+    return mode, [(src, min(n, cap)) for src, n in picks if min(n, cap) >= 400]
+
+
+def enrolment_reduce(embeddings, is_cluster=True, cluster_labels=None, output_embedding_list=True, dim=192):
+    """NaN filter, optional outlier drop by cluster label (-1 = noise; applied only to more than two embeddings and
+    only if something survives) and the final mean (TargetASR.py:235-258).  `cluster_labels(emb [n,dim]) -> [n]`
+    is the clusterer (the reference: hdbscan.HDBSCAN(min_cluster_size=2, metric="euclidean").fit_predict)."""
+    import numpy as np
+    kept = [np.asarray(e, dtype=np.float32).reshape(-1) for e in embeddings]
+    kept = [e for e in kept if not np.isnan(e).any()]
+    if is_cluster and len(kept) > 2:
+        if cluster_labels is None:
+            raise ValueError("is_cluster=True needs a cluster_labels callable")
+        labels = np.asarray(cluster_labels(np.stack(kept)))
+        valid = np.where(labels != -1)[0]
+        if len(valid) > 0:
+            kept = [kept[i] for i in valid]
+    if output_embedding_list:
+        return kept
+    if len(kept) == 0:
+        return np.zeros([dim], dtype=np.float32)
+    if len(kept) == 1:
+        return kept[0]
+    return np.mean(kept, axis=0)

@@ -127,3 +127,56 @@ def test_mossformer2_port_on_real_speech_excerpt():
     with torch.no_grad():
         y = mossformer2_forward(sd, x)
     assert snr_db(torch.from_numpy(gd["out"]), y) >= 90.0
+
+
+# ---------------------------------------------------------------------------------------------- enrolment rules
+def _toy_embedding(a):
+    """The stub embedding oracle/make_golden.py::make_enrolment gave the reference method."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    e = np.array([a.size, a.sum(), a[:7].sum(), a[-5:].sum()] + [np.sin(a.size * (k + 1) * 1e-3) for k in range(188)])
+    if a.size == 7777:
+        e[3] = np.nan
+    return e.astype(np.float32)
+
+
+def test_enrolment_rules_match_reference_run():
+    """plan.enrolment_select / enrolment_reduce against TargetASR.get_target_embedding executed from the reference
+    source (tests/golden/enrolment.npz): selection mode, 0.4 s / 400-sample / 30 s rules, NaN skip, outlier drop,
+    list and mean outputs - bit for bit."""
+    from targetdiarization_b200 import plan
+    z = np.load(os.path.join(GOLDEN, "enrolment.npz"))
+    n_cases, n_labels = (int(v) for v in z["n_cases"])
+    g = np.random.default_rng(int(z["seed"][0]))
+    label_sets = [[0, 0, -1, 1, 1, -1], [-1, -1, -1, -1, -1, -1], [0, 0, 0, 0, 0, 0]]
+    assert n_labels == len(label_sets)
+    for ci in range(n_cases):
+        lengths = [int(v) for v in z[f"c{ci}_lengths"]]
+        mode = ["auto", "separate", "merge", "longest"][int(z[f"c{ci}_mode"][0])]
+        pieces = [(g.standard_normal(n) * 0.1).astype(np.float32) for n in lengths]
+        _, picks = plan.enrolment_select(lengths, 16000, mode)
+        merged = np.concatenate(pieces) if len(pieces) > 1 else pieces[0]
+        embs = [_toy_embedding((merged if src < 0 else pieces[src])[:n]) for src, n in picks]
+        for li, labels in enumerate(label_sets):
+            for cluster in (False, True):
+                fn = lambda e, labels=labels: np.array(labels)[:len(e)]
+                lst = plan.enrolment_reduce(embs, cluster, fn, True)
+                one = plan.enrolment_reduce(embs, cluster, fn, False)
+                key = f"c{ci}_l{li}_k{int(cluster)}"
+                want = z[key + "_list"]
+                assert len(lst) == want.shape[0], (key, len(lst), want.shape)
+                if len(lst):
+                    assert np.array_equal(np.stack(lst), want), key
+                assert np.array_equal(np.asarray(one, dtype=np.float32), z[key + "_mean"]), key
+
+
+def test_is_same_person_matches_reference_run():
+    from oracle import stage_port
+    from targetdiarization_b200 import plan
+    z = np.load(os.path.join(GOLDEN, "enrolment.npz"))
+    a, t = z["same_a"], z["same_t"]
+    sim = stage_port.cosine_similarity(np.mean([a[i] for i in range(4)], axis=0), t)
+    sim0 = stage_port.cosine_similarity(a[0], t)
+    for row, thr in zip(z["same_res"], (0.2, 0.4, 0.9)):
+        r = plan.is_same_person(sim, thr, verbose_result=True)
+        assert float(r["is_same"]) == row[0] and r["score"] == row[1]
+        assert float(plan.is_same_person(sim0, thr)) == row[2]

@@ -160,3 +160,50 @@ def test_full_size_c2_batch_properties(stage):
     s1, s2 = st.separate_speaker(mix[5].cpu().numpy())
     a, b = est[5, 0].cpu().numpy(), est[5, 1].cpu().numpy()
     assert (np.array_equal(s1, a) and np.array_equal(s2, b)) or (np.array_equal(s1, b) and np.array_equal(s2, a))
+
+
+def test_get_target_embedding_batched_equals_per_piece_loop(stage):
+    """the enrolment path with ONE batched embedding call gives what the reference's per-piece loop
+    gives (TargetASR.py:229-258) - same pieces selected, embeddings equal to per-piece calls, same mean."""
+    torch, st = stage
+    from targetdiarization_b200 import plan
+    from targetdiarization_b200.synth import synthetic_mixture
+    lengths = [9000, 6400, 399, 20000, 9000, 7000]
+    pieces = [synthetic_mixture(1, n, seed=40 + i)[0].numpy() for i, n in enumerate(lengths)]
+    labels = lambda e: np.array([0, 0, -1, 1, 1])[:len(e)]
+    lst = st.get_target_embedding(pieces, is_preprocess=False, is_cluster=True, cluster_labels=labels)
+    _, picks = plan.enrolment_select(lengths, 16000, "separate")
+    assert [s for s, _ in picks] == [0, 1, 3, 4, 5]
+    loop = [st.get_speaker_embedding(pieces[s][:n]) for s, n in picks]
+    keep = [0, 1, 3, 4]
+    assert len(lst) == len(keep)
+    for got, k in zip(lst, keep):
+        c = float(np.dot(got, loop[k]) / (np.linalg.norm(got) * np.linalg.norm(loop[k])))
+        assert c > 0.99999, c
+    one = st.get_target_embedding(pieces, is_preprocess=False, is_cluster=True, cluster_labels=labels,
+                                  output_embedding_list=False)
+    assert np.allclose(one, np.mean(lst, axis=0), atol=1e-6)
+    # preprocessing hooks: VAD spans cut and concatenated, loudness callable applied, empty VAD -> piece dropped
+    vad = lambda a: [] if a.shape[0] == 6400 else [[0.0, 0.25], [0.3, 0.5]]
+    got = st.get_target_embedding(pieces[:2], is_preprocess=True, is_cluster=False, vad=vad,
+                                  loudness_control=lambda a, sr: 0.5 * a, audio_input_type="merge")
+    want = st.get_speaker_embedding(0.5 * np.concatenate([pieces[0][:4000], pieces[0][4800:8000]]))
+    assert len(got) == 1 and np.allclose(got[0], want, atol=2e-3)
+    # default clusterer (hdbscan / scikit-learn) runs on real embeddings
+    assert 1 <= len(st.get_target_embedding(pieces, is_preprocess=False, is_cluster=True)) <= 5
+
+
+def test_same_speaker_batch_equals_per_stream_rule4(stage):
+    """rule 4 of the streaming gate for several streams in one batched call."""
+    torch, st = stage
+    from targetdiarization_b200 import plan
+    from targetdiarization_b200.synth import synthetic_mixture
+    prev = [synthetic_mixture(1, n, seed=60 + i)[0].numpy() for i, n in enumerate([19200, 9600, 28800])]
+    cur = [synthetic_mixture(1, 9600, seed=70 + i)[0].numpy() for i in range(3)]
+    cur[1] = prev[1].copy()           # identical audio -> similarity 1 -> same speaker
+    got = st.same_speaker_batch(prev, cur, threshold=0.4, verbose_result=True)
+    for i in range(3):
+        sim = st.cosine_similarity(st.get_speaker_embedding(prev[i]), st.get_speaker_embedding(cur[i]))
+        want = plan.is_same_person(sim, 0.4, verbose_result=True)
+        assert got[i]["is_same"] == want["is_same"] and abs(got[i]["score"] - want["score"]) <= 0.002
+    assert got[1]["is_same"] and got[1]["score"] >= 0.999
