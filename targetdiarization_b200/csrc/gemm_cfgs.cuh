@@ -70,6 +70,7 @@ struct EpiConv {
 struct LinearParams {
   CUtensorMap tmA;  // 3-D {K, Sp, B}, box {KB, 128, 1}
   CUtensorMap tmB;  // 2-D {K, N},     box {KB, BLOCK_N} (split_n: {KB, BLOCK_N/2})
+  CUtensorMap tmAh; // conv GEMM, cta_group::2 form only: the activation with 128-row boxes (half an X tile per CTA)
   int B, Sp, S, N, K;
   int n_tiles;
   int shift_kblocks;  // leading k-blocks read one frame earlier (token shift, mossformer_block.py:204-207)

@@ -67,28 +67,29 @@ struct ConvTTile {
 // CTAs then share X tiles in L2 and walk through DRAM together; contiguous per-CTA ranges were measured 40 % slower
 // on TO_OUT).  The coordinates of the next tile follow from the current ones by increments - the two integer
 // divisions per tile and per role were a measurable part of the epilogue preamble.
-__device__ __forceinline__ void convt_tile(const LinearParams& P, int tile, ConvTTile& ti) {
-  const int mt = tile / P.n_tiles;      // (sample, time tile)
-  ti.ct = tile - mt * P.n_tiles;
+__device__ __forceinline__ void convt_tile(const LinearParams& P, int nct, int tile, ConvTTile& ti) {
+  const int mt = tile / nct;            // (sample, time tile)
+  ti.ct = tile - mt * nct;
   ti.b = mt / P.tps;
   ti.j = mt - ti.b * P.tps;
   ti.t0 = ti.j * CT_ROWS - 8;           // frame of accumulator column 0
   ti.srow = ti.b * P.Sp;
 }
 struct ConvTStep {
-  int dct, dmt;  // gridDim.x = dmt * n_tiles + dct
+  int nct, dct, dmt;  // channel tiles (or tile pairs) per time tile; stride = dmt * nct + dct
 };
-__device__ __forceinline__ ConvTStep convt_step(const LinearParams& P) {
+__device__ __forceinline__ ConvTStep convt_step(int nct, int stride) {
   ConvTStep st;
-  st.dmt = static_cast<int>(gridDim.x) / P.n_tiles;
-  st.dct = static_cast<int>(gridDim.x) - st.dmt * P.n_tiles;
+  st.nct = nct;
+  st.dmt = stride / nct;
+  st.dct = stride - st.dmt * nct;
   return st;
 }
 __device__ __forceinline__ void convt_next(const LinearParams& P, const ConvTStep& st, ConvTTile& ti) {
   ti.ct += st.dct;
   ti.j += st.dmt;
-  if (ti.ct >= P.n_tiles) {
-    ti.ct -= P.n_tiles;
+  if (ti.ct >= st.nct) {
+    ti.ct -= st.nct;
     ++ti.j;
   }
   while (ti.j >= P.tps) {
@@ -99,9 +100,20 @@ __device__ __forceinline__ void convt_next(const LinearParams& P, const ConvTSte
   ti.t0 = ti.j * CT_ROWS - 8;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_constant__ LinearParams P) {
+// CG2 = true: the CTA pair of a cluster owns two neighbouring channel tiles of the same time tile and executes one
+// tcgen05.mma.cta_group::2 (M = 256 channels) per k-step; each CTA stages its own weight tile and only half of the
+// X rows (32 KB per k-block instead of 48).  Used where the operand traffic matters (to_out, K = 1024: 2/3 of the
+// tile's L2 -> SM bytes were operands) and the channel-tile count is even; the epilogue is the same.
+constexpr int CT2_STAGES = 6;
+constexpr int CT2_STAGE_BYTES = GEMM_STAGE_A_BYTES + 128 * 128;  // W tile 16 KB + half an X tile 16 KB
+constexpr int CT2_SMEM_BYTES =
+    CT2_STAGES * CT2_STAGE_BYTES + 256 + CT_NBUF * CT_HRS_FLOATS * 4 + CT_NBUF * CT_CONST_FLOATS * 4 + 1024;
+
+template <int MODE, bool CG2>
+__device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   constexpr int LDW = (MODE == CONV_VUQK) ? 2176 : 512;  // leading dimension of the tap-major tap table
+  constexpr int CT_STAGES = CG2 ? CT2_STAGES : tdz::CT_STAGES;  // (shadow the single-CTA constants)
+  constexpr int CT_STAGE_BYTES = CG2 ? CT2_STAGE_BYTES : tdz::CT_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -115,46 +127,67 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmA);
     tma_prefetch_desc(&P.tmB);
+    if constexpr (CG2) tma_prefetch_desc(&P.tmAh);
     for (int s = 0; s < CT_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), CT_EPI_WARPS);
+      mbar_init(tempty_bar(s), CG2 ? 2 * CT_EPI_WARPS : CT_EPI_WARPS);  // CG2: the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&s_tmem_base), 512);
-    tmem_relinquish();
+    if constexpr (CG2) {
+      tmem_alloc_cg2(smem_u32(&s_tmem_base), 512);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(smem_u32(&s_tmem_base), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  const int ntiles = P.B * P.tps * P.n_tiles;
+  // work items: (channel tile, time tile); CG2: (pair of channel tiles, time tile), one per cluster
+  const int nct = CG2 ? P.n_tiles / 2 : P.n_tiles;
+  const int ntiles = P.B * P.tps * nct;
   const int nkb = P.K / 64;
-  const ConvTStep tstep = convt_step(P);
+  const int first = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const ConvTStep tstep = convt_step(nct, stride);
+  auto chan_tile = [&](const ConvTTile& t) { return CG2 ? 2 * t.ct + static_cast<int>(rank) : t.ct; };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       ConvTTile ti;
-      convt_tile(P, blockIdx.x, ti);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, convt_next(P, tstep, ti)) {
+      convt_tile(P, nct, first, ti);
+      [[maybe_unused]] const uint32_t leader_bars = CG2 ? mapa_shared(bar_base, 0) : 0u;
+      for (int tile = first; tile < ntiles; tile += stride, convt_next(P, tstep, ti)) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), CT_STAGE_BYTES);
           const uint32_t sa = smem_base + stage * CT_STAGE_BYTES;
           const int trow = ti.t0 - (kb < P.shift_kblocks ? 1 : 0);  // token shift (mossformer_block.py:204-207)
-          tma_load_2d(sa, &P.tmB, full_bar(stage), kb * 64, ti.ct * 128);                 // weights: M operand
-          tma_load_3d(sa + GEMM_STAGE_A_BYTES, &P.tmA, full_bar(stage), kb * 64, trow, ti.b);  // frames: N operand
+          if constexpr (CG2) {
+            // both CTAs' bytes are counted on the leader's barrier; each CTA: its weight tile + its half of X
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * CT_STAGE_BYTES);
+            const uint32_t fb = leader_bars + 8u * stage;
+            tma_load_2d_cg2(sa, &P.tmB, fb, kb * 64, chan_tile(ti) * 128);
+            tma_load_3d_cg2(sa + GEMM_STAGE_A_BYTES, &P.tmAh, fb, kb * 64, trow + 128 * static_cast<int>(rank), ti.b);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), CT_STAGE_BYTES);
+            tma_load_2d(sa, &P.tmB, full_bar(stage), kb * 64, ti.ct * 128);                 // weights: M operand
+            tma_load_3d(sa + GEMM_STAGE_A_BYTES, &P.tmA, full_bar(stage), kb * 64, trow, ti.b);  // frames: N operand
+          }
           if (++stage == CT_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -163,12 +196,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC = umma_idesc(1, GEMM_BLOCK_M, 256, 0, 0);
+    if (lane == 0 && rank == 0) {  // CG2: only the leader issues MMAs
+      constexpr uint32_t IDESC = umma_idesc(1, CG2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, 256, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = first; tile < ntiles; tile += stride, ++it) {
         const int as = it & 1;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
@@ -182,10 +215,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_smem_desc(sa + k * 32u, 16u, 1024u);
             const uint64_t db = umma_smem_desc(sb + k * 32u, 16u, 1024u);
-            umma_f16(tacc, da, db, IDESC, (kb | k) != 0);
+            if constexpr (CG2) umma_f16_cg2(tacc, da, db, IDESC, (kb | k) != 0);
+            else umma_f16(tacc, da, db, IDESC, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));
-          if (kb == nkb - 1) umma_commit(tfull_bar(as));
+          if constexpr (CG2) {
+            umma_commit_cg2_mc(empty_bar(stage), 0x3);
+            if (kb == nkb - 1) umma_commit_cg2_mc(tfull_bar(as), 0x3);
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == nkb - 1) umma_commit(tfull_bar(as));
+          }
           if (++stage == CT_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -206,7 +245,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
     const EpiGeneric& e = P.e;
     const EpiConv& cv = P.cv;
     auto prefetch = [&](const ConvTTile& tn, int buf) {  // asynchronous: completes before the tile that uses `buf`
-      const int c = tn.ct * 128 + q * 32 + lane;
+      const int c = chan_tile(tn) * 128 + q * 32 + lane;
       float* cs = cst_buf + buf * CT_CONST_FLOATS;
 #pragma unroll
       for (int k = 0; k < 17; ++k) cp_async4(cs + k * 128, cv.dw_t + k * LDW + c);
@@ -224,12 +263,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
     };
     int it = 0;
     ConvTTile ti, tn;
-    convt_tile(P, blockIdx.x, ti);
-    if (blockIdx.x < ntiles) prefetch(ti, 0);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it, ti = tn) {
+    [[maybe_unused]] const uint32_t leader_tempty = CG2 ? mapa_shared(tempty_bar(0), 0) : 0u;
+    convt_tile(P, nct, first, ti);
+    if (first < ntiles) prefetch(ti, 0);
+    for (int tile = first; tile < ntiles; tile += stride, ++it, ti = tn) {
       tn = ti;
       convt_next(P, tstep, tn);
-      const int c = ti.ct * 128 + q * 32 + lane;  // output channel of this thread
+      const int c = chan_tile(ti) * 128 + q * 32 + lane;  // output channel of this thread
       const int buf = it % CT_NBUF;
       cp_async_wait_all();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * CT_EPI_WARPS) : "memory");  // epilogue warps only
@@ -242,7 +282,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
       const float hb = 0.5f * cst_buf[buf * CT_CONST_FLOATS + 17 * 128];
       const float2 hb2 = make_float2(hb, hb);
       const float* hrs_s = hrs_buf + buf * CT_HRS_FLOATS;
-      if (tile + gridDim.x < ntiles) prefetch(tn, (it + 1) % CT_NBUF);
+      if (tile + stride < ntiles) prefetch(tn, (it + 1) % CT_NBUF);
       const int tbase = ti.t0 + col0;  // frame of accumulator column col0
       const bool all_valid = tbase >= 0 && tbase + 96 <= P.S;
 
@@ -340,7 +380,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
           if (itn == 3) {  // last TMEM read of this tile is done
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+              if constexpr (CG2) mbar_arrive_cluster(leader_tempty + 8u * as);
+              else mbar_arrive(tempty_bar(as));
+            }
           }
           activate(win + 16, 32 + 16 * itn, std::integral_constant<int, 16>{});
         }
@@ -379,11 +422,22 @@ __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_constant__ LinearParams P) {
+  gemm_convt_body<MODE, false>(P);
+}
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CT_THREADS, 1)
+    gemm_convt_cg2_kernel(const __grid_constant__ LinearParams P) {
+  gemm_convt_body<MODE, true>(P);
 }
 
 template <int MODE>
@@ -398,6 +452,23 @@ cudaError_t launch_gemm_convt(const LinearParams& P, int ntiles, int num_sms, cu
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   gemm_convt_kernel<MODE><<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(P);
+  return cudaGetLastError();
+}
+
+// cta_group::2 form; needs an even number of channel tiles and the tmB3 / tmAh maps.  npairs = work items.
+template <int MODE>
+cudaError_t launch_gemm_convt_cg2(const LinearParams& P, int npairs, int num_sms, cudaStream_t st) {
+  constexpr int smem = CT2_SMEM_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_convt_cg2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (npairs <= 0) return cudaSuccess;
+  const int grid = 2 * npairs < num_sms ? 2 * npairs : (num_sms & ~1);
+  gemm_convt_cg2_kernel<MODE><<<grid, CT_THREADS, smem, st>>>(P);
   return cudaGetLastError();
 }
 

@@ -449,10 +449,17 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       rowscale_kernel<false><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(o_ss, hrs, Sp, S, M, 0.03125f);
       P.e.ss_in = hrs;
       P.tmA = m_o256;
+      P.tmAh = m_o;
       P.tmB = LM.w_out128;
       P.n_tiles = 4;
       P.tps = tps_t;
-      CUDA_OK((launch_gemm_convt<CONV_RESX>(P, B * tps_t * 4, sms, st)));
+      // K = 1024: two thirds of a tile's L2 -> SM bytes are operands, so the CTA pair shares the X tile
+      // (cta_group::2, M = 256 channels); TDZ_CONVT_SINGLE selects the single-CTA form (development)
+      if (getenv("TDZ_CONVT_SINGLE")) {
+        CUDA_OK((launch_gemm_convt<CONV_RESX>(P, B * tps_t * 4, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_convt_cg2<CONV_RESX>(P, B * tps_t * 2, sms, st)));
+      }
     }
     // ---------------- GatedFSMNBlockDilated (mossformer_block.py:419-425)
     STEP(ST_FSMN_C1) {  // conv1 + PReLU + norm1 + inner LayerNorm statistics
@@ -475,10 +482,15 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.xuv = xuv;
       P.cv.xubf = xubf;
       P.tmA = m_nhat256;
+      P.tmAh = m_nhat;
       P.tmB = LM.w_uv128;
       P.n_tiles = 4;
       P.tps = tps_t;
-      CUDA_OK((launch_gemm_convt<CONV_UV>(P, B * tps_t * 4, sms, st)));
+      if (getenv("TDZ_CONVT_SINGLE")) {
+        CUDA_OK((launch_gemm_convt<CONV_UV>(P, B * tps_t * 4, sms, st)));
+      } else {
+        CUDA_OK((launch_gemm_convt_cg2<CONV_UV>(P, B * tps_t * 2, sms, st)));
+      }
     }
     STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;
