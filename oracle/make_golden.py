@@ -12,6 +12,9 @@ outputs of the reference itself on the GPU box, where the reference tree does no
                           recording stand-in for self.separater) -> chunk boundaries for a list of lengths;
                           look2hear.utils.wav_chunk_inference (imported by path) with a toy model -> stitched output;
                           TargetASR.cosine_similarity (extracted with `ast`) on fixed vectors
+  enrolment.npz           TargetASR.get_target_embedding (is_preprocess=False) and TargetASR.is_same_person, extracted
+                          with `ast` and run with stub models (deterministic toy embedding, fixed cluster labels):
+                          selection mode, 0.4 s / 400-sample / 30 s rules, NaN skip, outlier drop, list / mean outputs
   chat_mix_excerpt.npz    1.5 s of assets/chat_mix.wav (the reference's demo input, config C1) through the reference
                           MossFormer2 module with the seed-0 synthetic weights
   fbank.npz               torchaudio.compliance.kaldi.fbank (the function the modelscope pipeline calls) on a fixed
