@@ -97,6 +97,9 @@ typedef struct tdz_mossformer2_weights {
 } tdz_mossformer2_weights;
 
 /* ---- handle ---------------------------------------------------------------------------------- */
+/* A handle is bound to `device`: every compute entry point makes that device current for the duration of the
+ * call and restores the caller's current device, so handles on several GPUs may be driven from one thread. The
+ * pointers and the stream passed to a call must belong to the handle's device. */
 int tdz_create(int device, tdz_ctx** out);
 void tdz_destroy(tdz_ctx* ctx);
 const char* tdz_last_error(tdz_ctx* ctx);

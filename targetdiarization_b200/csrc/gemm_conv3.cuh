@@ -321,12 +321,9 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
 template <class Cfg>
 cudaError_t launch_gemm_conv3(const Conv3Params& CP, int ntiles, int num_sms, cudaStream_t st) {
   constexpr int smem = conv3_smem_bytes<Cfg>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_conv3_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_conv3_kernel<Cfg>), smem, configured); e != cudaSuccess)
+    return e;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   gemm_conv3_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_WARPS, smem, st>>>(CP);

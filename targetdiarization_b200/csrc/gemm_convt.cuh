@@ -442,13 +442,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CT_THREADS, 1)
 
 template <int MODE>
 cudaError_t launch_gemm_convt(const LinearParams& P, int ntiles, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_convt_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         CT_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_convt_kernel<MODE>), CT_SMEM_BYTES, configured); e != cudaSuccess)
+    return e;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   gemm_convt_kernel<MODE><<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(P);
@@ -459,13 +455,9 @@ cudaError_t launch_gemm_convt(const LinearParams& P, int ntiles, int num_sms, cu
 template <int MODE>
 cudaError_t launch_gemm_convt_cg2(const LinearParams& P, int npairs, int num_sms, cudaStream_t st) {
   constexpr int smem = CT2_SMEM_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_convt_cg2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_convt_cg2_kernel<MODE>), smem, configured); e != cudaSuccess)
+    return e;
   if (npairs <= 0) return cudaSuccess;
   const int grid = 2 * npairs < num_sms ? 2 * npairs : (num_sms & ~1);
   gemm_convt_cg2_kernel<MODE><<<grid, CT_THREADS, smem, st>>>(P);

@@ -9,6 +9,8 @@
 // for a k-block and what the epilogue does are supplied by a Cfg class, so every dense op of the
 // separator is an instance of this one pipeline.
 #pragma once
+#include <atomic>
+
 #include "ptx.cuh"
 
 namespace tdz {
@@ -25,6 +27,19 @@ struct TileInfo {
   int nkb;  // k-blocks to accumulate
   int aux;  // Cfg specific (group index, split index ...)
 };
+
+// The opt-in dynamic shared-memory size is a per-DEVICE attribute of a kernel: set it once per device (bit mask), so
+// that handles on several GPUs of one process - and concurrent first calls from several threads - both work.
+inline cudaError_t set_max_smem_once(const void* kernel, int smem_bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 // Shared memory of one CTA: operand stages | barriers (256 B) | optional fp32 epilogue panel (Cfg::PANEL_BYTES).
 template <int BLOCK_N, int STAGES, int PANEL_BYTES = 0>
@@ -480,12 +495,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
 template <class Cfg>
 cudaError_t launch_gemm_cg2(const typename Cfg::Params& P, int nwork, int num_sms, cudaStream_t st) {
   constexpr int smem = Cfg::CG2_STAGES * (GEMM_STAGE_A_BYTES + (Cfg::BLOCK_N / 2) * 128) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_cg2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_cg2_kernel<Cfg>), smem, configured); e != cudaSuccess)
+    return e;
   if (nwork <= 0) return cudaSuccess;
   int grid = 2 * nwork < num_sms ? 2 * nwork : (num_sms & ~1);
   gemm_cg2_kernel<Cfg><<<grid, gemm_threads(Cfg::CG2_EPI_SPLIT), smem, st>>>(P);
@@ -495,12 +507,9 @@ cudaError_t launch_gemm_cg2(const typename Cfg::Params& P, int nwork, int num_sm
 template <class Cfg>
 cudaError_t launch_gemm_pair(const typename Cfg::Params& P, int nwork, int num_sms, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES, 0>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_pair_kernel<Cfg>), smem, configured); e != cudaSuccess)
+    return e;
   if (nwork <= 0) return cudaSuccess;
   int grid = 2 * nwork < num_sms ? 2 * nwork : (num_sms & ~1);
   gemm_pair_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT), smem, st>>>(P);
@@ -510,12 +519,9 @@ cudaError_t launch_gemm_pair(const typename Cfg::Params& P, int nwork, int num_s
 template <class Cfg>
 cudaError_t launch_gemm(const typename Cfg::Params& P, int ntiles, int num_sms, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES, Cfg::PANEL_BYTES>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_kernel<Cfg>), smem, configured); e != cudaSuccess)
+    return e;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   gemm_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT), smem, st>>>(P);

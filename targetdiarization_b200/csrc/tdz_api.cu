@@ -61,6 +61,21 @@ static int fail(tdz_ctx* c, const char* fmt, ...) {
                                        __FILE__, __LINE__);                                        \
   } while (0)
 
+// A handle is bound to the device it was created on: the compute entry points make that device current for the
+// duration of the call (and restore the caller's), so handles on several GPUs can be driven from one thread.
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceScope() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 extern "C" const char* tdz_version(void) { return "tdz 0.1 (sm_100a)"; }
 
 extern "C" int tdz_create(int device, tdz_ctx** out) {
@@ -334,12 +349,9 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   dd.seg_len = 1024;  // fixed: per-segment fp32 partial sums must not depend on the batch (bit-identical batching)
   dd.nseg = (S + dd.seg_len - 1) / dd.seg_len;
   {
-    static bool dd_configured = false;
-    if (!dd_configured) {
-      CUDA_OK(cudaFuncSetAttribute(dd_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM_BYTES));
-      CUDA_OK(cudaFuncSetAttribute(dd_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DD_SMEM_BYTES));
-      dd_configured = true;
-    }
+    static std::atomic<unsigned long long> dd1_configured{0}, dd2_configured{0};
+    CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(dd_stream_kernel<1>), DD_SMEM_BYTES, dd1_configured));
+    CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(dd_stream_kernel<2>), DD_SMEM_BYTES, dd2_configured));
   }
 
   const int mtiles = static_cast<int>(M / 128);
@@ -611,12 +623,14 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
 extern "C" int tdz_separate(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* ws,
                             size_t ws_bytes, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   return run_separate(ctx, mix_dev, B, T, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), TDZ_NUM_LAYERS, 0, ST_COUNT);
 }
 extern "C" int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* ws,
                                   size_t ws_bytes, void* stream, int num_layers, int step_lo, int step_hi) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   if (num_layers < 0 || num_layers > TDZ_NUM_LAYERS) return fail(ctx, "bad num_layers");
   std::lock_guard<std::mutex> lk(ctx->mu);
   return run_separate(ctx, mix_dev, B, T, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), num_layers,
@@ -627,6 +641,7 @@ extern "C" int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B,
 extern "C" int tdz_gather_segments(tdz_ctx* ctx, const float* mix_dev, int64_t L, int64_t session, int64_t hop,
                                    int64_t seg_begin, int64_t n_seg, float* seg_dev, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   if (n_seg <= 0) return 0;
   const size_t total = static_cast<size_t>(n_seg) * session;
   gather_segments_kernel<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -638,6 +653,7 @@ extern "C" int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t sessio
                               int64_t n_seg, int64_t L, int64_t out_begin, int64_t n_out, float ratio, float* out_dev,
                               void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   if (n_out <= 0) return 0;
   const size_t total = static_cast<size_t>(n_out) * 2;
   stitch_ola_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -648,6 +664,7 @@ extern "C" int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t sessio
 extern "C" int tdz_stitch_concat(tdz_ctx* ctx, const float* est_dev, int64_t len, int64_t start, int64_t L,
                                  float* out_dev, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   if (start < 0 || start + len > L) return fail(ctx, "tdz_stitch_concat: chunk outside the output");
   CUDA_OK(cudaMemcpy2DAsync(out_dev + start, static_cast<size_t>(L) * 4, est_dev, static_cast<size_t>(len) * 4,
                             static_cast<size_t>(len) * 4, 2, cudaMemcpyDeviceToDevice,
@@ -657,6 +674,7 @@ extern "C" int tdz_stitch_concat(tdz_ctx* ctx, const float* est_dev, int64_t len
 extern "C" int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float* target_dev, int64_t N, int64_t dim,
                                  float* scores_dev, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   if (N <= 0) return 0;
   cosine_scores_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       emb_dev, target_dev, static_cast<int>(N), static_cast<int>(dim), scores_dev);
@@ -669,6 +687,7 @@ extern "C" int tdz_loudness_blocks(tdz_ctx* ctx, const float* x_dev, int64_t n_s
                                    const int64_t* lo_dev, const int64_t* hi_dev, int64_t nblk, double inv_len,
                                    double* ysq_dev, double* z_dev, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   if (n_streams <= 0 || L <= 0 || nblk <= 0) return fail(ctx, "tdz_loudness_blocks: empty input");
   KWeight kw;
   for (int f = 0; f < 2; ++f)
@@ -701,6 +720,7 @@ extern "C" int tdz_set_fbank_tables(tdz_ctx* ctx, const float* window_dev, const
 }
 extern "C" int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t T, float* feat_dev, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->have_fbank) return fail(ctx, "tdz_fbank: tables not set");
   const int64_t frames = tdz_fbank_frames(T);
@@ -736,6 +756,7 @@ extern "C" size_t tdz_embed_workspace_bytes(int64_t N, int64_t frames) {
 extern "C" int tdz_embed(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* emb_dev, void* ws,
                          size_t ws_bytes, void* stream) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->sv) return fail(ctx, "tdz_embed: weights not set");
   if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(ctx, "tdz_embed: workspace must be 1024 B aligned");
@@ -744,6 +765,7 @@ extern "C" int tdz_embed(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t
 extern "C" int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* out_dev, void* ws,
                                size_t ws_bytes, void* stream, int stop_block) {
   if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->sv) return fail(ctx, "tdz_embed: weights not set");
   return sv_embed(ctx, *ctx->sv, feat_dev, N, frames, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream),
