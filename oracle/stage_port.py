@@ -172,3 +172,50 @@ def integrated_loudness(audio, rate=16000, block=0.4):
 def meter_loudness(audio, rate=16000):
     """AudioProcessor.meter_loudness (AudioProcessor.py:1123-1127): integrated LUFS rounded to 0.1."""
     return round(integrated_loudness(audio, rate), 1)
+
+
+def get_target_embedding(audio_data_list, embed, cluster_labels, is_cluster=True, audio_input_type="separate",
+                         output_embedding_list=True, sampling_rate=16000):
+    """TargetASR.get_target_embedding after its preprocessing step (TargetASR.py:203-258), restated with the model
+    calls as parameters: `embed(audio) -> [192]`, `cluster_labels(emb [n,192]) -> [n]` (-1 = noise).  Pinned by
+    tests/golden/enrolment.npz (the reference method itself, run from source with the same stubs)."""
+    audio_data_list = list(audio_data_list)
+    if not audio_data_list:
+        return np.zeros([192], dtype=np.float32)
+    longest_audio = max(audio_data_list, key=lambda x: x.shape[0])
+    normal_len_audios = [a for a in audio_data_list if a.shape[0] >= int(sampling_rate * 0.4)]
+    merged_audio = audio_data_list[0] if len(audio_data_list) == 1 else np.concatenate(audio_data_list)
+    if audio_input_type == "auto":
+        if longest_audio.shape[0] >= 3.0 * sampling_rate:
+            audio_input_type = "longest"
+        elif len(normal_len_audios) <= 2:
+            audio_input_type = "merge"
+        else:
+            audio_input_type = "separate"
+    if audio_input_type == "merge":
+        chosen = [merged_audio]
+    elif audio_input_type == "longest":
+        chosen = [longest_audio]
+    else:
+        chosen = normal_len_audios
+    chosen = [a[:30 * sampling_rate] if a.shape[0] > 30 * sampling_rate else a for a in chosen]
+    embedding_list = []
+    for a in chosen:
+        if a.shape[0] < 400:
+            continue
+        e = embed(a)
+        if np.isnan(e).any():
+            continue
+        embedding_list.append(e)
+    if is_cluster and len(embedding_list) > 2:
+        labels = np.asarray(cluster_labels(np.stack(embedding_list)))
+        valid = np.where(labels != -1)[0]
+        if len(valid) > 0:
+            embedding_list = [embedding_list[i] for i in valid]
+    if output_embedding_list:
+        return embedding_list
+    if len(embedding_list) == 0:
+        return np.zeros([192], dtype=np.float32)
+    if len(embedding_list) == 1:
+        return embedding_list[0]
+    return np.mean(embedding_list, axis=0)

@@ -180,3 +180,27 @@ def test_is_same_person_matches_reference_run():
         r = plan.is_same_person(sim, thr, verbose_result=True)
         assert float(r["is_same"]) == row[0] and r["score"] == row[1]
         assert float(plan.is_same_person(sim0, thr)) == row[2]
+
+
+def test_oracle_enrolment_restatement_matches_reference_run():
+    """oracle.stage_port.get_target_embedding against the same golden vectors (oracle pinned)."""
+    from oracle import stage_port
+    z = np.load(os.path.join(GOLDEN, "enrolment.npz"))
+    n_cases, _ = (int(v) for v in z["n_cases"])
+    g = np.random.default_rng(int(z["seed"][0]))
+    label_sets = [[0, 0, -1, 1, 1, -1], [-1, -1, -1, -1, -1, -1], [0, 0, 0, 0, 0, 0]]
+    for ci in range(n_cases):
+        lengths = [int(v) for v in z[f"c{ci}_lengths"]]
+        mode = ["auto", "separate", "merge", "longest"][int(z[f"c{ci}_mode"][0])]
+        pieces = [(g.standard_normal(n) * 0.1).astype(np.float32) for n in lengths]
+        for li, labels in enumerate(label_sets):
+            for cluster in (False, True):
+                fn = lambda e, labels=labels: np.array(labels)[:len(e)]
+                lst = stage_port.get_target_embedding(pieces, _toy_embedding, fn, cluster, mode, True)
+                one = stage_port.get_target_embedding(pieces, _toy_embedding, fn, cluster, mode, False)
+                key = f"c{ci}_l{li}_k{int(cluster)}"
+                want = z[key + "_list"]
+                assert len(lst) == want.shape[0], key
+                if len(lst):
+                    assert np.array_equal(np.stack(lst), want), key
+                assert np.array_equal(np.asarray(one, dtype=np.float32), z[key + "_mean"]), key

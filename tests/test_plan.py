@@ -137,3 +137,36 @@ def test_per_segment_rules_match_reference_source():
                                           [None if r["audio"] is None else scores[r["audio"]] for r in result], "a", thr,
                                           method)
         assert got == want, (trial, got, want)
+
+
+# ---------------------------------------------------------------------------------------------- enrolment rules
+def _toy_embed(a):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    e = np.concatenate(([a.size, a.sum(), a[:3].sum()], np.cos(a.size * np.arange(1, 190) * 1e-3)))
+    if a.size % 13 == 0:
+        e[1] = np.nan
+    return e.astype(np.float32)
+
+
+@given(st.lists(st.integers(1, 70000), min_size=0, max_size=7),
+       st.sampled_from(["auto", "separate", "merge", "longest"]), st.booleans(), st.booleans(),
+       st.lists(st.sampled_from([-1, 0, 1]), min_size=7, max_size=7), st.integers(0, 2**31 - 1))
+@settings(max_examples=150, deadline=None)
+def test_enrolment_rules_equal_the_oracle_restatement(lengths, mode, is_cluster, as_list, labels, seed):
+    """plan.enrolment_select + enrolment_reduce == oracle.stage_port.get_target_embedding (the line-by-line
+    restatement of TargetASR.py:203-258) for random piece lengths, modes and cluster labels."""
+    g = np.random.default_rng(seed)
+    pieces = [(g.standard_normal(n) * 0.1).astype(np.float32) for n in lengths]
+    lab = lambda e: np.array(labels)[:len(e)]
+    want = stage_port.get_target_embedding(pieces, _toy_embed, lab, is_cluster, mode, as_list)
+    if not pieces:
+        assert np.array_equal(want, np.zeros(192, np.float32))
+        return
+    _, picks = plan.enrolment_select(lengths, 16000, mode)
+    merged = pieces[0] if len(pieces) == 1 else np.concatenate(pieces)
+    embs = [_toy_embed((merged if s < 0 else pieces[s])[:n]) for s, n in picks]
+    got = plan.enrolment_reduce(embs, is_cluster, lab, as_list)
+    if as_list:
+        assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+    else:
+        assert np.array_equal(np.asarray(got), np.asarray(want))
