@@ -33,6 +33,10 @@ struct tdz_ctx {
   std::string err;
   std::mutex mu;
   bool have_sep = false;
+  // development switches, read once from the environment when the handle is created: earlier kernel forms kept for
+  // A/B measurements (TDZ_ATT_SINGLE / TDZ_ATT_PAIR: attention output without cta_group::2; TDZ_CONVT_SINGLE: the
+  // to_out / to_u|to_v conv GEMMs without cta_group::2)
+  bool att_single = false, att_pair = false, convt_single = false;
   tdz_mossformer2_weights sep;
   // weight tensor maps (built once per tdz_set_mossformer2_weights)
   struct LayerMaps {
@@ -97,6 +101,9 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
     return 6;
   }
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  c->att_single = getenv("TDZ_ATT_SINGLE") != nullptr;
+  c->att_pair = getenv("TDZ_ATT_PAIR") != nullptr;
+  c->convt_single = getenv("TDZ_CONVT_SINGLE") != nullptr;
   *out = c;
   return 0;
 }
@@ -439,10 +446,10 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
           kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
     }
     STEP(ST_ATT_OUT) {
-      // default: one cta_group::2 MMA per CTA pair (M = 256); the env switches select the earlier forms (development)
-      if (getenv("TDZ_ATT_SINGLE")) {
+      // default: one cta_group::2 MMA per CTA pair (M = 256); the development switches select the earlier forms
+      if (ctx->att_single) {
         CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
-      } else if (getenv("TDZ_ATT_PAIR")) {
+      } else if (ctx->att_pair) {
         CUDA_OK((launch_gemm_pair<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
       } else {
         CUDA_OK((launch_gemm_cg2<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
@@ -466,8 +473,8 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.n_tiles = 4;
       P.tps = tps_t;
       // K = 1024: two thirds of a tile's L2 -> SM bytes are operands, so the CTA pair shares the X tile
-      // (cta_group::2, M = 256 channels); TDZ_CONVT_SINGLE selects the single-CTA form (development)
-      if (getenv("TDZ_CONVT_SINGLE")) {
+      // (cta_group::2, M = 256 channels); the convt_single development switch selects the single-CTA form
+      if (ctx->convt_single) {
         CUDA_OK((launch_gemm_convt<CONV_RESX>(P, B * tps_t * 4, sms, st)));
       } else {
         CUDA_OK((launch_gemm_convt_cg2<CONV_RESX>(P, B * tps_t * 2, sms, st)));
@@ -498,7 +505,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.tmB = LM.w_uv128;
       P.n_tiles = 4;
       P.tps = tps_t;
-      if (getenv("TDZ_CONVT_SINGLE")) {
+      if (ctx->convt_single) {
         CUDA_OK((launch_gemm_convt<CONV_UV>(P, B * tps_t * 4, sms, st)));
       } else {
         CUDA_OK((launch_gemm_convt_cg2<CONV_UV>(P, B * tps_t * 2, sms, st)));
