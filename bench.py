@@ -5,11 +5,25 @@ scored per wall-second).
   python bench.py [--gpus N] [--steps K] [--warmup W]            our sm_100a path (libtdz.so)
   python bench.py --impl reference [...]                          the reference's CPU path (oracle port), host cores
 
-One step = one pass of the hot path over one batch of synthetic mixtures: configs[1] of BASELINE.json,
-64 mixtures x 4 s at 16 kHz per GPU (weak scaling: every rank owns its own 64 independent chunks, no
-collective on the data path).  Prints ONE JSON line (rank 0).
+`value` / `e2e` (the headline): one step = one pass of the hot path over one batch of synthetic mixtures -
+configs[1] of BASELINE.json, 64 mixtures x 4 s at 16 kHz per GPU (weak scaling: every rank owns its own 64
+independent chunks, no collective on the data path).  The same JSON line carries, as extra records:
+
+  strong_c3   BASELINE config 3, the split the north_star names: ONE 1 h recording cut into per-rank spans (+ halos
+              in overlap-add mode), separated, cut into 4 s segments that are scored against the target (segments
+              dealt to the ranks), spans and scores gathered by NCCL; host array in -> host arrays out.  Strong
+              scaling; under torchrun the result is compared bit for bit with a single-rank run inside the bench.
+  score_c4    config 4: 4 096 separated segments embedded + scored vs one target (sharded over the ranks)
+  stream_c5   config 5: 600 ms chunks, batch 1 (p50 / p99 latency) and batch 256 concurrent streams (throughput)
+  gpu_eager_baseline   the reference's real incumbent on this box: the PyTorch restatement of the reference modules
+              run eagerly on the B200 (fp32 and TF32), same C2 shape
+  cpu_baseline the reference's CPU path on the box's host cores (a bounded sample)
+Prints ONE JSON line (rank 0).
 """
 import argparse
+import csv
+import glob
+import gzip
 import json
 import os
 import statistics
@@ -28,36 +42,42 @@ METRIC = "audio_seconds_separated_and_scored_per_second"
 UNIT = "audio-s/s"
 WORKLOAD = "C2: 64 synthetic 4 s 2-speaker mixtures/GPU, MossFormer2 separation + fbank/ERes2NetV2 scoring of both streams"
 
-# Algorithmic work per launch step, per frame (= 8 samples) of one chunk (DESIGN.md section 5).
-#   flops: dense contraction FLOPs;  bytes: compulsory HBM bytes (read + write) of that kernel
+# Algorithmic work per launch step, per frame (= 8 samples) of one chunk (DESIGN.md section 4).
+#   flops: dense contraction FLOPs;  bytes: compulsory HBM bytes (read + write) of that step;
+#   bound: what bounds the step ON THIS PART (HBM unless the contraction is deep enough to be tensor bound: the
+#   ridge is peak_flops / peak_bytes ~ 250 FLOP/B, i.e. a K=256 / K=512 projection of fp32 rows is HBM bound);
+#   fmt: operand format of the contraction (selects the tensor peak: tf32 runs at half the bf16 rate)
 STEP_TABLE = {
     "ENCODER": dict(bound="hbm", bytes=32 + 2048),
-    "ENC1X1": dict(bound="tensor", flops=524288, bytes=2048 + 2048 + 1024 + 8),
-    # Linear 512->2176 + SiLU + depthwise k17 (one kernel) + OffsetScale/rotary (small kernel): reads xbf, writes
-    # vu + qk4 + lin_q residual (bf16)
-    "FLASH_IN": dict(bound="tensor", flops=2 * 512 * 2176, bytes=1024 + 4096 + 1024 + 256),
-    "SIM": dict(bound="tensor", flops=2 * 256 * 128, bytes=512 + 512),
-    "KV": dict(bound="tensor", flops=2 * 128 * 2048, bytes=256 + 4096),
-    "ATT_OUT": dict(bound="tensor", flops=2 * 256 * 2048 + 2 * 128 * 2048, bytes=512 + 4096 + 256 + 4096 + 2048),
-    "TO_OUT": dict(bound="tensor", flops=2 * 1024 * 512, bytes=2048 + 2048 + 2048),
-    "FSMN_C1": dict(bound="tensor", flops=2 * 512 * 256, bytes=2048 + 1024 + 512),
-    "FSMN_UV": dict(bound="tensor", flops=2 * 256 * 512, bytes=512 + 2048 + 512),
-    "FSMN_LIN": dict(bound="tensor", flops=2 * 256 * 256, bytes=512 + 512),
-    "FSMN_PROJ": dict(bound="tensor", flops=2 * 256 * 256, bytes=512 + 1024),
+    "ENC1X1": dict(bound="hbm", fmt="tf32", flops=524288, bytes=2048 + 2048 + 1024 + 16),
+    # Linear 512->2176 + SiLU + depthwise k17 (one kernel) + OffsetScale/rotary: reads xbf, writes vu + qk4 + lin_q lo
+    "FLASH_IN": dict(bound="tensor", fmt="bf16", flops=2 * 512 * 2176, bytes=1024 + 4096 + 1024 + 256),
+    "SIM": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 128, bytes=512 + 512),
+    "KV": dict(bound="hbm", fmt="bf16", flops=2 * 128 * 2048, bytes=256 + 4096),
+    "ATT_OUT": dict(bound="tensor", fmt="bf16", flops=2 * 256 * 2048 + 2 * 128 * 2048, bytes=512 + 4096 + 256 + 4096 + 2048),
+    "TO_OUT": dict(bound="tensor", fmt="bf16", flops=2 * 1024 * 512, bytes=2048 + 2048 + 2048),
+    "FSMN_C1": dict(bound="hbm", fmt="tf32", flops=2 * 512 * 256, bytes=2048 + 1024 + 512),
+    "FSMN_UV": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 512, bytes=512 + 2048 + 512),
+    "FSMN_LIN": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 256, bytes=512 + 512),
+    "FSMN_PROJ": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 256, bytes=512 + 1024),
     "DD1": dict(bound="hbm", bytes=1024 + 1024),
     "DD2": dict(bound="hbm", bytes=2048 + 1024),
     "FSMN_TAIL": dict(bound="hbm", bytes=1024 + 2048 + 1024 + 1024),
-    "FSMN_C2": dict(bound="tensor", flops=2 * 256 * 512, bytes=1024 + 2048 + 2048 + 1024),
+    "FSMN_C2": dict(bound="hbm", fmt="tf32", flops=2 * 256 * 512, bytes=1024 + 2048 + 2048 + 1024),
     "FINAL_LN": dict(bound="hbm", bytes=4096),
     "FINAL_GN": dict(bound="hbm", bytes=6144),
-    "OUT1": dict(bound="tensor", flops=2 * 512 * 1024, bytes=2048 + 4096),
-    "TANHSIG": dict(bound="tensor", flops=2 * 2 * 512 * 1024, bytes=4096 + 4096),
-    "DEC1": dict(bound="tensor", flops=2 * 2 * 512 * 512, bytes=4096 + 2048 + 4096),
+    "OUT1": dict(bound="hbm", fmt="tf32", flops=2 * 512 * 1024, bytes=2048 + 4096),
+    "TANHSIG": dict(bound="tensor", fmt="tf32", flops=2 * 2 * 512 * 1024, bytes=4096 + 4096),
+    "DEC1": dict(bound="hbm", fmt="tf32", flops=2 * 2 * 512 * 512, bytes=4096 + 2048 + 4096),
     "DECODER": dict(bound="hbm", bytes=4096 + 64),
 }
 LAYER_STEPS = ["FLASH_IN", "SIM", "KV", "ATT_OUT", "TO_OUT", "FSMN_C1", "FSMN_UV", "FSMN_LIN", "FSMN_PROJ", "DD1",
                "DD2", "FSMN_TAIL", "FSMN_C2"]
 ALL_STEPS = ["ENCODER", "ENC1X1"] + LAYER_STEPS + ["FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1", "DECODER"]
+# the kernel that carries each step's time (name fragment in the ncu export), for `roofline.traffic`
+STEP_KERNEL = {"FLASH_IN": "gemm_convt_kernel<0>", "ATT_OUT": "gemm_cg2_kernel", "TO_OUT": "gemm_convt_cg2_kernel<1>",
+               "FSMN_UV": "gemm_convt_cg2_kernel<2>", "DD1": "dd_stream_kernel<1>", "DD2": "dd_stream_kernel<2>",
+               "FSMN_TAIL": "fsmn_tail_kernel", "DECODER": "decoder_kernel", "ENCODER": "encoder_kernel"}
 
 
 def load_peaks():
@@ -66,8 +86,44 @@ def load_peaks():
         with open(p) as f:
             d = json.load(f)
         return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"],
-                    source="measured")
-    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback")
+                    source="MEASURED_PEAKS.json (burst: each step is timed alone)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback of B200_PROFILING.md")
+
+
+def ncu_traffic(step):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernel, from the committed ncu export
+    (profiles/r2_ncu_raw.csv[.gz]: one `ncu --set full` capture of this bench command, `--page raw --csv`)."""
+    frag = STEP_KERNEL.get(step)
+    if frag is None:
+        return None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_ncu_raw*.csv*")), reverse=True):
+        op = gzip.open if path.endswith(".gz") else open
+        try:
+            with op(path, "rt", newline="") as f:
+                rows = list(csv.reader(f))
+        except OSError:
+            continue
+        if len(rows) < 3:
+            continue
+        hdr = rows[0]
+        try:
+            kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        units = rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for r in rows[2:]:
+            if len(r) > max(kn, rd, wr) and frag in r[kn].replace("(int)", ""):
+                try:
+                    vals.append(float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0)
+                                + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0))
+                except ValueError:
+                    pass
+        if vals:
+            return dict(bytes_per_launch=statistics.median(vals), launches_in_capture=len(vals),
+                        source=os.path.relpath(path, ROOT))
+    return None
 
 
 class ClockSampler:
@@ -114,6 +170,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------ baselines
 def cpu_leg(steps, warmup, sample_items=1):
     """The reference's CPU path for this stage: MossFormer2 forward per chunk (batch 1, serial, as
     AudioProcessor.separate_speaker does) + fbank/ERes2NetV2 embedding of both streams + cosine, fp32, all host
@@ -141,8 +198,46 @@ def cpu_leg(steps, warmup, sample_items=1):
                 times.append(dt)
     per_step = sum(times) / len(times)
     return dict(value=sample_items * SECONDS / per_step, seconds_per_step=per_step, cores=threads,
-                sample=f"{sample_items} x 4 s mixture per step (of the 64 in the workload), batch 1, fp32, "
+                sample=f"{sample_items} x 4 s mixture per step (of the 64 in the workload; the reference processes "
+                       f"chunks one at a time, so the figure does not depend on the batch), batch 1, fp32, "
                        f"{threads} torch threads")
+
+
+def gpu_eager_leg(dev, items=16):
+    """The reference's incumbent on THIS box: the PyTorch restatement of the reference modules run
+    eagerly on the B200, fp32 and TF32 (torch.backends.cuda.matmul.allow_tf32), separation + scoring of both
+    streams, batch `items` of the C2 shape (the eager path keeps every [B,S,2048] activation in fp32: 16 items
+    per call keep it well inside memory; the rate does not grow with a larger batch)."""
+    import torch
+    from oracle.mossformer2_port import mossformer2_forward
+    from oracle.synth import random_state_dict, synthetic_mixture
+    from oracle import eres2netv2_port as E
+    sd = {k: v.to(dev) for k, v in random_state_dict(seed=0).items()}
+    esd = {k: v.to(dev) for k, v in E.random_state_dict(seed=0).items()}
+    mix = synthetic_mixture(items, T, seed=1234).to(dev)
+    out = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            def step():
+                est = mossformer2_forward(sd, mix)                      # [items,2,T]
+                return E.embed(esd, est.view(2 * items, T))
+            step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        out[name] = dict(value=items * SECONDS / (e0.elapsed_time(e1) / 1e3), unit=UNIT, ms_per_step=e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out["sample"] = f"{items} x 4 s mixtures per call, PyTorch eager (cuBLAS / cuDNN kernels), 1 warm-up + 1 timed call"
+    out["kind"] = "port (PyTorch restatement of the reference modules) on cuda"
+    del sd, esd, mix
+    torch.cuda.empty_cache()
+    return out
 
 
 def reference_arm(args):
@@ -155,13 +250,154 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference modules restated in oracle/ (the reference tree cannot "
-                   "travel to the GPU box); CPU only"},
+        "config": {"workload": WORKLOAD, "sample": "each step = ONE 4 s mixture of the 64 (BASELINE.md section 3: a full C2 "
+                   "step takes ~3 min per repetition on the host cores); steps clamped to 3, warm-up to 1",
+                   "note": "reference modules restated in oracle/ (the reference tree cannot travel to the GPU box); "
+                   "CPU only, rank 0 only"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ extra records
+def long_recording(minutes):
+    """`minutes` of synthetic conversation: a 64 s synthetic mixture tiled with per-tile gains (cheap to generate,
+    identical on every rank)."""
+    import numpy as np
+    from targetdiarization_b200.synth import synthetic_mixture
+    L = int(minutes * 60 * SR)
+    base = synthetic_mixture(1, 64 * SR, seed=11)[0].numpy()
+    reps = -(-L // base.shape[0])
+    g = np.random.default_rng(5).uniform(0.5, 1.0, size=reps).astype(np.float32)
+    return (np.tile(base, reps).reshape(reps, -1) * g[:, None]).reshape(-1)[:L].copy()
+
+
+def strong_c3(stage, target_emb, world, rank, dev, minutes, modes):
+    """BASELINE config 3.  The stage is switched to the shared-input (sharded) form for the duration."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from targetdiarization_b200 import pipeline
+    audio = long_recording(minutes)
+    L = audio.shape[0]
+    group = dist.group.WORLD if world > 1 else None
+    stage.group, stage.gather_dst = group, 0
+    rec = {"audio_seconds": L / SR, "segments_scored": 2 * (L // T), "ranks": world, "scaling": "strong",
+           "what": "host ndarray in -> (spk1, spk2) host ndarrays on rank 0 + [2, n_seg] scores + per-segment pick; "
+                   "every rank uploads and separates only its span (+ halo), one NCCL gather of the spans, one "
+                   "all_gather of the scores"}
+    try:
+        for mode in modes:
+            stage.separate_and_score_long(audio[:30 * SR], target_emb, mode=mode, loudness=None)    # warm-up
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            res = stage.separate_and_score_long(audio, target_emb, mode=mode, loudness="device")
+            e1.record()
+            torch.cuda.synchronize(dev)
+            wall_local = time.perf_counter() - t0
+            ms = torch.tensor([e0.elapsed_time(e1), wall_local * 1e3], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.barrier()
+            dev_s, wall_s = float(ms[0]) / 1e3, float(ms[1]) / 1e3
+            # bytes that crossed PCIe on this rank
+            if mode == "concat":
+                b, e = pipeline.P.concat_shard(L, rank, world)[1:] if world > 1 else (0, L)
+            else:
+                plan = pipeline.P.ola_plan(L)
+                sh = pipeline.P.ola_shard(plan, rank, world) if world > 1 else (0, L, 0, plan.num_session)
+                b, e = pipeline.ola_input_range(plan, sh[2], sh[3])
+            r = {"seconds": wall_s, "device_seconds": dev_s, "value": L / SR / wall_s, "unit": UNIT,
+                 "h2d_bytes_rank0": int((e - b) * 4), "d2h_bytes_rank0": int(2 * L * 4 + 2 * (L // T) * 4),
+                 "targets_picked": int((res["target"] > 0).sum())}
+            # the gather alone (same buffers, no compute): what NCCL costs
+            if world > 1:
+                lens = [(L // world) + (1 if i < L % world else 0) for i in range(world)]
+                flat = torch.zeros(2 * max(lens), device=dev)
+                pipeline.gather_spans(stage.kern, flat, lens, group, 0)
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                pipeline.gather_spans(stage.kern, flat, lens, group, 0)
+                g1.record()
+                torch.cuda.synchronize(dev)
+                r["nccl_gather_ms"] = g0.elapsed_time(g1)
+                # bit identity with a single-rank run of the same recording (rank 0 recomputes alone)
+                stage.group = None
+                ok = None
+                if rank == 0:
+                    single = stage.separate_and_score_long(audio, target_emb, mode=mode, loudness="device")
+                    ok = bool(np.array_equal(single["spk1"], res["spk1"]) and np.array_equal(single["spk2"], res["spk2"])
+                              and np.array_equal(single["scores"], res["scores"]))
+                stage.group = group
+                dist.barrier()
+                r["bit_identical_to_single_rank"] = ok
+            rec[mode] = r
+    finally:
+        stage.group, stage.gather_dst = None, None
+    return rec
+
+
+def score_c4(stage, target_emb, world, dev, n_seg=4096):
+    """BASELINE config 4: 4 096 separated 4 s segments embedded + scored against one target (sharded over the ranks
+    when there are several; one all_gather of the scores)."""
+    import torch
+    import torch.distributed as dist
+    from targetdiarization_b200.synth import synthetic_mixture
+    base = synthetic_mixture(64, T + n_seg // 64 * 16, seed=41).to(dev)
+    segs = torch.stack([base[i % 64, (i // 64) * 16:(i // 64) * 16 + T] for i in range(n_seg)])
+    stage.group = dist.group.WORLD if world > 1 else None
+    try:
+        stage.score_segments(segs[:256 * world], target_emb)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scores = stage.score_segments(segs, target_emb)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ok = bool(torch.isfinite(scores).all() and ((scores >= 0) & (scores <= 1)).all())
+    finally:
+        stage.group = None
+    s = float(ms[0]) / 1e3
+    return {"segments": n_seg, "segment_seconds": SECONDS, "seconds": s, "segments_per_second": n_seg / s,
+            "value": n_seg * SECONDS / s, "unit": "audio-s/s (scoring only)", "scores_valid": ok, "ranks": world,
+            "scaling": "strong"}
+
+
+def stream_c5(stage, target_emb, dev, steps=100):
+    """BASELINE config 5: 600 ms chunks (T = 9 600) through separation + scoring of both streams, 100 consecutive
+    steps at batch 1 (latency, host-synchronised per step like a streaming server) and at 256 concurrent streams."""
+    import torch
+    from targetdiarization_b200.synth import synthetic_mixture
+    out = {"chunk_seconds": 0.6}
+    for B, n in ((1, steps), (256, max(steps // 4, 10))):
+        mix = synthetic_mixture(B, 9600, seed=51).to(dev)
+        for _ in range(3):
+            stage.run(mix, target_emb)
+        torch.cuda.synchronize(dev)
+        lat = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            est, scores = stage.run(mix, target_emb)
+            scores.cpu()                      # the pick needs the scores on the host
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        p50, p99 = lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))]
+        out[f"batch{B}"] = {"steps": n, "latency_ms_p50": p50, "latency_ms_p99": p99,
+                            "stream_seconds_per_second": B * 0.6 / (statistics.mean(lat) / 1e3)}
+    return out
 
 
 def main():
@@ -172,6 +408,9 @@ def main():
     ap.add_argument("--impl", default="tdz", choices=["tdz", "reference"])
     ap.add_argument("--items", type=int, default=ITEMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the C2 headline (value / e2e / roofline)")
+    ap.add_argument("--c3-minutes", type=float, default=60.0)
+    ap.add_argument("--c3-modes", default="concat,ola")
     ap.add_argument("--breakdown", default=None, help="write the per-step timing table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -192,7 +431,7 @@ def main():
     warmup = max(args.warmup, 3)
     B = args.items
 
-    stage = SeparationScoringStage.random_init(dev, seed=0)
+    stage = SeparationScoringStage.random_init(dev, seed=0)   # no process group: every rank owns its own mixtures
     mix_host = synthetic_mixture(B, T, seed=1234 + rank).pin_memory()
     target_host = synthetic_mixture(1, T, seed=99)
     target_emb = stage.embed(target_host.to(dev))[0]
@@ -210,8 +449,17 @@ def main():
         scores_host.copy_(scores, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    def timed(fn, k):
-        for _ in range(warmup):
+    mix_np = mix_host.numpy()
+    target_np = target_emb.cpu().numpy()
+
+    def step_dropin():
+        # the reference's own call granularity: one recording per call, numpy in / numpy out
+        # (AudioProcessor.separate_speaker + 2 x get_speaker_embedding + cosine_similarity, TargetASR.py:609-625)
+        for i in range(B):
+            stage.separate_and_score(mix_np[i], target_np, loudness=None)
+
+    def timed(fn, k, warm=warmup):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         if world > 1:
@@ -241,6 +489,8 @@ def main():
 
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = world * B * SECONDS / (ms_e2e / 1e3)
+    ms_dropin = timed(step_dropin, 1, warm=1)
+    dropin_value = world * B * SECONDS / (ms_dropin / 1e3)
 
     # ---- per-step breakdown of the separator (one layer instance of each launch step), CUDA events
     peaks = load_peaks()
@@ -254,33 +504,46 @@ def main():
             mult = 24 if name in LAYER_STEPS else 1
             info = STEP_TABLE[name]
             row = dict(step=name, ms=ms, launches_per_forward=mult, ms_per_forward=ms * mult, bound=info["bound"])
+            if "flops" in info:
+                row["tflops"] = info["flops"] * frames / (ms * 1e-3) / 1e12
+                row["operands"] = info["fmt"]
+            row["gbs"] = info["bytes"] * frames / (ms * 1e-3) / 1e9
             if info["bound"] == "tensor":
-                row["achieved"] = info["flops"] * frames / (ms * 1e-3) / 1e12
-                row["peak"] = peaks["tensor"]
+                row["achieved"] = row["tflops"]
+                row["peak"] = peaks["tensor"] * (0.5 if info["fmt"] == "tf32" else 1.0)   # tf32 MMA: half the bf16 rate
                 row["unit"] = "TFLOP/s"
             else:
-                row["achieved"] = info["bytes"] * frames / (ms * 1e-3) / 1e9
+                row["achieved"] = row["gbs"]
                 row["peak"] = peaks["hbm"]
                 row["unit"] = "GB/s"
             row["frac"] = row["achieved"] / row["peak"]
             rows.append(row)
         rows.sort(key=lambda r: -r["ms_per_forward"])
         top = rows[0]
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-        if os.path.isfile(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-            with open(tp) as f:
-                traffic = json.load(f).get(top["step"])
+        tr = ncu_traffic(top["step"])
         roof = dict(kernel=top["step"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"],
-                    unit=top["unit"], frac=top["frac"], traffic=traffic, peak_source=peaks["source"],
-                    share_of_separator=top["ms_per_forward"] / sum(r["ms_per_forward"] for r in rows))
+                    unit=top["unit"], frac=top["frac"], traffic=tr["bytes_per_launch"] if tr else None,
+                    traffic_source=tr["source"] if tr else None, peak_source=peaks["source"],
+                    algorithmic_bytes_per_launch=STEP_TABLE[top["step"]]["bytes"] * frames,
+                    share_of_separator=top["ms_per_forward"] / sum(r["ms_per_forward"] for r in rows),
+                    steps={r["step"]: dict(ms=round(r["ms"], 4), bound=r["bound"], frac=round(r["frac"], 3),
+                                           unit=r["unit"]) for r in rows})
         if args.breakdown:
             os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
             with open(args.breakdown, "w") as f:
                 json.dump(dict(ms_per_step=ms_step, B=B, T=T, rows=rows), f, indent=1)
 
+    c3 = c4 = c5 = eager = None
+    if not args.no_extras:
+        c3 = strong_c3(stage, target_emb, world, rank, dev, args.c3_minutes,
+                       [m for m in args.c3_modes.split(",") if m])
+        c4 = score_c4(stage, target_emb, world, dev)
+        if rank == 0 and world == 1:
+            c5 = stream_c5(stage, target_emb, dev)
+            eager = gpu_eager_leg(dev)
+
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_leg(1, 0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
@@ -292,16 +555,24 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "items_per_gpu": B, "samples_per_item": T, "weights": "random-init",
                        "l2": "per-step working set ~13 GB of intermediates >> 126 MB L2 (inputs 16 MB); no explicit flush needed",
-                       "parallelism": f"dp{world} (independent chunks, no data-path collective)"},
+                       "parallelism": f"dp{world} (independent chunks, no data-path collective); the sharded "
+                                      "one-recording split is the strong_c3 record"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * B * T * 4, "d2h_bytes_per_step": world * (B * 2 * T * 4 + B * 2 * 4)},
+            "e2e_dropin": {"value": dropin_value, "unit": UNIT, "ms_per_step": ms_dropin,
+                           "what": "the reference's call granularity: 64 x separate_and_score(np.ndarray) = "
+                                   "separate_speaker + 2 embeddings + cosine per recording, numpy in / numpy out, "
+                                   "batch 1 per call"},
             "gpu_launches": stage.launches_per_run(B, T) * args.steps,
             "roofline": roof,
+            "strong_c3": c3, "score_c4": c4, "stream_c5": c5,
+            "gpu_eager_baseline": eager,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

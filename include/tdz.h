@@ -120,6 +120,13 @@ size_t tdz_separate_workspace_bytes(int64_t B, int64_t T);
  * Replaces `self.separater(audio_data_tensor)` (AudioProcessor.py:943). */
 int tdz_separate(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* workspace_dev,
                  size_t workspace_bytes, void* stream);
+/* Same forward with a strided output: stream `spk` of chunk `b` is written to
+ * out_dev + b*out_chunk_stride + spk*out_spk_stride (strides in floats).  With out_chunk_stride = T and
+ * out_spk_stride = the length of the stitched stream, adjacent equal-length windows land directly in the
+ * concatenated [2][L] layout of AudioProcessor.separate_speaker (AudioProcessor.py:947-948): no stitch copy. */
+int tdz_separate_strided(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev,
+                         int64_t out_chunk_stride, int64_t out_spk_stride, void* workspace_dev, size_t workspace_bytes,
+                         void* stream);
 
 /* Test hook: run only the first `num_layers` layer pairs, and of the launch sequence only the steps whose
  * index lies in [step_lo, step_hi] (step numbering: enum Step in csrc/tdz_api.cu; 0..20).  The tests write
@@ -142,6 +149,13 @@ int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_layout* out);
  * [seg_begin, seg_begin+n_seg). */
 int tdz_gather_segments(tdz_ctx* ctx, const float* mix_dev, int64_t L, int64_t session, int64_t hop,
                         int64_t seg_begin, int64_t n_seg, float* seg_dev, void* stream);
+/* Same for a rank that holds only samples [mix_origin, mix_origin + mix_len) of the L-sample mixture (its output
+ * span plus the halo its segments reach into): mix_dev[0] is sample mix_origin.  Samples
+ * outside [0, L) are zeros as above; asking for a sample inside [0, L) but outside the resident range is an error
+ * caught on the host (the segment range is checked against the resident range before the launch). */
+int tdz_gather_segments_span(tdz_ctx* ctx, const float* mix_dev, int64_t mix_origin, int64_t mix_len, int64_t L,
+                             int64_t session, int64_t hop, int64_t seg_begin, int64_t n_seg, float* seg_dev,
+                             void* stream);
 /* Overlap-add (separator.py:126-130): out[trk][n] = (1/ratio) * sum_i est[i][trk][n + (session-hop) - i*hop]
  * over the segments covering n, ascending i (fixed order -> bit-reproducible across shardings).
  * est_dev fp32 [n_seg][2][session] holds segments [seg_begin, seg_begin+n_seg); out_dev fp32 [2][n_out]

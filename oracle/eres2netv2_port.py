@@ -38,8 +38,75 @@ def fbank_features(wav):
     return torch.stack(feats)
 
 
-from targetdiarization_b200.synth import block_specs  # noqa: E402  (architecture table shared with the generator)
-from targetdiarization_b200.synth import random_eres2netv2_state_dict as random_state_dict  # noqa: E402,F401
+# The oracle's OWN architecture table, written out row by row from the published ERes2NetV2 definition
+# (m_channels 64, num_blocks [3,4,6,3], expansion 4; stride 2 on the first block of layers 2-4; AFF joins in layers
+# 3-4) - deliberately not imported from the product package, so that a wrong table on either side shows up as a
+# parity failure (tests/test_oracle_port.py also checks the weight generator against THIS table).
+#   (name, in_planes, planes, stride, joins sub-bands by AFF)
+BLOCK_SPECS = (
+    ("layer1.0", 64, 64, 1, False), ("layer1.1", 256, 64, 1, False), ("layer1.2", 256, 64, 1, False),
+    ("layer2.0", 256, 128, 2, False), ("layer2.1", 512, 128, 1, False), ("layer2.2", 512, 128, 1, False),
+    ("layer2.3", 512, 128, 1, False),
+    ("layer3.0", 512, 256, 2, True), ("layer3.1", 1024, 256, 1, True), ("layer3.2", 1024, 256, 1, True),
+    ("layer3.3", 1024, 256, 1, True), ("layer3.4", 1024, 256, 1, True), ("layer3.5", 1024, 256, 1, True),
+    ("layer4.0", 1024, 512, 2, True), ("layer4.1", 2048, 512, 1, True), ("layer4.2", 2048, 512, 1, True),
+)
+
+
+def block_specs():
+    return list(BLOCK_SPECS)
+
+
+def expected_key_shapes():
+    """{key: shape} of the state dict this restatement consumes, derived from BLOCK_SPECS alone."""
+    sh = {"conv1.weight": (64, 1, 3, 3)}
+
+    def bn(name, c):
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            sh[f"{name}.{k}"] = (c,)
+
+    def aff(name, c):
+        sh[name + ".local_att.0.weight"] = (c // 4, 2 * c, 1, 1)
+        sh[name + ".local_att.0.bias"] = (c // 4,)
+        bn(name + ".local_att.1", c // 4)
+        sh[name + ".local_att.3.weight"] = (c, c // 4, 1, 1)
+        sh[name + ".local_att.3.bias"] = (c,)
+        bn(name + ".local_att.4", c)
+
+    bn("bn1", 64)
+    for name, in_planes, planes, stride, is_aff in BLOCK_SPECS:
+        width = planes * BASE_WIDTH // 64
+        sh[name + ".conv1.weight"] = (width * SCALE, in_planes, 1, 1)
+        bn(name + ".bn1", width * SCALE)
+        for i in range(SCALE):
+            sh[f"{name}.convs.{i}.weight"] = (width, width, 3, 3)
+            bn(f"{name}.bns.{i}", width)
+        if is_aff:
+            for i in range(SCALE - 1):
+                aff(f"{name}.fuse_models.{i}", width)
+        sh[name + ".conv3.weight"] = (planes * EXPANSION, width * SCALE, 1, 1)
+        bn(name + ".bn3", planes * EXPANSION)
+        if stride != 1 or in_planes != planes * EXPANSION:
+            sh[name + ".shortcut.0.weight"] = (planes * EXPANSION, in_planes, 1, 1)
+            bn(name + ".shortcut.1", planes * EXPANSION)
+    sh["layer3_ds.weight"] = (2048, 1024, 3, 3)
+    aff("fuse34", 2048)
+    sh["seg_1.weight"] = (EMBED_DIM, 2 * 2048 * (FEAT_DIM // 8))
+    sh["seg_1.bias"] = (EMBED_DIM,)
+    return sh
+
+
+def random_state_dict(seed=0):
+    """The shared synthetic-weight generator (data, not arithmetic); its keys / shapes are checked against
+    expected_key_shapes() above before use."""
+    from targetdiarization_b200.synth import random_eres2netv2_state_dict
+    sd = random_eres2netv2_state_dict(seed=seed)
+    want = expected_key_shapes()
+    got = {k: tuple(v.shape) for k, v in sd.items()}
+    if got != want:
+        diff = sorted(set(got.items()) ^ set(want.items()))[:6]
+        raise AssertionError(f"weight generator and oracle architecture table disagree: {diff}")
+    return sd
 
 
 def _bn(x, sd, name):

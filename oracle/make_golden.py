@@ -19,6 +19,14 @@ outputs of the reference itself on the GPU box, where the reference tree does no
                           MossFormer2 module with the seed-0 synthetic weights
   fbank.npz               torchaudio.compliance.kaldi.fbank (the function the modelscope pipeline calls) on a fixed
                           1 s signal, mean-normalised
+  c1_chat_mix.npz         BASELINE config 1 end to end: the WHOLE assets/chat_mix.wav (8.665 s, S = 17 328 frames)
+                          through the reference MossFormer2 module (seed-0 perturbed weights; every 4th output sample
+                          kept), assets/female_a.wav as the target, and the embeddings / cosine scores / pick the
+                          oracle embedder gives for the reference-separated streams
+  c2_item.npz             BASELINE config 2: item 0 of the benchmark batch (synthetic_mixture(64, 64000, seed=1234),
+                          the bench's seed-0 weights) through the reference module at T = 64 000 (every 4th sample)
+  mix_rule.npz            TargetASR.mix_audio_processor (extracted with `ast`, stub models) on score pairs incl. ties
+                          and NaN: which audio it returns and the score it reports (the >= tie rule, TargetASR.py:734-743)
 """
 import ast
 import io
@@ -265,6 +273,76 @@ def make_fbank():
     print("fbank.npz:", tuple(f.shape))
 
 
+def make_c1_chat_mix():
+    """Config C1 (target_diarization_test.py:26-40): the reference's demo mixture and target sample."""
+    from scipy.io import wavfile
+    from oracle import eres2netv2_port as E
+    from oracle import stage_port
+    sr, wav = wavfile.read(os.path.join(ref_loader.REF_ROOT, "assets", "chat_mix.wav"))
+    sr2, tgt = wavfile.read(os.path.join(ref_loader.REF_ROOT, "assets", "female_a.wav"))
+    assert sr == 16000 and sr2 == 16000 and wav.dtype == np.int16 and tgt.dtype == np.int16
+    pkg = ref_loader.load_reference_modules()
+    model = pkg.mossformer2.MossFormer2().eval()
+    model.load_state_dict(synth.random_state_dict(seed=0, perturb=True), strict=True)
+    x = torch.from_numpy(wav.astype(np.float32) / 32768.0)[None]   # AudioProcessor.int16_to_float32 (:1043-1048)
+    with torch.no_grad():
+        y = model(x)[0]                                             # [2, 138634]
+    esd = E.random_state_dict(seed=0)
+    t = torch.from_numpy(tgt.astype(np.float32) / 32768.0)[None]
+    emb = E.embed(esd, torch.cat((y, torch.nn.functional.pad(t, (0, y.shape[1] - t.shape[1])))))[:2]
+    emb_t = E.embed(esd, t)[0]
+    scores = [stage_port.cosine_similarity(emb[k].numpy(), emb_t.numpy()) for k in range(2)]
+    np.savez_compressed(os.path.join(GOLDEN, "c1_chat_mix.npz"), mix_pcm=wav, target_pcm=tgt, out_stride4=y[:, ::4].numpy(),
+                        emb=emb.numpy(), emb_target=emb_t.numpy(), scores=np.array(scores, dtype=np.float64),
+                        pick=np.array([stage_port.pick_target(scores[0], scores[1], 0.0) or 0], dtype=np.int64))
+    print("c1_chat_mix.npz:", tuple(y.shape), "scores", scores)
+
+
+def make_c2_item():
+    pkg = ref_loader.load_reference_modules()
+    model = pkg.mossformer2.MossFormer2().eval()
+    model.load_state_dict(synth.random_state_dict(seed=0), strict=True)
+    mix = synth.synthetic_mixture(64, 64000, seed=1234)[:1]
+    with torch.no_grad():
+        y = model(mix)[0]
+    np.savez_compressed(os.path.join(GOLDEN, "c2_item.npz"), cfg=np.array([0, 64, 64000, 1234, 0], dtype=np.int64),
+                        out_stride4=y[:, ::4].numpy())
+    print("c2_item.npz:", tuple(y.shape))
+
+
+def make_mix_rule():
+    """TargetASR.mix_audio_processor's choice between the unseparated input, spk1 and spk2."""
+    path = os.path.join(ref_loader.REF_ROOT, "TargetASR.py")
+    ns = {"np": np, "Union": typing.Union, "io": io}
+    for name in ("mix_audio_processor",):
+        exec(compile(extract_method(path, "TargetASR", name), "TargetASR." + name, "exec"), ns)
+    audio = np.full(16000, 0.25, dtype=np.float32)
+    s1, s2 = np.full(16000, 1.0, dtype=np.float32), np.full(16000, 2.0, dtype=np.float32)
+    cases = [(0.5, 0.5), (0.7, 0.2), (0.2, 0.7), (0.3, 0.3), (0.39999, 0.4), (0.4, 0.39999), (0.1, 0.2),
+             (float("nan"), 0.9), (0.9, float("nan")), (float("nan"), float("nan")), (1.0, 1.0), (0.0, 0.0),
+             (0.4, 0.4), (0.45, 0.450001)]
+    rows = []
+    for thr in (0.4, 0.0):
+        for a, b in cases:
+            scores = iter([a, b])
+            fake = types.SimpleNamespace(
+                input_audio_preprocess=lambda audio: (audio, 16000),
+                mdx_weights_file=None,
+                ap=types.SimpleNamespace(meter_loudness=lambda audio_data, sampling_rate: -20.0,
+                                         denoise_vocal=lambda audio_data, sampling_rate: audio_data,
+                                         audio_loudness_control=lambda audio_data, sampling_rate: audio_data,
+                                         separate_speaker=lambda audio_data: (s1, s2)),
+                asrp=types.SimpleNamespace(is_diarization=True,
+                                           speaker_diarization=lambda wav_file, sampling_rate: [1, 2]),
+                get_speaker_embedding=lambda wav_file, embedding_model="eres2netv2_large": wav_file[:1],
+                cosine_similarity=lambda embedding_a, embedding_b: next(scores))
+            r = ns["mix_audio_processor"](fake, audio, np.zeros(192, np.float32), thr, -40.0)
+            which = {0.25: 0, 1.0: 1, 2.0: 2}[float(r["audio"][0])]
+            rows.append([thr, a, b, which, r["score"]])
+    np.savez_compressed(os.path.join(GOLDEN, "mix_rule.npz"), rows=np.array(rows, dtype=np.float64))
+    print("mix_rule.npz:", len(rows), "cases")
+
+
 if __name__ == "__main__":
     if not ref_loader.reference_available():
         sys.exit("the reference tree is not present; golden vectors can only be generated in the build container")
@@ -274,3 +352,6 @@ if __name__ == "__main__":
     make_fbank()
     make_mossformer2()
     make_chat_mix_excerpt()
+    make_c1_chat_mix()
+    make_c2_item()
+    make_mix_rule()

@@ -111,9 +111,19 @@ def pick_target(spk1_score, spk2_score, threshold=0.0):
     return 1 if spk1_score > spk2_score else 2
 
 
-def pick_target_mix(spk1_score, spk2_score):
-    """mix_audio_processor (TargetASR.py:730-743) prefers spk1 on a tie (>=)."""
-    return 1 if spk1_score >= spk2_score else 2
+def pick_mix_audio(spk1_score, spk2_score, similarity_threshold=0.4):
+    """mix_audio_processor (TargetASR.py:734-743), branch by branch: 0 = the unseparated input, 1 = spk1 (also on a
+    tie: >=), 2 = spk2; the final else (every comparison false: NaN scores) returns the input.  Pinned by
+    tests/golden/mix_rule.npz (the reference method run from source)."""
+    if spk1_score < similarity_threshold and spk2_score < similarity_threshold:
+        which = 0
+    elif spk1_score >= spk2_score:
+        which = 1
+    elif spk2_score > spk1_score:
+        which = 2
+    else:
+        which = 0
+    return which
 
 
 # ---------------------------------------------------------------------------------------------- loudness

@@ -65,9 +65,11 @@ SIGNATURES = {
     "tdz_padded_frames": (_i64, [_i64]),
     "tdz_separate_workspace_bytes": (_sz, [_i64, _i64]),
     "tdz_separate": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "tdz_separate_strided": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _sz, _vp]),
     "tdz_separate_debug": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _int, _int, _int]),
     "tdz_separate_layout": (_int, [_i64, _i64, _int, ctypes.POINTER(SepLayout)]),
     "tdz_gather_segments": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "tdz_gather_segments_span": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "tdz_stitch_ola": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f, _vp, _vp]),
     "tdz_stitch_concat": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "tdz_loudness_blocks": (_int, [_vp, _vp, _i64, _i64, ctypes.POINTER(ctypes.c_double), _vp, _vp, _i64,
@@ -100,6 +102,24 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def resolve_device(device):
+    """torch.device with an explicit index: 'cuda' means the CURRENT device (like torch), not GPU 0."""
+    import torch
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
+def free_device_bytes(device, held=0):
+    """Bytes a workspace may grow to on `device`: what the driver reports free, plus what torch's caching allocator
+    holds but does not use, plus the workspace the caller already owns (`held`, reused when it grows)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info(device)
+    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return int(free + max(cached, 0) + held)
 
 
 class Handle:

@@ -605,8 +605,8 @@ __global__ void final_gn_kernel(const float* __restrict__ ln, const float* __res
 constexpr int DEC_FRAMES = 32;
 __global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ sep /*[2][Mtot][512]*/,
                                                       const float* __restrict__ w /*[512][16]*/,
-                                                      float* __restrict__ out /*[B][2][T]*/, int B, int Sp, int S,
-                                                      int T) {
+                                                      float* __restrict__ out, int64_t out_cs, int64_t out_ss,
+                                                      int B, int Sp, int S, int T) {
   __shared__ float ws[512 * 17];
   __shared__ float F[DEC_FRAMES + 1][16];
   const int strips = Sp / DEC_FRAMES;
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ 
   const int n = t * 8 + j;
   if (n < T) {
     const float v = F[f + 1][j] + F[f][8 + j];  // frames >= S contribute zeros
-    out[(static_cast<size_t>(b) * 2 + spk) * T + n] = v;
+    out[static_cast<int64_t>(b) * out_cs + static_cast<int64_t>(spk) * out_ss + n] = v;  // [B][2][T] when (2T, T)
   }
 }
 

@@ -148,4 +148,9 @@ __global__ void __launch_bounds__(256) sv_tstp_kernel(const float* __restrict__ 
   dst[C * H + c * H + h] = __float2bfloat16(sqrtf(var + 1e-8f));
 }
 
+__global__ void sv_fill_kernel(float* __restrict__ dst, int64_t n, float value) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = value;
+}
+
 }  // namespace tdz

@@ -269,12 +269,20 @@ constexpr int SV_RUN_ALL = 1000;
 static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N, int64_t frames, float* emb,
                     void* ws, size_t ws_bytes, cudaStream_t st, int stop_block = SV_RUN_ALL) {
   if (!M.ready) return fail(ctx, "tdz_embed: weights not set");
-  if (N <= 0 || frames < 8) return fail(ctx, "tdz_embed: need at least 8 feature frames per utterance");
+  if (N <= 0 || frames < 1) return fail(ctx, "tdz_embed: need at least one feature frame per utterance");
+  SvDims d;
+  sv_dims(N, frames, &d);
+  if (d.W[3] < 2 && stop_block == SV_RUN_ALL) {
+    // Fewer than 9 fbank frames leave ONE time step after the three stride-2 stages; TSTP's unbiased variance over
+    // one step is 0/0, so the reference model returns an all-NaN embedding (dropped by the enrolment path,
+    // TargetASR.py:235-236; scored 0.0 by cosine_similarity, :151).  Same result here, without running the network.
+    sv_fill_kernel<<<sv_grid(N * TDZ_SV_EMBED_DIM), 256, 0, st>>>(emb, N * TDZ_SV_EMBED_DIM, nanf(""));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   SvLayout L;
   sv_layout(N, frames, &L);
   if (ws_bytes < L.total) return fail(ctx, "tdz_embed: workspace too small (%zu < %zu)", ws_bytes, L.total);
-  SvDims d;
-  sv_dims(N, frames, &d);
   if (d.Pp[0] * 256 > 0x7fffffffll) return fail(ctx, "tdz_embed: batch too large for one call");
   uint8_t* base = static_cast<uint8_t*>(ws);
   auto Hh = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(base + o); };

@@ -87,7 +87,9 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
   *out = nullptr;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return 2;
-  if (cudaSetDevice(device) != cudaSuccess) return 3;
+  DeviceScope dev_scope(device);  // the caller's current device is restored on return
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return 3;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 4;
   if (prop.major != 10) return 5;  // hand-written for sm_100a; no fallback
@@ -275,8 +277,9 @@ enum Step : int {
   ST_DECODER, ST_COUNT
 };
 
-static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64, float* out, void* ws, size_t ws_bytes,
-                        cudaStream_t st, int num_layers, int step_lo, int step_hi) {
+static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64, float* out, int64_t out_cs,
+                        int64_t out_ss, void* ws, size_t ws_bytes, cudaStream_t st, int num_layers, int step_lo,
+                        int step_hi) {
 #define STEP(k) if ((k) >= step_lo && (k) <= step_hi)
   if (!ctx->have_sep) return fail(ctx, "tdz_separate: weights not set");
   if (B64 <= 0 || T64 < 16 || B64 > 65535) return fail(ctx, "tdz_separate: bad shape B=%lld T=%lld", (long long)B64, (long long)T64);
@@ -379,7 +382,10 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   // ---- front: encoder -> GroupNorm -> conv1d_encoder (+pos enc)   (mossformer2.py:573,487-496)
   STEP(ST_ENCODER) {
     CUDA_OK(cudaMemsetAsync(gn_stats, 0, static_cast<size_t>(B) * 4 * 8, st));
-    if (static_cast<int64_t>(Sp) * 8 < T) CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(B) * 2 * T * 4, st));
+    if (static_cast<int64_t>(Sp) * 8 < T) {  // samples beyond the last padded frame: the decoder never visits them
+      for (int spk = 0; spk < 2; ++spk)
+        CUDA_OK(cudaMemset2DAsync(out + spk * out_ss, static_cast<size_t>(out_cs) * 4, 0, static_cast<size_t>(T) * 4, B, st));
+    }
     if (Sp > S) {
       // padded frames of the attention operands stay zero for the whole forward (nobody writes them later)
       CUDA_OK(cudaMemset2DAsync(vu + static_cast<size_t>(S) * 2048, static_cast<size_t>(Sp) * 2048 * 2, 0,
@@ -621,7 +627,8 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
           P, mtiles * P.n_tiles, sms, st)));
     }
   }
-  STEP(ST_DECODER) decoder_kernel<<<dim3(B * (Sp / DEC_FRAMES), 2), 256, 0, st>>>(sep, W.dec_w, out, B, Sp, S, T);
+  STEP(ST_DECODER)
+  decoder_kernel<<<dim3(B * (Sp / DEC_FRAMES), 2), 256, 0, st>>>(sep, W.dec_w, out, out_cs, out_ss, B, Sp, S, T);
   CUDA_OK(cudaGetLastError());
 #undef STEP
   return 0;
@@ -632,7 +639,20 @@ extern "C" int tdz_separate(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64
   if (!ctx) return 1;
   DeviceScope dev_scope(ctx->device);
   std::lock_guard<std::mutex> lk(ctx->mu);
-  return run_separate(ctx, mix_dev, B, T, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), TDZ_NUM_LAYERS, 0, ST_COUNT);
+  return run_separate(ctx, mix_dev, B, T, out_dev, 2 * T, T, ws, ws_bytes, static_cast<cudaStream_t>(stream),
+                      TDZ_NUM_LAYERS, 0, ST_COUNT);
+}
+extern "C" int tdz_separate_strided(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev,
+                                    int64_t out_chunk_stride, int64_t out_spk_stride, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (out_chunk_stride < T || out_spk_stride < T)
+    return fail(ctx, "tdz_separate_strided: strides shorter than a chunk (%lld, %lld < %lld)",
+                (long long)out_chunk_stride, (long long)out_spk_stride, (long long)T);
+  return run_separate(ctx, mix_dev, B, T, out_dev, out_chunk_stride, out_spk_stride, ws, ws_bytes,
+                      static_cast<cudaStream_t>(stream), TDZ_NUM_LAYERS, 0, ST_COUNT);
 }
 extern "C" int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T, float* out_dev, void* ws,
                                   size_t ws_bytes, void* stream, int num_layers, int step_lo, int step_hi) {
@@ -640,21 +660,35 @@ extern "C" int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B,
   DeviceScope dev_scope(ctx->device);
   if (num_layers < 0 || num_layers > TDZ_NUM_LAYERS) return fail(ctx, "bad num_layers");
   std::lock_guard<std::mutex> lk(ctx->mu);
-  return run_separate(ctx, mix_dev, B, T, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), num_layers,
-                      step_lo, step_hi);
+  return run_separate(ctx, mix_dev, B, T, out_dev, 2 * T, T, ws, ws_bytes, static_cast<cudaStream_t>(stream),
+                      num_layers, step_lo, step_hi);
 }
 
 // ------------------------------------------------------------------------------------------------ stitching / scoring
-extern "C" int tdz_gather_segments(tdz_ctx* ctx, const float* mix_dev, int64_t L, int64_t session, int64_t hop,
-                                   int64_t seg_begin, int64_t n_seg, float* seg_dev, void* stream) {
+extern "C" int tdz_gather_segments_span(tdz_ctx* ctx, const float* mix_dev, int64_t mix_origin, int64_t mix_len,
+                                        int64_t L, int64_t session, int64_t hop, int64_t seg_begin, int64_t n_seg,
+                                        float* seg_dev, void* stream) {
   if (!ctx) return 1;
   DeviceScope dev_scope(ctx->device);
   if (n_seg <= 0) return 0;
+  if (session <= 0 || hop <= 0 || hop > session) return fail(ctx, "tdz_gather_segments: bad session / hop");
+  // samples of [0, L) the requested segments read must be resident
+  const int64_t pad = session - hop;
+  const int64_t need_lo = std::max<int64_t>(seg_begin * hop - pad, 0);
+  const int64_t need_hi = std::min<int64_t>((seg_begin + n_seg - 1) * hop - pad + session, L);
+  if (need_hi > need_lo && (need_lo < mix_origin || need_hi > mix_origin + mix_len))
+    return fail(ctx, "tdz_gather_segments: segments read samples [%lld, %lld), resident are [%lld, %lld)",
+                (long long)need_lo, (long long)need_hi, (long long)mix_origin, (long long)(mix_origin + mix_len));
   const size_t total = static_cast<size_t>(n_seg) * session;
-  gather_segments_kernel<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      mix_dev, L, session, hop, seg_begin, n_seg, seg_dev);
+  const size_t threads = (total + 3) / 4;  // one thread per 4 outputs, the last one possibly partial
+  gather_segments_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mix_dev - mix_origin, L, session, hop, seg_begin, n_seg, seg_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+extern "C" int tdz_gather_segments(tdz_ctx* ctx, const float* mix_dev, int64_t L, int64_t session, int64_t hop,
+                                   int64_t seg_begin, int64_t n_seg, float* seg_dev, void* stream) {
+  return tdz_gather_segments_span(ctx, mix_dev, 0, L, L, session, hop, seg_begin, n_seg, seg_dev, stream);
 }
 extern "C" int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t session, int64_t hop, int64_t seg_begin,
                               int64_t n_seg, int64_t L, int64_t out_begin, int64_t n_out, float ratio, float* out_dev,
@@ -755,7 +789,7 @@ extern "C" int tdz_set_eres2netv2_weights(tdz_ctx* ctx, const tdz_eres2netv2_wei
   return sv_set_weights(ctx, ctx->sv, w);
 }
 extern "C" size_t tdz_embed_workspace_bytes(int64_t N, int64_t frames) {
-  if (N <= 0 || frames < 8) return 0;
+  if (N <= 0 || frames < 1) return 0;
   SvLayout L;
   sv_layout(N, frames, &L);
   return L.total;

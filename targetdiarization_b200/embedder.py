@@ -21,14 +21,17 @@ class Embedder:
     # GEMM); fuse34/TSTP/Linear 5
     KERNELS_PER_FORWARD = 1 + 19 + 26 + 92 + 2 + 47 + 5
 
-    def __init__(self, state_dict=None, device="cuda:0", max_workspace_bytes=24 << 30, handle=None):
+    def __init__(self, state_dict=None, device="cuda:0", max_workspace_bytes=None, handle=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("tdz.Embedder runs on a CUDA (sm_100a) device only; there is no CPU fallback")
-        self._h = handle if handle is not None else _lib.Handle(self.device.index or 0)
+        self.device = _lib.resolve_device(self.device)
+        self._h = handle if handle is not None else _lib.Handle(self.device.index)
         self._packed = None
         self._ws = None
-        self.max_workspace_bytes = int(max_workspace_bytes)
+        # None: a share of the memory that is free when a batch is sized (capped at 24 GiB: larger sub-batches buy
+        # nothing, 128 x 4 s utterances need 9 GB)
+        self._max_workspace_bytes = None if max_workspace_bytes is None else int(max_workspace_bytes)
         win, tw = fbank.povey_window(), fbank.twiddles()
         mel, lo, hi = fbank.mel_banks()
         self._tables = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in (win, tw, mel, lo, hi)]
@@ -59,12 +62,20 @@ class Embedder:
                       "tdz_fbank")
         return feat
 
+    @property
+    def max_workspace_bytes(self):
+        if self._max_workspace_bytes is not None:
+            return self._max_workspace_bytes
+        held = self._ws_raw.numel() if self._ws is not None else 0
+        return min(24 << 30, _lib.free_device_bytes(self.device, held) // 4)
+
     def max_batch(self, frames):
         """Largest sub-batch whose workspace fits max_workspace_bytes (at least 1)."""
         lib = self._h.lib
+        budget = self.max_workspace_bytes
         per1 = int(lib.tdz_embed_workspace_bytes(1, frames))
-        n = max(1, min(256, self.max_workspace_bytes // max(per1, 1)))
-        while n > 1 and int(lib.tdz_embed_workspace_bytes(n, frames)) > self.max_workspace_bytes:
+        n = max(1, min(256, budget // max(per1, 1)))
+        while n > 1 and int(lib.tdz_embed_workspace_bytes(n, frames)) > budget:
             n -= 1
         return n
 
@@ -91,15 +102,31 @@ class Embedder:
 
     def embed_many(self, wavs):
         """Batched embedding.  wavs: device/host tensor [N,T], ndarray [N,T] or a list of 1-D arrays/tensors of
-        possibly different lengths (grouped by length).  Returns a device tensor [N,192]."""
+        possibly different lengths.  Returns a device tensor [N,192].
+
+        Ragged lists are grouped by their number of fbank frames m = 1 + (T-400)//160, not by T: with snip_edges the
+        features of a clip depend only on its first 400 + 160 (m-1) samples (torchaudio kaldi.py `_get_strided`), so
+        clips of one group are cut to that length and share one batched call - same numbers as the reference's
+        one-call-per-clip loops (TargetDiarization.py:588-594,612-618), hundreds instead of thousands of launches.
+        Clips that leave a single time step after the network's three stride-2 stages (fewer than 9 frames, i.e.
+        under 1 680 samples) come back as NaN rows exactly as from the reference model (TargetASR.get_target_embedding
+        drops such rows, :235-236; cosine_similarity scores them 0.0, :151)."""
         if isinstance(wavs, (list, tuple)):
             arrs = [self._to_dev(w).reshape(-1) for w in wavs]
             out = torch.empty(len(arrs), EMBED_DIM, dtype=torch.float32, device=self.device)
-            by_len = {}
+            by_frames = {}
             for i, a in enumerate(arrs):
-                by_len.setdefault(a.numel(), []).append(i)
-            for _, idx in sorted(by_len.items()):
-                out[idx] = self.embed_features(self.fbank(torch.stack([arrs[i] for i in idx])))
+                m = fbank.num_frames(a.numel())
+                if m < 1:
+                    raise ValueError(f"utterance {i} has {a.numel()} samples, shorter than one 25 ms fbank window")
+                by_frames.setdefault(m, []).append(i)
+            for m, idx in sorted(by_frames.items()):
+                n = fbank.WIN + fbank.SHIFT * (m - 1)
+                batch = arrs[idx[0]][:n].unsqueeze(0) if len(idx) == 1 else torch.stack([arrs[i][:n] for i in idx])
+                emb = self.embed_features(self.fbank(batch))
+                if len(idx) == len(arrs):
+                    return emb
+                out[idx] = emb
             return out
         w = self._to_dev(wavs)
         if w.ndim == 1:

@@ -21,12 +21,22 @@ from .separator import Separator
 
 class CudaKernels:
     """The libtdz.so entry points the stage needs, on device tensors.  (The gloo/CPU tests of the sharding logic
-    substitute a numpy stand-in for this object; the product has no other implementation.)"""
+    substitute a stand-in for this object; the product has no other implementation.)"""
 
-    def __init__(self, separator, max_workspace_bytes=100 << 30):
+    def __init__(self, separator, max_workspace_bytes=None):
         self.sep = separator
         self.device = separator.device
-        self.max_workspace_bytes = int(max_workspace_bytes)
+        # None: sized from the memory that is free when a batch is planned (a shared or smaller GPU gets smaller
+        # sub-batches instead of an out-of-memory error); capped at 100 GiB
+        self._max_workspace_bytes = None if max_workspace_bytes is None else int(max_workspace_bytes)
+
+    @property
+    def max_workspace_bytes(self):
+        if self._max_workspace_bytes is not None:
+            return self._max_workspace_bytes
+        from . import _lib
+        held = self.sep._ws_raw.numel() if self.sep._ws is not None else 0
+        return min(100 << 30, (_lib.free_device_bytes(self.device, held) * 3) // 4)
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -36,139 +46,211 @@ class CudaKernels:
             audio = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
         return audio.to(self.device, torch.float32, non_blocking=True).contiguous()
 
+    def to_host(self, dev):
+        """Device tensor -> numpy through page-locked memory (torch's caching host allocator keeps the buffer for
+        the next call; a pageable `.cpu()` of an hour of audio costs more than the separation of a window)."""
+        host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
     def max_batch(self, T):
         per1 = self.sep.workspace_bytes(1, T)
         frames = -(-max(T // 8, 1) // 256) * 256
         return int(max(1, min(4096, self.max_workspace_bytes // max(per1, 1), (1 << 23) // frames)))
 
-    def separate(self, chunks):
-        """[n,T] -> [n,2,T], in sub-batches that fit the workspace budget."""
+    def separate(self, chunks, out=None, out_strides=None):
+        """[n,T] -> [n,2,T] (or into `out` with `out_strides`, see Separator.__call__), in sub-batches that fit the
+        workspace budget."""
         n, T = chunks.shape
         nb = self.max_batch(T)
-        if n <= nb:
-            return self.sep(chunks)
-        out = self.empty(n, 2, T)
+        if out is None:
+            out = self.empty(n, 2, T)
+            out_strides = (2 * T, T)
+        elif out_strides is None:
+            out_strides = (2 * T, T)
         for i in range(0, n, nb):
-            out[i:i + nb] = self.sep(chunks[i:i + nb])
+            o = out.reshape(-1)[i * out_strides[0]:]
+            self.sep(chunks[i:i + nb], out=o, out_strides=out_strides)
         return out
 
-    def gather_segments(self, mix, plan, seg_lo, n_seg):
+    def gather_segments(self, mix, plan, seg_lo, n_seg, mix_origin=0):
+        """Segments [seg_lo, seg_lo + n_seg) of the plan; `mix` holds samples [mix_origin, mix_origin + len(mix))."""
         h = self.sep._h
         seg = self.empty(n_seg, plan.session)
-        h.check(h.lib.tdz_gather_segments(h.ptr, mix.data_ptr(), plan.length, plan.session, plan.hop, seg_lo, n_seg,
-                                          seg.data_ptr(), self._stream()), "tdz_gather_segments")
+        h.check(h.lib.tdz_gather_segments_span(h.ptr, mix.data_ptr(), mix_origin, mix.shape[0], plan.length,
+                                               plan.session, plan.hop, seg_lo, n_seg, seg.data_ptr(), self._stream()),
+                "tdz_gather_segments_span")
         return seg
 
-    def stitch_ola(self, est, plan, seg_lo, out_begin, n_out):
+    def stitch_ola(self, est, plan, seg_lo, out_begin, n_out, out=None):
         h = self.sep._h
-        out = self.empty(2, n_out)
+        if out is None:
+            out = self.empty(2, n_out)
         h.check(h.lib.tdz_stitch_ola(h.ptr, est.data_ptr(), plan.session, plan.hop, seg_lo, est.shape[0], plan.length,
                                      out_begin, n_out, float(plan.ratio), out.data_ptr(), self._stream()),
                 "tdz_stitch_ola")
         return out
 
-    def stitch_concat(self, est, out, start):
-        """est [2,len] (one chunk) -> out[:, start:start+len]."""
-        h = self.sep._h
-        h.check(h.lib.tdz_stitch_concat(h.ptr, est.data_ptr(), est.shape[-1], start, out.shape[-1], out.data_ptr(),
-                                        self._stream()), "tdz_stitch_concat")
-
 
 # ------------------------------------------------------------------------------------------------ span engines
-def concat_span(kern, mix, bounds, span_begin, span_end):
-    """Concat mode over the windows `bounds` (absolute sample indices inside `mix`): equal-length windows share one
-    batched separator call.  Returns [2, span_end - span_begin]."""
-    out = kern.empty(2, span_end - span_begin)
-    by_len = {}
-    for b, e in bounds:
-        by_len.setdefault(e - b, []).append(b)
-    for T, starts in sorted(by_len.items()):
-        nb = kern.max_batch(T)
-        for i in range(0, len(starts), nb):
-            grp = starts[i:i + nb]
-            chunks = torch.stack([mix[s:s + T] for s in grp]) if len(grp) > 1 else mix[grp[0]:grp[0] + T].unsqueeze(0)
-            est = kern.separate(chunks.contiguous())
-            for j, s in enumerate(grp):
-                kern.stitch_concat(est[j], out, s - span_begin)
+def _span_buffer(kern, n, flat):
+    """[2, n] output of a span engine: a view of the caller's flat buffer (the rank's slot of the gather) or new."""
+    if flat is None:
+        return kern.empty(2, n)
+    return flat[:2 * n].view(2, n)
+
+
+def concat_span(kern, mix, bounds, span_begin, span_end, mix_origin=0, out_flat=None):
+    """Concat mode over the windows `bounds` (absolute sample indices; `mix` holds the samples from `mix_origin` on).
+    Runs of adjacent equal-length windows are ONE batched separator call that reads the windows in place (a view, no
+    copy) and writes both streams straight into the stitched output (strided store, no stitch pass).
+    Returns [2, span_end - span_begin]."""
+    n_out = span_end - span_begin
+    out = _span_buffer(kern, n_out, out_flat)
+    i = 0
+    while i < len(bounds):
+        b, e = bounds[i]
+        T = e - b
+        j = i + 1
+        while j < len(bounds) and bounds[j][0] == bounds[j - 1][1] and bounds[j][1] - bounds[j][0] == T:
+            j += 1
+        n = j - i
+        chunks = mix[b - mix_origin:b - mix_origin + n * T].view(n, T)
+        # stream s of window k -> out[s, b - span_begin + k T : ...] = flat offset s * n_out + (b - span_begin) + k T
+        kern.separate(chunks, out=out.reshape(-1)[b - span_begin:], out_strides=(T, n_out))
+        i = j
     return out
 
 
-def ola_span(kern, mix, plan, out_begin, out_end, seg_lo, seg_hi, batch_size=None):
-    """Overlap-add mode for output samples [out_begin, out_end) from segments [seg_lo, seg_hi).  Returns [2, n]."""
+def ola_span(kern, mix, plan, out_begin, out_end, seg_lo, seg_hi, batch_size=None, mix_origin=0, out_flat=None):
+    """Overlap-add mode for output samples [out_begin, out_end) from segments [seg_lo, seg_hi).  Returns [2, n].
+    batch_size bounds the number of segments per separator call (None: as many as the workspace budget allows)."""
     n_seg = seg_hi - seg_lo
-    if n_seg <= 0 or out_end <= out_begin:
-        return kern.empty(2, max(out_end - out_begin, 0))
-    seg = kern.gather_segments(mix, plan, seg_lo, n_seg)
+    n_out = max(out_end - out_begin, 0)
+    out = _span_buffer(kern, n_out, out_flat)
+    if n_seg <= 0 or n_out == 0:
+        return out
+    seg = kern.gather_segments(mix, plan, seg_lo, n_seg, mix_origin)
     if batch_size is None:
         est = kern.separate(seg)
     else:
         est = kern.empty(n_seg, 2, plan.session)
-        for i in range(0, n_seg, batch_size):
-            est[i:i + batch_size] = kern.separate(seg[i:i + batch_size])
-    return kern.stitch_ola(est, plan, seg_lo, out_begin, out_end - out_begin)
+        for i in range(0, n_seg, int(batch_size)):
+            kern.separate(seg[i:i + batch_size], out=est[i:i + batch_size])
+    return kern.stitch_ola(est, plan, seg_lo, out_begin, n_out, out=out)
 
 
-def all_gather_spans(local, span_lens, group=None):
-    """One collective: every rank contributes its [2, n_r] span, everyone receives [2, sum n_r] (rank order).
-    Spans are padded to the longest one for the fixed-size all_gather (NCCL on device tensors, gloo on CPU)."""
-    import torch.distributed as dist
-    world = len(span_lens)
-    n_max = max(max(span_lens), 1)
-    buf = torch.zeros(2, n_max, dtype=local.dtype, device=local.device)
-    buf[:, :local.shape[1]] = local
-    allbuf = torch.empty(world * 2, n_max, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(allbuf, buf, group=group)  # concatenation along dim 0 (NCCL and gloo)
-    allbuf = allbuf.view(world, 2, n_max)
-    return torch.cat([allbuf[r, :, :span_lens[r]] for r in range(world)], dim=1)
+def ola_input_range(plan, seg_lo, seg_hi):
+    """Samples of [0, L) that segments [seg_lo, seg_hi) read: the rank's output span plus its halo."""
+    if seg_hi <= seg_lo:
+        return 0, 0
+    lo = max(plan.segment_range(seg_lo)[0], 0)
+    hi = min(plan.segment_range(seg_hi - 1)[1], plan.length)
+    return lo, max(hi, lo)
 
 
 def _rank_world(group):
+    """Sharding is opt-in: without an explicit process group a call never talks to other ranks, whatever the state of
+    torch.distributed (one process per GPU normally means every rank holds DIFFERENT audio)."""
+    if group is None:
+        return 0, 1
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(group), dist.get_world_size(group)
-    return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
 
 
-def separate_concat(kern, audio, window=P.WINDOW, vad_frames=None, group=None):
-    """The chunk loop of separate_speaker on the device.  audio [L] (device tensor) -> [2, L_out].
+def _check_same_input(length, group, device):
+    """A sharded call is collective: every rank of `group` must hold the same recording.  Cheap guard against
+    stitching spans of different inputs together (or hanging in a size-mismatched collective)."""
+    import torch.distributed as dist
+    t = torch.tensor([length, -length], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = -int(t[1].item()), int(t[0].item())
+    if lo != hi:
+        raise RuntimeError(f"sharded separation: ranks hold inputs of different lengths ({lo} .. {hi} samples); pass "
+                           "group=None for independent per-rank inputs")
+
+
+def gather_spans(kern, local_flat, span_lens, group, dst=None):
+    """The one data-path collective: every rank contributes its [2, n_r] span, stored flat in
+    a buffer of 2 * max(n_r) floats; the consumer(s) get the stitched [2, sum n_r] streams.  dst=None: every rank
+    (all_gather); dst=r: only rank r (gather), the others return None."""
+    import torch.distributed as dist
+    world = len(span_lens)
+    n_max = max(max(span_lens), 1)
+    rank = dist.get_rank(group)
+    if dst is None:
+        allbuf = torch.empty(world, 2 * n_max, dtype=local_flat.dtype, device=local_flat.device)
+        dist.all_gather_into_tensor(allbuf, local_flat.view(1, -1), group=group)
+    else:
+        allbuf = torch.empty(world, 2 * n_max, dtype=local_flat.dtype, device=local_flat.device) if rank == dst else None
+        dist.gather(local_flat, list(allbuf.unbind(0)) if rank == dst else None,
+                    dst=dist.get_global_rank(group, dst) if group is not dist.group.WORLD else dst, group=group)
+        if rank != dst:
+            return None
+    total = sum(span_lens)
+    out = torch.empty(2, total, dtype=local_flat.dtype, device=local_flat.device)
+    pos = 0
+    for r, n in enumerate(span_lens):
+        if n:
+            out[:, pos:pos + n] = allbuf[r, :2 * n].view(2, n)
+        pos += n
+    return out
+
+
+def separate_concat(kern, audio, window=P.WINDOW, vad_frames=None, group=None, dst=None):
+    """The chunk loop of separate_speaker on the device.  audio [L] (device tensor or host ndarray) -> [2, L_out].
 
     vad_frames=None is the reference's no-VAD path (one frame [0, L)).  With frames given (low_gpu_ram mode,
-    AudioProcessor.py:902-919) the gaps before each frame are zero filled and the output ends at the last frame."""
+    AudioProcessor.py:902-919) the gaps before each frame are zero filled and the output ends at the last frame.
+    group = the ranks that share THIS input (sharding is opt-in): rank r separates its contiguous range of windows,
+    uploading only those samples when `audio` is a host array; one collective stitches the spans (see gather_spans)."""
     L = int(audio.shape[0])
     rank, world = _rank_world(group)
     if vad_frames is None:
         if world == 1:
-            return concat_span(kern, audio, P.chunk_bounds(L, window), 0, L)
+            return concat_span(kern, kern.to_device(audio), P.chunk_bounds(L, window), 0, L)
+        _check_same_input(L, group, kern.device)
         spans = [P.concat_shard(L, r, world, window) for r in range(world)]
         mine, b, e = spans[rank]
-        local = concat_span(kern, audio, mine, b, e)
-        return all_gather_spans(local, [s[2] - s[1] for s in spans], group)
+        lens = [s[2] - s[1] for s in spans]
+        flat = kern.empty(2 * max(max(lens), 1))
+        concat_span(kern, kern.to_device(audio[b:e]), mine, b, e, mix_origin=b, out_flat=flat)
+        return gather_spans(kern, flat, lens, group, dst)
+    audio = kern.to_device(audio)
     pieces = []
     total = 0
     for i, (fb, fe) in enumerate(vad_frames):
         if fb > total:
             gap = fb if i == 0 else fb - vad_frames[i - 1][1]
-            pieces.append(torch.zeros(2, gap, dtype=torch.float32, device=audio.device))
+            pieces.append(kern.zeros(2, gap))
             total += gap
         pieces.append(concat_span(kern, audio, P.chunk_bounds(fe - fb, window, fb), fb, fe))
         total += fe - fb
-    return torch.cat(pieces, dim=1) if pieces else torch.zeros(2, 0, dtype=torch.float32, device=audio.device)
+    return torch.cat(pieces, dim=1) if pieces else kern.zeros(2, 0)
 
 
-def separate_ola(kern, audio, sr=16000, target_length=12.0, hop_length=4.0, batch_size=None, group=None):
-    """wav_chunk_inference on the device.  audio [L] -> [2, L]."""
+def separate_ola(kern, audio, sr=16000, target_length=12.0, hop_length=4.0, batch_size=None, group=None, dst=None):
+    """wav_chunk_inference on the device.  audio [L] (device tensor or host ndarray) -> [2, L]."""
     L = int(audio.shape[0])
     plan = P.ola_plan(L, sr, target_length, hop_length)
     rank, world = _rank_world(group)
     if world == 1:
-        return ola_span(kern, audio, plan, 0, L, 0, plan.num_session, batch_size)
+        return ola_span(kern, kern.to_device(audio), plan, 0, L, 0, plan.num_session, batch_size)
+    _check_same_input(L, group, kern.device)
     shards = [P.ola_shard(plan, r, world) for r in range(world)]
     ob, oe, lo, hi = shards[rank]
-    local = ola_span(kern, audio, plan, ob, oe, lo, hi, batch_size)
-    return all_gather_spans(local, [s[1] - s[0] for s in shards], group)
+    lens = [s[1] - s[0] for s in shards]
+    flat = kern.empty(2 * max(max(lens), 1))
+    a, b = ola_input_range(plan, lo, hi)      # the span and the halo the rank's segments reach into
+    ola_span(kern, kern.to_device(audio[a:b]), plan, ob, oe, lo, hi, batch_size, mix_origin=a, out_flat=flat)
+    return gather_spans(kern, flat, lens, group, dst)
 
 
 # ------------------------------------------------------------------------------------------------ loudness
@@ -245,11 +327,16 @@ class SeparationScoringStage:
     """Owns one Separator and one Embedder on one GPU (one process per GPU; `group` = the ranks that share a long
     input).  Method names and arguments follow the reference methods they stand behind."""
 
-    def __init__(self, separator, embedder, group=None, similarity_threshold=0.0):
+    def __init__(self, separator, embedder, group=None, similarity_threshold=0.0, gather_dst=None):
+        """group: the torch.distributed process group whose ranks SHARE every input given to separate_speaker /
+        wav_chunk_inference / score_segments (a long recording cut into per-rank spans).  None (default) = this
+        stage never communicates: the normal one-process-per-GPU deployment where every rank serves its own audio.
+        gather_dst: group rank that receives the stitched result (None = every rank)."""
         self.separator = separator
         self.embedder = embedder
         self.device = separator.device
         self.group = group
+        self.gather_dst = gather_dst
         self.kern = CudaKernels(separator)
         self.similarity_threshold = similarity_threshold
         self.is_separate_audio = True
@@ -274,7 +361,11 @@ class SeparationScoringStage:
         segments by overlap-add (wav_chunk_inference).  loudness: "device" (BS.1770 meter on the GPU), a callable
         (audio, rate) -> LUFS such as AudioProcessor.meter_loudness, or None (keep the separator's order).  low_gpu_ram=True uses 1 s windows inside `vad_frames`
         (which the caller's VAD supplies; the reference runs silero-vad there).  `resample(audio, orig_sr,
-        target_sr) -> audio` is needed only when sampling_rate != 16000 (the reference calls librosa)."""
+        target_sr) -> audio` is needed only when sampling_rate != 16000 (the reference calls librosa).
+
+        With a process group (see __init__) the call is collective: every rank passes the same recording, uploads and
+        separates only its span (+ overlap-add halo), and the spans are gathered by one NCCL collective; ranks other
+        than `gather_dst` return (None, None)."""
         if not self.is_separate_audio:
             return audio_data, audio_data
         orig_sr = sampling_rate
@@ -287,13 +378,19 @@ class SeparationScoringStage:
             raise ValueError("separate_speaker: low_gpu_ram=True needs `vad_frames` ([[start, end], ...] from the "
                              "caller's VAD, AudioProcessor.py:902-905)")
         window = P.WINDOW_LOW_RAM if low_gpu_ram else P.WINDOW
-        mix = self.kern.to_device(audio_data).reshape(-1)
+        if isinstance(audio_data, np.ndarray):
+            mix = np.ascontiguousarray(audio_data, dtype=np.float32).reshape(-1)   # spans are uploaded by the engines
+        else:
+            mix = self.kern.to_device(audio_data).reshape(-1)
         if mode == "concat":
-            est = separate_concat(self.kern, mix, window, vad_frames if low_gpu_ram else None, self.group)
+            est = separate_concat(self.kern, mix, window, vad_frames if low_gpu_ram else None, self.group,
+                                  self.gather_dst)
         elif mode == "ola":
-            est = separate_ola(self.kern, mix, sampling_rate, group=self.group, **ola_kw)
+            est = separate_ola(self.kern, mix, sampling_rate, group=self.group, dst=self.gather_dst, **ola_kw)
         else:
             raise ValueError(f"unknown mode {mode!r}")
+        if est is None:        # sharded call, this rank is not the consumer
+            return None, None
         if return_device and loudness is None:
             return est[0], est[1]
         swap = False
@@ -302,7 +399,9 @@ class SeparationScoringStage:
                 raise ValueError(f"unknown loudness meter {loudness!r}")
             l1, l2 = self.meter_loudness_device(est, sampling_rate)
             swap = l1 < l2
-        host = est.cpu().numpy()
+        if return_device:
+            return (est[1], est[0]) if swap else (est[0], est[1])
+        host = self.kern.to_host(est)
         spk1, spk2 = host[0], host[1]
         if callable(loudness):
             swap = loudness(spk1, sampling_rate) < loudness(spk2, sampling_rate)
@@ -337,12 +436,14 @@ class SeparationScoringStage:
     def wav_chunk_inference(self, mixture_tensor, sr=16000, target_length=12.0, hop_length=4.0, batch_size=10,
                             n_tracks=2):
         """mixture [1, 1, L] (or [1, L] / [L]) -> [n_tracks=2, 1, L] like the reference with the MossFormer2 adapter
-        `lambda x: model(x).unsqueeze(2)`.  batch_size only bounds the sub-batch, not the result."""
+        `lambda x: model(x).unsqueeze(2)`.  batch_size = segments per separator call as in the
+        reference (separator.py:115-124); it bounds the scratch memory, not the result (batch-invariant bits).
+        batch_size=None lets the workspace budget decide."""
         if n_tracks != 2:
             raise ValueError("the separator has 2 output tracks")
         mix = self.kern.to_device(mixture_tensor).reshape(-1)
-        est = separate_ola(self.kern, mix, sr, target_length, hop_length, None, self.group)
-        return est.unsqueeze(1)
+        est = separate_ola(self.kern, mix, sr, target_length, hop_length, batch_size, self.group, self.gather_dst)
+        return None if est is None else est.unsqueeze(1)
 
     # ---- TargetASR scoring
     def get_speaker_embedding(self, wav_file, embedding_model="eres2netv2_large"):
@@ -371,8 +472,69 @@ class SeparationScoringStage:
                     spk2_score=scores[1], spk1_audio=spk1, spk2_audio=spk2)
 
     def score_segments(self, segments, target_embedding):
-        """Batched form of the per-segment loops (TargetDiarization.py:581-629): [N] cosine scores on the device."""
-        return self.embedder.score_many(segments, target_embedding)
+        """Batched form of the per-segment loops (TargetDiarization.py:581-629): [N] cosine scores on the device
+        (0.0 where the reference's embedding is NaN, i.e. clips of fewer than 9 fbank frames: TargetASR.py:151 computes
+        max(0.0, min(nan, 1.0)) = 0.0 for them).  segments: [N,T] tensor / ndarray or a ragged list of clips.
+
+        With a process group the N segments are dealt to the ranks (longest first, round robin - every rank gets the
+        same mix of lengths), each rank embeds and scores its share, and one all_gather returns all N scores to every
+        rank ("[n_seg] fp32 scores")."""
+        rank, world = _rank_world(self.group)
+        if world == 1:
+            return self.embedder.score_many(segments, target_embedding)
+        import torch.distributed as dist
+        n = len(segments)
+        lengths = [int(segments[i].shape[-1]) for i in range(n)]
+        owners = P.deal_segments(lengths, world)
+        mine = owners[rank]
+        n_max = max(max(len(o) for o in owners), 1)
+        local = torch.full((n_max,), float("nan"), dtype=torch.float32, device=self.device)
+        if mine:
+            if isinstance(segments, (list, tuple)):
+                share = [segments[i] for i in mine]
+            else:
+                share = segments[torch.as_tensor(mine, device=segments.device)] if torch.is_tensor(segments) \
+                    else segments[np.asarray(mine)]
+            local[:len(mine)] = self.embedder.score_many(share, target_embedding)
+        allbuf = torch.empty(world, n_max, dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(allbuf, local.view(1, -1), group=self.group)
+        scores = torch.empty(n, dtype=torch.float32, device=self.device)
+        for r, idx in enumerate(owners):
+            if idx:
+                scores[torch.as_tensor(idx, device=self.device)] = allbuf[r, :len(idx)]
+        return scores
+
+    def separate_and_score_long(self, audio_data, target_embedding, segment_seconds=4.0, threshold=None,
+                                mode="concat", sampling_rate=16000, **kw):
+        """The whole stage on one long recording (BASELINE.json config 3): separate (sharded over the stage's process
+        group when it has one), cut both separated streams into fixed-length segments, score every segment against
+        the target (sharded again, scores gathered) and pick target / non-target per segment (TargetASR.py:612-625
+        per segment pair).  The streams stay on the device between the two halves.  Returns a dict:
+        spk1 / spk2 (np.float32 [L], louder first; None on ranks other than gather_dst), scores np.float32 [2, n_seg],
+        target [n_seg] (1, 2 or 0 for "neither reaches the threshold")."""
+        threshold = self.similarity_threshold if threshold is None else threshold
+        keep_dst, self.gather_dst = self.gather_dst, None        # scoring shards read the gathered streams
+        try:
+            s1, s2 = self.separate_speaker(audio_data, sampling_rate, mode=mode, return_device=True, **kw)
+        finally:
+            self.gather_dst = keep_dst
+        L = int(s1.shape[0])
+        seg = int(segment_seconds * 16000)
+        n_seg = L // seg
+        if n_seg == 0:
+            raise ValueError("recording shorter than one scoring segment")
+        both = torch.stack((s1[:n_seg * seg].view(n_seg, seg), s2[:n_seg * seg].view(n_seg, seg))).view(2 * n_seg, seg)
+        scores = self.score_segments(both, target_embedding).view(2, n_seg)
+        rank, _ = _rank_world(self.group)
+        out = dict(spk1=None, spk2=None)
+        if keep_dst is None or rank == keep_dst:
+            host = self.kern.to_host(torch.stack((s1, s2)))
+            out = dict(spk1=host[0], spk2=host[1])
+        sc = scores.cpu().numpy()
+        out["scores"] = sc
+        out["target"] = np.array([P.pick_target(float(a), float(b), threshold) or 0 for a, b in zip(sc[0], sc[1])],
+                                 dtype=np.int64)
+        return out
 
     # ---- SURVEY.md 8f-2: enrolment (TargetASR.get_target_embedding, TargetASR.py:166-258)
     def get_target_embedding(self, target_audio, is_preprocess=True, is_cluster=True, audio_input_type="separate",

@@ -97,12 +97,34 @@ def ola_shard(plan, rank, world):
     return out_begin, out_end, seg_lo, seg_hi
 
 
+def deal_segments(lengths, world):
+    """Which rank scores which segment: indices sorted by length (longest first, ties by index) are dealt round robin,
+    so every rank gets the same number of segments (+-1) and the same mix of lengths.  Pure function of the lengths:
+    every rank computes the same table.  Returns [indices of rank 0, indices of rank 1, ...]."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return [order[r::world] for r in range(world)]
+
+
 def pick_target(spk1_score, spk2_score, threshold=0.0):
     """Target/non-target assignment of one separated pair (TargetASR.py:612-625, 541-553): None when both scores
     are below `threshold`; 1 iff spk1_score > spk2_score (strict), else 2."""
     if spk1_score < threshold and spk2_score < threshold:
         return None
     return 1 if spk1_score > spk2_score else 2
+
+
+def pick_mix_audio(spk1_score, spk2_score, similarity_threshold=0.4):
+    """Which audio TargetASR.mix_audio_processor returns for a two-speaker clip (TargetASR.py:734-743): 0 = the
+    unseparated input when both scores are below the threshold, 1 = spk1 iff spk1_score >= spk2_score (ties go to
+    spk1 - unlike pick_target's strict >), 2 = spk2 iff spk2_score > spk1_score, else 0 (reached with NaN scores,
+    for which every comparison is false).  The reported score is round(max(spk1_score, spk2_score), 3)."""
+    if spk1_score < similarity_threshold and spk2_score < similarity_threshold:
+        return 0
+    if spk1_score >= spk2_score:
+        return 1
+    if spk2_score > spk1_score:
+        return 2
+    return 0
 
 
 # ---------------------------------------------------------------------------------------------- per-segment rules

@@ -10,6 +10,32 @@ from . import _lib
 from .weights import PackedMossFormer2
 
 
+# MossFormer2.__init__ (look2hear/models/mossformer2.py:532-541), in positional order.  The kernels are written for
+# exactly this architecture (tile shapes, channel counts and the 24-layer weight table of include/tdz.h are
+# compile-time); any other value is refused instead of silently ignored.
+MODEL_ARGS = (("in_channels", 512), ("out_channels", 512), ("num_blocks", 24), ("kernel_size", 16), ("norm", "ln"),
+              ("num_spks", 2), ("skip_around_intra", True), ("use_global_pos_enc", True), ("max_length", 20000))
+
+
+def check_model_args(*args, **kwargs):
+    """Validates the constructor arguments the reference passes through `from_pretrain(path, **cfg.model)`
+    (AudioProcessor.py:269-273, base_model.py:118-130) against the one architecture libtdz.so implements."""
+    names = [n for n, _ in MODEL_ARGS]
+    if len(args) > len(names):
+        raise TypeError(f"MossFormer2 takes at most {len(names)} positional arguments, got {len(args)}")
+    given = dict(zip(names, args))
+    for k, v in kwargs.items():
+        if k not in names:
+            raise TypeError(f"MossFormer2.__init__() got an unexpected keyword argument {k!r}")
+        if k in given:
+            raise TypeError(f"MossFormer2.__init__() got multiple values for argument {k!r}")
+        given[k] = v
+    for k, want in MODEL_ARGS:
+        if k in given and given[k] != want:
+            raise ValueError(f"tdz.Separator implements MossFormer2({k}={want!r}) only; the checkpoint / config asks "
+                             f"for {k}={given[k]!r}")
+
+
 class Separator:
     sample_rate = 16000
     num_spks = 2
@@ -18,7 +44,8 @@ class Separator:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("tdz.Separator runs on a CUDA (sm_100a) device only; there is no CPU fallback")
-        self._h = _lib.Handle(self.device.index or 0)
+        self.device = _lib.resolve_device(self.device)
+        self._h = _lib.Handle(self.device.index)
         self._packed = None
         self._ws = None
         if state_dict is not None:
@@ -30,14 +57,31 @@ class Separator:
         return cls(state_dict, device)
 
     @classmethod
-    def from_pretrain(cls, pretrained_model_conf_or_path, device="cuda:0", **kwargs):
-        """Checkpoint layout of BaseModel.serialize (base_model.py:132-146): {'model_name','state_dict',...}."""
-        conf = torch.load(pretrained_model_conf_or_path, map_location="cpu")
-        if conf.get("model_name", "MossFormer2") != "MossFormer2":
+    def from_pretrain(cls, pretrained_model_conf_or_path, *args, device="cuda:0", **kwargs):
+        """BaseModel.from_pretrain (base_model.py:118-130): the file holds what BaseModel.serialize wrote (:132-146) -
+        {'model_name', 'state_dict', 'model_args', 'infos'}; *args / **kwargs are the constructor arguments the
+        reference forwards from its config.yaml (`from_pretrain(path, **cfg.model)`, AudioProcessor.py:269-273).
+        Anything but the default MossFormer2 architecture is refused (ValueError / TypeError), never ignored."""
+        try:
+            conf = torch.load(pretrained_model_conf_or_path, map_location="cpu", weights_only=True)
+        except Exception:
+            # BaseModel.serialize stores version objects under 'infos' (base_model.py:141-145), which the tensors-only
+            # loader refuses; the reference itself unpickles the whole file (torch.load without restrictions)
+            conf = torch.load(pretrained_model_conf_or_path, map_location="cpu", weights_only=False)
+        if "model_name" not in conf or "state_dict" not in conf:
+            raise KeyError("checkpoint lacks 'model_name' / 'state_dict' (BaseModel.serialize layout)")
+        if conf["model_name"] != "MossFormer2":
             raise ValueError(f"tdz implements MossFormer2 only, checkpoint holds {conf['model_name']}")
+        check_model_args(*args, **kwargs)
+        if isinstance(conf.get("model_args"), dict):
+            check_model_args(**conf["model_args"])
         return cls(conf["state_dict"], device)
 
     def load_state_dict(self, state_dict, strict=True):
+        """Same contract as nn.Module.load_state_dict(strict=True) for the reference's 1 099-key dict: missing /
+        unexpected keys and shape mismatches raise RuntimeError (a checkpoint of another architecture must not load)."""
+        from .weights import check_mossformer2_state_dict
+        check_mossformer2_state_dict(state_dict, strict=strict)
         self._packed = PackedMossFormer2(state_dict, self.device)
         self._h.check(self._h.lib.tdz_set_mossformer2_weights(self._h.ptr, ctypes.byref(self._packed.table)),
                       "tdz_set_mossformer2_weights")
@@ -73,7 +117,11 @@ class Separator:
             raise RuntimeError("tdz_separate_layout failed")
         return lay
 
-    def __call__(self, mix, _debug=None):
+    def __call__(self, mix, _debug=None, out=None, out_strides=None):
+        """mix [T] / [B,T] / [B,1,T] -> [B,2,T].  `out` (optional) = a caller-owned fp32 device buffer to write
+        into; with `out_strides=(chunk_stride, speaker_stride)` (in floats) stream s of chunk b goes to
+        out.data_ptr() + 4*(b*chunk_stride + s*speaker_stride) - how the chunk loop writes windows straight into
+        the stitched [2, L] streams."""
         if self._packed is None:
             raise RuntimeError("Separator has no weights; call load_state_dict first")
         x = mix
@@ -85,12 +133,20 @@ class Separator:
             raise RuntimeError(f"input is on {x.device}, separator on {self.device}")
         x = x.to(torch.float32).contiguous()
         B, T = x.shape
-        out = torch.empty(B, 2, T, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(B, 2, T, dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or out.device != self.device:
+            raise RuntimeError("`out` must be a float32 tensor on the separator's device")
         nbytes = self.workspace_bytes(B, T)
         ws = self._workspace(nbytes)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         lib, h = self._h.lib, self._h
-        if _debug is None:
+        if _debug is None and out_strides is not None:
+            rc = lib.tdz_separate_strided(h.ptr, x.data_ptr(), B, T, out.data_ptr(), int(out_strides[0]),
+                                          int(out_strides[1]), ws.data_ptr(), nbytes, stream)
+        elif _debug is None:
+            if out.numel() < B * 2 * T or not out.is_contiguous():
+                raise RuntimeError("`out` must be contiguous and hold [B,2,T]")
             rc = lib.tdz_separate(h.ptr, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), nbytes, stream)
         else:
             rc = lib.tdz_separate_debug(h.ptr, x.data_ptr(), B, T, out.data_ptr(), ws.data_ptr(), nbytes, stream,

@@ -24,6 +24,76 @@ def round_tf32(x):
     return ((xi + r) & ~0x1FFF).view(torch.float32)
 
 
+def mossformer2_key_shapes(num_layers=_lib.NUM_LAYERS):
+    """{key: shape} of the reference MossFormer2().state_dict() (1 099 entries for 24 layers; SURVEY.md 8a13,
+    checked key for key against the reference module by tests/test_oracle_port.py)."""
+    sh = {"enc.conv1d.weight": (512, 1, 16), "mask_net.norm.weight": (512,), "mask_net.norm.bias": (512,),
+          "mask_net.conv1d_encoder.weight": (512, 512, 1), "mask_net.pos_enc.scale": (1,),
+          "mask_net.pos_enc.inv_freq": (256,), "mask_net.mdl.intra_mdl.norm.weight": (512,),
+          "mask_net.mdl.intra_mdl.norm.bias": (512,), "mask_net.mdl.intra_norm.weight": (512,),
+          "mask_net.mdl.intra_norm.bias": (512,), "mask_net.conv1d_out.weight": (1024, 512, 1),
+          "mask_net.conv1d_out.bias": (1024,), "mask_net.conv1_decoder.weight": (512, 512, 1),
+          "mask_net.prelu.weight": (1,), "mask_net.output.0.weight": (512, 512, 1), "mask_net.output.0.bias": (512,),
+          "mask_net.output_gate.0.weight": (512, 512, 1), "mask_net.output_gate.0.bias": (512,),
+          "dec.weight": (512, 1, 16)}
+    for i in range(num_layers):
+        p, q = LAYER.format(i), FSMN.format(i)
+        sh[p + "rotary_pos_emb.freqs"] = (16,)
+        for n, (o, k) in (("to_hidden", (2048, 512)), ("to_qk", (128, 512)), ("to_out", (512, 1024))):
+            sh[p + f"{n}.mdl.0.g"] = (1,)
+            sh[p + f"{n}.mdl.1.weight"] = (o, k)
+            sh[p + f"{n}.mdl.1.bias"] = (o,)
+            sh[p + f"{n}.mdl.3.sequential.1.conv.weight"] = (o, 1, 17)
+        sh[p + "qk_offset_scale.gamma"] = (4, 128)
+        sh[p + "qk_offset_scale.beta"] = (4, 128)
+        sh[q + "conv1.0.weight"] = (256, 512, 1)
+        sh[q + "conv1.0.bias"] = (256,)
+        sh[q + "conv1.1.weight"] = (1,)
+        sh[q + "conv2.weight"] = (512, 256, 1)
+        sh[q + "conv2.bias"] = (512,)
+        for n in ("norm1", "norm2"):
+            sh[q + n + ".weight"] = (256,)
+            sh[q + n + ".bias"] = (256,)
+        for n in ("to_u", "to_v"):
+            sh[q + f"gated_fsmn.{n}.mdl.0.weight"] = (256,)
+            sh[q + f"gated_fsmn.{n}.mdl.0.bias"] = (256,)
+            sh[q + f"gated_fsmn.{n}.mdl.1.weight"] = (256, 256)
+            sh[q + f"gated_fsmn.{n}.mdl.1.bias"] = (256,)
+            sh[q + f"gated_fsmn.{n}.mdl.3.sequential.1.conv.weight"] = (256, 1, 17)
+        sh[q + "gated_fsmn.fsmn.linear.weight"] = (256, 256)
+        sh[q + "gated_fsmn.fsmn.linear.bias"] = (256,)
+        sh[q + "gated_fsmn.fsmn.project.weight"] = (256, 256)
+        c = q + "gated_fsmn.fsmn.conv."
+        sh[c + "conv1.weight"] = (256, 1, 39, 1)
+        sh[c + "conv2.weight"] = (256, 2, 39, 1)
+        for n in ("norm1", "norm2"):
+            sh[c + n + ".weight"] = (256,)
+            sh[c + n + ".bias"] = (256,)
+        sh[c + "prelu1.weight"] = (256,)
+        sh[c + "prelu2.weight"] = (256,)
+    return sh
+
+
+def check_mossformer2_state_dict(state_dict, strict=True):
+    """nn.Module.load_state_dict(strict=True) semantics against the architecture the kernels implement."""
+    want = mossformer2_key_shapes()
+    errors = []
+    missing = [k for k in want if k not in state_dict]
+    unexpected = [k for k in state_dict if k not in want]
+    if missing:
+        errors.append("Missing key(s) in state_dict: " + ", ".join(repr(k) for k in missing[:8])
+                      + (f" ... ({len(missing)} in total)" if len(missing) > 8 else ""))
+    if strict and unexpected:
+        errors.append("Unexpected key(s) in state_dict: " + ", ".join(repr(k) for k in unexpected[:8])
+                      + (f" ... ({len(unexpected)} in total)" if len(unexpected) > 8 else ""))
+    for k, shape in want.items():
+        if k in state_dict and tuple(state_dict[k].shape) != shape:
+            errors.append(f"size mismatch for {k}: copying a param with shape {tuple(state_dict[k].shape)} from "
+                          f"checkpoint, the shape in tdz.Separator (MossFormer2 default architecture) is {shape}")
+    if errors:
+        raise RuntimeError("Error(s) in loading state_dict for tdz.Separator (MossFormer2):\n\t" + "\n\t".join(errors[:12]))
+
+
 class PackedMossFormer2:
     """Device tensors + the ctypes pointer table.  Keeps every tensor alive for as long as the table is used."""
 

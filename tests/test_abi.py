@@ -27,7 +27,8 @@ def lib():
 
 def test_header_declares_the_expected_surface():
     names = declared_functions()
-    for must in ("tdz_create", "tdz_separate", "tdz_stitch_ola", "tdz_stitch_concat", "tdz_gather_segments",
+    for must in ("tdz_create", "tdz_separate", "tdz_stitch_ola", "tdz_stitch_concat", "tdz_gather_segments", "tdz_separate_strided",
+                 "tdz_gather_segments_span",
                  "tdz_fbank", "tdz_embed", "tdz_cosine_scores", "tdz_last_error"):
         assert must in names
     assert len(names) >= 20
@@ -81,3 +82,50 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_from_pretrain_argument_validation():
+    """`from_pretrain(path, **cfg.model)` (AudioProcessor.py:269-273): the constructor arguments of the reference
+    MossFormer2 (mossformer2.py:532-541) are validated, never silently ignored."""
+    from targetdiarization_b200.separator import MODEL_ARGS, check_model_args
+    check_model_args()
+    check_model_args(**dict(MODEL_ARGS))
+    check_model_args(512, 512, 24, 16, "ln", 2)
+    for bad in (dict(num_blocks=12), dict(in_channels=256), dict(num_spks=3), dict(norm="gln"),
+                dict(skip_around_intra=False), dict(kernel_size=8)):
+        with pytest.raises(ValueError):
+            check_model_args(**bad)
+    with pytest.raises(TypeError):
+        check_model_args(sample_rate=16000)          # MossFormer2.__init__ has no such argument either
+    with pytest.raises(TypeError):
+        check_model_args(512, in_channels=512)
+    with pytest.raises(ValueError):
+        check_model_args(512, 512, 6)
+
+
+def test_state_dict_contract():
+    """load_state_dict(strict=True) semantics for the reference's 1 099-key dict."""
+    from targetdiarization_b200 import synth, weights
+    sd = synth.random_state_dict(seed=0)
+    assert len(weights.mossformer2_key_shapes()) == 1099
+    weights.check_mossformer2_state_dict(sd)
+    extra = dict(sd, bogus=sd["dec.weight"])
+    with pytest.raises(RuntimeError, match="Unexpected"):
+        weights.check_mossformer2_state_dict(extra)
+    weights.check_mossformer2_state_dict(extra, strict=False)
+    with pytest.raises(RuntimeError, match="Missing"):
+        weights.check_mossformer2_state_dict({k: v for k, v in sd.items() if k != "dec.weight"})
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        weights.check_mossformer2_state_dict(dict(sd, **{"dec.weight": sd["dec.weight"][:256]}))
+
+
+def test_embedder_oracle_owns_its_architecture_table():
+    """The ERes2NetV2 oracle's block table is its own (not imported from the product) and the shared weight
+    generator agrees with it key for key."""
+    import inspect
+    from oracle import eres2netv2_port as E
+    from targetdiarization_b200 import synth
+    assert "import block_specs" not in inspect.getsource(E)
+    assert [tuple(r) for r in E.block_specs()] == [tuple(r) for r in synth.block_specs()]
+    sd = E.random_state_dict(seed=1)      # raises if the generator's keys / shapes differ from the oracle's table
+    assert len(sd) == len(E.expected_key_shapes())

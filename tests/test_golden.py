@@ -204,3 +204,46 @@ def test_oracle_enrolment_restatement_matches_reference_run():
                 if len(lst):
                     assert np.array_equal(np.stack(lst), want), key
                 assert np.array_equal(np.asarray(one, dtype=np.float32), z[key + "_mean"]), key
+
+
+# ------------------------------------------------------------------------------- round 2: the BASELINE configurations
+def test_mix_audio_processor_tie_rule_matches_reference_run():
+    """TargetASR.mix_audio_processor (TargetASR.py:734-743) run from the reference source: which audio it returns for
+    score pairs incl. exact ties (spk1 wins: >=), threshold edges and NaN scores, and the score it reports."""
+    rows = np.load(os.path.join(GOLDEN, "mix_rule.npz"))["rows"]
+    assert len(rows) == 28
+    ties = 0
+    for thr, a, b, which, score in rows:
+        assert plan.pick_mix_audio(a, b, thr) == int(which), (thr, a, b)
+        assert stage_port.pick_mix_audio(a, b, thr) == int(which)
+        want = round(max(a, b), 3)
+        assert (np.isnan(score) and np.isnan(want)) or score == want
+        if a == b and not (a < thr):
+            ties += 1
+            assert int(which) == 1 and plan.pick_target(a, b, thr) == 2     # the two rules differ exactly on ties
+    assert ties >= 4
+
+
+def test_port_matches_reference_run_at_benchmark_shape():
+    """oracle/mossformer2_port.py at T = 64 000 (item 0 of the C2 benchmark batch, 32 attention groups, 4 fixed-size
+    linear-attention splits in the CUDA path) against the reference module's output on the same input."""
+    gd = np.load(os.path.join(GOLDEN, "c2_item.npz"))
+    seed, items, T, data_seed, _ = (int(v) for v in gd["cfg"])
+    mix = synth.synthetic_mixture(items, T, seed=data_seed)[:1]
+    with torch.no_grad():
+        y = mossformer2_forward(synth.random_state_dict(seed=seed), mix)[0]
+    assert snr_db(torch.from_numpy(gd["out_stride4"]), y[:, ::4]) >= 90.0
+
+
+def test_port_and_embedder_oracle_on_the_whole_c1_file():
+    """Config C1: the whole assets/chat_mix.wav through the port vs the reference run (>= 90 dB), and the oracle
+    embedder's scores for the reference-separated streams are reproducible from the stored embeddings."""
+    gd = np.load(os.path.join(GOLDEN, "c1_chat_mix.npz"))
+    assert gd["mix_pcm"].shape == (138634,) and gd["target_pcm"].shape == (30768,)
+    x = torch.from_numpy(gd["mix_pcm"].astype(np.float32) / 32768.0)[None]
+    with torch.no_grad():
+        y = mossformer2_forward(synth.random_state_dict(seed=0, perturb=True), x)[0]
+    assert snr_db(torch.from_numpy(gd["out_stride4"]), y[:, ::4]) >= 90.0
+    for k in range(2):
+        assert stage_port.cosine_similarity(gd["emb"][k], gd["emb_target"]) == pytest.approx(gd["scores"][k], abs=1e-7)
+    assert int(gd["pick"][0]) == (stage_port.pick_target(gd["scores"][0], gd["scores"][1], 0.0) or 0)

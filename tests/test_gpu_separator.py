@@ -100,12 +100,10 @@ def test_real_speech_excerpt_against_reference_run():
 
 @pytest.mark.parametrize("T", [16, 23, 100, 2055])
 def test_tiny_inputs(T):
-    """Shortest inputs the encoder accepts (T = 16 -> one frame) up to just over one attention group.  With a handful
-    of frames the per-chunk statistics (GroupNorm over frames, InstanceNorm over time) are degenerate and amplify
-    rounding differences, and the reference's own chunk loop cannot process such inputs (pyloudnorm needs 0.4 s), so
-    the three shortest cases are a robustness check with a 35 dB floor (measured 40.8 / 47.9 / 41.4 dB); from one
-    attention group on the 40 dB contract applies."""
-    _full(1, T, 4, min_db=40.0 if T >= 2048 else 35.0)
+    """Shortest inputs the encoder accepts (T = 16 -> one frame) up to just over one attention group, all under the
+    40 dB contract (with a handful of frames the per-chunk statistics - GroupNorm over frames, InstanceNorm over time -
+    are degenerate and amplify rounding differences: measured 40.8 / 47.9 / 41.4 dB in round 1)."""
+    _full(1, T, 4, min_db=40.0)
 
 
 def test_too_short_input_is_an_error():
