@@ -29,6 +29,7 @@ class Embedder:
         self._h = handle if handle is not None else _lib.Handle(self.device.index)
         self._packed = None
         self._ws = None
+        self._ws_generation = 0
         # None: a share of the memory that is free when a batch is sized (capped at 24 GiB: larger sub-batches buy
         # nothing, 128 x 4 s utterances need 9 GB)
         self._max_workspace_bytes = None if max_workspace_bytes is None else int(max_workspace_bytes)
@@ -67,7 +68,9 @@ class Embedder:
         if self._max_workspace_bytes is not None:
             return self._max_workspace_bytes
         held = self._ws_raw.numel() if self._ws is not None else 0
-        return min(24 << 30, _lib.free_device_bytes(self.device, held) // 4)
+        if torch.cuda.is_current_stream_capturing():   # no driver queries while a graph is being captured
+            return max(held - 1024, 0)
+        return min(24 << 30, max(_lib.free_device_bytes(self.device, held) // 4, held - 1024))
 
     def max_batch(self, frames):
         """Largest sub-batch whose workspace fits max_workspace_bytes (at least 1)."""
@@ -91,6 +94,7 @@ class Embedder:
             n = min(nb, N - i)
             nbytes = int(lib.tdz_embed_workspace_bytes(n, frames))
             if self._ws is None or self._ws.numel() < nbytes:
+                self._ws_generation += 1
                 self._ws = None
                 self._ws_raw = None
                 self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)

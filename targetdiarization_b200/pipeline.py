@@ -36,7 +36,9 @@ class CudaKernels:
             return self._max_workspace_bytes
         from . import _lib
         held = self.sep._ws_raw.numel() if self.sep._ws is not None else 0
-        return min(100 << 30, (_lib.free_device_bytes(self.device, held) * 3) // 4)
+        if torch.cuda.is_current_stream_capturing():   # no driver queries while a graph is being captured
+            return max(held - 1024, 0)
+        return min(100 << 30, max((_lib.free_device_bytes(self.device, held) * 3) // 4, held - 1024))
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -595,11 +597,51 @@ class SeparationScoringStage:
 
     # ---- the benchmark step: B independent chunks, both streams scored
     def run(self, mix_dev, target_embedding):
-        """mix_dev [B,T] on the device -> (est [B,2,T], scores [B,2]); target pick = scores[:,0] > scores[:,1]."""
+        """mix_dev [B,T] on the device -> (est [B,2,T], scores [B,2]); target pick = scores[:,0] > scores[:,1].
+
+        Small calls (the streaming shapes: a few 600 ms chunks) are launch-bound - ~660 kernels of a few microseconds:
+        from the second call of a shape on, the whole sequence (separation, fbank, ERes2NetV2, cosine) replays as ONE
+        captured CUDA graph."""
+        B, T = mix_dev.shape
+        sep = self.separator
+        if (sep.graph_max_frames and B * int(sep._h.lib.tdz_padded_frames(T)) <= sep.graph_max_frames
+                and not torch.cuda.is_current_stream_capturing()):
+            r = self._run_graphed(mix_dev, target_embedding, B, T)
+            if r is not None:
+                return r
         est = self.kern.separate(mix_dev)
-        B, _, T = est.shape
         scores = self.embedder.score_many(est.view(2 * B, T), target_embedding)
         return est, scores.view(B, 2)
+
+    def _run_graphed(self, mix_dev, target_embedding, B, T):
+        cache = self.__dict__.setdefault("_run_graphs", {})
+        gen = (self.separator._ws_generation, self.embedder._ws_generation)
+        ent = cache.get((B, T))
+        if ent is None or ent["gen"] != gen:
+            if ent is None:                      # first sight of the shape: eager (also sizes both workspaces)
+                cache[(B, T)] = dict(gen=None, graph=None)
+                if len(cache) > 16:
+                    cache.pop(next(iter(cache)))
+                return None
+            graphs, sep = self.separator.graph_max_frames, self.separator
+            s_in = torch.empty(B, T, dtype=torch.float32, device=self.device)
+            s_tgt = torch.empty(192, dtype=torch.float32, device=self.device)
+            sep.graph_max_frames = 0             # the inner call must launch, not replay its own graph
+            try:
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    est = self.kern.separate(s_in)
+                    scores = self.embedder.score_many(est.view(2 * B, T), s_tgt)
+            finally:
+                sep.graph_max_frames = graphs
+            ent = dict(gen=(self.separator._ws_generation, self.embedder._ws_generation), graph=g, s_in=s_in,
+                       s_tgt=s_tgt, est=est, scores=scores)
+            cache[(B, T)] = ent
+        ent["s_in"].copy_(mix_dev)
+        ent["s_tgt"].copy_(self.embedder._to_dev(target_embedding).reshape(-1))
+        ent["graph"].replay()
+        return ent["est"].clone(), ent["scores"].clone().view(B, 2)
 
     def embed(self, wav_dev):
         return self.embedder.embed_many(wav_dev)

@@ -36,6 +36,13 @@ def check_model_args(*args, **kwargs):
                              f"for {k}={given[k]!r}")
 
 
+# Calls of at most this many padded frames (B * Sp) are launch-bound: ~470 kernels of a few microseconds each.  From the
+# second call of a shape on they replay a CUDA graph captured from the same launch sequence (one submission instead of
+# ~470; same kernels, same bits).  32 768 frames = 16 concurrent 10 s windows or 25 concurrent 600 ms chunks.
+GRAPH_MAX_FRAMES = 32768
+GRAPH_CACHE = 16
+
+
 class Separator:
     sample_rate = 16000
     num_spks = 2
@@ -48,6 +55,9 @@ class Separator:
         self._h = _lib.Handle(self.device.index)
         self._packed = None
         self._ws = None
+        self._ws_generation = 0      # bumped when the workspace moves: captured CUDA graphs hold its address
+        self._graphs = {}            # (B, T) -> [times seen, CUDAGraph | None, static input, static output]
+        self.graph_max_frames = GRAPH_MAX_FRAMES
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -103,12 +113,45 @@ class Separator:
         """Caller-owned scratch, grown on demand; 1024 B aligned (TMA / swizzle atoms), which the caching allocator
         alone does not guarantee (512 B)."""
         if self._ws is None or self._ws.numel() < nbytes:
+            self._graphs.clear()
+            self._ws_generation += 1
             self._ws = None
             self._ws_raw = None
             self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
             off = (-self._ws_raw.data_ptr()) % 1024
             self._ws = self._ws_raw[off:off + nbytes]
         return self._ws
+
+    def _graphed(self, x, B, T):
+        """Small calls: eager the first time a shape is seen, captured into a CUDA graph the second time, replayed
+        from then on (the library only launches on the caller's stream and never allocates, so its launch sequence
+        is capturable as it is).  Returns None when this call should take the eager path."""
+        key = (B, T)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= GRAPH_CACHE:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = [1, None, None, None]
+            return None
+        if ent[1] is None:
+            nbytes = self.workspace_bytes(B, T)
+            ws = self._workspace(nbytes)
+            ent = self._graphs.setdefault(key, [1, None, None, None])   # _workspace may have cleared the cache
+            s_in = torch.empty(B, T, dtype=torch.float32, device=self.device)
+            s_out = torch.empty(B, 2, T, dtype=torch.float32, device=self.device)
+            lib, h = self._h.lib, self._h
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.current_stream(self.device).synchronize()
+            with torch.cuda.graph(g):
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                rc = lib.tdz_separate(h.ptr, s_in.data_ptr(), B, T, s_out.data_ptr(), ws.data_ptr(), nbytes, stream)
+            h.check(rc, "tdz_separate (graph capture)")
+            ent[1], ent[2], ent[3] = g, s_in, s_out
+        ent[0] += 1
+        ent[2].copy_(x)
+        ent[1].replay()
+        return ent[3].clone()
+
 
     def layout(self, B, T):
         lay = _lib.SepLayout()
@@ -133,6 +176,12 @@ class Separator:
             raise RuntimeError(f"input is on {x.device}, separator on {self.device}")
         x = x.to(torch.float32).contiguous()
         B, T = x.shape
+        if (out is None and _debug is None and self.graph_max_frames
+                and B * int(self._h.lib.tdz_padded_frames(T)) <= self.graph_max_frames and T >= 16
+                and not torch.cuda.is_current_stream_capturing()):
+            y = self._graphed(x, B, T)
+            if y is not None:
+                return y
         if out is None:
             out = torch.empty(B, 2, T, dtype=torch.float32, device=self.device)
         elif out.dtype != torch.float32 or out.device != self.device:

@@ -248,3 +248,45 @@ def test_strided_output_and_device_resolution():
     assert bool((out[:, :5] == 7.0).all()) and bool((out[:, -2:] == 7.0).all())
     with pytest.raises(RuntimeError):
         sep(x, out=out, out_strides=(100, 100))
+
+
+def test_cuda_graph_replay_equals_eager(stage):
+    """Small (launch-bound) calls replay a captured CUDA graph from the second call of a shape on: same kernels, same
+    bits as the eager launch sequence, for the separator alone and for the whole run() step; a workspace that moves
+    (larger call in between) invalidates the captured graphs instead of leaving them with stale pointers."""
+    torch, st = stage
+    from targetdiarization_b200.synth import synthetic_mixture
+    sep = st.separator
+    mix = synthetic_mixture(3, 9600, seed=61).cuda()
+    tgt = st.embed(synthetic_mixture(1, 16000, seed=62).cuda())[0]
+    keep = sep.graph_max_frames
+    sep.graph_max_frames = 0
+    eager = sep(mix[:1]).clone()
+    eager_run = [t.clone() for t in st.run(mix, tgt)]
+    sep.graph_max_frames = keep
+    sep._graphs.clear()
+    first = sep(mix[:1]).clone()          # eager (first sight of the shape)
+    second = sep(mix[:1]).clone()         # captured + replayed
+    third = sep(mix[:1] * 1.0).clone()    # replayed
+    assert sep._graphs[(1, 9600)][1] is not None and sep._graphs[(1, 9600)][0] >= 3
+    assert torch.equal(first, eager) and torch.equal(second, eager) and torch.equal(third, eager)
+    other = sep(mix[1:2])                 # different data through the same graph
+    sep.graph_max_frames = 0
+    assert torch.equal(other, sep(mix[1:2]))
+    sep.graph_max_frames = keep
+    for _ in range(3):
+        est, scores = st.run(mix, tgt)
+        assert torch.equal(est, eager_run[0]) and torch.equal(scores, eager_run[1])
+    assert st._run_graphs[(3, 9600)]["graph"] is not None
+    # a larger call moves the workspace: graphs are dropped, results stay right
+    gen = sep._ws_generation
+    big = synthetic_mixture(2, 16000 * 200, seed=63).cuda()
+    if sep.workspace_bytes(2, big.shape[1]) > sep._ws.numel():
+        sep(big)
+        assert sep._ws_generation == gen + 1 and not sep._graphs
+    del big
+    assert torch.equal(sep(mix[:1]), eager) and torch.equal(sep(mix[:1]), eager)
+    est, scores = st.run(mix, tgt)
+    assert torch.equal(est, eager_run[0]) and torch.equal(scores, eager_run[1])
+    est, scores = st.run(mix, tgt)
+    assert torch.equal(est, eager_run[0]) and torch.equal(scores, eager_run[1])
