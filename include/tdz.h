@@ -43,12 +43,13 @@ typedef struct tdz_ctx tdz_ctx;
 typedef struct tdz_layer_weights {
   const void* w_in;        /* bf16 [2176][512]: to_hidden (2048 rows, ScaleNorm g folded) | to_qk (128 rows) */
   const float* b_in;       /* [2176] */
-  const float* dw_in;      /* [17][2176] depthwise taps of the two ConvModules, tap-major */
+  const float* dw_in;      /* [2176][20] per channel: the 17 depthwise taps of its ConvModule with +1 added to the
+                              centre tap (x + conv(x), conv_module.py:219), then b_in / 2, then two zeros */
   const float* os_gamma;   /* [4][128] OffsetScale */
   const float* os_beta;    /* [4][128] */
   const void* w_out;       /* bf16 [512][1024], ScaleNorm g folded */
   const float* b_out;      /* [512] */
-  const float* dw_out;     /* [17][512] tap-major */
+  const float* dw_out;     /* [512][20], same layout as dw_in */
   const float* w_c1;       /* fp32 [256][512] fsmn.conv1 (tf32 operand) */
   const float* b_c1;       /* [256] */
   const float* prelu_c1;   /* [1] */
@@ -56,7 +57,7 @@ typedef struct tdz_layer_weights {
   const float* ln1_b;      /* [256] */
   const void* w_uv;        /* bf16 [512][256]: to_u | to_v with their LayerNorm affine folded */
   const float* b_uv;       /* [512] */
-  const float* dw_uv;      /* [17][512] tap-major */
+  const float* dw_uv;      /* [512][20], same layout as dw_in */
   const void* w_lin;       /* bf16 [256][256] fsmn.linear */
   const float* b_lin;      /* [256] */
   const void* w_proj;      /* bf16 [256][256] fsmn.project (no bias) */

@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtdz.so")
+# TDZ_LIB: development switch, another build of the same library (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("TDZ_LIB") or os.path.join(_HERE, "libtdz.so")
 
 NUM_LAYERS = 24
 c_f32p = ctypes.c_void_p  # device pointers travel as integers

@@ -54,8 +54,8 @@ struct EpiGeneric {
 // Outputs of the GEMMs whose epilogue also runs the depthwise k=17 time convolution of the ConvModule that
 // follows the Linear in every FFConvM (mossformer_block.py:89-102, conv_module.py:209-220).
 struct EpiConv {
-  const float* dw_t;   // taps, tap-major [17][ldw]; column index = output column of the GEMM
-  int ldw;
+  const float* dw_t;   // per output channel 20 floats: 17 taps (tap 8 + 1 = the residual of y + conv(y)), bias / 2, 0, 0
+  int ldw;             // (unused)
   // CONV_VUQK: to_hidden|to_qk  -> (v|u) bf16 and the to_qk activations fp32
   __nv_bfloat16* vu;   // [Mtot][2048]
   float* qkf;          // [Mtot][128] to_qk output (fp32; the four heads are made by qk_heads_kernel)

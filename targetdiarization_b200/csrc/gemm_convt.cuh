@@ -10,7 +10,9 @@
 //
 //   warp 0        TMA producer          {W 128 x 64, X 256 x 64} bf16 k-blocks, token shift = X row offset -1
 //   warp 1        tcgen05.mma issuer    fp32 accumulators in TMEM, two accumulator stages
-//   warps 2..13   epilogue              lane quarter (32 channels) x time third (80 output frames + 16 halo)
+//   warps 2..13   epilogue              lane quarter (32 channels) x time third (80 output frames + 16 halo);
+//                                       per warp a software pipeline tcgen05.ld | SiLU (MUFU) | k17 window (FMA pipe)
+//                                       over a four-block register ring, see convt_epilogue_tile
 //
 // A tile covers frames [240 j - 8, 240 j + 248) of a sample, of which the inner 240 are outputs (TMA zero-fills
 // rows outside the sample; activations of frames outside [0,S) are forced to zero = the convolution's padding).
@@ -27,34 +29,9 @@ constexpr int CT_ROWS = 240;                                     // output frame
 constexpr int CT_EPI_WARPS = 12;                                 // 4 lane quarters x 3 time thirds
 constexpr int CT_THREADS = 64 + 32 * CT_EPI_WARPS;
 constexpr int CT_SCR = 96;                                       // frames per epilogue warp (80 outputs + 16 halo)
-constexpr int CT_CONST_FLOATS = 18 * 128;                        // per channel of the tile: 17 taps + bias
-// Both scratch tables are written (cp.async) one tile ahead into the other of two buffers.  Warps share table
-// entries, and the two TMEM stages would let a fast warp run two tiles ahead of a slow one, so the epilogue warps
-// meet at a named barrier at the top of every tile: nobody overwrites a buffer that a straggler has yet to read.
-constexpr int CT_NBUF = 2;
-constexpr int CT_HRS_FLOATS = 3 * CT_SCR;                        // one row of scales per time third
-// operand ring | barriers | frame scales [2 buffers] | per-channel constants [2 buffers]
-constexpr int CT_SMEM_BYTES =
-    CT_STAGES * CT_STAGE_BYTES + 256 + CT_NBUF * CT_HRS_FLOATS * 4 + CT_NBUF * CT_CONST_FLOATS * 4 + 1024;
-
-// 4-byte asynchronous global -> shared copy (the per-tile constants of the NEXT tile are fetched this way while
-// the current tile is being processed, so no global-load latency sits on the per-tile critical path)
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  tmem_ld16(taddr, v);
-  tmem_ld16(taddr + 16, v + 16);
-}
+constexpr int CT_CPC = 20;                                       // floats per channel: 17 taps, bias / 2, 2 pad (80 B)
+// operand ring | barriers
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + 256 + 1024;
 
 // SiLU through one MUFU.TANH: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx: relative error 2^-11 on the
 // tanh, i.e. an absolute error below 5e-4*|h| - smaller than the bf16 rounding of the operand copy that follows).
@@ -100,18 +77,169 @@ __device__ __forceinline__ void convt_next(const LinearParams& P, const ConvTSte
   ti.t0 = ti.j * CT_ROWS - 8;
 }
 
+// tcgen05.ld of 16 columns into 8 register pairs.  No "memory" clobber: tensor memory is not addressable memory, and
+// with the clobber the compiler would pin every global store of the surrounding code to its side of the load.
+__device__ __forceinline__ void tmem_ld16_regs(uint32_t taddr, float2* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15}, [%16];"
+      : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x),
+        "=f"(r[3].y), "=f"(r[4].x), "=f"(r[4].y), "=f"(r[5].x), "=f"(r[5].y), "=f"(r[6].x), "=f"(r[6].y),
+        "=f"(r[7].x), "=f"(r[7].y)
+      : "r"(taddr));
+}
+// tcgen05.wait::ld that also names the 16 registers of an earlier tcgen05.ld as read-write operands: uses of those
+// registers cannot be scheduled above the wait, other arithmetic can (the load of the next block stays in flight
+// behind the convolution of the current one)
+__device__ __forceinline__ void tmem_ld_wait_dep(float2* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(r[0].x), "+f"(r[0].y), "+f"(r[1].x), "+f"(r[1].y), "+f"(r[2].x), "+f"(r[2].y), "+f"(r[3].x),
+                 "+f"(r[3].y), "+f"(r[4].x), "+f"(r[4].y), "+f"(r[5].x), "+f"(r[5].y), "+f"(r[6].x), "+f"(r[6].y),
+                 "+f"(r[7].x), "+f"(r[7].y));
+}
+
+// Epilogue of one tile for one thread (= one output channel): 96 accumulator columns = 6 blocks of 16 frames -> 80
+// outputs in 5 steps; step k convolves blocks k, k+1 (32-frame window).  Software pipeline over a four-block register
+// ring with static indices (everything is unrolled: no register moves, immediate TMEM / global offsets):
+//     tcgen05.ld of block k+3   |   activation of block k+2 (MUFU)   |   convolution of blocks k, k+1 (FMA pipe)
+// The activation and the convolution of a step form one straight-line region, so their instruction streams are
+// interleaved by the scheduler and the two pipes work at the same time inside ONE warp (three epilogue warps per
+// scheduler cannot hide a serial MUFU phase behind each other).
+//   even taps: packed FMAs on the aligned frame pairs; odd taps: scalar FMAs into the same accumulators (as fast as
+//   the packed even/odd form + combining adds in tools/micro/conv_bench.cu, and 18 registers lighter)
+// IS_QK: the tile holds the to_qk channels of CONV_VUQK (fp32 output); a template argument so that the whole tile
+// epilogue is ONE basic block and the scheduler may run the stores of a step under the FMAs of the next one.
+template <int MODE, bool MASKED, bool IS_QK, class Release>
+__device__ __forceinline__ void convt_epilogue_tile(const LinearParams& P, const ConvTTile& ti, int c,
+                                                    const float (&w)[17], float hb, const float* hrs_s, uint32_t tacc,
+                                                    int tbase, Release release) {
+  const EpiConv& cv = P.cv;
+  float2 R[32];  // ring: block b lives in R[(b & 3) * 8 .. +8), pair i = frames (2i, 2i+1) of the block
+  const float2 hb2 = make_float2(hb, hb);
+  const unsigned Su = static_cast<unsigned>(P.S);
+  auto ld_block = [&](int b) { tmem_ld16_regs(tacc + 16 * b, &R[(b & 3) * 8]); };
+  auto wait_block = [&](int b) { tmem_ld_wait_dep(&R[(b & 3) * 8]); };
+  // SiLU(scale * acc + bias) of block b, in place: h = scale/2 * acc + bias/2, a = h + h tanh(h)
+  auto activate = [&](int b) {
+    float2* r = &R[(b & 3) * 8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 hs = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+      if constexpr (MODE != CONV_UV) hs = __ldg(reinterpret_cast<const float4*>(hrs_s + 16 * b + 4 * i));
+      const float2 h01 = fma2(r[2 * i], make_float2(hs.x, hs.y), hb2);
+      const float2 h23 = fma2(r[2 * i + 1], make_float2(hs.z, hs.w), hb2);
+#ifndef TDZ_ABL_NOACT
+      float2 a01 = fma2(h01, make_float2(tanh_approx(h01.x), tanh_approx(h01.y)), h01);
+      float2 a23 = fma2(h23, make_float2(tanh_approx(h23.x), tanh_approx(h23.y)), h23);
+#else
+      float2 a01 = h01, a23 = h23;
+#endif
+      if constexpr (MASKED) {
+        // frames outside [0,S) are SELECTED to zero (= the convolution's padding; their accumulators may hold
+        // anything, also NaN: rows of the N operand beyond S are not written by every producer)
+        const unsigned t = static_cast<unsigned>(tbase + 16 * b + 4 * i);  // negative frames wrap to huge values
+        a01.x = (t + 0u < Su) ? a01.x : 0.f;
+        a01.y = (t + 1u < Su) ? a01.y : 0.f;
+        a23.x = (t + 2u < Su) ? a23.x : 0.f;
+        a23.y = (t + 3u < Su) ? a23.y : 0.f;
+      }
+      r[2 * i] = a01;
+      r[2 * i + 1] = a23;
+    }
+  };
+  ld_block(0);
+  ld_block(1);
+  wait_block(0);
+  wait_block(1);
+  ld_block(2);
+  activate(0);
+  activate(1);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k + 2 <= 5) wait_block(k + 2);
+    if (k + 3 <= 5) ld_block(k + 3);
+    if (k == 3) release();
+    const int tt0 = tbase + 8 + 16 * k;    // frame of output 0 of this step
+    const size_t grow0 = static_cast<size_t>(ti.srow) + tt0;
+    [[maybe_unused]] float rin[16];
+    if constexpr (MODE == CONV_RESX) {  // residual stream of these 16 frames: in flight during the FMAs
+      const float* src = cv.x_in + grow0 * 512 + c;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if constexpr (MASKED) rin[j] = (tt0 + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
+        else rin[j] = src[static_cast<size_t>(j) * 512];
+      }
+    }
+    if (k + 2 <= 5) activate(k + 2);
+    // out[j] = sum_t w[t] a[16 k + j + t], j = 0..15 (tap 8 carries the +1 of y + conv(y)); window pair i of the step
+    // = frames (16 k + 2 i, + 1) = pair (i & 7) of block k + (i >> 3)
+    auto Pw = [&](int i) -> const float2& { return R[((k + (i >> 3)) & 3) * 8 + (i & 7)]; };
+    float2 acc[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] = mul2(make_float2(w[0], w[0]), Pw(m));
+#ifndef TDZ_ABL_NOCONV
+#pragma unroll
+    for (int qq = 0; qq < 9; ++qq) {
+      if (qq > 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m] = fma2(make_float2(w[2 * qq], w[2 * qq]), Pw(m + qq), acc[m]);
+      }
+      if (qq < 8) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          acc[m].x = fmaf(w[2 * qq + 1], Pw(m + qq).y, acc[m].x);      // output 2m   <- frame 2m + 2qq + 1
+          acc[m].y = fmaf(w[2 * qq + 1], Pw(m + qq + 1).x, acc[m].y);  // output 2m+1 <- frame 2m + 2qq + 2
+        }
+      }
+    }
+#else
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m] = fma2(make_float2(w[16], w[16]), Pw(m + 8), acc[m]);
+#endif
+    auto out = [&](int j) { return (j & 1) ? acc[j >> 1].y : acc[j >> 1].x; };
+    const int nrow = MASKED ? min(P.S - tt0, 16) : 16;  // rows j < nrow are inside the sample (may be <= 0)
+    auto store_rows = [&](auto* dst, size_t ld, auto conv) {
+#ifdef TDZ_ABL_NOSTORE
+      if (w[3] != 12345.678f) return;
+#endif
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if constexpr (MASKED) {
+          if (j < nrow) dst[static_cast<size_t>(j) * ld] = conv(j);
+        } else {
+          dst[static_cast<size_t>(j) * ld] = conv(j);
+        }
+      }
+    };
+    if constexpr (MODE == CONV_VUQK) {
+      if constexpr (!IS_QK) {
+        store_rows(cv.vu + grow0 * 2048 + c, 2048, [&](int j) { return __float2bfloat16(out(j)); });
+      } else {
+        // to_qk channels: fp32, OffsetScale + rotary + bf16 split happen in qk_heads_kernel (the 32 rotary
+        // channels all sit in one TMEM lane quarter, i.e. on one scheduler: doing that work here serialises it)
+        store_rows(cv.qkf + grow0 * 128 + (c - 2048), 128, [&](int j) { return out(j); });
+      }
+    }
+    if constexpr (MODE == CONV_RESX) {
+      store_rows(cv.x_out + grow0 * 512 + c, 512, [&](int j) { return rin[j] + out(j); });
+    }
+    if constexpr (MODE == CONV_UV) {
+      store_rows(cv.xuv + grow0 * 512 + c, 512, [&](int j) { return out(j); });
+      if (c < 256) store_rows(cv.xubf + grow0 * 256 + c, 256, [&](int j) { return __float2bfloat16(out(j)); });
+    }
+  }
+}
+
 // CG2 = true: the CTA pair of a cluster owns two neighbouring channel tiles of the same time tile and executes one
 // tcgen05.mma.cta_group::2 (M = 256 channels) per k-step; each CTA stages its own weight tile and only half of the
 // X rows (32 KB per k-block instead of 48).  Used where the operand traffic matters (to_out, K = 1024: 2/3 of the
 // tile's L2 -> SM bytes were operands) and the channel-tile count is even; the epilogue is the same.
 constexpr int CT2_STAGES = 6;
 constexpr int CT2_STAGE_BYTES = GEMM_STAGE_A_BYTES + 128 * 128;  // W tile 16 KB + half an X tile 16 KB
-constexpr int CT2_SMEM_BYTES =
-    CT2_STAGES * CT2_STAGE_BYTES + 256 + CT_NBUF * CT_HRS_FLOATS * 4 + CT_NBUF * CT_CONST_FLOATS * 4 + 1024;
+constexpr int CT2_SMEM_BYTES = CT2_STAGES * CT2_STAGE_BYTES + 256 + 1024;
 
 template <int MODE, bool CG2>
 __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
-  constexpr int LDW = (MODE == CONV_VUQK) ? 2176 : 512;  // leading dimension of the tap-major tap table
   constexpr int CT_STAGES = CG2 ? CT2_STAGES : tdz::CT_STAGES;  // (shadow the single-CTA constants)
   constexpr int CT_STAGE_BYTES = CG2 ? CT2_STAGE_BYTES : tdz::CT_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -122,7 +250,6 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   auto empty_bar = [&](int s) { return bar_base + 8u * (CT_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * CT_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * CT_STAGES + 2 + s); };
-  float* scratch = reinterpret_cast<float*>(smem_al + CT_STAGES * CT_STAGE_BYTES + 256);
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5;
@@ -237,52 +364,37 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
     const int q = warp & 3;           // TMEM lane quarter -> 32 channels
     const int tq = (warp - 2) >> 2;   // time third
     const int col0 = 80 * tq;         // first accumulator column this warp reads
-    // shared scratch: the 96 per-frame scales of this warp's time third (0.5 / ScaleNorm denominator, precomputed
-    // per frame by rowscale_kernel) and the per-channel constants of the tile (taps, bias); warps that share an
-    // entry copy the same values (benign)
-    float* hrs_buf = scratch + tq * CT_SCR;                                // + buf * CT_HRS_FLOATS
-    float* cst_buf = scratch + CT_NBUF * CT_HRS_FLOATS + q * 32 + lane;    // + buf * CT_CONST_FLOATS + k * 128
     const EpiGeneric& e = P.e;
     const EpiConv& cv = P.cv;
-    auto prefetch = [&](const ConvTTile& tn, int buf) {  // asynchronous: completes before the tile that uses `buf`
-      const int c = chan_tile(tn) * 128 + q * 32 + lane;
-      float* cs = cst_buf + buf * CT_CONST_FLOATS;
-#pragma unroll
-      for (int k = 0; k < 17; ++k) cp_async4(cs + k * 128, cv.dw_t + k * LDW + c);
-      cp_async4(cs + 17 * 128, e.bias + c);
-      if constexpr (MODE != CONV_UV) {
-        float* hs = hrs_buf + buf * CT_HRS_FLOATS;
-        const int tb = tn.t0 + col0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int i = lane + 32 * r;
-          const int t = min(max(tb + i, 0), P.S - 1);  // frames outside [0,S) are masked later; any valid address
-          cp_async4(hs + i, e.ss_in + static_cast<size_t>(tn.srow) + t);
-        }
-      }
-    };
+    // No shared scratch and no barrier among the epilogue warps: the three warps of a scheduler run the SAME
+    // instruction stream, and a barrier per tile kept them in lock step - all in their FMA phase together (contending
+    // for the pipe), all in their store / TMEM-wait phase together (pipe idle): tile time = sum of the phases, not the
+    // maximum.  Free-running warps, started one third of a step apart, keep the FMA pipe fed from one warp while
+    // another stores.  The per-channel constants (80 B) and per-frame scales come straight from global memory (L1 /
+    // L2 hits: the tables are a few hundred KB and shared by every CTA).
+    if (tq > 0) __nanosleep(400u * tq);
     int it = 0;
     ConvTTile ti, tn;
     [[maybe_unused]] const uint32_t leader_tempty = CG2 ? mapa_shared(tempty_bar(0), 0) : 0u;
     convt_tile(P, nct, first, ti);
-    if (first < ntiles) prefetch(ti, 0);
     for (int tile = first; tile < ntiles; tile += stride, ++it, ti = tn) {
       tn = ti;
       convt_next(P, tstep, tn);
       const int c = chan_tile(ti) * 128 + q * 32 + lane;  // output channel of this thread
-      const int buf = it % CT_NBUF;
-      cp_async_wait_all();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * CT_EPI_WARPS) : "memory");  // epilogue warps only
-      float2 wt[17];  // (w_k, w_k): operand of the packed FMA
-#pragma unroll
-      for (int k = 0; k < 17; ++k) {
-        const float wk = cst_buf[buf * CT_CONST_FLOATS + k * 128];
-        wt[k] = make_float2(wk, wk);
+      float w[17];
+      float hb;
+      {
+        const float4* cs = reinterpret_cast<const float4*>(cv.dw_t + static_cast<size_t>(c) * CT_CPC);
+        const float4 c0 = __ldg(cs), c1 = __ldg(cs + 1), c2 = __ldg(cs + 2), c3 = __ldg(cs + 3), c4 = __ldg(cs + 4);
+        w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
+        w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
+        w[8] = c2.x; w[9] = c2.y; w[10] = c2.z; w[11] = c2.w;
+        w[12] = c3.x; w[13] = c3.y; w[14] = c3.z; w[15] = c3.w;
+        w[16] = c4.x;
+        hb = c4.y;
       }
-      const float hb = 0.5f * cst_buf[buf * CT_CONST_FLOATS + 17 * 128];
-      const float2 hb2 = make_float2(hb, hb);
-      const float* hrs_s = hrs_buf + buf * CT_HRS_FLOATS;
-      if (tile + stride < ntiles) prefetch(tn, (it + 1) % CT_NBUF);
+      // scales of this warp's 96 frames (the table is padded: rows 8 before and 256 after the samples are readable)
+      const float* hrs_s = (MODE != CONV_UV) ? e.ss_in + static_cast<ptrdiff_t>(ti.srow) + (ti.t0 + col0) : nullptr;
       const int tbase = ti.t0 + col0;  // frame of accumulator column col0
       const bool all_valid = tbase >= 0 && tbase + 96 <= P.S;
 
@@ -290,133 +402,25 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
       mbar_wait(tfull_bar(as), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * 256 + (static_cast<uint32_t>(q * 32) << 16) + col0;
-
-      // SiLU(scale * acc + bias) of N freshly loaded accumulator columns, in place; sidx = index of the first one
-      // in the per-frame scratch (a multiple of 4)
-      // window of 32 consecutive frames as 16 register pairs (frames 2m, 2m+1): the operand form of FFMA2
-      float2 P0[16];
-      float* win = reinterpret_cast<float*>(P0);
-      auto activate_t = [&](float* w, int sidx, auto n_tag, auto masked_tag) {
-        constexpr int N = decltype(n_tag)::value;
-        constexpr bool MASKED = decltype(masked_tag)::value;
-#pragma unroll
-        for (int i = 0; i < N; i += 4) {  // four frames at a time keeps the scale / mask operands short-lived
-          float4 hs = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-          if constexpr (MODE != CONV_UV) hs = *reinterpret_cast<const float4*>(hrs_s + sidx + i);
-          // h = scale * acc + bias/2 and h + h tanh(h) as packed FMAs on frame pairs
-          const float2 h01 = fma2(make_float2(w[i + 0], w[i + 1]), make_float2(hs.x, hs.y), hb2);
-          const float2 h23 = fma2(make_float2(w[i + 2], w[i + 3]), make_float2(hs.z, hs.w), hb2);
-          const float2 a01 = fma2(h01, make_float2(tanh_approx(h01.x), tanh_approx(h01.y)), h01);
-          const float2 a23 = fma2(h23, make_float2(tanh_approx(h23.x), tanh_approx(h23.y)), h23);
-          if constexpr (!MASKED) {
-            w[i + 0] = a01.x;
-            w[i + 1] = a01.y;
-            w[i + 2] = a23.x;
-            w[i + 3] = a23.y;
-          } else {
-            // frames outside [0,S) are SELECTED to zero (their accumulators may hold anything, also NaN: the rows
-            // of the N operand beyond S are never written by the producer kernels)
-            const unsigned t = static_cast<unsigned>(tbase + sidx + i);  // negative frames wrap to huge values
-            const unsigned Su = static_cast<unsigned>(P.S);
-            w[i + 0] = (t + 0u < Su) ? a01.x : 0.f;
-            w[i + 1] = (t + 1u < Su) ? a01.y : 0.f;
-            w[i + 2] = (t + 2u < Su) ? a23.x : 0.f;
-            w[i + 3] = (t + 3u < Su) ? a23.y : 0.f;
-          }
+      auto release = [&]() {  // the last TMEM read of this tile is done
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG2) mbar_arrive_cluster(leader_tempty + 8u * as);
+          else mbar_arrive(tempty_bar(as));
         }
       };
-      auto activate = [&](float* w, int sidx, auto n_tag) {  // warp-uniform: interior tiles carry no masks
-        if (all_valid) {
-          activate_t(w, sidx, n_tag, std::false_type{});
-        } else {
-          activate_t(w, sidx, n_tag, std::true_type{});
-        }
-      };
-      tmem_ld32(tacc, win);
-      tmem_ld_wait();
-      activate(win, 0, std::integral_constant<int, 32>{});
-#pragma unroll 1
-      for (int itn = 0; itn < 5; ++itn) {
-        [[maybe_unused]] float rin[16];
-        if constexpr (MODE == CONV_RESX) {  // residual stream of these 16 frames: in flight during the FMAs
-          const int tt0r = tbase + 8 + 16 * itn;
-          const float* src = cv.x_in + (static_cast<size_t>(ti.srow) + tt0r) * 512 + c;
-          if (tt0r + 16 <= P.S) {  // warp-uniform fast path: no per-row predicates
-#pragma unroll
-            for (int j = 0; j < 16; ++j) rin[j] = src[static_cast<size_t>(j) * 512];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) rin[j] = (tt0r + j < P.S) ? src[static_cast<size_t>(j) * 512] : 0.f;
-          }
-        }
-        // y + dwconv17(y) for 16 frames with packed FMAs (two fp32 FMAs per issue slot).  Even taps accumulate
-        // into pairs (out[2m], out[2m+1]), odd taps into pairs (out[2m-1], out[2m]): both then read ALIGNED window
-        // pairs P0[m+q], so no shifted copy of the window is needed; the two partial sums are added at the end.
-        float2 accA[8], accB[9];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) accA[m] = P0[m + 4];
-#pragma unroll
-        for (int m = 0; m < 9; ++m) accB[m] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < 9; ++q) {
-#pragma unroll
-          for (int m = 0; m < 8; ++m) accA[m] = fma2(wt[2 * q], P0[m + q], accA[m]);
-          if (q < 8) {
-#pragma unroll
-            for (int m = 0; m < 9; ++m) accB[m] = fma2(wt[2 * q + 1], P0[m + q], accB[m]);
-          }
-        }
-        float acc[16];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          acc[2 * m] = accA[m].x + accB[m].y;
-          acc[2 * m + 1] = accA[m].y + accB[m + 1].x;
-        }
-        if (itn < 4) {  // slide the window: the next 16 accumulator columns
-#pragma unroll
-          for (int i = 0; i < 16; ++i) win[i] = win[16 + i];
-          tmem_ld16(tacc + 32 + 16 * itn, win + 16);
-          tmem_ld_wait();
-          if (itn == 3) {  // last TMEM read of this tile is done
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CG2) mbar_arrive_cluster(leader_tempty + 8u * as);
-              else mbar_arrive(tempty_bar(as));
-            }
-          }
-          activate(win + 16, 32 + 16 * itn, std::integral_constant<int, 16>{});
-        }
-        const int tt0 = tbase + 8 + 16 * itn;  // frame of acc[0]
-        const int nrow = min(P.S - tt0, 16);   // rows j < nrow are inside the sample (may be <= 0)
-        const size_t grow0 = static_cast<size_t>(ti.srow) + tt0;
-        // rows j < nrow are stored; interior tiles (nrow == 16, warp-uniform) take the unpredicated form
-        auto store_rows = [&](auto* dst, size_t ld, auto conv) {
-          if (nrow >= 16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) dst[static_cast<size_t>(j) * ld] = conv(j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nrow) dst[static_cast<size_t>(j) * ld] = conv(j);
-          }
-        };
+      // interior tiles (warp-uniform) carry no masks and no store predicates
+      const bool is_qk = MODE == CONV_VUQK && c >= 2048;  // warp-uniform: the to_qk channels are one whole tile
+      if (is_qk) {
         if constexpr (MODE == CONV_VUQK) {
-          if (c < 2048) {  // warp-uniform (the qk channels are one whole channel tile)
-            store_rows(cv.vu + grow0 * 2048 + c, 2048, [&](int j) { return __float2bfloat16(acc[j]); });
-          } else {
-            // to_qk channels: fp32, OffsetScale + rotary + bf16 split happen in qk_heads_kernel (the 32 rotary
-            // channels all sit in one TMEM lane quarter, i.e. on one scheduler: doing that work here serialises it)
-            store_rows(cv.qkf + grow0 * 128 + (c - 2048), 128, [&](int j) { return acc[j]; });
-          }
+          if (all_valid) convt_epilogue_tile<MODE, false, true>(P, ti, c, w, hb, hrs_s, tacc, tbase, release);
+          else convt_epilogue_tile<MODE, true, true>(P, ti, c, w, hb, hrs_s, tacc, tbase, release);
         }
-        if constexpr (MODE == CONV_RESX) {
-          store_rows(cv.x_out + grow0 * 512 + c, 512, [&](int j) { return rin[j] + acc[j]; });
-        }
-        if constexpr (MODE == CONV_UV) {
-          store_rows(cv.xuv + grow0 * 512 + c, 512, [&](int j) { return acc[j]; });
-          if (c < 256) store_rows(cv.xubf + grow0 * 256 + c, 256, [&](int j) { return __float2bfloat16(acc[j]); });
-        }
+      } else if (all_valid) {
+        convt_epilogue_tile<MODE, false, false>(P, ti, c, w, hb, hrs_s, tacc, tbase, release);
+      } else {
+        convt_epilogue_tile<MODE, true, false>(P, ti, c, w, hb, hrs_s, tacc, tbase, release);
       }
     }
   }
@@ -430,6 +434,7 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   }
 }
 
+// 14 warps = 4 + 4 + 3 + 3 per scheduler, and a scheduler owns 16 K registers: 128 registers per thread is the limit
 template <int MODE>
 __global__ void __launch_bounds__(CT_THREADS, 1) gemm_convt_kernel(const __grid_constant__ LinearParams P) {
   gemm_convt_body<MODE, false>(P);

@@ -189,6 +189,7 @@ extern "C" int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_w
 }
 
 // ------------------------------------------------------------------------------------------------ layout
+constexpr size_t TDZ_HRS_FRONT = 8;
 extern "C" int64_t tdz_num_frames(int64_t T) { return T < 16 ? 0 : (T - 16) / 8 + 1; }
 extern "C" int64_t tdz_padded_frames(int64_t T) {
   const int64_t S = tdz_num_frames(T);
@@ -255,7 +256,9 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->in_ss = take(static_cast<size_t>(B) * 256 * 8 * 2);        // their (scale, shift) tables
   L->samp = take(static_cast<size_t>(B) * 4 * 4);               // A,B for each GroupNorm
   L->rot = take(static_cast<size_t>(Sp) * 16 * 8);
-  L->hrs = take(m * 4);                                         // per-frame ScaleNorm scale of the next conv GEMM
+  // per-frame ScaleNorm scale of the next conv GEMM; its epilogue reads whole 96-frame runs around a tile without
+  // clamping (frames outside a sample are masked afterwards): TDZ_HRS_FRONT floats before and 256 after stay readable
+  L->hrs = take((m + TDZ_HRS_FRONT + 256) * 4);
   L->total = off;
   return 0;
 }
@@ -304,7 +307,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
   float2* in_ss = reinterpret_cast<float2*>(base + L.in_ss);
   float2* rot = reinterpret_cast<float2*>(base + L.rot);
-  float* hrs = F(L.hrs);
+  float* hrs = F(L.hrs) + TDZ_HRS_FRONT;
   // mask-head buffers (second view of the layer region, used after the layer loop)
   float *lnb = F(L.lnb), *ab = F(L.ab), *mb = F(L.mb), *gated = F(L.gated), *sep = F(L.sep);
 

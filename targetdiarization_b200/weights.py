@@ -24,6 +24,18 @@ def round_tf32(x):
     return ((xi + r) & ~0x1FFF).view(torch.float32)
 
 
+def conv_constants(taps, bias):
+    """Per-channel constants of a Linear + SiLU + ConvModule epilogue (csrc/gemm_convt.cuh), [C][20]: the 17 depthwise
+    taps with the +1 of `x + conv(x)` (conv_module.py:219) folded into the centre tap, bias / 2 (the SiLU is evaluated
+    as h + h tanh(h) with h = x / 2), two zeros (80-byte rows: five 16-byte asynchronous copies per channel)."""
+    C = taps.shape[0]
+    out = torch.zeros(C, 20, dtype=torch.float32)
+    out[:, :17] = taps
+    out[:, 8] += 1.0
+    out[:, 17] = 0.5 * bias
+    return out
+
+
 def mossformer2_key_shapes(num_layers=_lib.NUM_LAYERS):
     """{key: shape} of the reference MossFormer2().state_dict() (1 099 entries for 24 layers; SURVEY.md 8a13,
     checked key for key against the reference module by tests/test_oracle_port.py)."""
@@ -121,14 +133,16 @@ class PackedMossFormer2:
             p = LAYER.format(i)
             gh, gq, go = (sd[p + f"{n}.mdl.0.g"] for n in ("to_hidden", "to_qk", "to_out"))
             L.w_in = bf16(torch.cat((sd[p + "to_hidden.mdl.1.weight"] * gh, sd[p + "to_qk.mdl.1.weight"] * gq), 0))
-            L.b_in = f32(torch.cat((sd[p + "to_hidden.mdl.1.bias"], sd[p + "to_qk.mdl.1.bias"]), 0))
-            L.dw_in = f32(torch.cat((sd[p + "to_hidden.mdl.3.sequential.1.conv.weight"][:, 0, :],
-                                     sd[p + "to_qk.mdl.3.sequential.1.conv.weight"][:, 0, :]), 0).t())  # tap-major
+            b_in = torch.cat((sd[p + "to_hidden.mdl.1.bias"], sd[p + "to_qk.mdl.1.bias"]), 0)
+            L.b_in = f32(b_in)
+            L.dw_in = f32(conv_constants(torch.cat((sd[p + "to_hidden.mdl.3.sequential.1.conv.weight"][:, 0, :],
+                                                    sd[p + "to_qk.mdl.3.sequential.1.conv.weight"][:, 0, :]), 0), b_in))
             L.os_gamma = f32(sd[p + "qk_offset_scale.gamma"])
             L.os_beta = f32(sd[p + "qk_offset_scale.beta"])
             L.w_out = bf16(sd[p + "to_out.mdl.1.weight"] * go)
             L.b_out = f32(sd[p + "to_out.mdl.1.bias"])
-            L.dw_out = f32(sd[p + "to_out.mdl.3.sequential.1.conv.weight"][:, 0, :].t())
+            L.dw_out = f32(conv_constants(sd[p + "to_out.mdl.3.sequential.1.conv.weight"][:, 0, :],
+                                          sd[p + "to_out.mdl.1.bias"]))
             q = FSMN.format(i)
             L.w_c1 = tf32(sd[q + "conv1.0.weight"][:, :, 0])
             L.b_c1 = f32(sd[q + "conv1.0.bias"])
@@ -144,7 +158,7 @@ class PackedMossFormer2:
                 dws.append(sd[q + f"gated_fsmn.{n}.mdl.3.sequential.1.conv.weight"][:, 0, :])
             L.w_uv = bf16(torch.cat(ws, 0))
             L.b_uv = f32(torch.cat(bs, 0))
-            L.dw_uv = f32(torch.cat(dws, 0).t())
+            L.dw_uv = f32(conv_constants(torch.cat(dws, 0), torch.cat(bs, 0)))
             L.w_lin = bf16(sd[q + "gated_fsmn.fsmn.linear.weight"])
             L.b_lin = f32(sd[q + "gated_fsmn.fsmn.linear.bias"])
             L.w_proj = bf16(sd[q + "gated_fsmn.fsmn.project.weight"])
