@@ -659,9 +659,7 @@ struct AttnParams {
   CUtensorMap tmQKmn;  // 3-D {512, Sp, B}  box {64, 64, 1}   MN-major atoms (A of kv: lin_k^T)
   CUtensorMap tmVUmn;  // 3-D {2048, Sp, B} box {64, 64, 1}   MN-major atoms (B of quad*VU and of kv)
   CUtensorMap tmP;     // 3-D {256, Sp, B}  box {64, 128, 1}  relu^2 attention weights
-  CUtensorMap tmKVmn;  // 3-D {2048, 256, B} box {64, 64, 1}  MN-major atoms of lin_kv | lin_ku: rows 0..127 the bf16
-                       //     value, rows 128..255 the bf16 of the rounding residual (two-term split)
-  CUtensorMap tmLQlo;  // 3-D {128, Sp, B}  box {64, 128, 1}  rounding residual of lin_q (two-term split)
+  CUtensorMap tmKVmn;  // 3-D {2048, 128, B} box {64, 64, 1}  MN-major atoms of lin_kv | lin_ku (FP16, like lin_q)
   int B, Sp, S;
   int nsplit;          // kv: splits of the frame axis
   int kb_per_split;
@@ -769,18 +767,21 @@ struct AttnKV {
 // att = attn @ [v|u] (per 256-frame group) + lin_q @ [lin_kv|lin_ku]; out = (att_u*v)*sigmoid(att_v*u)
 // (mossformer_block.py:269-270,287-294,217).  One accumulator tile = 128 v-columns next to the matching
 // 128 u-columns, so the gate runs in the epilogue and the [.,2048] attention output never reaches HBM.
+// Runs as gemm_cg2_kernel: the CTA pair that owns the two query tiles of a 256-frame group executes ONE
+// tcgen05.mma.cta_group::2 (M = 256) per k-step; rank 0 stages the 128 v columns of B, rank 1 the 128 u columns, each
+// its own A rows.  k-blocks 0..3: quadratic part (bf16, K = 256 keys); k-blocks 4..5: linear part lin_q @ lin_kv with
+// FP16 operands (K = 128, see qk_heads_kernel) - two instruction descriptors accumulate into one TMEM tile.
 struct AttnOut {
   using Params = AttnParams;
   static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 1, EPI_SPLIT = 2;
+  static constexpr int F16_FROM_KB = 4;  // k-blocks from this one on use fp16 operands (instruction descriptor fmt 0)
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmP);
     tma_prefetch_desc(&P.tmVUmn);
     tma_prefetch_desc(&P.tmQK);
     tma_prefetch_desc(&P.tmKVmn);
-    tma_prefetch_desc(&P.tmLQlo);
   }
-  __device__ static int num_tiles(const Params& P) { return (P.B * P.Sp / GEMM_BLOCK_M) * 8; }
   __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
     const int mt = tile >> 3;
     const int nt = tile & 7;
@@ -788,72 +789,13 @@ struct AttnOut {
     ti.n0 = nt * 128;  // first v channel; the u channel is 1024 + n0
     ti.b = ti.m0 / P.Sp;
     ti.t0 = ti.m0 - ti.b * P.Sp;
-    ti.nkb = 10;  // 4 quadratic (256 keys) + 6 linear: q_hi kv_hi, q_hi kv_lo, q_lo kv_hi (128 each)
+    ti.nkb = 6;  // 4 quadratic (256 keys) + 2 linear (128 features)
     ti.aux = nt;
   }
-  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
-    if (kb < 4) {
-      const int g0 = (ti.t0 / 256) * 256;
-      tma_load_3d(sa, &P.tmP, bar, kb * 64, ti.t0, ti.b);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
-        tma_load_3d(sb + j * 8192, &P.tmVUmn, bar, ch, g0 + kb * 64, ti.b);
-      }
-    } else {
-      // The linear-attention product lin_q @ lin_kv carries the largest rounding error of the whole network when
-      // both operands are single bf16 values (measured: +4.8 dB of output SNR without it), so it runs as a
-      // three-term split: (q_hi + q_lo)(kv_hi + kv_lo) ~ q_hi kv_hi + q_hi kv_lo + q_lo kv_hi.
-      const int kk = kb - 4;               // 0,1: q_hi kv_hi   2,3: q_hi kv_lo   4,5: q_lo kv_hi
-      const int k0 = (kk & 1) * 64;
-      if (kk < 4) {
-        tma_load_3d(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);  // lin_q
-      } else {
-        tma_load_3d(sa, &P.tmLQlo, bar, k0, ti.t0, ti.b);      // lin_q - bf16(lin_q)
-      }
-      const int kvrow = ((kk >> 1) == 1 ? 128 : 0) + k0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
-        tma_load_3d(sb + j * 8192, &P.tmKVmn, bar, ch, kvrow, ti.b);
-      }
-    }
-  }
-  // ---- paired launch: the two query tiles of one 256-frame group share the whole B operand (keys / kv rows)
   __device__ static int num_pair_tiles(const Params& P) { return (P.B * P.Sp / 256) * 8; }
   __device__ static void pair_tile_info(const Params& P, int w, uint32_t rank, TileInfo& ti) {
     tile_info(P, ((w >> 3) * 2 + static_cast<int>(rank)) * 8 + (w & 7), ti);
   }
-  __device__ static void load_pair(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar,
-                                   uint32_t rank) {
-    const int j0 = 2 * static_cast<int>(rank);  // this CTA multicasts B boxes j0, j0+1 (of 4) to both CTAs
-    if (kb < 4) {
-      const int g0 = (ti.t0 / 256) * 256;
-      tma_load_3d(sa, &P.tmP, bar, kb * 64, ti.t0, ti.b);
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = j0 + jj;
-        const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
-        tma_load_3d_mc(sb + j * 8192, &P.tmVUmn, bar, ch, g0 + kb * 64, ti.b, 0x3);
-      }
-    } else {
-      const int kk = kb - 4;
-      const int k0 = (kk & 1) * 64;
-      if (kk < 4) {
-        tma_load_3d(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);
-      } else {
-        tma_load_3d(sa, &P.tmLQlo, bar, k0, ti.t0, ti.b);
-      }
-      const int kvrow = ((kk >> 1) == 1 ? 128 : 0) + k0;
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = j0 + jj;
-        const int ch = (j < 2 ? ti.n0 + j * 64 : 1024 + ti.n0 + (j - 2) * 64);
-        tma_load_3d_mc(sb + j * 8192, &P.tmKVmn, bar, ch, kvrow, ti.b, 0x3);
-      }
-    }
-  }
-  // ---- cta_group::2 launch: rank 0 stages the 128 v columns of B, rank 1 the 128 u columns; each its own A rows
   static constexpr int CG2_STAGES = 6;
   __device__ static void load_cg2(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar,
                                   uint32_t rank) {
@@ -864,21 +806,15 @@ struct AttnOut {
       tma_load_3d_cg2(sb, &P.tmVUmn, bar, ch0, g0 + kb * 64, ti.b);
       tma_load_3d_cg2(sb + 8192, &P.tmVUmn, bar, ch0 + 64, g0 + kb * 64, ti.b);
     } else {
-      const int kk = kb - 4;
-      const int k0 = (kk & 1) * 64;
-      if (kk < 4) {
-        tma_load_3d_cg2(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);
-      } else {
-        tma_load_3d_cg2(sa, &P.tmLQlo, bar, k0, ti.t0, ti.b);
-      }
-      const int kvrow = ((kk >> 1) == 1 ? 128 : 0) + k0;
-      tma_load_3d_cg2(sb, &P.tmKVmn, bar, ch0, kvrow, ti.b);
-      tma_load_3d_cg2(sb + 8192, &P.tmKVmn, bar, ch0 + 64, kvrow, ti.b);
+      const int k0 = (kb - 4) * 64;
+      tma_load_3d_cg2(sa, &P.tmQK, bar, 128 + k0, ti.t0, ti.b);  // lin_q (fp16)
+      tma_load_3d_cg2(sb, &P.tmKVmn, bar, ch0, k0, ti.b);
+      tma_load_3d_cg2(sb + 8192, &P.tmKVmn, bar, ch0 + 64, k0, ti.b);
     }
   }
-  // ---- epilogue of the cta_group::2 launch: 16 warps, thread = one row x 32 v/u columns; v / u are fetched one
-  //      tile ahead with 256-bit loads and the gated output leaves with 256-bit stores (the 128-bit row-per-thread
-  //      form kept the LSU busy for longer than the tile's MMAs take: ncu, stall_lg / long scoreboard on LDTM)
+  // ---- epilogue: 16 warps, thread = one row x 32 v/u columns; v / u are fetched one tile ahead with 256-bit loads
+  //      and the gated output leaves with 256-bit stores (the 128-bit row-per-thread form kept the LSU busy for
+  //      longer than the tile's MMAs take: ncu, stall_lg / long scoreboard on LDTM)
   static constexpr int CG2_EPI_SPLIT = 4;
   struct EpiPre4 {
     U8 v[2], u[2];
@@ -892,6 +828,8 @@ struct AttnOut {
   }
   // `pre` holds v / u of this tile on entry and of tile `nx` (if has_next) on exit: each half is re-requested as
   // soon as it has been consumed, so the loads of the next tile fly during the rest of this tile's epilogue.
+  // o_ss holds 32 partial sums per row, part-major ([32][Mtot]: a warp stores 128 contiguous bytes): index =
+  // 4 * n_tile + column quarter (the consumer adds them in index order)
   __device__ static void epilogue4(const Params& P, const TileInfo& ti, const TileInfo& nx, bool has_next,
                                    uint32_t tacc, int row, int part, EpiPre4& pre) {
     const bool valid = ti.t0 + row < P.S;
@@ -922,104 +860,6 @@ struct AttnOut {
       if (valid) st_global_256(P.o + grow * 1024 + ti.n0 + c0, o);
     }
     P.o_ss[(ti.aux * 4 + part) * (static_cast<size_t>(P.B) * P.Sp) + grow] = valid ? ssq : 0.f;
-  }
-  // v / u of this thread's row and 64 columns (bf16), fetched ahead of the accumulator
-  struct EpiPrefetch {
-    uint4 v[8], u[8];
-  };
-  __device__ static void epi_prefetch(const Params& P, const TileInfo& ti, int row, int half, EpiPrefetch& pre) {
-    const int t = ti.t0 + row;
-    if (t < P.S) {
-      const size_t grow = static_cast<size_t>(ti.m0) + row;
-      const uint4* vp = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + ti.n0 + half * 64);
-      const uint4* up = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + 1024 + ti.n0 + half * 64);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        pre.v[i] = vp[i];
-        pre.u[i] = up[i];
-      }
-    }
-  }
-  __device__ static void epilogue_pre(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
-                                      const EpiPrefetch& pre) {
-    const int t = ti.t0 + row;
-    const bool valid = t < P.S;
-    const size_t grow = static_cast<size_t>(ti.m0) + row;
-    float ssq = 0.f;
-#pragma unroll
-    for (int cc = 0; cc < 64; cc += 16) {
-      const int c0 = half * 64 + cc;
-      float av[16], au[16];
-      tmem_ld16(tacc + c0, av);
-      tmem_ld16(tacc + 128 + c0, au);
-      tmem_ld_wait();
-      if (!valid) continue;
-      const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&pre.v[cc / 8]);
-      const __nv_bfloat16* ub = reinterpret_cast<const __nv_bfloat16*>(&pre.u[cc / 8]);
-      float o[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float v = __bfloat162float(vb[j]);
-        const float u = __bfloat162float(ub[j]);
-        const float x = (au[j] * v) * sigmoid_f(av[j] * u);
-        o[j] = x;
-        ssq += x * x;
-      }
-      uint4* dst = reinterpret_cast<uint4*>(P.o + grow * 1024 + ti.n0 + c0);
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
-                            pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-    }
-    const size_t mtot = static_cast<size_t>(P.B) * P.Sp;
-    P.o_ss[(ti.aux * 4 + half * 2) * mtot + grow] = valid ? ssq : 0.f;
-    P.o_ss[(ti.aux * 4 + half * 2 + 1) * mtot + grow] = 0.f;
-  }
-  // o_ss holds 32 partial sums per row, part-major ([32][Mtot]: a warp stores 128 contiguous bytes): index =
-  // 4 * n_tile + column quarter (the consumer adds them in index order)
-  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
-                                  const EpiCtx&) {
-    const int t = ti.t0 + row;
-    const bool valid = t < P.S;
-    const size_t grow = static_cast<size_t>(ti.m0) + row;
-    float ssq = 0.f;
-#pragma unroll 1
-    for (int cc = 0; cc < 64; cc += 16) {
-      const int c0 = half * 64 + cc;
-      float av[16], au[16];
-      tmem_ld16(tacc + c0, av);
-      tmem_ld16(tacc + 128 + c0, au);
-      uint4 vr[2], ur[2];
-      if (valid) {
-        const uint4* vp = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + ti.n0 + c0);
-        const uint4* up = reinterpret_cast<const uint4*>(P.vu + grow * 2048 + 1024 + ti.n0 + c0);
-        vr[0] = vp[0];
-        vr[1] = vp[1];
-        ur[0] = up[0];
-        ur[1] = up[1];
-      }
-      tmem_ld_wait();
-      if (!valid) continue;
-      const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(vr);
-      const __nv_bfloat16* ub = reinterpret_cast<const __nv_bfloat16*>(ur);
-      float o[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float v = __bfloat162float(vb[j]);
-        const float u = __bfloat162float(ub[j]);
-        const float x = (au[j] * v) * sigmoid_f(av[j] * u);
-        o[j] = x;
-        ssq += x * x;
-      }
-      uint4* dst = reinterpret_cast<uint4*>(P.o + grow * 1024 + ti.n0 + c0);
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        dst[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
-                            pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-    }
-    const size_t mtot = static_cast<size_t>(P.B) * P.Sp;
-    P.o_ss[(ti.aux * 4 + half * 2) * mtot + grow] = valid ? ssq : 0.f;
-    P.o_ss[(ti.aux * 4 + half * 2 + 1) * mtot + grow] = 0.f;
   }
 };
 

@@ -198,148 +198,6 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
   }
 }
 
-// Paired variant: a cluster of two CTAs works on two tiles that share their B operand (Cfg::pair_tile_info gives
-// CTA `rank` its tile, Cfg::load_pair loads its own A operand and multicasts ITS HALF of the B operand to both
-// CTAs).  Each CTA still issues its own cta_group::1 MMAs into its own TMEM; what changes is that a k-block costs
-// 16 + 16 KB of L2 reads per CTA instead of 16 + 32.  A stage may be refilled only when BOTH CTAs' MMAs have
-// released it (both producers write into both CTAs), so the MMA commit arrives on the empty barrier of both.
-template <class Cfg>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1)
-    gemm_pair_kernel(const __grid_constant__ typename Cfg::Params P) {
-  constexpr int BLOCK_N = Cfg::BLOCK_N;
-  constexpr int STAGES = Cfg::STAGES;
-  constexpr int STAGE_B_BYTES = BLOCK_N * 128;
-  constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
-  constexpr uint32_t TMEM_COLS = 512;
-  static_assert(BLOCK_N == 256, "paired kernel is written for 256-column tiles");
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  __shared__ uint32_t s_tmem_base;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-
-  if (warp == 0 && lane == 0) {
-    Cfg::prefetch(P);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 2);  // released by the MMA threads of both CTAs
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * Cfg::EPI_SPLIT);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(smem_u32(&s_tmem_base), TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  cluster_sync_all();  // barriers of both CTAs exist before anybody multicasts into them
-  tc_fence_after();
-  const uint32_t tmem_base = s_tmem_base;
-
-  const int nwork = Cfg::num_pair_tiles(P);
-  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = cluster_id; w < nwork; w += nclusters) {
-        TileInfo ti;
-        Cfg::pair_tile_info(P, w, rank, ti);
-        for (int kb = 0; kb < ti.nkb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          Cfg::load_pair(P, ti, kb, sa, sa + GEMM_STAGE_A_BYTES, full_bar(stage), rank);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC = umma_idesc(Cfg::FMT, GEMM_BLOCK_M, BLOCK_N, Cfg::A_MN, Cfg::B_MN);
-      constexpr uint32_t A_STEP = Cfg::A_MN ? 2048u : 32u;
-      constexpr uint32_t B_STEP = Cfg::B_MN ? 2048u : 32u;
-      constexpr uint32_t A_LBO = Cfg::A_MN ? 8192u : 16u;
-      constexpr uint32_t B_LBO = Cfg::B_MN ? 8192u : 16u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int w = cluster_id; w < nwork; w += nclusters, ++it) {
-        TileInfo ti;
-        Cfg::pair_tile_info(P, w, rank, ti);
-        const int as = it & 1;
-        mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1u);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < ti.nkb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * A_STEP, A_LBO, 1024u);
-            const uint64_t db = umma_smem_desc(sb + k * B_STEP, B_LBO, 1024u);
-            umma_f16(tacc, da, db, IDESC, (kb | k) != 0);
-          }
-          umma_commit_mc(empty_bar(stage), 0x3);  // this stage is free in my CTA: tell both producers
-          if (kb == ti.nkb - 1) umma_commit(tfull_bar(as));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int half = (warp - 2) >> 2;
-    EpiCtx ectx;
-    ectx.tid = threadIdx.x - 64;
-    ectx.panel = nullptr;
-    int it = 0;
-    for (int w = cluster_id; w < nwork; w += nclusters, ++it) {
-      TileInfo ti;
-      Cfg::pair_tile_info(P, w, rank, ti);
-      const int as = it & 1;
-      // global operands of the epilogue are requested BEFORE waiting for the accumulator: their latency hides
-      // behind the tile's MMAs instead of sitting on the epilogue's critical path
-      typename Cfg::EpiPrefetch pre;
-      Cfg::epi_prefetch(P, ti, row, half, pre);
-      mbar_wait(tfull_bar(as), (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-      Cfg::epilogue_pre(P, ti, tacc, row, half, pre);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();  // nobody leaves while its partner may still multicast into it or arrive on its barriers
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // cta_group::2 variant: the CTA pair executes ONE 256 x 256 MMA per k-step.  Each CTA stages its own 128 rows of A
 // and only its own 128 of the 256 B columns (32 KB per k-block instead of 48), and its tensor core receives the
@@ -420,6 +278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t IDESC = umma_idesc(Cfg::FMT, 2 * GEMM_BLOCK_M, BLOCK_N, Cfg::A_MN, Cfg::B_MN);
+      constexpr uint32_t IDESC_F16 = umma_idesc(0, 2 * GEMM_BLOCK_M, BLOCK_N, Cfg::A_MN, Cfg::B_MN);
       constexpr uint32_t A_STEP = Cfg::A_MN ? 2048u : 32u;
       constexpr uint32_t B_STEP = Cfg::B_MN ? 2048u : 32u;
       constexpr uint32_t A_LBO = Cfg::A_MN ? 8192u : 16u;
@@ -443,7 +302,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_smem_desc(sa + k * A_STEP, A_LBO, 1024u);
             const uint64_t db = umma_smem_desc(sb + k * B_STEP, B_LBO, 1024u);
-            umma_f16_cg2(tacc, da, db, IDESC, (kb | k) != 0);
+            umma_f16_cg2(tacc, da, db, kb >= Cfg::F16_FROM_KB ? IDESC_F16 : IDESC, (kb | k) != 0);
           }
           umma_commit_cg2_mc(empty_bar(stage), 0x3);
           if (kb == ti.nkb - 1) umma_commit_cg2_mc(tfull_bar(as), 0x3);
@@ -501,18 +360,6 @@ cudaError_t launch_gemm_cg2(const typename Cfg::Params& P, int nwork, int num_sm
   if (nwork <= 0) return cudaSuccess;
   int grid = 2 * nwork < num_sms ? 2 * nwork : (num_sms & ~1);
   gemm_cg2_kernel<Cfg><<<grid, gemm_threads(Cfg::CG2_EPI_SPLIT), smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-template <class Cfg>
-cudaError_t launch_gemm_pair(const typename Cfg::Params& P, int nwork, int num_sms, cudaStream_t st) {
-  constexpr int smem = gemm_smem_bytes<Cfg::BLOCK_N, Cfg::STAGES, 0>();
-  static std::atomic<unsigned long long> configured{0};
-  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(gemm_pair_kernel<Cfg>), smem, configured); e != cudaSuccess)
-    return e;
-  if (nwork <= 0) return cudaSuccess;
-  int grid = 2 * nwork < num_sms ? 2 * nwork : (num_sms & ~1);
-  gemm_pair_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT), smem, st>>>(P);
   return cudaGetLastError();
 }
 

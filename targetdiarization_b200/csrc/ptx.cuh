@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -259,7 +260,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // Instruction descriptor (upper 32 bits of the idesc operand): fp32 accumulate, dense.
-//   fmt: 1 = bf16, 2 = tf32.  a_mn / b_mn: 1 = MN-major operand.
+//   fmt: 0 = fp16, 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32).  a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn,
                                                   uint32_t b_mn) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -318,6 +319,14 @@ __device__ __forceinline__ float round_tf32_rn(float x) {
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// two fp32 -> packed fp16, clamped to the finite range (an overflow must not turn into inf / NaN downstream)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 

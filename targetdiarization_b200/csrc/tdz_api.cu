@@ -33,10 +33,9 @@ struct tdz_ctx {
   std::string err;
   std::mutex mu;
   bool have_sep = false;
-  // development switches, read once from the environment when the handle is created: earlier kernel forms kept for
-  // A/B measurements (TDZ_ATT_SINGLE / TDZ_ATT_PAIR: attention output without cta_group::2; TDZ_CONVT_SINGLE: the
-  // to_out / to_u|to_v conv GEMMs without cta_group::2)
-  bool att_single = false, att_pair = false, convt_single = false;
+  // development switch, read once from the environment when the handle is created: TDZ_CONVT_SINGLE runs the
+  // to_out / to_u|to_v conv GEMMs without cta_group::2 (A/B measurements)
+  bool convt_single = false;
   tdz_mossformer2_weights sep;
   // weight tensor maps (built once per tdz_set_mossformer2_weights)
   struct LayerMaps {
@@ -103,8 +102,6 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
     return 6;
   }
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  c->att_single = getenv("TDZ_ATT_SINGLE") != nullptr;
-  c->att_pair = getenv("TDZ_ATT_PAIR") != nullptr;
   c->convt_single = getenv("TDZ_CONVT_SINGLE") != nullptr;
   *out = c;
   return 0;
@@ -227,7 +224,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   const size_t region = off;
   L->vu = take(m * 2048 * 2);
   L->qk4 = take(m * 512 * 2);
-  L->lq_lo = take(m * 128 * 2);
+  L->lq_lo = off;  // (no longer used: lin_q is stored as fp16 inside qk4)
   L->qkf = take(m * 128 * 4);
   L->P = take(m * 256 * 2);
   L->o = take(m * 1024 * 2);
@@ -250,7 +247,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->sep = take(m * 1024 * 4);
   off = std::max(off, layer_end);
   L->kv_part = take(static_cast<size_t>(B) * nsplit * 128 * 2048 * 4);
-  L->kv = take(static_cast<size_t>(B) * 256 * 2048 * 2);           // two-term bf16 split: value | residual
+  L->kv = take(static_cast<size_t>(B) * 128 * 2048 * 2);           // lin_kv | lin_ku, fp16
   L->gn_stats = take(static_cast<size_t>(B) * 2 * 8 * 2);       // two GroupNorms
   L->in_stats = take(static_cast<size_t>(B) * 256 * 2 * 8 * 2); // two InstanceNorms (re-zeroed per layer)
   L->in_ss = take(static_cast<size_t>(B) * 256 * 8 * 2);        // their (scale, shift) tables
@@ -302,7 +299,8 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   float *enc = F(L.enc), *x0 = F(L.x0), *x = F(L.x), *ss = F(L.ss), *o_ss = F(L.o_ss), *c = F(L.c), *xuv = F(L.xuv),
         *p = F(L.p), *y1 = F(L.y1), *y2 = F(L.y2), *g = F(L.g), *kv_part = F(L.kv_part), *samp = F(L.samp), *qkf = F(L.qkf);
   __nv_bfloat16 *xbf = H(L.xbf), *vu = H(L.vu), *qk4 = H(L.qk4), *Pm = H(L.P), *o = H(L.o), *nhat = H(L.nhat),
-                *xubf = H(L.xubf), *f1 = H(L.f1), *kv = H(L.kv), *lq_lo = H(L.lq_lo);
+                *xubf = H(L.xubf), *f1 = H(L.f1);
+  __half* kv = reinterpret_cast<__half*>(base + L.kv);
   double* gn_stats = reinterpret_cast<double*>(base + L.gn_stats);
   double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
   float2* in_ss = reinterpret_cast<float2*>(base + L.in_ss);
@@ -337,8 +335,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   if (act_map(ctx, &AP.tmQKmn, qk4, false, 512, Sp, B, 64, 64)) return 1;
   if (act_map(ctx, &AP.tmVUmn, vu, false, 2048, Sp, B, 64, 64)) return 1;
   if (act_map(ctx, &AP.tmP, Pm, false, 256, Sp, B, 64, 128)) return 1;
-  if (act_map(ctx, &AP.tmKVmn, kv, false, 2048, 256, B, 64, 64)) return 1;
-  if (act_map(ctx, &AP.tmLQlo, lq_lo, false, 128, Sp, B, 64, 128)) return 1;
+  if (act_map(ctx, &AP.tmKVmn, kv, false, 2048, 128, B, 64, 64)) return 1;  // (fp16: same 16-bit element size)
   AP.B = B;
   AP.Sp = Sp;
   AP.S = S;
@@ -444,8 +441,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.n_tiles = 17;
       P.tps = tps_t;
       CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
-      qk_heads_kernel<<<static_cast<unsigned>((M + 4 * QKH_FRAMES - 1) / (4 * QKH_FRAMES)), 256, 0, st>>>(qkf, LW.os_gamma, LW.os_beta, rot, qk4, lq_lo,
-                                                                           Sp, S, M);
+      qk_heads_kernel<<<static_cast<unsigned>((M + 4 * QKH_FRAMES - 1) / (4 * QKH_FRAMES)), 256, 0, st>>>(qkf, LW.os_gamma, LW.os_beta, rot, qk4, Sp, S, M);
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {
@@ -455,14 +451,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
           kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
     }
     STEP(ST_ATT_OUT) {
-      // default: one cta_group::2 MMA per CTA pair (M = 256); the development switches select the earlier forms
-      if (ctx->att_single) {
-        CUDA_OK((launch_gemm<AttnOut>(AP, mtiles * 8, sms, st)));
-      } else if (ctx->att_pair) {
-        CUDA_OK((launch_gemm_pair<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
-      } else {
-        CUDA_OK((launch_gemm_cg2<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));
-      }
+      CUDA_OK((launch_gemm_cg2<AttnOut>(AP, (mtiles / 2) * 8, sms, st)));  // one cta_group::2 MMA per CTA pair
     }
     STEP(ST_TO_OUT) {  // ScaleNorm(1024) + to_out Linear + SiLU + ConvModule + FLASH residual (mossformer_block.py:219)
       LinearParams P;

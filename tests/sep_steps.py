@@ -81,8 +81,9 @@ class Harness:
                                               self.torch.stack([self.pad(x) for x in t]))
         v.copy_(t.to(dtype).cuda())
 
-    def get(self, name, dtype, cols, valid_only=True, **kw):
-        v = self.view(name, dtype, cols, **kw).float().cpu()
+    def get(self, name, dtype, cols, valid_only=True, as_float=True, **kw):
+        v = self.view(name, dtype, cols, **kw)
+        v = v.float().cpu() if as_float else v.cpu()
         return v[..., :self.S, :] if valid_only else v
 
     def poison(self):
@@ -106,6 +107,22 @@ class Harness:
     def get_raw(self, off, dtype, n):
         es = self.torch.empty(0, dtype=dtype).element_size()
         return self.ws[off:off + n * es].view(dtype).cpu()
+
+
+def _qk4_to_float(raw):
+    """qk4 as stored ([.., 512] 16-bit: quad_q | lin_q | quad_k | lin_k, lin_q in fp16, the others in bf16) -> fp32."""
+    import torch
+    out = raw.float()
+    out[..., 128:256] = raw[..., 128:256].contiguous().view(torch.float16).float()
+    return out
+
+
+def _qk4_padded(h, qk4):
+    """fp32 heads [B,S,512] -> the stored form, padded to Sp with zeros (bf16-typed tensor holding fp16 bits for lin_q)."""
+    import torch
+    q = h.pad(qk4).to(torch.bfloat16)
+    q[..., 128:256] = h.pad(qk4)[..., 128:256].to(torch.float16).view(torch.bfloat16)
+    return q
 
 
 def _check(metrics, name, ref, est, min_db):
@@ -169,33 +186,28 @@ def run_step(h, step):
         ok &= _check(m, "vu", tp["vu"], vu, 40)
         ok &= _check(m, "vu_first_frames", tp["vu"][:, :12], vu[:, :12], 40)
         ok &= _check(m, "vu_last_frames", tp["vu"][:, -12:], vu[:, -12:], 40)
-        qk = h.get("qk4", bf, 512)
+        qk = _qk4_to_float(h.get("qk4", bf, 512, as_float=False))
         ok &= _check(m, "qk4", tp["qk4"], qk, 40)
         for i, n in enumerate(("quad_q", "lin_q", "quad_k", "lin_k")):
             ok &= _check(m, n, tp["qk4"][..., i * 128:(i + 1) * 128], qk[..., i * 128:(i + 1) * 128], 40)
-        # two-term split of lin_q: value + residual
-        ok &= _check(m, "lin_q_split", tp["qk4"][..., 128:256], qk[..., 128:256] + h.get("lq_lo", bf, 128), 50)
+        # lin_q is stored as fp16 (11 mantissa bits)
+        ok &= _check(m, "lin_q_fp16", tp["qk4"][..., 128:256], qk[..., 128:256], 55)
     elif step == "SIM":
-        h.put("qk4", tp["qk4"], bf)
+        h.put_raw(h.lay.qk4, _qk4_padded(h, tp["qk4"]))
         h.run(k)
         P = h.get("P", bf, 256, valid_only=False)
         ok &= _check(m, "P", tp["P"], P, 38)
     elif step == "KV":
-        h.put("qk4", tp["qk4"], bf)
+        h.put_raw(h.lay.qk4, _qk4_padded(h, tp["qk4"]))
         h.put("vu", tp["vu"], bf)
         h.run(k)
-        kv = h.get_raw(h.lay.kv, bf, B * 256 * 2048).float().view(B, 2, 128, 2048)
-        ok &= _check(m, "kv", tp["kv"], kv[:, 0], 40)
-        ok &= _check(m, "kv_split", tp["kv"], kv[:, 0] + kv[:, 1], 50)
+        kv = h.get_raw(h.lay.kv, torch.float16, B * 128 * 2048).float().view(B, 128, 2048)
+        ok &= _check(m, "kv_fp16", tp["kv"], kv, 50)
     elif step == "ATT_OUT":
-        h.put("qk4", tp["qk4"], bf)
+        h.put_raw(h.lay.qk4, _qk4_padded(h, tp["qk4"]))
         h.put("vu", tp["vu"], bf)
         h.put("P", tp["P"], bf)
-        kv_hi = tp["kv"].to(bf)
-        kv_lo = (tp["kv"] - kv_hi.float()).to(bf)
-        h.put_raw(h.lay.kv, torch.stack((kv_hi, kv_lo), dim=1))   # [B][2][128][2048]: value | residual
-        lq = tp["qk4"][..., 128:256]
-        h.put("lq_lo", lq - lq.to(bf).float(), bf)
+        h.put_raw(h.lay.kv, tp["kv"].to(torch.float16))           # [B][128][2048] fp16
         h.run(k)
         ok &= _check(m, "o", tp["o"], h.get("o", bf, 1024), 38)
         oss = h.get_raw(h.lay.o_ss, f32, 32 * B * h.Sp).view(32, B, h.Sp)[:, :, :S].sum(0)   # part-major [32][Mtot]
