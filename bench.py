@@ -291,13 +291,18 @@ def strong_c3(stage, target_emb, world, rank, dev, minutes, modes):
     try:
         for mode in modes:
             stage.separate_and_score_long(audio[:30 * SR], target_emb, mode=mode, loudness=None)    # warm-up
+            # steady state of a long-lived server: the page-locked result buffer comes out of torch's caching host
+            # allocator (the first cudaHostAlloc of 460 MB alone costs ~0.15 s); touch it once, untimed
+            if rank == 0:
+                torch.empty(2, L, dtype=torch.float32, pin_memory=True)
             torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
-            res = stage.separate_and_score_long(audio, target_emb, mode=mode, loudness="device")
+            split = {}
+            res = stage.separate_and_score_long(audio, target_emb, mode=mode, loudness="device", timings=split)
             e1.record()
             torch.cuda.synchronize(dev)
             wall_local = time.perf_counter() - t0
@@ -315,7 +320,8 @@ def strong_c3(stage, target_emb, world, rank, dev, minutes, modes):
                 b, e = pipeline.ola_input_range(plan, sh[2], sh[3])
             r = {"seconds": wall_s, "device_seconds": dev_s, "value": L / SR / wall_s, "unit": UNIT,
                  "h2d_bytes_rank0": int((e - b) * 4), "d2h_bytes_rank0": int(2 * L * 4 + 2 * (L // T) * 4),
-                 "targets_picked": int((res["target"] > 0).sum())}
+                 "targets_picked": int((res["target"] > 0).sum()),
+                 "split_seconds_rank0": {k: round(v, 4) for k, v in split.items()}}
             # the gather alone (same buffers, no compute): what NCCL costs
             if world > 1:
                 lens = [(L // world) + (1 if i < L % world else 0) for i in range(world)]

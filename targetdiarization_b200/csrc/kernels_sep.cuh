@@ -163,7 +163,18 @@ constexpr int DD_CHUNK = 64;                 // rows per ring slot / outputs per
 constexpr int DD_SLOTS = 5;
 constexpr int DD_RING_ROWS = DD_CHUNK * DD_SLOTS;
 constexpr int DD_ROW_BYTES = 512;            // 128 fp32 channels
-constexpr int DD_SMEM_BYTES = DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8 + 64 /*barriers*/ + 1024 * 8 /*stats*/ + 128;
+// DD_NQ time groups of DD_OUT outputs per 64-row step: 8 x 8 = 512 threads, four warps per scheduler.  (With 4 x 16 =
+// 256 threads - two warps per scheduler, a 54-deep window - the FMA pipe was 45 % busy: nothing to issue while a
+// warp refills its window or stores.)
+#ifndef TDZ_DD_NQ
+#define TDZ_DD_NQ 8
+#endif
+constexpr int DD_NQ = TDZ_DD_NQ;
+constexpr int DD_OUT = DD_CHUNK / DD_NQ;
+constexpr int DD_WIN = DD_OUT + 38;
+constexpr int DD_THREADS = 64 * DD_NQ;
+constexpr int DD_SMEM_BYTES =
+    DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8 + 64 /*barriers*/ + DD_NQ * 64 * 4 * 8 /*stats*/ + 128;
 
 struct DdParams {
   CUtensorMap tmA;       // stage 1: p;  stage 2: y1          3-D {256, Sp, B}, box {128, 64, 1}, no swizzle
@@ -177,7 +188,7 @@ struct DdParams {
 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant__ DdParams P) {
+__global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_constant__ DdParams P) {
   constexpr int NCG = STAGE == 1 ? 2 : 4;
   constexpr int HALO = STAGE == 1 ? 19 : 38;
   constexpr int STEP = STAGE == 1 ? 1 : 2;   // dilation
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
   const CUtensorMap* map = (STAGE == 2 && !from_y1) ? &P.tmB : &P.tmA;
 
   const int cp = tid & 63;   // channel pair (stage 1) / output channel (stage 2) inside the group
-  const int q = tid >> 6;    // which 16 outputs of the step
+  const int q = tid >> 6;    // which DD_OUT outputs of the step
   for (int k = 0; k < 39; ++k) {
     if (tid < 64) {
       if (STAGE == 1) {
@@ -251,8 +262,8 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
     if (!from_y1 && all_valid) return;
     float* base = ring + ((m + 1) % DD_SLOTS) * DD_CHUNK * 128 + fc4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = (tid >> 5) + 8 * i;
+    for (int i = 0; i < DD_CHUNK / (DD_THREADS / 32); ++i) {
+      const int rr = (tid >> 5) + (DD_THREADS / 32) * i;
       const int t = t0 + rr;
       float4* ptr = reinterpret_cast<float4*>(base + rr * 128);
       float4 v = *ptr;
@@ -286,35 +297,35 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
     // first input row of this thread's window, relative to the ring origin (row -64 of the segment = ring row 0)
     int r_out0, r_in0;
     if (STAGE == 1) {
-      r_out0 = DD_CHUNK * n + 16 * q;
+      r_out0 = DD_CHUNK * n + DD_OUT * q;
       r_in0 = r_out0 - HALO;
     } else {
-      r_out0 = DD_CHUNK * n + (q & 1) + 32 * (q >> 1);
+      r_out0 = DD_CHUNK * n + (q & 1) + 2 * DD_OUT * (q >> 1);
       r_in0 = r_out0 - HALO;
     }
     int R = (r_in0 + DD_CHUNK) % DD_RING_ROWS;
-    float2 buf[54];
+    float2 buf[DD_WIN];
     const float* col = ring + 2 * cp;
 #pragma unroll
-    for (int i = 0; i < 54; ++i) {
+    for (int i = 0; i < DD_WIN; ++i) {
       buf[i] = *reinterpret_cast<const float2*>(col + R * 128);
       R += STEP;
       if (R >= DD_RING_ROWS) R -= DD_RING_ROWS;
     }
     if (STAGE == 1) {
-      float2 acc[16];
+      float2 acc[DD_OUT];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < DD_OUT; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 39; ++k) {
         const float2 wk = ws[k * 64 + cp];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fma2(wk, buf[j + k], acc[j]);
+        for (int j = 0; j < DD_OUT; ++j) acc[j] = fma2(wk, buf[j + k], acc[j]);
       }
       const int t0 = seg_lo + r_out0;
       float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 128 + 2 * cp;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < DD_OUT; ++j) {
         if (t0 + j < seg_hi) {
           *reinterpret_cast<float2*>(dst + static_cast<size_t>(j) * 256) = acc[j];
           s1x += acc[j].x;
@@ -325,22 +336,22 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
       }
     } else {
       // the two input channels of an output accumulate side by side (packed FMA) and are added at the end
-      float2 acc2[16];
+      float2 acc2[DD_OUT];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc2[j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < DD_OUT; ++j) acc2[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 39; ++k) {
         const float2 wk = ws[k * 64 + cp];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc2[j] = fma2(wk, buf[j + k], acc2[j]);
+        for (int j = 0; j < DD_OUT; ++j) acc2[j] = fma2(wk, buf[j + k], acc2[j]);
       }
-      float acc[16];
+      float acc[DD_OUT];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = acc2[j].x + acc2[j].y;
+      for (int j = 0; j < DD_OUT; ++j) acc[j] = acc2[j].x + acc2[j].y;
       const int t0 = seg_lo + r_out0;
       float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 64 + cp;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < DD_OUT; ++j) {
         if (t0 + 2 * j < seg_hi) {
           dst[static_cast<size_t>(2 * j) * 256] = acc[j];
           s1x += acc[j];
@@ -349,22 +360,22 @@ __global__ void __launch_bounds__(256, 1) dd_stream_kernel(const __grid_constant
       }
     }
   }
-  // statistics: reduce the four time groups of a channel, then one fp64 atomic pair per channel
+  // statistics: reduce the time groups of a channel, then one fp64 atomic pair per channel
   red[(q * 64 + cp) * 2 + 0] = static_cast<double>(s1x);
   red[(q * 64 + cp) * 2 + 1] = static_cast<double>(s2x);
   if (STAGE == 1) {
-    red[512 + (q * 64 + cp) * 2 + 0] = static_cast<double>(s1y);
-    red[512 + (q * 64 + cp) * 2 + 1] = static_cast<double>(s2y);
+    red[DD_NQ * 128 + (q * 64 + cp) * 2 + 0] = static_cast<double>(s1y);
+    red[DD_NQ * 128 + (q * 64 + cp) * 2 + 1] = static_cast<double>(s2y);
   }
   __syncthreads();
   if (tid < 64) {
     double a = 0, c2 = 0, ay = 0, cy = 0;
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < DD_NQ; ++g) {
       a += red[(g * 64 + tid) * 2];
       c2 += red[(g * 64 + tid) * 2 + 1];
       if (STAGE == 1) {
-        ay += red[512 + (g * 64 + tid) * 2];
-        cy += red[512 + (g * 64 + tid) * 2 + 1];
+        ay += red[DD_NQ * 128 + (g * 64 + tid) * 2];
+        cy += red[DD_NQ * 128 + (g * 64 + tid) * 2 + 1];
       }
     }
     if (STAGE == 1) {

@@ -534,7 +534,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       D.out = y1;
       D.stats = st1;
       D.tmA = m_p;
-      dd_stream_kernel<1><<<B * dd.nseg * 2, 256, DD_SMEM_BYTES, st>>>(D);
+      dd_stream_kernel<1><<<B * dd.nseg * 2, DD_THREADS, DD_SMEM_BYTES, st>>>(D);
     }
     float2* in_ss1 = in_ss;
     float2* in_ss2 = in_ss + static_cast<size_t>(B) * 256;
@@ -548,7 +548,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       D.stats = st2;
       D.tmA = m_y1;
       D.tmB = m_p;
-      dd_stream_kernel<2><<<B * dd.nseg * 4, 256, DD_SMEM_BYTES, st>>>(D);
+      dd_stream_kernel<2><<<B * dd.nseg * 4, DD_THREADS, DD_SMEM_BYTES, st>>>(D);
     }
     STEP(ST_FSMN_TAIL) {
       in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));

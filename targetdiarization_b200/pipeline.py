@@ -279,9 +279,11 @@ def _block_bounds(n_samples, rate, block=0.4):
     """[lo, hi) of the 400 ms / 75 %-overlap blocks with pyloudnorm's float arithmetic (so the integers agree)."""
     T = n_samples / rate
     nblk = int(np.round((T - block) / (block * 0.25)) + 1)
-    j = np.arange(nblk)
-    lo = np.array([int(block * (k * 0.25) * rate) for k in j], dtype=np.int64)
-    hi = np.minimum(np.array([int(block * (k * 0.25 + 1) * rate) for k in j], dtype=np.int64), n_samples)
+    j = np.arange(nblk, dtype=np.float64)
+    # the same float64 operations, in the same order, as pyloudnorm's per-block Python expressions
+    # int(block * (j * 0.25) * rate) and int(block * (j * 0.25 + 1) * rate), vectorised (an hour has 36 000 blocks)
+    lo = ((block * (j * 0.25)) * rate).astype(np.int64)
+    hi = np.minimum(((block * (j * 0.25 + 1)) * rate).astype(np.int64), n_samples)
     return lo, hi
 
 
@@ -515,24 +517,59 @@ class SeparationScoringStage:
         spk1 / spk2 (np.float32 [L], louder first; None on ranks other than gather_dst), scores np.float32 [2, n_seg],
         target [n_seg] (1, 2 or 0 for "neither reaches the threshold")."""
         threshold = self.similarity_threshold if threshold is None else threshold
+        timings = kw.pop("timings", None)          # optional dict: seconds per phase (each phase is synchronised)
+
+        def mark(name, t_prev):
+            if timings is None:
+                return t_prev
+            import time
+            torch.cuda.synchronize(self.device)
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_prev
+            return now
+        import time
+        t = time.perf_counter()
         keep_dst, self.gather_dst = self.gather_dst, None        # scoring shards read the gathered streams
+        loudness = kw.pop("loudness", "device")
         try:
-            s1, s2 = self.separate_speaker(audio_data, sampling_rate, mode=mode, return_device=True, **kw)
+            s1, s2 = self.separate_speaker(audio_data, sampling_rate, mode=mode, return_device=True, loudness=None, **kw)
         finally:
             self.gather_dst = keep_dst
+        t = mark("upload_separate_gather", t)
+        if loudness is not None:       # louder stream first (AudioProcessor.py:949-952), metered on the device
+            if loudness != "device":
+                raise ValueError("separate_and_score_long meters loudness on the device (loudness='device' or None)")
+            l1, l2 = self.meter_loudness_device(torch.stack((s1, s2)), sampling_rate)
+            if l1 < l2:
+                s1, s2 = s2, s1
+        t = mark("loudness", t)
         L = int(s1.shape[0])
         seg = int(segment_seconds * 16000)
         n_seg = L // seg
         if n_seg == 0:
             raise ValueError("recording shorter than one scoring segment")
-        both = torch.stack((s1[:n_seg * seg].view(n_seg, seg), s2[:n_seg * seg].view(n_seg, seg))).view(2 * n_seg, seg)
-        scores = self.score_segments(both, target_embedding).view(2, n_seg)
         rank, _ = _rank_world(self.group)
         out = dict(spk1=None, spk2=None)
+        side = None
         if keep_dst is None or rank == keep_dst:
-            host = self.kern.to_host(torch.stack((s1, s2)))
-            out = dict(spk1=host[0], spk2=host[1])
+            # the consumer's device -> host copy runs on a side stream, under the scoring of the segments
+            host = torch.empty(2, L, dtype=torch.float32, pin_memory=True)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                host[0].copy_(s1, non_blocking=True)
+                host[1].copy_(s2, non_blocking=True)
+            hn = host.numpy()
+            out = dict(spk1=hn[0], spk2=hn[1])
+        both = torch.cat((s1[:n_seg * seg], s2[:n_seg * seg])).view(2 * n_seg, seg)
+        scores = self.score_segments(both, target_embedding).view(2, n_seg)
         sc = scores.cpu().numpy()
+        t = mark("score_segments", t)
+        if side is not None:
+            side.synchronize()
+            s1.record_stream(side)
+            s2.record_stream(side)
+        t = mark("download_tail", t)
         out["scores"] = sc
         out["target"] = np.array([P.pick_target(float(a), float(b), threshold) or 0 for a, b in zip(sc[0], sc[1])],
                                  dtype=np.int64)
