@@ -95,6 +95,7 @@ typedef struct tdz_mossformer2_weights {
   const float* b_tg;         /* [1024] */
   const float* w_dec1;       /* fp32 [512][512] conv1_decoder */
   const float* dec_w;        /* [512][16] dec (ConvTranspose1d) */
+  const float* dec_wt;       /* fp32 [16][512] the same taps transposed, rounded to tf32 (N operand of the decoder GEMM) */
 } tdz_mossformer2_weights;
 
 /* ---- handle ---------------------------------------------------------------------------------- */
@@ -138,7 +139,7 @@ int tdz_separate_debug(tdz_ctx* ctx, const float* mix_dev, int64_t B, int64_t T,
 
 typedef struct tdz_sep_layout {
   size_t enc, x0, x, xbf, ss, vu, qk4, lq_lo, qkf, P, o, o_ss, c, nhat, xuv, xubf, f1, p, y1, y2, g, lnb, ab, mb, gated, sep,
-      kv_part, kv, gn_stats, in_stats, in_ss, samp, rot, hrs, total;
+      kv_part, kv, gn_stats, in_stats, in_ss, samp, rot, hrs, pos, total;
   int64_t S, Sp, Mtot;
   int32_t kv_nsplit, kv_kb_per_split;
 } tdz_sep_layout;

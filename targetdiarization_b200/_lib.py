@@ -24,13 +24,13 @@ class MossFormer2Weights(ctypes.Structure):
         + [("layers", LayerWeights * NUM_LAYERS)]
         + [(n, ctypes.c_void_p) for n in (
             "fln_g", "fln_b", "fgn_g", "fgn_b", "mask_prelu", "w_out1", "b_out1", "w_tg", "b_tg", "w_dec1",
-            "dec_w")])
+            "dec_w", "dec_wt")])
 
 
 class SepLayout(ctypes.Structure):
     _names = ("enc", "x0", "x", "xbf", "ss", "vu", "qk4", "lq_lo", "qkf", "P", "o", "o_ss", "c", "nhat", "xuv", "xubf", "f1", "p", "y1",
               "y2", "g", "lnb", "ab", "mb", "gated", "sep", "kv_part", "kv", "gn_stats", "in_stats", "in_ss", "samp",
-              "rot", "hrs", "total")
+              "rot", "hrs", "pos", "total")
     _fields_ = ([(n, ctypes.c_size_t) for n in _names]
                 + [("S", ctypes.c_int64), ("Sp", ctypes.c_int64), ("Mtot", ctypes.c_int64),
                    ("kv_nsplit", ctypes.c_int32), ("kv_kb_per_split", ctypes.c_int32)])

@@ -39,8 +39,9 @@ struct EpiGeneric {
   int resid_ld;
   const float* mul;        // [Mtot][mul_ld]
   int mul_ld;
-  const float* pos_inv_freq;  // [N/2]
+  const float* pos_inv_freq;  // [N/2]   (LinearGeneric: computed in the epilogue)
   const float* pos_scale;     // [1]
+  const float* pos_tab;       // [Sp][N] scale * (sin | cos)(t f_j), built once per forward (LinearPanel)
   float* out_f32;
   int out_ld;
   int out_col0;            // column offset added when storing
@@ -371,14 +372,6 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
       {
         const int col = pc0 + 4 * lane;
         const bool col_ok = col < P.N;  // N is a multiple of 4
-        float pf[4] = {0.f, 0.f, 0.f, 0.f};
-        float pscale = 0.f;
-        if constexpr ((EF & EF_POS) != 0) {
-          pscale = e.pos_scale[0];
-          const int hlf = P.N >> 1;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pf[i] = __ldg(e.pos_inv_freq + ((col + i) < hlf ? (col + i) : (col + i) - hlf));
-        }
 #pragma unroll 1
         for (int r0 = w * PROWS; r0 < w * PROWS + PROWS; r0 += RB) {
           // The global operands of all RB rows are requested by UNCONDITIONAL loads issued back to back (padded
@@ -434,6 +427,12 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
             float xv[4] = {x4[i].x, x4[i].y, x4[i].z, x4[i].w};
             const float rv[4] = {rq.x, rq.y, rq.z, rq.w};
             const float mv[4] = {mq.x, mq.y, mq.z, mq.w};
+            [[maybe_unused]] float pv[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr ((EF & EF_POS) != 0) {  // ScaledSinuEmbedding row of frame t (table shared by all samples)
+              const float4 pt = __ldg(reinterpret_cast<const float4*>(
+                  e.pos_tab + static_cast<size_t>(min(t, P.Sp - 1)) * P.N + colc));
+              pv[0] = pt.x; pv[1] = pt.y; pv[2] = pt.z; pv[3] = pt.w;
+            }
             float ssq = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -447,10 +446,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
                 if constexpr ((EF & EF_RESID) != 0) x += rv[j];
                 if constexpr ((EF & EF_MUL) != 0) x *= mv[j];
               }
-              if constexpr ((EF & EF_POS) != 0) {
-                const float a = static_cast<float>(t) * pf[j];
-                x += pscale * ((col + j) < (P.N >> 1) ? sinf(a) : cosf(a));
-              }
+              if constexpr ((EF & EF_POS) != 0) x += pv[j];
               if (!valid[i]) x = 0.f;
               if constexpr ((EF & EF_SS_OUT) != 0) ssq += x * x;
               if constexpr ((EF & EF_ROUND_TF32) != 0) x = round_tf32_rn(x);
@@ -640,12 +636,85 @@ struct LinearTanhSig : LinearBase<FMT_, 256, STAGES_> {
       for (int j = 0; j < 16; ++j) {
         const float xa = a[j] + ba[j];
         const float xg = g[j] + bg[j];
-        o[j] = round_tf32_rn(tanhf(xa) * (1.f / (1.f + expf(-xg))));
+        o[j] = round_tf32_rn(tanh_approx(xa) * sigmoid_f(xg));  // MUFU forms: 2^-11 on the tanh = the tf32 rounding
       }
       float4* dst = reinterpret_cast<float4*>(e.out_f32 + grow * e.out_ld + e.out_col0 + oc0 + c0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
     }
+  }
+};
+
+// Decoder: ConvTranspose1d(512 -> 1, k 16, stride 8) + overlap-by-2 add + pad / trim to T (mossformer2.py:213-257,
+// 579-589) as a skinny tf32 GEMM: D[t][j] = sum_c sep[t][c] w[c][j] (N = 16), out[8 t + j] = D[t][j] + D[t-1][8 + j].
+// A tile holds 128 frames of which the first is the halo row t0 - 1 (tiles advance by 127 frames; TMA zero-fills rows
+// outside the sample, the producer zero-fills frames >= S), so the overlap add needs no second pass: a thread owns a
+// frame, takes the upper half of the previous frame's 16 taps from the neighbouring lane (warp shuffle; across warps
+// through 8 floats of shared memory) and writes 8 consecutive samples - a warp writes 1 KB contiguous.
+// "Batch" dimension of A = (speaker, sample): sep is [2][B][Sp][512].
+struct DecParams {
+  CUtensorMap tmA;  // 3-D {512, Sp, 2 B} fp32, box {32, 128, 1}
+  CUtensorMap tmB;  // 2-D {512, 16} fp32 (w transposed: [16][512]), box {32, 16}
+  float* out;       // stream spk of sample b at out + b * out_cs + spk * out_ss
+  int64_t out_cs, out_ss;
+  int B, Sp, S, T, tps;  // tps = tiles per (speaker, sample) = ceil((S + 1) / 127)
+};
+constexpr int DEC_TILE_FRAMES = 127;
+struct DecoderGemm {
+  using Params = DecParams;
+  static constexpr int FMT = 2, BLOCK_N = 16, STAGES = 8, A_MN = 0, B_MN = 0, EPI_SPLIT = 1, PANEL_BYTES = 0;
+  __device__ static void prefetch(const Params& P) {
+    tma_prefetch_desc(&P.tmA);
+    tma_prefetch_desc(&P.tmB);
+  }
+  __device__ static int num_tiles(const Params& P) { return 2 * P.B * P.tps; }
+  __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
+    ti.b = tile / P.tps;                       // speaker * B + sample
+    ti.aux = tile - ti.b * P.tps;
+    ti.t0 = ti.aux * DEC_TILE_FRAMES - 1;      // frame of tile row 0 (the halo row)
+    ti.m0 = 0;
+    ti.n0 = 0;
+    ti.nkb = 16;
+  }
+  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
+    tma_load_3d(sa, &P.tmA, bar, kb * 32, ti.t0, ti.b);
+    tma_load_2d(sb, &P.tmB, bar, kb * 32, 0);
+  }
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int, const EpiCtx& cx) {
+    __shared__ float exch[4][8];
+    float v[16];
+    tmem_ld16(tacc, v);
+    tmem_ld_wait();
+    const int w = row >> 5, lane = row & 31;  // TMEM lane quarter = 32 consecutive frames (not the warp's launch order)
+    (void)cx;
+    if (lane == 31) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) exch[w][j] = v[8 + j];
+    }
+    float prev[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) prev[j] = __shfl_up_sync(0xffffffffu, v[8 + j], 1);
+    epi_bar_sync<128>();
+    if (lane == 0 && w > 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) prev[j] = exch[w - 1][j];
+    }
+    const int t = ti.t0 + row;  // output frame: samples [8 t, 8 t + 8)
+    const int spk = ti.b / P.B, b = ti.b - spk * P.B;
+    if (row > 0 && t <= P.S) {
+      float* dst = P.out + static_cast<int64_t>(b) * P.out_cs + static_cast<int64_t>(spk) * P.out_ss;
+      const int64_t n0 = static_cast<int64_t>(t) * 8;
+      if (n0 + 8 <= P.T && ((reinterpret_cast<uintptr_t>(dst + n0) & 15) == 0)) {
+        float4* o = reinterpret_cast<float4*>(dst + n0);
+        o[0] = make_float4(v[0] + prev[0], v[1] + prev[1], v[2] + prev[2], v[3] + prev[3]);
+        o[1] = make_float4(v[4] + prev[4], v[5] + prev[5], v[6] + prev[6], v[7] + prev[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < P.T) dst[n0 + j] = v[j] + prev[j];
+      }
+    }
+    epi_bar_sync<128>();  // exch is reused by the next tile
   }
 };
 

@@ -14,7 +14,7 @@ constexpr int ENC_FRAMES = 64;
 __global__ void __launch_bounds__(512) encoder_kernel(const float* __restrict__ mix, int T, const float* __restrict__ w,
                                                       float* __restrict__ enc, double* __restrict__ gn_stats, int B,
                                                       int Sp, int S) {
-  __shared__ float xs[ENC_FRAMES * 8 + 8];
+  __shared__ __align__(16) float xs[ENC_FRAMES * 8 + 8];
   __shared__ float red[2][16];
   const int strips = Sp / ENC_FRAMES;
   const int b = blockIdx.x / strips;
@@ -29,11 +29,23 @@ __global__ void __launch_bounds__(512) encoder_kernel(const float* __restrict__ 
   for (int j = 0; j < 16; ++j) wr[j] = w[c * 16 + j];
   __syncthreads();
   float s1 = 0.f, s2 = 0.f;
+  // the 16-sample input window of a frame lives in registers and slides by 8 samples per frame: two 128-bit
+  // broadcast loads per frame instead of sixteen scalar ones (the loop was shared-memory-issue bound)
+  float xw[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) xw[8 + j] = xs[j];
+#pragma unroll 4
   for (int f = 0; f < ENC_FRAMES; ++f) {
     const int t = t0 + f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xw[j] = xw[8 + j];
+    const float4 n0 = *reinterpret_cast<const float4*>(xs + f * 8 + 8);
+    const float4 n1 = *reinterpret_cast<const float4*>(xs + f * 8 + 12);
+    xw[8] = n0.x; xw[9] = n0.y; xw[10] = n0.z; xw[11] = n0.w;
+    xw[12] = n1.x; xw[13] = n1.y; xw[14] = n1.z; xw[15] = n1.w;
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc = fmaf(wr[j], xs[f * 8 + j], acc);
+    for (int j = 0; j < 16; ++j) acc = fmaf(wr[j], xw[j], acc);
     acc = (t < S) ? fmaxf(acc, 0.f) : 0.f;
     enc[(static_cast<size_t>(b) * Sp + t) * 512 + c] = acc;
     s1 += acc;
@@ -78,6 +90,18 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
   const int t = i >> 4, j = i & 15;
   const float a = static_cast<float>(t) * freqs[j];
   tab[i] = make_float2(cosf(a), sinf(a));
+}
+
+// ScaledSinuEmbedding table (mossformer_block.py:60-73): tab[t][c] = scale * sin(t f_c) for c < N/2, scale * cos(t
+// f_{c-N/2}) above; fp32 positions.  Built once per forward (the rows are shared by every sample of the batch), so the
+// GEMM epilogue that adds it reads a float4 instead of evaluating four sinf / cosf per output.
+__global__ void posenc_table_kernel(const float* __restrict__ inv_freq, const float* __restrict__ scale,
+                                    float* __restrict__ tab, int Sp, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Sp * N) return;
+  const int t = i / N, c = i - t * N, hlf = N >> 1;
+  const float a = static_cast<float>(t) * inv_freq[c < hlf ? c : c - hlf];
+  tab[i] = scale[0] * (c < hlf ? sinf(a) : cosf(a));
 }
 
 // OffsetScale (4 heads) + rotary on dims 0..31 (interleaved pairs, rotary_embedding_torch) of the to_qk output
@@ -163,11 +187,11 @@ constexpr int DD_CHUNK = 64;                 // rows per ring slot / outputs per
 constexpr int DD_SLOTS = 5;
 constexpr int DD_RING_ROWS = DD_CHUNK * DD_SLOTS;
 constexpr int DD_ROW_BYTES = 512;            // 128 fp32 channels
-// DD_NQ time groups of DD_OUT outputs per 64-row step: 8 x 8 = 512 threads, four warps per scheduler.  (With 4 x 16 =
-// 256 threads - two warps per scheduler, a 54-deep window - the FMA pipe was 45 % busy: nothing to issue while a
-// warp refills its window or stores.)
+// DD_NQ time groups of DD_OUT outputs per 64-row step.  4 x 16 (256 threads, two warps per scheduler) is the default:
+// the 8 x 8 form (512 threads, four warps per scheduler) was measured 15 % SLOWER - its windows overlap more, so it
+// issues 85 shared-memory loads per 312 packed FMAs instead of 93 per 624 and becomes shared-memory bound.
 #ifndef TDZ_DD_NQ
-#define TDZ_DD_NQ 8
+#define TDZ_DD_NQ 4
 #endif
 constexpr int DD_NQ = TDZ_DD_NQ;
 constexpr int DD_OUT = DD_CHUNK / DD_NQ;
@@ -600,53 +624,6 @@ __global__ void final_gn_kernel(const float* __restrict__ ln, const float* __res
   *reinterpret_cast<float4*>(out + e) = o;
 }
 
-// ---------------------------------------------------------------- decoder  (mossformer2.py:213-257,579-589)
-// ConvTranspose1d(512->1,k=16,stride=8): out[8t+j] += sum_c sep[t,c] * w[c,j]; then zero-pad / trim to T.
-// Block = 32 output frames (+1 halo frame) of one (speaker, sample); warp per frame for the 16 dot products.
-constexpr int DEC_FRAMES = 32;
-__global__ void __launch_bounds__(256) decoder_kernel(const float* __restrict__ sep /*[2][Mtot][512]*/,
-                                                      const float* __restrict__ w /*[512][16]*/,
-                                                      float* __restrict__ out, int64_t out_cs, int64_t out_ss,
-                                                      int B, int Sp, int S, int T) {
-  __shared__ float ws[512 * 17];
-  __shared__ float F[DEC_FRAMES + 1][16];
-  const int strips = Sp / DEC_FRAMES;
-  const int spk = blockIdx.y;
-  const int b = blockIdx.x / strips;
-  const int t0 = (blockIdx.x - b * strips) * DEC_FRAMES;
-  for (int i = threadIdx.x; i < 512 * 16; i += 256) ws[(i >> 4) * 17 + (i & 15)] = w[i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* base = sep + (static_cast<size_t>(spk) * B * Sp + static_cast<size_t>(b) * Sp) * 512;
-  for (int f = warp; f < DEC_FRAMES + 1; f += 8) {
-    const int t = t0 - 1 + f;
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    if (t >= 0 && t < S) {
-      for (int i = 0; i < 16; ++i) {
-        const int c = i * 32 + lane;
-        const float s = base[static_cast<size_t>(t) * 512 + c];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fmaf(s, ws[c * 17 + j], acc[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) F[f][j] = acc[j];
-    }
-  }
-  __syncthreads();
-  // sample n = 8t + j (j<8) gets F[t][j] + F[t-1][8+j]
-  const int f = threadIdx.x >> 3, j = threadIdx.x & 7;
-  const int t = t0 + f;
-  const int n = t * 8 + j;
-  if (n < T) {
-    const float v = F[f + 1][j] + F[f][8 + j];  // frames >= S contribute zeros
-    out[static_cast<int64_t>(b) * out_cs + static_cast<int64_t>(spk) * out_ss + n] = v;  // [B][2][T] when (2T, T)
-  }
-}
+// (decoder: ConvTranspose1d as a skinny tf32 GEMM, struct DecoderGemm in gemm_cfgs.cuh)
 
 }  // namespace tdz

@@ -42,7 +42,7 @@ struct tdz_ctx {
     CUtensorMap w_in, w_out, w_c1, w_uv, w_lin, w_proj, w_c2;
     CUtensorMap w_in128, w_out128, w_uv128;  // 128-row boxes: M operand of the channel-major conv GEMMs
   } lm[TDZ_NUM_LAYERS];
-  CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1;
+  CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1, m_dec;
   bool have_fbank = false;
   FbankTables fb;
   struct SvModel* sv = nullptr;
@@ -181,6 +181,7 @@ extern "C" int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_w
   if (w_map(ctx, &ctx->m_out1, w->w_out1, true, 1024, 512, 256)) return 1;
   if (w_map(ctx, &ctx->m_tg, w->w_tg, true, 1024, 512, 128)) return 1;  // split-N: two 128-row boxes per tile
   if (w_map(ctx, &ctx->m_dec1, w->w_dec1, true, 512, 512, 256)) return 1;
+  if (w_map(ctx, &ctx->m_dec, w->dec_wt, true, 16, 512, 16)) return 1;
   ctx->have_sep = true;
   return 0;
 }
@@ -253,6 +254,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->in_ss = take(static_cast<size_t>(B) * 256 * 8 * 2);        // their (scale, shift) tables
   L->samp = take(static_cast<size_t>(B) * 4 * 4);               // A,B for each GroupNorm
   L->rot = take(static_cast<size_t>(Sp) * 16 * 8);
+  L->pos = take(static_cast<size_t>(Sp) * 512 * 4);                // ScaledSinuEmbedding rows (shared by the batch)
   // per-frame ScaleNorm scale of the next conv GEMM; its epilogue reads whole 96-frame runs around a tile without
   // clamping (frames outside a sample are masked afterwards): TDZ_HRS_FRONT floats before and 256 after stay readable
   L->hrs = take((m + TDZ_HRS_FRONT + 256) * 4);
@@ -305,6 +307,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   double* in_stats = reinterpret_cast<double*>(base + L.in_stats);
   float2* in_ss = reinterpret_cast<float2*>(base + L.in_ss);
   float2* rot = reinterpret_cast<float2*>(base + L.rot);
+  float* pos_tab = F(L.pos);
   float* hrs = F(L.hrs) + TDZ_HRS_FRONT;
   // mask-head buffers (second view of the layer region, used after the layer loop)
   float *lnb = F(L.lnb), *ab = F(L.ab), *mb = F(L.mb), *gated = F(L.gated), *sep = F(L.sep);
@@ -382,10 +385,6 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   // ---- front: encoder -> GroupNorm -> conv1d_encoder (+pos enc)   (mossformer2.py:573,487-496)
   STEP(ST_ENCODER) {
     CUDA_OK(cudaMemsetAsync(gn_stats, 0, static_cast<size_t>(B) * 4 * 8, st));
-    if (static_cast<int64_t>(Sp) * 8 < T) {  // samples beyond the last padded frame: the decoder never visits them
-      for (int spk = 0; spk < 2; ++spk)
-        CUDA_OK(cudaMemset2DAsync(out + spk * out_ss, static_cast<size_t>(out_cs) * 4, 0, static_cast<size_t>(T) * 4, B, st));
-    }
     if (Sp > S) {
       // padded frames of the attention operands stay zero for the whole forward (nobody writes them later)
       CUDA_OK(cudaMemset2DAsync(vu + static_cast<size_t>(S) * 2048, static_cast<size_t>(Sp) * 2048 * 2, 0,
@@ -398,14 +397,14 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     rotary_table_kernel<<<(Sp * 16 + 255) / 256, 256, 0, st>>>(W.rot_freqs, rot, Sp);
   }
   STEP(ST_ENC1X1) {
+    posenc_table_kernel<<<(Sp * 512 + 255) / 256, 256, 0, st>>>(W.pos_inv_freq, W.pos_scale, pos_tab, Sp, 512);
     LinearParams P;
     lin_base(P, m_enc, ctx->m_enc1x1, 512, 512, 256);
     P.e.sampA = samp;
     P.e.sampB = samp + B;
     P.e.colsum = W.enc1x1_colsum;
     P.e.bias = W.enc1x1_bias;
-    P.e.pos_inv_freq = W.pos_inv_freq;
-    P.e.pos_scale = W.pos_scale;
+    P.e.pos_tab = pos_tab;
     P.e.out_f32 = x0;
     P.e.out_ld = 512;
     P.e.out_bf16 = xbf;
@@ -615,12 +614,32 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.mul_ld = 512;
       P.e.out_f32 = sep + static_cast<size_t>(spk) * M * 512;
       P.e.out_ld = 512;
-      CUDA_OK((launch_gemm<LinearPanel<2, 256, 3, EF_MUL | EF_OUT_F32 | EF_ZERO_PAD, ACT_RELU, 4>>(
+      // relu(mask) * encoder output: only the tf32 operand of the decoder GEMM -> rounded to nearest tf32 on store
+      CUDA_OK((launch_gemm<LinearPanel<2, 256, 3, EF_MUL | EF_OUT_F32 | EF_ZERO_PAD | EF_ROUND_TF32, ACT_RELU, 4>>(
           P, mtiles * P.n_tiles, sms, st)));
     }
   }
-  STEP(ST_DECODER)
-  decoder_kernel<<<dim3(B * (Sp / DEC_FRAMES), 2), 256, 0, st>>>(sep, W.dec_w, out, out_cs, out_ss, B, Sp, S, T);
+  STEP(ST_DECODER) {
+    DecParams D;
+    memset(&D, 0, sizeof D);
+    if (act_map(ctx, &D.tmA, sep, true, 512, Sp, 2 * B64, 32, 128)) return 1;
+    D.tmB = ctx->m_dec;
+    D.out = out;
+    D.out_cs = out_cs;
+    D.out_ss = out_ss;
+    D.B = B;
+    D.Sp = Sp;
+    D.S = S;
+    D.T = T;
+    D.tps = (S + 1 + DEC_TILE_FRAMES - 1) / DEC_TILE_FRAMES;
+    // samples from 8 (S + 1) on (at most 7: T < 8 S + 16) are the zero pad of mossformer2.py:585-586
+    if (static_cast<int64_t>(S + 1) * 8 < T64) {
+      for (int spk = 0; spk < 2; ++spk)
+        CUDA_OK(cudaMemset2DAsync(out + spk * out_ss + static_cast<int64_t>(S + 1) * 8, static_cast<size_t>(out_cs) * 4, 0,
+                                  static_cast<size_t>(T64 - static_cast<int64_t>(S + 1) * 8) * 4, B, st));
+    }
+    CUDA_OK((launch_gemm<DecoderGemm>(D, 2 * B * D.tps, sms, st)));
+  }
   CUDA_OK(cudaGetLastError());
 #undef STEP
   return 0;

@@ -209,7 +209,7 @@ class Separator:
                   "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2", "FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1",
                   "DECODER")
     LAYER_STEPS = STEP_NAMES[2:15]
-    KERNELS_PER_FORWARD = 4 + 24 * 19 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
+    KERNELS_PER_FORWARD = 5 + 24 * 19 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
 
     def time_steps(self, mix, reps=5):
         """CUDA-event time (ms) of every launch step of the forward run alone (layer 0 instance), after a

@@ -188,6 +188,7 @@ class PackedMossFormer2:
         t.b_tg = f32(torch.cat((sd["mask_net.output.0.bias"], sd["mask_net.output_gate.0.bias"]), 0))
         t.w_dec1 = tf32(sd["mask_net.conv1_decoder.weight"][:, :, 0])
         t.dec_w = f32(sd["dec.weight"][:, 0, :])
+        t.dec_wt = tf32(sd["dec.weight"][:, 0, :].t())
 
     def _put(self, x, dtype):
         x = x.contiguous().to(dtype).to(self.device)

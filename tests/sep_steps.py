@@ -321,7 +321,8 @@ def run_step(h, step):
     elif step == "DECODER":
         h.put("sep", torch.stack(tp["sep"]), f32, lead=2)
         out = h.run(k)
-        ok &= _check(m, "out", h.ref_out, out, 100)
+        ok &= _check(m, "out", h.ref_out, out, 60)      # tf32 GEMM (operands truncated to 10 mantissa bits)
+        ok &= bool((out[..., (h.S - 1) * 8 + 16:] == 0).all())   # zero pad beyond T' = 8 (S - 1) + 16
     else:
         raise ValueError(step)
     return bool(ok), m

@@ -112,7 +112,8 @@ def test_run_batch_step(stage):
     again = st.score_segments(est.view(6, 16000), tgt).view(3, 2)
     assert torch.equal(scores, again)
     assert bool(((scores >= 0) & (scores <= 1)).all())
-    assert st.launches_per_run(3, 16000) == 469 + 2 + 192 + 1
+    from targetdiarization_b200 import Embedder, Separator
+    assert st.launches_per_run(3, 16000) == Separator.KERNELS_PER_FORWARD + 2 + Embedder.KERNELS_PER_FORWARD + 1
 
 
 def test_device_loudness_meter(stage):
