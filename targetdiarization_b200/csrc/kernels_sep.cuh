@@ -179,14 +179,23 @@ __global__ void rowscale_kernel(const float* __restrict__ parts, float* __restri
 // stage 2: y2[c] = sum_{j<2} conv39_dilation2( cat[2c+j] ), cat = [PReLU(IN(y1)) ; p], pad 38.
 //
 // Streaming kernel: a CTA owns (sample, group of 128 input channels, time segment) and walks along time.
-// Thread 0 keeps TMA loads of 64-row x 512 B chunks two steps ahead in a 5-slot shared-memory ring, so every
+// Thread 0 keeps TMA loads of 64-row x 512 B chunks one step ahead in a 4-slot shared-memory ring, so every
 // input element is read from HBM once and the loads overlap the FMAs; a fix-up pass applies InstanceNorm +
 // PReLU (stage 2, y1 half) and the zero padding in place in shared memory, after which the inner loop is pure
 // FMA: thread = one channel (pair) x 16 outputs, 54-deep register window, taps from shared memory.
 constexpr int DD_CHUNK = 64;                 // rows per ring slot / outputs per step
-constexpr int DD_SLOTS = 5;
+constexpr int DD_SLOTS = 4;                  // 256 ring rows: a power of two, so the wrap is a mask
 constexpr int DD_RING_ROWS = DD_CHUNK * DD_SLOTS;
-constexpr int DD_ROW_BYTES = 512;            // 128 fp32 channels
+// DD_CH input channels per CTA.  64 (two channel-pair warps x DD_NQ time groups = 128 threads, 80 KB of shared memory)
+// lets TWO independent CTAs share an SM: a CTA's warps run in lock step through its phases (chunk wait / fix-up /
+// window loads / FMAs / stores, one __syncthreads per step), so with ONE 256-thread CTA per SM the FMA pipe idled
+// during every non-FMA phase (45 % busy); two CTAs drift apart and fill each other's gaps.
+#ifndef TDZ_DD_CH
+#define TDZ_DD_CH 64
+#endif
+constexpr int DD_CH = TDZ_DD_CH;
+constexpr int DD_CP = DD_CH / 2;             // channel pairs (stage 1) / output channels (stage 2) per CTA
+constexpr int DD_ROW_BYTES = DD_CH * 4;
 // DD_NQ time groups of DD_OUT outputs per 64-row step.  4 x 16 (256 threads, two warps per scheduler) is the default:
 // the 8 x 8 form (512 threads, four warps per scheduler) was measured 15 % SLOWER - its windows overlap more, so it
 // issues 85 shared-memory loads per 312 packed FMAs instead of 93 per 624 and becomes shared-memory bound.
@@ -196,9 +205,15 @@ constexpr int DD_ROW_BYTES = 512;            // 128 fp32 channels
 constexpr int DD_NQ = TDZ_DD_NQ;
 constexpr int DD_OUT = DD_CHUNK / DD_NQ;
 constexpr int DD_WIN = DD_OUT + 38;
-constexpr int DD_THREADS = 64 * DD_NQ;
-constexpr int DD_SMEM_BYTES =
-    DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8 + 64 /*barriers*/ + DD_NQ * 64 * 4 * 8 /*stats*/ + 128;
+constexpr int DD_THREADS = DD_CP * DD_NQ;
+static_assert(DD_CP % 32 == 0, "a warp must not straddle two time groups");
+// ring | taps | barriers (the fp64 statistics scratch of the epilogue reuses the ring)
+constexpr int DD_SMEM_BYTES = DD_RING_ROWS * DD_ROW_BYTES + 39 * DD_CP * 8 + 64 /*barriers*/ + 128;
+#ifndef TDZ_DD_CTAS
+#define TDZ_DD_CTAS 3
+#endif
+constexpr int DD_CTAS_PER_SM = TDZ_DD_CTAS;  // 3 x 75 KB of shared memory, 3 x 128 threads x <= 168 registers
+static_assert(DD_NQ * DD_CP * 4 * 8 <= DD_RING_ROWS * DD_ROW_BYTES, "statistics scratch must fit in the ring");
 
 struct DdParams {
   CUtensorMap tmA;       // stage 1: p;  stage 2: y1          3-D {256, Sp, B}, box {128, 64, 1}, no swizzle
@@ -212,16 +227,16 @@ struct DdParams {
 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_constant__ DdParams P) {
-  constexpr int NCG = STAGE == 1 ? 2 : 4;
+__global__ void __launch_bounds__(DD_THREADS, DD_CTAS_PER_SM) dd_stream_kernel(const __grid_constant__ DdParams P) {
+  constexpr int NCG = (STAGE == 1 ? 256 : 512) / DD_CH;  // channel groups: stage 2 reads y1 (first half) and p
   constexpr int HALO = STAGE == 1 ? 19 : 38;
   constexpr int STEP = STAGE == 1 ? 1 : 2;   // dilation
   extern __shared__ uint8_t dd_smem_raw[];
   uint8_t* sm = dd_smem_raw + ((128u - (smem_u32(dd_smem_raw) & 127u)) & 127u);
   float* ring = reinterpret_cast<float*>(sm);
   float2* ws = reinterpret_cast<float2*>(sm + DD_RING_ROWS * DD_ROW_BYTES);
-  const uint32_t bar0 = smem_u32(sm + DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8);
-  double* red = reinterpret_cast<double*>(sm + DD_RING_ROWS * DD_ROW_BYTES + 39 * 64 * 8 + 64);
+  const uint32_t bar0 = smem_u32(sm + DD_RING_ROWS * DD_ROW_BYTES + 39 * DD_CP * 8);
+  double* red = reinterpret_cast<double*>(sm);  // reuses the ring after the last step
 
   const int tid = threadIdx.x;
   int bid = blockIdx.x;
@@ -233,20 +248,20 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
   if (seg_lo >= P.S) return;
   const int seg_hi = min(seg_lo + P.seg_len, P.S);
   const int nsteps = (seg_hi - seg_lo + DD_CHUNK - 1) / DD_CHUNK;
-  const bool from_y1 = (STAGE == 2) && cg < 2;
-  const int cin0 = (STAGE == 1) ? cg * 128 : (cg & 1) * 128;
+  const bool from_y1 = (STAGE == 2) && cg < NCG / 2;
+  const int cin0 = (STAGE == 1) ? cg * DD_CH : (cg % (NCG / 2)) * DD_CH;
   const CUtensorMap* map = (STAGE == 2 && !from_y1) ? &P.tmB : &P.tmA;
 
-  const int cp = tid & 63;   // channel pair (stage 1) / output channel (stage 2) inside the group
-  const int q = tid >> 6;    // which DD_OUT outputs of the step
+  const int cp = tid % DD_CP;   // channel pair (stage 1) / output channel (stage 2) inside the group
+  const int q = tid / DD_CP;    // which DD_OUT outputs of the step
   for (int k = 0; k < 39; ++k) {
-    if (tid < 64) {
+    if (tid < DD_CP) {
       if (STAGE == 1) {
-        const int c = cg * 128 + 2 * cp;
-        ws[k * 64 + cp] = make_float2(P.taps[c * 39 + k], P.taps[(c + 1) * 39 + k]);
+        const int c = cg * DD_CH + 2 * cp;
+        ws[k * DD_CP + cp] = make_float2(P.taps[c * 39 + k], P.taps[(c + 1) * 39 + k]);
       } else {
-        const int oc = cg * 64 + cp;
-        ws[k * 64 + cp] = make_float2(P.taps[(oc * 2 + 0) * 39 + k], P.taps[(oc * 2 + 1) * 39 + k]);
+        const int oc = cg * DD_CP + cp;
+        ws[k * DD_CP + cp] = make_float2(P.taps[(oc * 2 + 0) * 39 + k], P.taps[(oc * 2 + 1) * 39 + k]);
       }
     }
   }
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
   }
   __syncthreads();
 
-  auto issue = [&](int m) {  // chunk m = rows [seg_lo + 64 m, +64) of the 128 channels -> slot (m+1) % 5
+  auto issue = [&](int m) {  // chunk m = rows [seg_lo + 64 m, +64) of the 128 channels -> slot (m+1) % 4
     const int slot = (m + 1) % DD_SLOTS;
     const uint32_t bar = bar0 + 8u * slot;
     mbar_arrive_expect_tx(bar, DD_CHUNK * DD_ROW_BYTES);
@@ -265,11 +280,15 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
   };
   auto wait_chunk = [&](int m) { mbar_wait(bar0 + 8u * ((m + 1) % DD_SLOTS), ((m + 1) / DD_SLOTS) & 1); };
   if (tid == 0) {
-    for (int m = -1; m <= 2 && m <= nsteps; ++m) issue(m);
+    for (int m = -1; m <= 1 && m <= nsteps; ++m) issue(m);
   }
 
-  // fix-up pass constants: this thread touches 4 fixed channels
-  const int fc4 = (tid & 31) * 4;
+  // fix-up pass constants: this thread touches 4 fixed channels (DD_THREADS is a multiple of the DD_CH / 4 vectors
+  // of a row, so a thread's vector column never changes)
+  constexpr int VPR = DD_CH / 4;                     // float4 vectors per ring row
+  constexpr int FIX_ROWS = DD_THREADS / VPR;         // rows covered by one pass of the CTA
+  static_assert(DD_THREADS % VPR == 0 && DD_CHUNK % FIX_ROWS == 0, "fix-up tiling");
+  const int fc4 = (tid % VPR) * 4;
   float fsc[4] = {1.f, 1.f, 1.f, 1.f}, fsh[4] = {0.f, 0.f, 0.f, 0.f}, fal[4] = {1.f, 1.f, 1.f, 1.f};
   if (from_y1) {
 #pragma unroll
@@ -284,12 +303,12 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
     const int t0 = seg_lo + DD_CHUNK * m;
     const bool all_valid = t0 >= 0 && t0 + DD_CHUNK <= P.S;
     if (!from_y1 && all_valid) return;
-    float* base = ring + ((m + 1) % DD_SLOTS) * DD_CHUNK * 128 + fc4;
+    float* base = ring + ((m + 1) % DD_SLOTS) * DD_CHUNK * DD_CH + fc4;
 #pragma unroll
-    for (int i = 0; i < DD_CHUNK / (DD_THREADS / 32); ++i) {
-      const int rr = (tid >> 5) + (DD_THREADS / 32) * i;
+    for (int i = 0; i < DD_CHUNK / FIX_ROWS; ++i) {
+      const int rr = tid / VPR + FIX_ROWS * i;
       const int t = t0 + rr;
-      float4* ptr = reinterpret_cast<float4*>(base + rr * 128);
+      float4* ptr = reinterpret_cast<float4*>(base + rr * DD_CH);
       float4 v = *ptr;
       if (t < 0 || t >= P.S) {
         v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -314,9 +333,9 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
     wait_chunk(n + 1);
     fixup(n + 1);
     __syncthreads();  // fix-ups visible; everybody is done with step n-1, so the slot of chunk n-2 is free
-    if (tid == 0 && n + 3 <= nsteps) {
+    if (tid == 0 && n + 2 <= nsteps) {
       fence_proxy_async();
-      issue(n + 3);
+      issue(n + 2);  // into the slot of chunk n-2; needed at the top of step n+1: a whole step of latency hiding
     }
     // first input row of this thread's window, relative to the ring origin (row -64 of the segment = ring row 0)
     int r_out0, r_in0;
@@ -327,14 +346,18 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
       r_out0 = DD_CHUNK * n + (q & 1) + 2 * DD_OUT * (q >> 1);
       r_in0 = r_out0 - HALO;
     }
-    int R = (r_in0 + DD_CHUNK) % DD_RING_ROWS;
+    static_assert((DD_RING_ROWS & (DD_RING_ROWS - 1)) == 0, "ring rows must be a power of two");
+    const int R = (r_in0 + DD_CHUNK) & (DD_RING_ROWS - 1);
     float2 buf[DD_WIN];
     const float* col = ring + 2 * cp;
+    if (R + (DD_WIN - 1) * STEP < DD_RING_ROWS) {  // warp-uniform: the window does not wrap -> immediate offsets
+      const float* base = col + R * DD_CH;
 #pragma unroll
-    for (int i = 0; i < DD_WIN; ++i) {
-      buf[i] = *reinterpret_cast<const float2*>(col + R * 128);
-      R += STEP;
-      if (R >= DD_RING_ROWS) R -= DD_RING_ROWS;
+      for (int i = 0; i < DD_WIN; ++i) buf[i] = *reinterpret_cast<const float2*>(base + i * STEP * DD_CH);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DD_WIN; ++i)
+        buf[i] = *reinterpret_cast<const float2*>(col + ((R + i * STEP) & (DD_RING_ROWS - 1)) * DD_CH);
     }
     if (STAGE == 1) {
       float2 acc[DD_OUT];
@@ -342,12 +365,12 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
       for (int j = 0; j < DD_OUT; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 39; ++k) {
-        const float2 wk = ws[k * 64 + cp];
+        const float2 wk = ws[k * DD_CP + cp];
 #pragma unroll
         for (int j = 0; j < DD_OUT; ++j) acc[j] = fma2(wk, buf[j + k], acc[j]);
       }
       const int t0 = seg_lo + r_out0;
-      float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 128 + 2 * cp;
+      float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * DD_CH + 2 * cp;
 #pragma unroll
       for (int j = 0; j < DD_OUT; ++j) {
         if (t0 + j < seg_hi) {
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
       for (int j = 0; j < DD_OUT; ++j) acc2[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 39; ++k) {
-        const float2 wk = ws[k * 64 + cp];
+        const float2 wk = ws[k * DD_CP + cp];
 #pragma unroll
         for (int j = 0; j < DD_OUT; ++j) acc2[j] = fma2(wk, buf[j + k], acc2[j]);
       }
@@ -373,7 +396,7 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < DD_OUT; ++j) acc[j] = acc2[j].x + acc2[j].y;
       const int t0 = seg_lo + r_out0;
-      float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * 64 + cp;
+      float* dst = P.out + (static_cast<size_t>(b) * P.Sp + t0) * 256 + cg * DD_CP + cp;
 #pragma unroll
       for (int j = 0; j < DD_OUT; ++j) {
         if (t0 + 2 * j < seg_hi) {
@@ -385,31 +408,32 @@ __global__ void __launch_bounds__(DD_THREADS, 1) dd_stream_kernel(const __grid_c
     }
   }
   // statistics: reduce the time groups of a channel, then one fp64 atomic pair per channel
-  red[(q * 64 + cp) * 2 + 0] = static_cast<double>(s1x);
-  red[(q * 64 + cp) * 2 + 1] = static_cast<double>(s2x);
+  __syncthreads();  // everybody is done reading the ring
+  red[(q * DD_CP + cp) * 2 + 0] = static_cast<double>(s1x);
+  red[(q * DD_CP + cp) * 2 + 1] = static_cast<double>(s2x);
   if (STAGE == 1) {
-    red[DD_NQ * 128 + (q * 64 + cp) * 2 + 0] = static_cast<double>(s1y);
-    red[DD_NQ * 128 + (q * 64 + cp) * 2 + 1] = static_cast<double>(s2y);
+    red[DD_NQ * DD_CP * 2 + (q * DD_CP + cp) * 2 + 0] = static_cast<double>(s1y);
+    red[DD_NQ * DD_CP * 2 + (q * DD_CP + cp) * 2 + 1] = static_cast<double>(s2y);
   }
   __syncthreads();
-  if (tid < 64) {
+  if (tid < DD_CP) {
     double a = 0, c2 = 0, ay = 0, cy = 0;
     for (int g = 0; g < DD_NQ; ++g) {
-      a += red[(g * 64 + tid) * 2];
-      c2 += red[(g * 64 + tid) * 2 + 1];
+      a += red[(g * DD_CP + tid) * 2];
+      c2 += red[(g * DD_CP + tid) * 2 + 1];
       if (STAGE == 1) {
-        ay += red[DD_NQ * 128 + (g * 64 + tid) * 2];
-        cy += red[DD_NQ * 128 + (g * 64 + tid) * 2 + 1];
+        ay += red[DD_NQ * DD_CP * 2 + (g * DD_CP + tid) * 2];
+        cy += red[DD_NQ * DD_CP * 2 + (g * DD_CP + tid) * 2 + 1];
       }
     }
     if (STAGE == 1) {
-      double* st = P.stats + (static_cast<size_t>(b) * 256 + cg * 128 + 2 * tid) * 2;
+      double* st = P.stats + (static_cast<size_t>(b) * 256 + cg * DD_CH + 2 * tid) * 2;
       atomicAdd(st + 0, a);
       atomicAdd(st + 1, c2);
       atomicAdd(st + 2, ay);
       atomicAdd(st + 3, cy);
     } else {
-      double* st = P.stats + (static_cast<size_t>(b) * 256 + cg * 64 + tid) * 2;
+      double* st = P.stats + (static_cast<size_t>(b) * 256 + cg * DD_CP + tid) * 2;
       atomicAdd(st + 0, a);
       atomicAdd(st + 1, c2);
     }

@@ -149,7 +149,7 @@ static int act_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, bool f32, int 
 // fp32 activation [B][Sp][256] read in un-swizzled {128 channels, 64 rows} chunks (DilatedDenseNet ring)
 static int dd_map(tdz_ctx* ctx, CUtensorMap* m, const void* ptr, int64_t Sp, int64_t B) {
   const uint64_t dims[3] = {256, static_cast<uint64_t>(Sp), static_cast<uint64_t>(B)};
-  const uint32_t box[3] = {128, DD_CHUNK, 1};
+  const uint32_t box[3] = {DD_CH, DD_CHUNK, 1};
   return make_tmap(ctx, m, ptr, true, 3, dims, box, false);
 }
 // weight [N][K] -> 2-D map {K, N}
@@ -533,7 +533,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       D.out = y1;
       D.stats = st1;
       D.tmA = m_p;
-      dd_stream_kernel<1><<<B * dd.nseg * 2, DD_THREADS, DD_SMEM_BYTES, st>>>(D);
+      dd_stream_kernel<1><<<B * dd.nseg * (256 / DD_CH), DD_THREADS, DD_SMEM_BYTES, st>>>(D);
     }
     float2* in_ss1 = in_ss;
     float2* in_ss2 = in_ss + static_cast<size_t>(B) * 256;
@@ -547,7 +547,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       D.stats = st2;
       D.tmA = m_y1;
       D.tmB = m_p;
-      dd_stream_kernel<2><<<B * dd.nseg * 4, DD_THREADS, DD_SMEM_BYTES, st>>>(D);
+      dd_stream_kernel<2><<<B * dd.nseg * (512 / DD_CH), DD_THREADS, DD_SMEM_BYTES, st>>>(D);
     }
     STEP(ST_FSMN_TAIL) {
       in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
