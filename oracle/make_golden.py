@@ -25,6 +25,9 @@ outputs of the reference itself on the GPU box, where the reference tree does no
                           oracle embedder gives for the reference-separated streams
   c2_item.npz             BASELINE config 2: item 0 of the benchmark batch (synthetic_mixture(64, 64000, seed=1234),
                           the bench's seed-0 weights) through the reference module at T = 64 000 (every 4th sample)
+  streaming.npz           TargetDiarizationStream.asr_audio_streaming + TargetASR.multi_speakers_separate_asr /
+                          single_speaker_asr / is_same_person (all extracted with `ast`, toy models of
+                          oracle/stream_toys.py): 7 steps x 4 concurrent streams, results and per-stream state
   mix_rule.npz            TargetASR.mix_audio_processor (extracted with `ast`, stub models) on score pairs incl. ties
                           and NaN: which audio it returns and the score it reports (the >= tie rule, TargetASR.py:734-743)
 """
@@ -343,6 +346,61 @@ def make_mix_rule():
     print("mix_rule.npz:", len(rows), "cases")
 
 
+def make_streaming():
+    """TargetDiarizationStream.asr_audio_streaming and the TargetASR methods it calls (multi_speakers_separate_asr,
+    single_speaker_asr, is_same_person, cosine_similarity), all extracted from the reference source and run on the
+    scenario of oracle/stream_toys.py with the toy models: per call the returned dict (or None) and the stream state."""
+    import re
+    from oracle import stream_toys as T
+    tasr_path = os.path.join(ref_loader.REF_ROOT, "TargetASR.py")
+    stream_path = os.path.join(ref_loader.REF_ROOT, "TargetDiarizationStream.py")
+    ns = {"np": np, "Union": typing.Union, "Literal": typing.Literal, "io": io, "re": re}
+    for name in ("multi_speakers_separate_asr", "single_speaker_asr", "is_same_person", "cosine_similarity"):
+        exec(compile(extract_method(tasr_path, "TargetASR", name), "TargetASR." + name, "exec"), ns)
+    exec(compile(extract_method(stream_path, "TargetDiarizationStream", "asr_audio_streaming"),
+                 "TargetDiarizationStream.asr_audio_streaming", "exec"), ns)
+
+    def make_stream():
+        tasr = types.SimpleNamespace(
+            mdx_weights_file=None, restorer_weights_folder=None, silero_vad=None,
+            input_audio_preprocess=lambda audio: (audio, 16000),
+            get_speaker_embedding=lambda wav_file, embedding_model="eres2netv2_large": T.embedding(wav_file),
+            ap=types.SimpleNamespace(separate_speaker=lambda audio_data: T.separate_speaker(audio_data)),
+            asrp=types.SimpleNamespace(
+                vad_detection=lambda wav_file, min_silence_sec=None: T.vad(wav_file, min_silence_sec),
+                asr_detection=lambda wav_file, asr_engine, prompt, output_text_only, no_punc: T.asr(wav_file, prompt)))
+        for name in ("multi_speakers_separate_asr", "single_speaker_asr", "is_same_person", "cosine_similarity"):
+            setattr(tasr, name, types.MethodType(ns[name], tasr))
+        return types.SimpleNamespace(
+            current_time=0.0, target_embedding=None, prev_asr_text="", system_loudness_diff=0.0,
+            use_asr_prompt=True, similarity_threshold=0.4, loudness_diff_threshold=12.0, tasr=tasr,
+            ap=types.SimpleNamespace(meter_loudness=lambda audio_data, sampling_rate: T.meter_loudness(audio_data)),
+            audio_preprocess=lambda audio_data, sampling_rate, stream_mode, output_audio_only: T.audio_preprocess(audio_data))
+
+    chunks, overlap = T.scenario()
+    n_steps, n_streams = len(chunks), len(chunks[0])
+    streams = [make_stream() for _ in range(n_streams)]
+    rec = {"shape": np.array([n_steps, n_streams], dtype=np.int64)}
+    texts = []
+    for s in range(n_steps):
+        for k in range(n_streams):
+            r = ns["asr_audio_streaming"](streams[k], chunks[s][k], overlap[s][k])
+            if r is not None:                       # process_single_chunk (:184-186)
+                streams[k].prev_asr_text = r["text"]
+            st = streams[k]
+            te = np.zeros(192, np.float32) if st.target_embedding is None else st.target_embedding
+            rec[f"r{s}_{k}"] = np.array([0.0] if r is None else
+                                        [1.0, float(r["speaker"]), r["timerange"][0], r["timerange"][1],
+                                         float(r["type"] == "overlap")], dtype=np.float64)
+            rec[f"s{s}_{k}"] = np.array([st.current_time, st.system_loudness_diff, float(te.sum()),
+                                         float(np.abs(te).sum())], dtype=np.float64)
+            texts.append("" if r is None else r["text"])
+    rec["texts"] = np.array(texts)
+    np.savez_compressed(os.path.join(GOLDEN, "streaming.npz"), **rec)
+    n_res = sum(1 for t in texts if t)
+    print("streaming.npz:", n_steps, "steps x", n_streams, "streams,", n_res, "results")
+
+
 if __name__ == "__main__":
     if not ref_loader.reference_available():
         sys.exit("the reference tree is not present; golden vectors can only be generated in the build container")
@@ -355,3 +413,4 @@ if __name__ == "__main__":
     make_c1_chat_mix()
     make_c2_item()
     make_mix_rule()
+    make_streaming()

@@ -290,3 +290,43 @@ def test_cuda_graph_replay_equals_eager(stage):
     assert torch.equal(est, eager_run[0]) and torch.equal(scores, eager_run[1])
     est, scores = st.run(mix, tgt)
     assert torch.equal(est, eager_run[0]) and torch.equal(scores, eager_run[1])
+
+
+def test_streaming_step_batched_on_gpu(stage):
+    """asr_audio_streaming for 6 concurrent streams through the real kernels: the batched step gives, stream by
+    stream, what one-stream-at-a-time calls give (same decisions, same time ranges, same enrolment embeddings -
+    batch-invariant bits), with one separator batch per step instead of one call per overlapped stream."""
+    torch, st = stage
+    from oracle import stream_toys as T
+    from targetdiarization_b200 import streaming
+    from targetdiarization_b200.synth import synthetic_mixture
+    n_streams, n_steps = 6, 3
+    g = np.random.default_rng(3)
+    chunks = [[(synthetic_mixture(1, 9600, seed=100 + 10 * s + k)[0].numpy() * np.float32(0.2 + 0.1 * k))
+               for k in range(n_streams)] for s in range(n_steps)]
+    chunks[1][2] = np.zeros(9600, np.float32)                 # a silent chunk: gated out
+    chunks[2][4] = chunks[2][4][:4800].copy()                 # under 0.4 s: ignored, clock not advanced
+    overlap = [[False] * n_streams] + [[bool((s + k) % 2) for k in range(n_streams)] for s in range(1, n_steps)]
+    kw = dict(asr=T.asr, vad=lambda a: T.vad(a), vad_inner=lambda a: T.vad(a, 0.0), similarity_threshold=0.4,
+              separation_threshold=0.0)
+    eng = streaming.StageEngine(st)
+
+    def run(batched):
+        states = [streaming.StreamState() for _ in range(n_streams)]
+        out = []
+        for s in range(n_steps):
+            if batched:
+                out.append(streaming.asr_audio_streaming_batch(eng, chunks[s], states, overlap[s], **kw))
+            else:
+                out.append([streaming.asr_audio_streaming_batch(eng, [chunks[s][k]], [states[k]], [overlap[s][k]],
+                                                                **kw)[0] for k in range(n_streams)])
+        return out, states
+    a, sa = run(True)
+    b, sb = run(False)
+    assert a == b
+    for x, y in zip(sa, sb):
+        assert x.current_time == y.current_time and x.system_loudness_diff == y.system_loudness_diff
+        assert np.array_equal(x.target_embedding, y.target_embedding)
+    assert a[1][2] is None and a[2][4] is None
+    assert sum(r is not None and r["type"] == "overlap" for row in a for r in row) >= 3
+    assert sa[4].current_time == pytest.approx(1.2)
