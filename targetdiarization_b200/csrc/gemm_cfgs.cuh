@@ -288,31 +288,104 @@ struct LinearGeneric : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   }
 };
 
-constexpr int PANEL_LD = 132;  // floats per panel row: 128 + 4 keeps the row-wise float4 stores conflict free
+constexpr int PANEL_LD = 132;  // floats per panel row: 128 + 4 keeps the row-wise float4 stores conflict free (LN256)
+constexpr int HP_COLS = 64;    // LinearPanel: half panels of 64 columns ...
+constexpr int HP_LD = 68;      // ... 64 + 4 floats per row (conflict-free row-wise float4 stores)
 
-// LinearGeneric with a coalescing epilogue for BLOCK_N = 128 / 256.  With tcgen05.ld a thread owns a tile ROW, so
-// the direct epilogue above reads / writes global memory in 64 B pieces that are a whole row pitch apart (32
-// different lines per warp instruction): measured 13 % tensor-pipe activity and L2 at 65 % for the FSMN conv2
-// GEMM.  Here the accumulator goes through a 128 x 128 fp32 shared-memory panel:
-//   phase 1  thread = row : tcgen05.ld -> row scale / GroupNorm fold / bias -> panel
-//   phase 2  warp = row, lane = 4 consecutive columns: residual / gate operands are read and all outputs written
-//            as 512 B (fp32) or 256 B (bf16) contiguous row segments; activation, AFF gate, positional encoding,
-//            tf32 rounding and the ScaleNorm partial sums (one warp reduction per row) happen here.
-template <int FMT_, int BLOCK_N_, int STAGES_, unsigned EF, int ACT, int ES = 2>
+// LinearGeneric with a coalescing, self-overlapping epilogue for BLOCK_N = 128 / 256.  With tcgen05.ld a thread owns
+// a tile ROW, so a direct epilogue reads / writes global memory in pieces that are a whole row pitch apart (32
+// different lines per warp instruction).  Here the accumulator goes through shared memory in half panels of 128 rows
+// x 64 columns:
+//   phase 1  thread = row : tcgen05.ld -> row scale / GroupNorm fold / bias -> half panel
+//   phase 2  half warp = row, lane = 4 consecutive columns: residual / gate operands are read and all outputs written
+//            as 256 B (fp32) or 128 B (bf16) contiguous row segments; activation, AFF gate, positional encoding, tf32
+//            rounding and the ScaleNorm partial sums (one half-warp reduction per row) happen here.
+// The 16 epilogue warps form TWO groups of 8 with a half panel and a named barrier each; group g takes the half
+// panels g, g + 2 of a tile.  The groups are not synchronised with each other, so one group's phase 1 (TMEM ->
+// shared memory, no global traffic) runs under the other group's phase 2 (global loads / stores): with one 128-column
+// panel and all 16 warps in lock step the memory system idled during every phase 1 (FSMN conv2 at 63 % of the HBM
+// peak, the embedder's 1x1 convolutions at 45 %).
+template <int FMT_, int BLOCK_N_, int STAGES_, unsigned EF, int ACT, int ES = 4>
 struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
   using Params = LinearParams;
-  static_assert(BLOCK_N_ == 128 || BLOCK_N_ == 256, "panel epilogue handles 128-column panels");
-  static_assert(ES == 2 || ES == 4, "8 or 16 epilogue warps");
+  static_assert(BLOCK_N_ == 128 || BLOCK_N_ == 256, "panel epilogue handles 128 / 256-column tiles");
+  static_assert(ES == 4, "16 epilogue warps: two groups of 8");
   static constexpr int BLOCK_N = BLOCK_N_;
-  static constexpr int EPI_SPLIT = ES;      // ES = 4: 16 epilogue warps, twice the rows (global loads) in flight
-  static constexpr int PCOLS = 128 / ES;    // panel columns per thread in phase 1
-  static constexpr int PROWS = 128 / (4 * ES);  // panel rows per warp in phase 2
-  static constexpr int PANEL_BYTES = 128 * PANEL_LD * 4;
-  // rows a warp has in flight in phase 2: the global operand loads of RB rows (512 B each) are issued together
-  static constexpr int RB = ((EF & EF_MUL) != 0 || ACT == ACT_AFF) ? 4 : 8;
-
+  static constexpr int EPI_SPLIT = ES;
+  static constexpr int PANEL_BYTES = 2 * 128 * HP_LD * 4;
+  // row pairs a warp has in flight in phase 2: the global operand loads of 2 RB rows are issued together.  All 16
+  // rows of the warp at once where one operand is read (memory-level parallelism is what bounds these kernels: one
+  // CTA per SM must keep ~35 KB of reads in flight to cover the DRAM latency at 44 GB/s per SM), 8 rows with two.
+#ifndef TDZ_PANEL_RB
+#define TDZ_PANEL_RB 8
+#endif
+  static constexpr int RB = ((EF & EF_MUL) != 0 || ACT == ACT_AFF) ? TDZ_PANEL_RB / 2 : TDZ_PANEL_RB;
+  static constexpr bool HAS_R = (EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF;
+  static constexpr bool HAS_M = (EF & EF_MUL) != 0 || ACT == ACT_AFF;
+  static constexpr bool OPS16 = (EF & EF_OPS_BF16) != 0;
+  // The global operands (residual / gate rows) of a half panel are requested ONE HALF PANEL AHEAD and travel in
+  // registers across the phase-1 work, the group barrier and - for the last half panel of a tile - the tile
+  // boundary: with the loads issued at the start of phase 2 every half panel paid a full DRAM latency (ncu: 51 % of
+  // the stall samples on the first use of a loaded row), which bounded the kernel, not bandwidth.
+  // (Measured and rejected: requesting these operands one half panel AHEAD - registers carried across phase 1, the group
+  // barrier and the tile boundary - made FSMN conv2 35 % slower (0.77 -> 1.04 ms) and the embedder 5 % slower: the
+  // 96-register cap of 18 warps forces spills, and the kernel is not bound by the latency of these loads.)
+  static constexpr bool PIPELINED = false;
+  struct EpiState {
+    float4 rsd[OPS16 || !HAS_R ? 1 : RB], ml[OPS16 || !HAS_M ? 1 : RB];
+    uint2 rraw[OPS16 && HAS_R ? RB : 1], mraw[OPS16 && HAS_M ? RB : 1];
+  };
+  struct Coord {  // warp-level constants of the thread
+    int grp, sub, wg, lane, rsub, c4;
+  };
+  __device__ static Coord coord(int row, int half, const EpiCtx& cx) {
+    Coord c;
+    c.grp = half >> 1;               // epilogue group (8 warps) = half-panel buffer
+    c.sub = half & 1;                // which 32 of the half panel's 64 columns this thread fills in phase 1
+    c.wg = (row >> 5) + 4 * c.sub;   // warp index inside the group, 0..7
+    c.lane = cx.tid & 31;
+    c.rsub = c.lane >> 4;            // phase 2: a half warp per row
+    c.c4 = (c.lane & 15) * 4;        //          4 consecutive columns per lane
+    return c;
+  }
+  // operands of rows [r0, r0 + 2 RB) of half panel pn of tile ti -> st (unconditional loads, issued back to back:
+  // padded rows / columns read an allocated, ignored location; bf16 data stays raw until the compute loop)
+  __device__ static void load_ops(const Params& P, const TileInfo& ti, int pn, int r0, const Coord& c, EpiState& st) {
+    const EpiGeneric& e = P.e;
+    const int col = ti.n0 + pn * HP_COLS + c.c4;
+    const int colc = col < P.N ? col : 0;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const size_t grow = static_cast<size_t>(ti.m0) + r0 + 2 * i + c.rsub;
+      if constexpr (HAS_R) {
+        if constexpr (OPS16)
+          st.rraw[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
+                                                       grow * e.resid_ld + colc);
+        else
+          st.rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + colc);
+      }
+      if constexpr (HAS_M) {
+        if constexpr (OPS16)
+          st.mraw[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.mul) +
+                                                       grow * e.mul_ld + colc);
+        else
+          st.ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + colc);
+      }
+    }
+  }
+  __device__ static void epi_begin(const Params& P, const TileInfo& ti, int row, int half, const EpiCtx& cx,
+                                   EpiState& st) {
+    const Coord c = coord(row, half, cx);
+    if (ti.n0 + c.grp * HP_COLS < P.N) load_ops(P, ti, c.grp, c.wg * 16, c, st);
+  }
   __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
                                   const EpiCtx& cx) {
+    EpiState st;
+    epilogue(P, ti, ti, false, tacc, row, half, cx, st);
+  }
+
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, const TileInfo& nx, bool has_next, uint32_t tacc,
+                                  int row, int half, const EpiCtx& cx, EpiState& st) {
     const EpiGeneric& e = P.e;
     const size_t grow_t = static_cast<size_t>(ti.m0) + row;  // this thread's row (phase 1)
     float rs = 1.f;
@@ -340,75 +413,63 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
       sA = e.sampA[ti.b];
       sB = e.sampB[ti.b];
     }
-    const int w = cx.tid >> 5, lane = cx.tid & 31;
-    float* prow = cx.panel + row * PANEL_LD + half * PCOLS;
+    const Coord c = coord(row, half, cx);
+    const int grp = c.grp, sub = c.sub, wg = c.wg, lane = c.lane, rsub = c.rsub, c4 = c.c4;
+    float* panel = cx.panel + grp * (128 * HP_LD);
+    float* prow = panel + row * HP_LD + sub * 32;
+    auto group_sync = [&]() {
+      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
 #pragma unroll 1
-    for (int pn = 0; pn < BLOCK_N / 128; ++pn) {
-      const int pc0 = ti.n0 + pn * 128;  // first output column of the panel
-      if (pc0 >= P.N) break;             // warp-uniform
+    for (int pn = grp; pn < BLOCK_N / HP_COLS; pn += 2) {
+      const int pc0 = ti.n0 + pn * HP_COLS;  // first output column of the half panel
+      if (pc0 >= P.N) break;                 // uniform inside the group
       // ---- phase 1
-#pragma unroll 1
-      for (int cc = 0; cc < PCOLS; cc += 16) {
-        const int c0 = pn * 128 + half * PCOLS + cc;
-        if (ti.n0 + c0 >= P.N) break;
-        float v[16], bias[16], cs[16];
-        tmem_ld16(tacc + c0, v);
-        if constexpr ((EF & EF_BIAS) != 0) ld_f32x16(e.bias + ti.n0 + c0, bias);
-        if constexpr ((EF & EF_SAMP) != 0) ld_f32x16(e.colsum + ti.n0 + c0, cs);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = v[j] * rs;
-          if constexpr ((EF & EF_SAMP) != 0) x = x * sA + sB * cs[j];
-          if constexpr ((EF & EF_BIAS) != 0) x += bias[j];
-          v[j] = x;
+      for (int cc = 0; cc < 32; cc += 16) {
+        const int c0 = pn * HP_COLS + sub * 32 + cc;
+        if (ti.n0 + c0 < P.N) {
+          float v[16], bias[16], cs[16];
+          tmem_ld16(tacc + c0, v);
+          if constexpr ((EF & EF_BIAS) != 0) ld_f32x16(e.bias + ti.n0 + c0, bias);
+          if constexpr ((EF & EF_SAMP) != 0) ld_f32x16(e.colsum + ti.n0 + c0, cs);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = v[j] * rs;
+            if constexpr ((EF & EF_SAMP) != 0) x = x * sA + sB * cs[j];
+            if constexpr ((EF & EF_BIAS) != 0) x += bias[j];
+            v[j] = x;
+          }
+          float4* dst = reinterpret_cast<float4*>(prow + cc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        float4* dst = reinterpret_cast<float4*>(prow + cc);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
-      epi_bar_sync<128 * ES>();
-      // ---- phase 2
+      group_sync();
+      // ---- phase 2: warp wg owns rows 16 wg .. 16 wg + 15, two rows per instruction
       {
-        const int col = pc0 + 4 * lane;
+        const int col = pc0 + c4;
         const bool col_ok = col < P.N;  // N is a multiple of 4
+        const int colc = col_ok ? col : 0;
+        // where this warp's NEXT half panel is: same tile (pn + 2) or the first one of the next tile
+        const bool next_here = pn + 2 < BLOCK_N / HP_COLS && ti.n0 + (pn + 2) * HP_COLS < P.N;
+        const bool next_any = next_here || (has_next && nx.n0 + grp * HP_COLS < P.N);
 #pragma unroll 1
-        for (int r0 = w * PROWS; r0 < w * PROWS + PROWS; r0 += RB) {
-          // The global operands of all RB rows are requested by UNCONDITIONAL loads issued back to back (padded
-          // rows / columns read an allocated, ignored location; bf16 data stays raw until the compute loop).  With
-          // the loads inside `if (valid)` blocks next to their conversion the compiler serialised them - each row
-          // then paid its own DRAM latency (ncu: 42 % of the epilogue's samples on the first use of a load).
+        for (int r0 = wg * 16; r0 < wg * 16 + 16; r0 += 2 * RB) {
           float4 x4[RB];
           bool valid[RB];
-          constexpr bool HAS_R = (EF & (EF_RESID | EF_RESID_PRE)) != 0 || ACT == ACT_AFF;
-          constexpr bool HAS_M = (EF & EF_MUL) != 0 || ACT == ACT_AFF;
-          constexpr bool OPS16 = (EF & EF_OPS_BF16) != 0;
-          [[maybe_unused]] float4 rsd[OPS16 ? 1 : RB], ml[OPS16 ? 1 : RB];
-          [[maybe_unused]] uint2 rraw[OPS16 ? RB : 1], mraw[OPS16 ? RB : 1];
-          const int colc = col_ok ? col : 0;
-#pragma unroll
-          for (int i = 0; i < RB; ++i) {
-            const size_t grow = static_cast<size_t>(ti.m0) + r0 + i;
-            if constexpr (HAS_R) {
-              if constexpr (OPS16)
-                rraw[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
-                                                          grow * e.resid_ld + colc);
-              else
-                rsd[i] = *reinterpret_cast<const float4*>(e.resid + grow * e.resid_ld + colc);
-            }
-            if constexpr (HAS_M) {
-              if constexpr (OPS16)
-                mraw[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.mul) +
-                                                          grow * e.mul_ld + colc);
-              else
-                ml[i] = *reinterpret_cast<const float4*>(e.mul + grow * e.mul_ld + colc);
-            }
+          if constexpr (PIPELINED) {   // batch 0 arrives in `st`; later batches (two-operand forms) load here
+            if (r0 != wg * 16) load_ops(P, ti, pn, r0, c, st);
+          } else if constexpr (HAS_R || HAS_M) {
+            load_ops(P, ti, pn, r0, c, st);
           }
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
-            const int r = r0 + i;
+            const int r = r0 + 2 * i + rsub;
             valid[i] = (ti.t0 + r) < P.S;
-            x4[i] = *reinterpret_cast<const float4*>(cx.panel + r * PANEL_LD + 4 * lane);
+            x4[i] = *reinterpret_cast<const float4*>(panel + r * HP_LD + c4);
           }
           auto bf4 = [](const uint2& u) {
             const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
@@ -416,17 +477,29 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
             return make_float4(__bfloat162float(a.x), __bfloat162float(a.y), __bfloat162float(b.x),
                                __bfloat162float(b.y));
           };
+          float4 rq[RB], mq[RB];
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
-            const int r = r0 + i;
+            rq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            mq[i] = rq[i];
+            if constexpr (HAS_R) rq[i] = OPS16 ? bf4(st.rraw[OPS16 ? i : 0]) : st.rsd[OPS16 ? 0 : i];
+            if constexpr (HAS_M) mq[i] = OPS16 ? bf4(st.mraw[OPS16 ? i : 0]) : st.ml[OPS16 ? 0 : i];
+          }
+          // the registers are free again: request batch 0 of the next half panel before the arithmetic and the stores
+          if constexpr (PIPELINED) {
+            if (r0 + 2 * RB >= wg * 16 + 16 && next_any) {
+              if (next_here) load_ops(P, ti, pn + 2, wg * 16, c, st);
+              else load_ops(P, nx, grp, wg * 16, c, st);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int r = r0 + 2 * i + rsub;
             const int t = ti.t0 + r;
             const size_t grow = static_cast<size_t>(ti.m0) + r;
-            float4 rq = make_float4(0.f, 0.f, 0.f, 0.f), mq = rq;
-            if constexpr (HAS_R) rq = OPS16 ? bf4(rraw[OPS16 ? i : 0]) : rsd[OPS16 ? 0 : i];
-            if constexpr (HAS_M) mq = OPS16 ? bf4(mraw[OPS16 ? i : 0]) : ml[OPS16 ? 0 : i];
             float xv[4] = {x4[i].x, x4[i].y, x4[i].z, x4[i].w};
-            const float rv[4] = {rq.x, rq.y, rq.z, rq.w};
-            const float mv[4] = {mq.x, mq.y, mq.z, mq.w};
+            const float rv[4] = {rq[i].x, rq[i].y, rq[i].z, rq[i].w};
+            const float mv[4] = {mq[i].x, mq[i].y, mq[i].z, mq[i].w};
             [[maybe_unused]] float pv[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr ((EF & EF_POS) != 0) {  // ScaledSinuEmbedding row of frame t (table shared by all samples)
               const float4 pt = __ldg(reinterpret_cast<const float4*>(
@@ -452,9 +525,10 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
               if constexpr ((EF & EF_ROUND_TF32) != 0) x = round_tf32_rn(x);
               xv[j] = x;
             }
-            if constexpr ((EF & EF_SS_OUT) != 0) {
-              ssq = warp_sum(ssq);
-              if (lane == 0) e.ss_out[grow * e.ss_out_ld + pc0 / 128] = ssq;
+            if constexpr ((EF & EF_SS_OUT) != 0) {  // one partial per 64 output columns: sum over the row's 16 lanes
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+              if ((lane & 15) == 0) e.ss_out[grow * e.ss_out_ld + pc0 / HP_COLS] = ssq;
             }
             if ((valid[i] || (EF & EF_ZERO_PAD) != 0) && col_ok) {
               if constexpr ((EF & EF_OUT_F32) != 0)
@@ -467,7 +541,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
           }
         }
       }
-      epi_bar_sync<128 * ES>();
+      group_sync();  // the half panel is free again
     }
   }
 };

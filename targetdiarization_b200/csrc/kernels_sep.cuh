@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) qk_heads_kernel(const float* __restrict__
 // ScaleNorm (mossformer_block.py:44-54) as one scale per frame: out[row] = 0.5 / clamp(||x_row|| dim^-0.5, 1e-5),
 // from the partial sums of squares the producing GEMM epilogue left behind.  The factor 0.5 belongs to the
 // tanh form of SiLU the consumer uses.  SHIFT: the row is the token-shifted frame (channels 0..255 of the
-// previous frame | channels 256..511 of this frame, :204-207) and `parts` holds 4 sums of 128 channels per frame;
+// previous frame | channels 256..511 of this frame, :204-207) and `parts` holds 8 sums of 64 channels per frame;
 // otherwise `parts` holds 32 sums per frame, part-major ([32][rows]).
 template <bool SHIFT>
 __global__ void rowscale_kernel(const float* __restrict__ parts, float* __restrict__ out, int Sp, int S, size_t rows,
@@ -158,11 +158,11 @@ __global__ void rowscale_kernel(const float* __restrict__ parts, float* __restri
   if (t >= S) return;
   float ss;
   if (SHIFT) {
-    const float4 cur = *reinterpret_cast<const float4*>(parts + row * 4);
-    ss = cur.z + cur.w;
+    const float4 cur = *reinterpret_cast<const float4*>(parts + row * 8 + 4);   // channels 256..511 of this frame
+    ss = (cur.x + cur.y) + (cur.z + cur.w);
     if (t > 0) {
-      const float4 prv = *reinterpret_cast<const float4*>(parts + (row - 1) * 4);
-      ss += prv.x + prv.y;
+      const float4 prv = *reinterpret_cast<const float4*>(parts + (row - 1) * 8);  // channels 0..255 of the previous
+      ss += (prv.x + prv.y) + (prv.z + prv.w);
     }
   } else {
     ss = 0.f;

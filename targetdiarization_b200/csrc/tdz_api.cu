@@ -220,7 +220,7 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   L->x0 = take(m * 512 * 4);
   L->x = take(m * 512 * 4);
   L->xbf = take(m * 512 * 2);
-  L->ss = take(m * 4 * 4);
+  L->ss = take(m * 8 * 4);     // ScaleNorm partial sums: 8 x 64 channels per frame
   // one region, two views: the per-layer intermediates, and (after the 24 layers) the mask-head buffers
   const size_t region = off;
   L->vu = take(m * 2048 * 2);
@@ -410,7 +410,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     P.e.out_bf16 = xbf;
     P.e.out_bf_ld = 512;
     P.e.ss_out = ss;
-    P.e.ss_out_ld = 4;
+    P.e.ss_out_ld = 8;
     CUDA_OK((launch_gemm<LinearPanel<2, 256, 3,
                                        EF_SAMP | EF_BIAS | EF_POS | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT | EF_ZERO_PAD,
                                        ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));
@@ -565,7 +565,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.e.out_bf16 = xbf;
       P.e.out_bf_ld = 512;
       P.e.ss_out = ss;
-      P.e.ss_out_ld = 4;
+      P.e.ss_out_ld = 8;
       CUDA_OK((launch_gemm<LinearPanel<2, 256, 3,
                                          EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT | EF_ZERO_PAD,
                                          ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));

@@ -144,8 +144,8 @@ def run_step(h, step):
     h.poison()
     zpad_ok = lambda v: bool((v[:, S:] == 0).all())
 
-    def ss_of(x):  # ScaleNorm partial sums: one per 128 channels
-        return (x ** 2).reshape(*x.shape[:-1], 4, 128).sum(-1)
+    def ss_of(x):  # ScaleNorm partial sums: one per 64 channels
+        return (x ** 2).reshape(*x.shape[:-1], 8, 64).sum(-1)
 
     if step == "ENCODER":
         h.run(k)
@@ -173,7 +173,7 @@ def run_step(h, step):
         xb = h.get("xbf", bf, 512, valid_only=False)
         ok &= _check(m, "xbf", tp["x0"], xb[:, :S], 45)
         ok &= zpad_ok(xb)
-        ok &= _check(m, "ss", ss_of(tp["x0"]), h.get("ss", f32, 4), 55)
+        ok &= _check(m, "ss", ss_of(tp["x0"]), h.get("ss", f32, 8), 55)
     elif step == "FLASH_IN":
         # token shift + ScaleNorm + Linear + SiLU + ConvModule (+ OffsetScale / rotary) in one kernel
         h.put("xbf", tp["x0"], bf)
@@ -281,7 +281,7 @@ def run_step(h, step):
         xb = h.get("xbf", bf, 512, valid_only=False)
         ok &= _check(m, "xbf", tp["layer0"], xb[:, :S], 45)
         ok &= zpad_ok(xb)
-        ok &= _check(m, "ss", ss_of(tp["layer0"]), h.get("ss", f32, 4), 55)
+        ok &= _check(m, "ss", ss_of(tp["layer0"]), h.get("ss", f32, 8), 55)
     elif step == "FINAL_LN":
         h.put("x", tp["layer0"], f32)
         h.run(k)
