@@ -57,9 +57,9 @@ def test_layout_helpers_without_gpu(lib):
 
 
 def test_struct_sizes_match_header(lib):
-    # pointer tables only: 29 pointers per layer; 7 + 24*29 + 11 for the model
+    # pointer tables only: 29 pointers per layer; 7 + 24*29 + 12 for the model
     assert ctypes.sizeof(lib.LayerWeights) == 29 * 8
-    assert ctypes.sizeof(lib.MossFormer2Weights) == (7 + 24 * 29 + 11) * 8
+    assert ctypes.sizeof(lib.MossFormer2Weights) == (7 + 24 * 29 + 12) * 8
     assert ctypes.sizeof(lib.EresBlock) == (1 + 4 + 3 + 3 + 1 + 1) * 16
     assert ctypes.sizeof(lib.Eres2NetV2Weights) == 16 + 16 * ctypes.sizeof(lib.EresBlock) + 4 * 16
 
