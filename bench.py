@@ -80,6 +80,9 @@ STEP_KERNEL = {"FLASH_IN": "gemm_convt_kernel<0>", "ATT_OUT": "gemm_cg2_kernel",
                "FSMN_TAIL": "fsmn_tail_kernel", "DECODER": "decoder_kernel", "ENCODER": "encoder_kernel"}
 
 
+NCU_CAPTURE_ITEMS = 16   # batch of the committed capture (tools/ncu_steps.sh default), same T as the bench
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -527,9 +530,15 @@ def main():
         rows.sort(key=lambda r: -r["ms_per_forward"])
         top = rows[0]
         tr = ncu_traffic(top["step"])
+        # the ncu capture runs the same kernel on NCU_CAPTURE_ITEMS items (ncu cannot replay the 64-item batch: it
+        # saves / restores all touched memory around every pass); DRAM bytes are proportional to the frame count
         roof = dict(kernel=top["step"], bound=top["bound"], achieved=top["achieved"], peak=top["peak"],
-                    unit=top["unit"], frac=top["frac"], traffic=tr["bytes_per_launch"] if tr else None,
-                    traffic_source=tr["source"] if tr else None, peak_source=peaks["source"],
+                    unit=top["unit"], frac=top["frac"],
+                    traffic=tr["bytes_per_launch"] * B / NCU_CAPTURE_ITEMS if tr else None,
+                    traffic_source=(f'{tr["source"]}: dram__bytes_read.sum + dram__bytes_write.sum of one launch at '
+                                    f'{NCU_CAPTURE_ITEMS} items x {T} samples = {tr["bytes_per_launch"]:.0f} B, '
+                                    f'scaled by {B}/{NCU_CAPTURE_ITEMS} to this launch') if tr else None,
+                    peak_source=peaks["source"],
                     algorithmic_bytes_per_launch=STEP_TABLE[top["step"]]["bytes"] * frames,
                     share_of_separator=top["ms_per_forward"] / sum(r["ms_per_forward"] for r in rows),
                     steps={r["step"]: dict(ms=round(r["ms"], 4), bound=r["bound"], frac=round(r["frac"], 3),

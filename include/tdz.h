@@ -16,6 +16,10 @@
  *       -> tdz_fbank() + tdz_embed()                           (modelscope ERes2NetV2 pipeline)
  *   TargetASR.cosine_similarity                                TargetASR.py:144-152
  *       -> tdz_cosine_scores()
+ *   ConvTDFNet.stft / .istft (MDX-Net front / back end)        AudioProcessor.py:82-120
+ *       -> tdz_stft() / tdz_istft()
+ *   AudioProcessor.restorer(tensor[1,nch,T]) (Apollo)          AudioProcessor.py:279,970
+ *       -> tdz_apollo_restore()                                (look2hear/models/apollo.py:278-297)
  *
  * Conventions: all pointers named *_dev are device pointers owned by the caller (PyTorch allocates);
  * the library never allocates on the hot path, the caller passes a workspace sized by the matching
@@ -237,6 +241,77 @@ int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t fram
  * (all-zero vector -> 1.0; result clamped to [0,1]).  emb_dev [N][dim], target_dev [dim] -> scores_dev [N]. */
 int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float* target_dev, int64_t N, int64_t dim,
                       float* scores_dev, void* stream);
+
+/* ---- STFT / inverse STFT -------------------------------------------------------------
+ * torch.stft / torch.istft with the arguments the reference passes (center = True, reflect padding, periodic Hann
+ * window, one-sided, un-normalised): ConvTDFNet.stft / .istft (AudioProcessor.py:82-120, n_fft 6144) and the Apollo
+ * restorer (look2hear/models/apollo.py:261-262, 294-295, n_fft 882).  n_fft must factor into 2, 3, 5, 7.
+ * The spectrogram element (row r, bin k, frame t, re/im c) lives at spec_dev[r*s_row + k*s_bin + t*s_frame + c*s_reim],
+ * so the MDX layout [B, 4 = channel*2 + re/im, dim_f, dim_t] is (2*dim_f*dim_t, dim_t, 1, dim_f*dim_t) with r = 2*b +
+ * channel, and frame-major complex [rows, T, bins] is (T*bins*2, 2, bins*2, 1).  Bins [0, n_keep) are written / read;
+ * tdz_istft takes the others as zero (the freq_pad of ConvTDFNet.istft). */
+typedef struct tdz_stft_plan {
+  int32_t n_fft, hop;
+  const float* window_dev;   /* [n_fft] */
+  const float* twiddle_dev;  /* [n_fft][2]: cos(2 pi k / n_fft), -sin(2 pi k / n_fft), rounded from double */
+} tdz_stft_plan;
+int64_t tdz_stft_frames(int64_t L, int64_t hop);   /* 1 + L / hop */
+/* x_dev fp32 [rows][L] -> spectrogram of tdz_stft_frames(L, hop) frames.  Needs n_fft / 2 < L (reflect padding). */
+int tdz_stft(tdz_ctx* ctx, const tdz_stft_plan* plan, const float* x_dev, int64_t rows, int64_t L, int64_t n_keep,
+             float* spec_dev, int64_t s_row, int64_t s_bin, int64_t s_frame, int64_t s_reim, void* stream);
+/* spectrogram of T frames -> out_dev fp32 [rows][out_len] (torch.istft(..., length = out_len); without `length` the
+ * reference gets out_len = hop * (T - 1)).  frames_ws_dev: fp32 scratch of rows * T * n_fft values. */
+int tdz_istft(tdz_ctx* ctx, const tdz_stft_plan* plan, const float* spec_dev, int64_t rows, int64_t T, int64_t n_keep,
+              int64_t s_row, int64_t s_bin, int64_t s_frame, int64_t s_reim, float* frames_ws_dev, float* out_dev,
+              int64_t out_len, void* stream);
+
+/* ---- Apollo restorer (look2hear/models/apollo.py; AudioProcessor.restore_audio, AudioProcessor.py:959-980) ------
+ * The architecture AudioProcessor.init_restorer_model builds (AudioProcessor.py:279): Apollo(sr 44100, win 20 ms ->
+ * n_fft 882 / hop 441, feature_dim 256, layer 6), 80 bands (79 x 5 bins + 47).  GEMM operands are bf16 [N][K]
+ * row-major with the RMSNorm gain in front of a conv folded into its columns (targetdiarization_b200/weights.py). */
+#define TDZ_AP_LAYERS 6
+#define TDZ_AP_NBAND 80
+#define TDZ_AP_BINS 442
+typedef struct tdz_apollo_icb {
+  const float* dw;     /* [7][256] depthwise taps, tap-major */
+  const float* dw_b;   /* [256] */
+  const void* w1;      /* bf16 [1024][256], RMSNorm gain folded */
+  const float* b1;     /* [1024] */
+  const void* w2;      /* bf16 [256][1024] */
+  const float* b2;     /* [256] */
+} tdz_apollo_icb;
+typedef struct tdz_apollo_layer {
+  const void* w_qkv;   /* bf16 [768][256]  band_net.weight, input_norm gain folded; row = head*96 + (q|k|v)*32 + d */
+  const void* w_out;   /* bf16 [256][256]  band_net.output */
+  const void* w_mlp1;  /* bf16 [2048][256] band_net.MLP.1 (rows 0..1023 gate, 1024..2047 z), MLP.0 gain folded */
+  const void* w_mlp2;  /* bf16 [256][1024] band_net.MLP_output */
+  tdz_apollo_icb icb[3];
+} tdz_apollo_layer;
+typedef struct tdz_apollo_weights {
+  const float* bn_g;     /* [964]      BN[i].0 gains, bands concatenated (2*BW+1 each) */
+  const float* bn_w;     /* [964][256] BN[i].1 weights transposed: (band, input feature)-major, output contiguous */
+  const float* bn_b;     /* [80][256] */
+  const float* rot_cos;  /* [100][32]  band_net.cos_freq (identical in every layer) */
+  const float* rot_sin;  /* [100][32] */
+  tdz_apollo_layer layers[TDZ_AP_LAYERS];
+  const float* out_g;    /* [80][256]  output[i].0 gains */
+  const float* out_wv;   /* [256][884] output[i].1 rows that GLU keeps (real BW | imag BW per band), transposed */
+  const float* out_wg;   /* [256][884] the matching gate rows, transposed */
+  const float* out_bv;   /* [884] */
+  const float* out_bg;   /* [884] */
+  tdz_stft_plan plan;    /* n_fft 882, hop 441 */
+} tdz_apollo_weights;
+int tdz_set_apollo_weights(tdz_ctx* ctx, const tdz_apollo_weights* w);
+size_t tdz_apollo_workspace_bytes(int64_t rows, int64_t nsample);
+/* self.restorer(tensor[B, nch, nsample]) (AudioProcessor.py:970; Apollo.forward, apollo.py:278-297):
+ * wav_dev fp32 [rows = B * nch][nsample] -> out_dev fp32 [rows][nsample]. */
+int tdz_apollo_restore(tdz_ctx* ctx, const float* wav_dev, int64_t rows, int64_t nsample, float* out_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Test hook: runs up to a tap and copies it to out_dev (fp32): 0 = spectrogram [rows*T][442][2]; 1 = band-split
+ * features [tokens][256]; 2 = attention output of layer 0 (bf16 widened) [tokens][256]; 3 = layer 0 after the
+ * Roformer [tokens][256]; 4 + l = output of layer l; 10 = estimated spectrogram [rows*T][442][2]. */
+int tdz_apollo_debug(tdz_ctx* ctx, const float* wav_dev, int64_t rows, int64_t nsample, float* out_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream, int tap);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,12 @@ outputs of the reference itself on the GPU box, where the reference tree does no
                           oracle/stream_toys.py): 7 steps x 4 concurrent streams, results and per-stream state
   mix_rule.npz            TargetASR.mix_audio_processor (extracted with `ast`, stub models) on score pairs incl. ties
                           and NaN: which audio it returns and the score it reports (the >= tie rule, TargetASR.py:734-743)
+  apollo_small.npz        SURVEY.md 8f-4: the reference Apollo module (look2hear/models/apollo.py, the configuration of
+                          AudioProcessor.py:279) loaded with synth.random_apollo_state_dict(0) on a [1, 2, 22 173]
+                          full-band signal (T = 51 frames) and on a [2, 1, 4 500] one: the restored waveforms
+  mdx_stft.npz            the reference's ConvTDFNet (AudioProcessor.py:65-120, compiled from its source lines):
+                          stft of two stereo chunks at n_fft 6144 / hop 1024 / dim_f 3072 / dim_t 8 (every 5th bin kept)
+                          and istft of a fixed random spectrogram
 """
 import ast
 import io
@@ -401,6 +407,29 @@ def make_streaming():
     print("streaming.npz:", n_steps, "steps x", n_streams, "streams,", n_res, "results")
 
 
+def make_apollo():
+    sd = synth.random_apollo_state_dict(0)
+    m = ref_loader.build_reference_apollo(sd)
+    xa = synth.synthetic_fullband(2, 22050 + 123, seed=4321).reshape(1, 2, -1)
+    xb = synth.synthetic_fullband(2, 4500, seed=77).reshape(2, 1, -1)
+    with torch.no_grad():
+        ya, yb = m(xa), m(xb)
+    np.savez_compressed(os.path.join(GOLDEN, "apollo_small.npz"), out_a=ya.numpy(), out_b=yb.numpy())
+
+
+def make_mdx():
+    cls = ref_loader.load_reference_conv_tdf_net()
+    net = cls(target_name="vocals", L=11, dim_f=3072, dim_t=3, n_fft=6144, hop=1024, device="cpu")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 2, net.chunk_size, generator=g) * 0.1
+    spec_in = torch.randn(2, 4, 3072, 8, generator=g)
+    with torch.no_grad():
+        spec = net.stft(x)
+        wav = net.istft(spec_in)
+    np.savez_compressed(os.path.join(GOLDEN, "mdx_stft.npz"), x=x.numpy(), spec_bins5=spec[:, :, ::5].numpy(),
+                        spec_in_seed=np.int64(5), wav=wav.numpy(), chunk_size=np.int64(net.chunk_size))
+
+
 if __name__ == "__main__":
     if not ref_loader.reference_available():
         sys.exit("the reference tree is not present; golden vectors can only be generated in the build container")
@@ -414,3 +443,5 @@ if __name__ == "__main__":
     make_c2_item()
     make_mix_rule()
     make_streaming()
+    make_apollo()
+    make_mdx()

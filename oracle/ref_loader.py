@@ -54,3 +54,49 @@ def load_reference_wav_chunk_inference():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.wav_chunk_inference
+
+
+def load_reference_apollo():
+    """look2hear/models/apollo.py loaded by path (its only relative import is base_model)."""
+    pkg = load_reference_modules()
+    if hasattr(pkg, "apollo"):
+        return pkg.apollo
+    spec = importlib.util.spec_from_file_location("l2h.apollo", os.path.join(_MODELS, "apollo.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["l2h.apollo"] = mod
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+    pkg.apollo = mod
+    return mod
+
+
+def build_reference_apollo(state_dict=None):
+    """Apollo(sr=44100, win=20, feature_dim=256, layer=6) as AudioProcessor.init_restorer_model builds it
+    (AudioProcessor.py:279), in eval mode, optionally loaded with `state_dict`."""
+    import contextlib
+    import io
+    mod = load_reference_apollo()
+    with contextlib.redirect_stdout(io.StringIO()):   # the constructor prints its band table
+        m = mod.Apollo(sr=44100, win=20, feature_dim=256, layer=6).eval()
+    if state_dict is not None:
+        m.load_state_dict(state_dict)
+    return m
+
+
+def load_reference_conv_tdf_net():
+    """The ConvTDFNet class of AudioProcessor.py (:65-120), compiled from its source lines alone: the module itself
+    imports packages that are absent here (onnxruntime, librosa, ...)."""
+    import ast
+    import textwrap
+    import torch
+    path = os.path.join(REF_ROOT, "AudioProcessor.py")
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == "ConvTDFNet":
+            code = textwrap.dedent("\n".join(src.splitlines()[node.lineno - 1:node.end_lineno]))
+            ns = {"torch": torch}
+            exec(compile(code, "AudioProcessor.ConvTDFNet", "exec"), ns)
+            return ns["ConvTDFNet"]
+    raise KeyError("ConvTDFNet not found")

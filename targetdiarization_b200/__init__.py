@@ -9,6 +9,8 @@ Drop-in pieces:
   pick_mix_audio    <-> TargetASR.mix_audio_processor's choice         (TargetASR.py:734-743)
   asr_audio_streaming_batch <-> TargetDiarizationStream.asr_audio_streaming for S concurrent streams
                                                                        (TargetDiarizationStream.py:189-258)
+  Restorer          <-> AudioProcessor.restorer (Apollo)               (AudioProcessor.py:276-281, 970)
+  ConvTDFNet        <-> AudioProcessor.mdx_net STFT / iSTFT            (AudioProcessor.py:65-120)
 """
 from ._lib import Handle, load  # noqa: F401
 from .separator import Separator  # noqa: F401
@@ -16,3 +18,5 @@ from .embedder import Embedder  # noqa: F401
 from .pipeline import SeparationScoringStage, meter_loudness  # noqa: F401
 from .plan import chunk_bounds, ola_plan, pick_mix_audio, pick_target  # noqa: F401
 from .streaming import StageEngine, StreamState, asr_audio_streaming_batch  # noqa: F401
+from .restorer import Restorer  # noqa: F401
+from .mdx import ConvTDFNet  # noqa: F401

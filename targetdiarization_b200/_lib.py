@@ -55,6 +55,29 @@ class Eres2NetV2Weights(ctypes.Structure):
 
 # name -> (restype, argtypes); mirrors include/tdz.h one to one
 _vp, _i64, _sz, _int, _f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
+AP_LAYERS = 6
+
+
+class StftPlan(ctypes.Structure):
+    _fields_ = [("n_fft", ctypes.c_int32), ("hop", ctypes.c_int32), ("window_dev", ctypes.c_void_p),
+                ("twiddle_dev", ctypes.c_void_p)]
+
+
+class ApolloIcb(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("dw", "dw_b", "w1", "b1", "w2", "b2")]
+
+
+class ApolloLayer(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w_qkv", "w_out", "w_mlp1", "w_mlp2")] + [("icb", ApolloIcb * 3)]
+
+
+class ApolloWeights(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("bn_g", "bn_w", "bn_b", "rot_cos", "rot_sin")]
+                + [("layers", ApolloLayer * AP_LAYERS)]
+                + [(n, ctypes.c_void_p) for n in ("out_g", "out_wv", "out_wg", "out_bv", "out_bg")]
+                + [("plan", StftPlan)])
+
+
 SIGNATURES = {
     "tdz_create": (_int, [_int, ctypes.POINTER(_vp)]),
     "tdz_destroy": (None, [_vp]),
@@ -83,6 +106,14 @@ SIGNATURES = {
     "tdz_embed": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "tdz_embed_debug": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _int]),
     "tdz_cosine_scores": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "tdz_stft_frames": (_i64, [_i64, _i64]),
+    "tdz_stft": (_int, [_vp, ctypes.POINTER(StftPlan), _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "tdz_istft": (_int, [_vp, ctypes.POINTER(StftPlan), _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64,
+                         _vp]),
+    "tdz_set_apollo_weights": (_int, [_vp, ctypes.POINTER(ApolloWeights)]),
+    "tdz_apollo_workspace_bytes": (_sz, [_i64, _i64]),
+    "tdz_apollo_restore": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "tdz_apollo_debug": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _int]),
 }
 
 _lib = None

@@ -26,6 +26,7 @@ enum EpiFlags : unsigned {
   EF_ZERO_PAD = 1u << 11,   // padded frames (t >= S) are written as zeros instead of skipped
   EF_ROUND_TF32 = 1u << 12, // fp32 output rounded to nearest tf32 (buffer is only a tf32 MMA operand)
   EF_OPS_BF16 = 1u << 13,   // resid / mul point to bf16 data (LinearPanel only)
+  EF_RMS4 = 1u << 14,       // RMSNorm row scale rsqrt(sum of 4 partial sums * ss_dim_rsqrt [= 1 / dim] + 1e-5) (apollo.py:7-23)
 };
 
 struct EpiGeneric {
@@ -127,6 +128,11 @@ struct LinearBase {
 __device__ __forceinline__ float scalenorm_rscale(float ss, float dim_rsqrt) {
   // x / clamp(||x|| * dim^-0.5, 1e-5)   (mossformer_block.py:52-54)
   return 1.f / fmaxf(sqrtf(ss) * dim_rsqrt, 1e-5f);
+}
+
+__device__ __forceinline__ float rms4_rscale(const float* ss4, float inv_dim) {
+  const float4 a = *reinterpret_cast<const float4*>(ss4);
+  return rsqrtf(((a.x + a.y) + (a.z + a.w)) * inv_dim + 1e-5f);
 }
 
 template <int ACT>
@@ -408,6 +414,7 @@ struct LinearPanel : LinearBase<FMT_, BLOCK_N_, STAGES_> {
       }
       rs = scalenorm_rscale(ss, e.ss_dim_rsqrt);
     }
+    if constexpr ((EF & EF_RMS4) != 0) rs = rms4_rscale(e.ss_in + grow_t * 4, e.ss_dim_rsqrt);
     float sA = 1.f, sB = 0.f;
     if constexpr ((EF & EF_SAMP) != 0) {
       sA = e.sampA[ti.b];
@@ -715,6 +722,41 @@ struct LinearTanhSig : LinearBase<FMT_, 256, STAGES_> {
       float4* dst = reinterpret_cast<float4*>(e.out_f32 + grow * e.out_ld + e.out_col0 + oc0 + c0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+  }
+};
+
+// Gated pair of linear maps in one tile (Apollo restorer, look2hear/models/apollo.py:137-139): W = [W_gate; W_z]
+// stacked (2 * split_n rows), split_n puts gate column j next to z column j in one 256-column tile; the RMSNorm in
+// front of the conv is a row scale (its gain is folded into W by the packer):
+//   out[row][j] = silu(silu(rs * acc_gate[j])) * silu(rs * acc_z[j])  -> bf16
+// (nn.Sequential applies SiLU to all 2 * split_n channels, then F.silu is applied to the gate half again.)
+template <int STAGES_>
+struct LinearGLU : LinearBase<1, 256, STAGES_> {
+  using Params = LinearParams;
+  static constexpr int EPI_SPLIT = 2;
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
+    const EpiGeneric& e = P.e;
+    const bool valid = ti.t0 + row < P.S;  // no early return: tcgen05.ld is warp-collective
+    const size_t grow = static_cast<size_t>(ti.m0) + row;
+    const float rs = rms4_rscale(e.ss_in + grow * 4, e.ss_dim_rsqrt);
+    const int oc0 = ti.n0 / 2;  // first output column of this tile
+#pragma unroll 1
+    for (int cc = 0; cc < 64; cc += 16) {
+      const int c0 = half * 64 + cc;
+      float a[16], z[16];
+      tmem_ld16(tacc + c0, a);
+      tmem_ld16(tacc + 128 + c0, z);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = silu_f(silu_f(a[j] * rs)) * silu_f(z[j] * rs);
+      uint4* dst = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.out_bf_ld + oc0 + c0);
+      dst[0] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      dst[1] = make_uint4(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]), pack_bf16(o[12], o[13]),
+                          pack_bf16(o[14], o[15]));
     }
   }
 };

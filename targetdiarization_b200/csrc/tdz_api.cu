@@ -46,6 +46,7 @@ struct tdz_ctx {
   bool have_fbank = false;
   FbankTables fb;
   struct SvModel* sv = nullptr;
+  struct ApModel* ap = nullptr;
 };
 
 static int fail(tdz_ctx* c, const char* fmt, ...) {
@@ -107,8 +108,10 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
   return 0;
 }
 static void sv_free(tdz_ctx* ctx);
+static void ap_free(tdz_ctx* ctx);
 extern "C" void tdz_destroy(tdz_ctx* ctx) {
   if (ctx) sv_free(ctx);
+  if (ctx) ap_free(ctx);
   delete ctx;
 }
 extern "C" const char* tdz_last_error(tdz_ctx* ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
@@ -822,4 +825,59 @@ extern "C" int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, i
   if (!ctx->sv) return fail(ctx, "tdz_embed: weights not set");
   return sv_embed(ctx, *ctx->sv, feat_dev, N, frames, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream),
                   stop_block);
+}
+
+// ------------------------------------------------------------------------------------------------ STFT + Apollo restorer
+#include "ap_api.cuh"
+
+static void ap_free(tdz_ctx* ctx) {
+  delete ctx->ap;
+  ctx->ap = nullptr;
+}
+extern "C" int64_t tdz_stft_frames(int64_t L, int64_t hop) { return hop > 0 && L >= 0 ? 1 + L / hop : 0; }
+extern "C" int tdz_stft(tdz_ctx* ctx, const tdz_stft_plan* plan, const float* x_dev, int64_t rows, int64_t L,
+                        int64_t n_keep, float* spec_dev, int64_t s_row, int64_t s_bin, int64_t s_frame, int64_t s_reim,
+                        void* stream) {
+  if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
+  FftPlan f;
+  if (stft_plan_init(ctx, plan, &f)) return 1;
+  return stft_launch(ctx, f, x_dev, rows, L, n_keep, spec_dev, SpecStrides{s_row, s_bin, s_frame, s_reim},
+                     static_cast<cudaStream_t>(stream));
+}
+extern "C" int tdz_istft(tdz_ctx* ctx, const tdz_stft_plan* plan, const float* spec_dev, int64_t rows, int64_t T,
+                         int64_t n_keep, int64_t s_row, int64_t s_bin, int64_t s_frame, int64_t s_reim,
+                         float* frames_ws_dev, float* out_dev, int64_t out_len, void* stream) {
+  if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
+  FftPlan f;
+  if (stft_plan_init(ctx, plan, &f)) return 1;
+  return istft_launch(ctx, f, spec_dev, rows, T, n_keep, SpecStrides{s_row, s_bin, s_frame, s_reim}, frames_ws_dev,
+                      out_dev, out_len, static_cast<cudaStream_t>(stream));
+}
+extern "C" int tdz_set_apollo_weights(tdz_ctx* ctx, const tdz_apollo_weights* w) {
+  if (!ctx || !w) return 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->ap) ctx->ap = new ApModel();
+  ctx->ap->ready = false;
+  return ap_set_weights(ctx, ctx->ap, w);
+}
+extern "C" size_t tdz_apollo_workspace_bytes(int64_t rows, int64_t nsample) {
+  if (rows <= 0 || nsample <= 441) return 0;
+  ApLayout L;
+  ap_layout(rows, nsample, &L);
+  return L.total;
+}
+extern "C" int tdz_apollo_debug(tdz_ctx* ctx, const float* wav_dev, int64_t rows, int64_t nsample, float* out_dev,
+                                void* ws, size_t ws_bytes, void* stream, int tap) {
+  if (!ctx) return 1;
+  DeviceScope dev_scope(ctx->device);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->ap) return fail(ctx, "tdz_apollo_restore: weights not set");
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(ctx, "tdz_apollo_restore: workspace must be 1024 B aligned");
+  return ap_forward(ctx, *ctx->ap, wav_dev, rows, nsample, out_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream), tap);
+}
+extern "C" int tdz_apollo_restore(tdz_ctx* ctx, const float* wav_dev, int64_t rows, int64_t nsample, float* out_dev,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  return tdz_apollo_debug(ctx, wav_dev, rows, nsample, out_dev, ws, ws_bytes, stream, AP_RUN_ALL);
 }

@@ -185,3 +185,78 @@ def random_eres2netv2_state_dict(seed=0):
     sd["seg_1.bias"] = (torch.rand(EMBED_DIM, generator=g) * 2 - 1) * bound
     return sd
 
+
+
+# ------------------------------------------------------------------------------------------------ Apollo restorer
+def apollo_band_widths(sr=44100, win_ms=20):
+    """Band split of look2hear/models/apollo.py:232-236: 79 bands of int(win / 160) bins + the rest."""
+    win = int(sr * win_ms // 1000)
+    enc_dim = win // 2 + 1
+    bw = [int(win / 160)] * 79
+    bw.append(enc_dim - sum(bw))
+    return win, enc_dim, bw
+
+
+def random_apollo_state_dict(seed=0, perturb=True, sr=44100, win_ms=20, feature_dim=256, layer=6):
+    """Random-init weights with the key names / shapes of the reference's Apollo(sr, win, feature_dim, layer)
+    (look2hear/models/apollo.py:215-257; checked key for key against the reference module by
+    tests/test_apollo_oracle.py).  Conv1d default init; `perturb` randomises the RMSNorm gains."""
+    g = torch.Generator().manual_seed(seed)
+    _, _, bw = apollo_band_widths(sr, win_ms)
+    N = feature_dim
+    sd = {}
+
+    def gain(name, n):
+        sd[name] = 1.0 + 0.2 * torch.randn(n, generator=g) if perturb else torch.ones(n)
+
+    def conv(name, out_c, in_c, k=1, bias=True, groups=1):
+        fan = in_c // groups * k
+        sd[name + ".weight"] = _uniform(g, (out_c, in_c // groups, k), fan)
+        if bias:
+            sd[name + ".bias"] = _uniform(g, (out_c,), fan)
+
+    for i, w in enumerate(bw):
+        gain(f"BN.{i}.0.weight", 2 * w + 1)
+        conv(f"BN.{i}.1", N, 2 * w + 1)
+    hd = N // 8
+    freq = 1.0 / (10000 ** (torch.arange(0, hd, 2)[: hd // 2] / hd))
+    ang = torch.arange(0, 100).reshape(-1, 1) * freq.reshape(1, -1)
+    cos = torch.stack([torch.cos(ang)] * 2, -1).reshape(100, hd)
+    sin = torch.stack([torch.sin(ang)] * 2, -1).reshape(100, hd)
+    for l in range(layer):
+        p = f"net.{l}.band_net."
+        sd[p + "cos_freq"] = cos.clone()
+        sd[p + "sin_freq"] = sin.clone()
+        gain(p + "input_norm.weight", N)
+        conv(p + "weight", 3 * N, N, bias=False)
+        conv(p + "output", N, N, bias=False)
+        gain(p + "MLP.0.weight", N)
+        conv(p + "MLP.1", 8 * N, N, bias=False)
+        conv(p + "MLP_output", N, 4 * N, bias=False)
+        for b in range(3):
+            q = f"net.{l}.seq_net.blocks.{b}.conv."
+            conv(q + "0", N, N, k=7, groups=N)
+            gain(q + "1.weight", N)
+            conv(q + "2", 4 * N, N)
+            conv(q + "4", N, 4 * N)
+    for i, w in enumerate(bw):
+        gain(f"output.{i}.0.weight", N)
+        conv(f"output.{i}.1", 4 * w, N)
+    return sd
+
+
+def synthetic_fullband(n_items, n_samples, seed=4321, sr=44100):
+    """A 44.1 kHz test signal for the restorer: a few decaying harmonics + low-passed noise, peak 0.5."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n_samples, dtype=torch.float32) / sr
+    out = torch.zeros(n_items, n_samples)
+    for i in range(n_items):
+        f0 = 110.0 + 60.0 * float(torch.rand(1, generator=g))
+        for h in range(1, 9):
+            out[i] += torch.sin(2 * math.pi * f0 * h * t + 6.28 * float(torch.rand(1, generator=g))) / h
+    x = torch.randn(n_items, n_samples, generator=g)
+    X = torch.fft.rfft(x, dim=-1)
+    f = torch.fft.rfftfreq(n_samples, 1.0 / sr)
+    x = torch.fft.irfft(X / (1.0 + (f / 3000.0) ** 2), n=n_samples, dim=-1)
+    out = out / out.abs().amax(dim=-1, keepdim=True) + 0.5 * x / x.abs().amax(dim=-1, keepdim=True)
+    return (out / out.abs().amax(dim=-1, keepdim=True).clamp(min=1e-9) * 0.5).contiguous()

@@ -279,3 +279,126 @@ class PackedEres2NetV2:
         x = x.contiguous().to(dtype).to(self.device)
         self._keep.append(x)
         return ctypes.c_void_p(x.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------------ STFT tables + Apollo
+def stft_tables(n_fft, device):
+    """Periodic Hann window [n_fft] (torch.hann_window(n_fft), what AudioProcessor.py:76 and apollo.py:262 build) and
+    the forward twiddles W^k = (cos, -sin)(2 pi k / n_fft), both computed in float64 and rounded once."""
+    k = torch.arange(n_fft, dtype=torch.float64)
+    win = 0.5 - 0.5 * torch.cos(2.0 * torch.pi * k / n_fft)
+    ang = 2.0 * torch.pi * k / n_fft
+    tw = torch.stack((torch.cos(ang), -torch.sin(ang)), -1)
+    return win.to(torch.float32).to(device).contiguous(), tw.to(torch.float32).to(device).contiguous()
+
+
+def make_stft_plan(n_fft, hop, device):
+    """(tdz_stft_plan, tensors to keep alive)."""
+    win, tw = stft_tables(n_fft, device)
+    plan = _lib.StftPlan(int(n_fft), int(hop), ctypes.c_void_p(win.data_ptr()), ctypes.c_void_p(tw.data_ptr()))
+    return plan, (win, tw)
+
+
+APOLLO_ARGS = (("sr", 44100), ("win", 20), ("feature_dim", 256), ("layer", 6))
+
+
+def apollo_key_shapes():
+    """{key: shape} of the reference Apollo(sr=44100, win=20, feature_dim=256, layer=6).state_dict() (654 entries;
+    look2hear/models/apollo.py:215-257), checked against the reference module by tests/test_apollo_oracle.py."""
+    bw = [5] * 79 + [47]
+    sh = {}
+    for i, w in enumerate(bw):
+        sh[f"BN.{i}.0.weight"] = (2 * w + 1,)
+        sh[f"BN.{i}.1.weight"] = (256, 2 * w + 1, 1)
+        sh[f"BN.{i}.1.bias"] = (256,)
+        sh[f"output.{i}.0.weight"] = (256,)
+        sh[f"output.{i}.1.weight"] = (4 * w, 256, 1)
+        sh[f"output.{i}.1.bias"] = (4 * w,)
+    for l in range(_lib.AP_LAYERS):
+        p = f"net.{l}.band_net."
+        sh[p + "cos_freq"] = (100, 32)
+        sh[p + "sin_freq"] = (100, 32)
+        sh[p + "input_norm.weight"] = (256,)
+        sh[p + "weight.weight"] = (768, 256, 1)
+        sh[p + "output.weight"] = (256, 256, 1)
+        sh[p + "MLP.0.weight"] = (256,)
+        sh[p + "MLP.1.weight"] = (2048, 256, 1)
+        sh[p + "MLP_output.weight"] = (256, 1024, 1)
+        for b in range(3):
+            q = f"net.{l}.seq_net.blocks.{b}.conv."
+            sh[q + "0.weight"] = (256, 1, 7)
+            sh[q + "0.bias"] = (256,)
+            sh[q + "1.weight"] = (256,)
+            sh[q + "2.weight"] = (1024, 256, 1)
+            sh[q + "2.bias"] = (1024,)
+            sh[q + "4.weight"] = (256, 1024, 1)
+            sh[q + "4.bias"] = (256,)
+    return sh
+
+
+def check_apollo_state_dict(state_dict, strict=True):
+    want = apollo_key_shapes()
+    missing = [k for k in want if k not in state_dict]
+    unexpected = [k for k in state_dict if k not in want]
+    bad = [f"{k}: {tuple(state_dict[k].shape)} != {want[k]}" for k in want
+           if k in state_dict and tuple(state_dict[k].shape) != want[k]]
+    if bad or (strict and (missing or unexpected)) or missing:
+        raise RuntimeError("Error(s) in loading state_dict for Apollo: "
+                           f"missing {missing[:5]}{'...' if len(missing) > 5 else ''}, "
+                           f"unexpected {unexpected[:5]}{'...' if len(unexpected) > 5 else ''}, size mismatch {bad[:5]}")
+
+
+class PackedApollo:
+    """Apollo state dict -> include/tdz.h: tdz_apollo_weights.  RMSNorm gains in front of a 1x1 conv are folded into
+    the conv's columns (W diag(g)); the per-band input / output convs are concatenated and transposed so that the
+    band split / merge kernels read them with the output index contiguous."""
+
+    def __init__(self, state_dict, device):
+        self.device = torch.device(device)
+        self._keep = []
+        sd = {k: v.detach().to(torch.float64).cpu() for k, v in state_dict.items()}
+        t = self.table = _lib.ApolloWeights()
+        bw = [5] * 79 + [47]
+        f32 = lambda x: self._put(x, torch.float32)      # noqa: E731
+        bf16 = lambda x: self._put(x, torch.bfloat16)    # noqa: E731
+        t.bn_g = f32(torch.cat([sd[f"BN.{i}.0.weight"] for i in range(80)]))
+        t.bn_w = f32(torch.cat([sd[f"BN.{i}.1.weight"][:, :, 0].t() for i in range(80)], 0))     # [964][256]
+        t.bn_b = f32(torch.stack([sd[f"BN.{i}.1.bias"] for i in range(80)]))
+        cos, sin = sd["net.0.band_net.cos_freq"], sd["net.0.band_net.sin_freq"]
+        for l in range(1, _lib.AP_LAYERS):
+            if not (torch.equal(sd[f"net.{l}.band_net.cos_freq"], cos) and torch.equal(sd[f"net.{l}.band_net.sin_freq"], sin)):
+                raise ValueError("tdz.Restorer expects the same rotary tables in every layer (apollo.py:82-91)")
+        t.rot_cos, t.rot_sin = f32(cos), f32(sin)
+        for l in range(_lib.AP_LAYERS):
+            p = f"net.{l}.band_net."
+            L = t.layers[l]
+            L.w_qkv = bf16(sd[p + "weight.weight"][:, :, 0] * sd[p + "input_norm.weight"][None, :])
+            L.w_out = bf16(sd[p + "output.weight"][:, :, 0])
+            L.w_mlp1 = bf16(sd[p + "MLP.1.weight"][:, :, 0] * sd[p + "MLP.0.weight"][None, :])
+            L.w_mlp2 = bf16(sd[p + "MLP_output.weight"][:, :, 0])
+            for b in range(3):
+                q = f"net.{l}.seq_net.blocks.{b}.conv."
+                I = L.icb[b]
+                I.dw = f32(sd[q + "0.weight"][:, 0, :].t())                                      # [7][256]
+                I.dw_b = f32(sd[q + "0.bias"])
+                I.w1 = bf16(sd[q + "2.weight"][:, :, 0] * sd[q + "1.weight"][None, :])
+                I.b1 = f32(sd[q + "2.bias"])
+                I.w2 = bf16(sd[q + "4.weight"][:, :, 0])
+                I.b2 = f32(sd[q + "4.bias"])
+        t.out_g = f32(torch.stack([sd[f"output.{i}.0.weight"] for i in range(80)]))
+        wv, wg, bv, bg = [], [], [], []
+        for i, w in enumerate(bw):
+            W, b = sd[f"output.{i}.1.weight"][:, :, 0], sd[f"output.{i}.1.bias"]
+            wv.append(W[:2 * w]); wg.append(W[2 * w:]); bv.append(b[:2 * w]); bg.append(b[2 * w:])
+        t.out_wv = f32(torch.cat(wv, 0).t())      # [256][884]
+        t.out_wg = f32(torch.cat(wg, 0).t())
+        t.out_bv = f32(torch.cat(bv))
+        t.out_bg = f32(torch.cat(bg))
+        plan, keep = make_stft_plan(882, 441, self.device)
+        self._keep.extend(keep)
+        t.plan = plan
+
+    def _put(self, x, dtype):
+        x = x.contiguous().to(dtype).to(self.device)
+        self._keep.append(x)
+        return ctypes.c_void_p(x.data_ptr())
