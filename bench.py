@@ -409,6 +409,66 @@ def stream_c5(stage, target_emb, dev, steps=100):
     return out
 
 
+def restore_f4(dev, seconds=10.0):
+    """the Apollo restorer on `seconds` of mono 44.1 kHz audio (host array in, host array out, like
+    AudioProcessor.restore_audio) and the MDX-Net STFT / inverse STFT pair on 8 stereo chunks of the production shape
+    (n_fft 6144, hop 1024, 256 frames), with the oracle port timed on the host cores on a 1 s sample."""
+    import time
+    import numpy as np
+    import torch
+    from oracle import apollo_port as AP
+    from targetdiarization_b200 import ConvTDFNet, Restorer, synth
+    sd = synth.random_apollo_state_dict(0)
+    rest = Restorer(sd, dev)
+    ns = int(seconds * 44100)
+    audio = synth.synthetic_fullband(1, ns, seed=1).numpy()
+    pinned = torch.from_numpy(audio).pin_memory()
+
+    def ev(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    x_dev = pinned.to(dev).reshape(1, 1, ns)
+    ms_res = ev(lambda: rest(x_dev))
+    ms_e2e = ev(lambda: rest(pinned.to(dev, non_blocking=True).reshape(1, 1, ns)).cpu())
+    tokens = (1 + ns // 441) * 80
+    flop = tokens * 6 * 2 * (256 * 768 + 256 * 256 + 256 * 2048 + 1024 * 256 + 3 * 2 * 256 * 1024)
+    xs = torch.from_numpy(audio[:, :44100]).reshape(1, 1, -1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        AP.apollo_forward(sd, xs)
+        t0 = time.time()
+        ref = AP.apollo_forward(sd, xs)
+        cpu_s = time.time() - t0
+    snr = AP.snr_db(ref, rest(xs.to(dev)).cpu())
+    net = ConvTDFNet("vocals", 11, 3072, 8, 6144, 1024, dev)
+    xm = torch.randn(8, 2, net.chunk_size, device=dev) * 0.1
+    spec = net.stft(xm)
+    ms_stft = ev(lambda: net.stft(xm))
+    ms_istft = ev(lambda: net.istft(spec))
+    mdx_s = 8 * net.chunk_size / 44100
+    t0 = time.time()
+    AP.mdx_istft(AP.mdx_stft(xm[:2].cpu(), 6144, 1024, 3072), 6144, 1024)
+    mdx_cpu = (time.time() - t0) / (2 * net.chunk_size / 44100)
+    del rest, net
+    torch.cuda.empty_cache()
+    return {"apollo": {"audio_s": seconds, "ms_resident": ms_res, "x_realtime_resident": seconds / (ms_res / 1e3),
+                       "ms_host_to_host": ms_e2e, "x_realtime": seconds / (ms_e2e / 1e3),
+                       "gemm_tflops": flop / (ms_res * 1e-3) / 1e12, "kernels_per_forward": Restorer.KERNELS_PER_FORWARD,
+                       "snr_db_vs_oracle_1s": snr,
+                       "cpu_port": {"x_realtime": 1.0 / cpu_s, "cores": torch.get_num_threads(), "sample": "1 s, 1 warm-up + 1 run"}},
+            "mdx_stft_istft": {"audio_s": mdx_s, "stft_ms": ms_stft, "istft_ms_incl_d2h": ms_istft,
+                               "x_realtime": mdx_s / ((ms_stft + ms_istft) / 1e3),
+                               "cpu_torch_x_realtime": 1.0 / mdx_cpu}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -548,7 +608,7 @@ def main():
             with open(args.breakdown, "w") as f:
                 json.dump(dict(ms_per_step=ms_step, B=B, T=T, rows=rows), f, indent=1)
 
-    c3 = c4 = c5 = eager = None
+    c3 = c4 = c5 = eager = f4 = None
     if not args.no_extras:
         c3 = strong_c3(stage, target_emb, world, rank, dev, args.c3_minutes,
                        [m for m in args.c3_modes.split(",") if m])
@@ -556,6 +616,7 @@ def main():
         if rank == 0 and world == 1:
             c5 = stream_c5(stage, target_emb, dev)
             eager = gpu_eager_leg(dev)
+            f4 = restore_f4(dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -581,7 +642,7 @@ def main():
                                    "batch 1 per call"},
             "gpu_launches": stage.launches_per_run(B, T) * args.steps,
             "roofline": roof,
-            "strong_c3": c3, "score_c4": c4, "stream_c5": c5,
+            "strong_c3": c3, "score_c4": c4, "stream_c5": c5, "restore_f4": f4,
             "gpu_eager_baseline": eager,
             "cpu_baseline": cpu,
         }

@@ -35,11 +35,10 @@ __global__ void __launch_bounds__(256) ap_bandsplit_kernel(const float2* __restr
                                                            float* __restrict__ ss) {
   __shared__ float2 s_spec[AP_BINS];
   __shared__ float s_feat[AP_FEAT];
-  __shared__ float s_ss[AP_NBAND];
+  __shared__ float s_ss[8][AP_NBAND];   // per-warp partial sums of squares (added in warp order: no atomics)
   const int64_t frame = blockIdx.x;
   const int tid = threadIdx.x;
   for (int k = tid; k < AP_BINS; k += 256) s_spec[k] = spec[frame * AP_BINS + k];
-  if (tid < AP_NBAND) s_ss[tid] = 0.f;
   __syncthreads();
   // per band: power, normalised (re | im | log power), RMSNorm over the 2 BW + 1 features - a warp per band
   const int warp = tid >> 5, lane = tid & 31;
@@ -84,12 +83,13 @@ __global__ void __launch_bounds__(256) ap_bandsplit_kernel(const float2* __restr
     float q = acc * acc;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (lane == 0) atomicAdd(&s_ss[band], q);
+    if (lane == 0) s_ss[warp][band] = q;
   }
   __syncthreads();
   if (tid < AP_NBAND) {
     float* d = ss + (static_cast<size_t>(frame) * AP_NBAND + tid) * 4;
-    *reinterpret_cast<float4*>(d) = make_float4(s_ss[tid], 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(d) = make_float4(s_ss[0][tid] + s_ss[1][tid], s_ss[2][tid] + s_ss[3][tid],
+                                                s_ss[4][tid] + s_ss[5][tid], s_ss[6][tid] + s_ss[7][tid]);
   }
 }
 

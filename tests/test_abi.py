@@ -29,7 +29,8 @@ def test_header_declares_the_expected_surface():
     names = declared_functions()
     for must in ("tdz_create", "tdz_separate", "tdz_stitch_ola", "tdz_stitch_concat", "tdz_gather_segments", "tdz_separate_strided",
                  "tdz_gather_segments_span",
-                 "tdz_fbank", "tdz_embed", "tdz_cosine_scores", "tdz_last_error"):
+                 "tdz_fbank", "tdz_embed", "tdz_cosine_scores", "tdz_last_error", "tdz_stft", "tdz_istft",
+                 "tdz_set_apollo_weights", "tdz_apollo_restore"):
         assert must in names
     assert len(names) >= 20
 
@@ -54,6 +55,18 @@ def test_layout_helpers_without_gpu(lib):
     assert so.tdz_separate_layout(64, 64000, 148, ctypes.byref(lay)) == 0
     assert (lay.S, lay.Sp, lay.Mtot) == (7999, 8192, 64 * 8192)
     assert lay.total % 1024 == 0 and lay.total > lay.Mtot * 16384
+
+
+def test_restorer_tables_without_gpu(lib):
+    so = lib.load()
+    assert so.tdz_stft_frames(261120, 1024) == 256 and so.tdz_stft_frames(22173, 441) == 51
+    assert so.tdz_apollo_workspace_bytes(1, 441) == 0          # too short for the reflect padding
+    n = so.tdz_apollo_workspace_bytes(2, 44100)                # 2 rows x 101 frames x 80 bands = 16 160 tokens
+    assert n % 1024 == 0 and n > 16160 * 6000
+    # tdz_stft_plan = 2 int32 + 2 pointers; per layer 4 + 3*6 pointers; model 5 + 6*22 + 5 pointers + the plan
+    assert ctypes.sizeof(lib.StftPlan) == 24
+    assert ctypes.sizeof(lib.ApolloLayer) == 22 * 8
+    assert ctypes.sizeof(lib.ApolloWeights) == (5 + 6 * 22 + 5) * 8 + 24
 
 
 def test_struct_sizes_match_header(lib):
