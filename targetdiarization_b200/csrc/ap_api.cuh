@@ -172,8 +172,6 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
   if (act_map(ctx, &m_att, att, false, 256, Mp, 1, 64, 128)) return 1;
   if (act_map(ctx, &m_h, h, false, 1024, Mp, 1, 64, 128)) return 1;
   if (act_map(ctx, &m_u, u, false, 256, Mp, 1, 64, 128)) return 1;
-  static std::atomic<unsigned long long> attn_cfg{0};
-  CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(ap_attn_kernel), static_cast<int>(sizeof(ApAttnSmem)), attn_cfg));
   const int runs = static_cast<int>((T + AP_DW_RUN - 1) / AP_DW_RUN);
   const int64_t dw_warps = rows * runs * AP_NBAND;
 
@@ -188,7 +186,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     P.e.out_bf16 = qkv;
     P.e.out_bf_ld = 768;
     CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_RMS4 | EF_OUT_BF16, ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));
-    ap_attn_kernel<<<static_cast<unsigned>(nframes), 256, sizeof(ApAttnSmem), st>>>(qkv, W.rot_cos, W.rot_sin, att);
+    ap_attn_kernel<<<static_cast<unsigned>(nframes), 256, 0, st>>>(qkv, W.rot_cos, W.rot_sin, att);
     CUDA_OK(cudaGetLastError());
     if (l == 0 && tap == AP_TAP_ATT0) {
       ap_widen_kernel<<<static_cast<unsigned>((tokens * 256 + 255) / 256), 256, 0, st>>>(att, out, tokens * 256);

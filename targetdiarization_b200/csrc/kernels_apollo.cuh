@@ -97,80 +97,117 @@ __global__ void __launch_bounds__(256) ap_bandsplit_kernel(const float2* __restr
 // qkv [tokens][768] bf16, channel = head * 96 + (q 0..31 | k 32..63 | v 64..95); rotary embedding on q, k with the
 // position = band index (interleaved pairs, cos / sin tables [100][32] of the checkpoint); softmax(q k^T / sqrt(32)) v;
 // output [tokens][256] bf16, channel = head * 32 + d.
-constexpr int AP_KLD = AP_HD + 1;   // padded K rows: lane = key reads K[key][d] conflict-free
+// K and V of the head live in REGISTERS: lane l holds the rotated keys l, l + 32, l + 64 (3 x 32 values) and column l
+// of V (80 values); per query only q (32 floats) and the 80 softmax weights go through shared memory as broadcast
+// 128-bit reads.  (The first version kept K / V in shared memory: 350 LDS per query and warp, LSU bound at 845 us per
+// layer for 10 s of audio - 42 % of the forward.)
 struct ApAttnSmem {
-  float k[AP_HEADS][AP_NBAND][AP_KLD];
-  float v[AP_HEADS][AP_NBAND][AP_HD];
   float q[AP_HEADS][AP_HD];
   float p[AP_HEADS][96];
 };
-__global__ void __launch_bounds__(256) ap_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                      const float* __restrict__ rot_cos,
-                                                      const float* __restrict__ rot_sin,
-                                                      __nv_bfloat16* __restrict__ out) {
-  extern __shared__ uint8_t ap_smem_raw[];
-  ApAttnSmem& S = *reinterpret_cast<ApAttnSmem*>(ap_smem_raw);
+__global__ void __launch_bounds__(256, 1) ap_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                         const float* __restrict__ rot_cos,
+                                                         const float* __restrict__ rot_sin,
+                                                         __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) ApAttnSmem S;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t tok0 = static_cast<size_t>(blockIdx.x) * AP_NBAND;
   const __nv_bfloat16* base = qkv + tok0 * 768 + h * 96;
-  // lane = feature d; the rotary partner of d is d ^ 1: (a, b) -> (a cos - b sin, b cos + a sin)
-  const float sgn = (lane & 1) ? 1.f : -1.f;
-  for (int j = 0; j < AP_NBAND; ++j) {
-    const float kv = __bfloat162float(base[static_cast<size_t>(j) * 768 + 32 + lane]);
-    const float kp = __shfl_xor_sync(0xffffffffu, kv, 1);
-    const float c = __ldg(rot_cos + j * AP_HD + lane), s = __ldg(rot_sin + j * AP_HD + lane);
-    S.k[h][j][lane] = kv * c + sgn * kp * s;
-    S.v[h][j][lane] = __bfloat162float(base[static_cast<size_t>(j) * 768 + 64 + lane]);
+  // ---- keys lane, lane + 32, lane + 64, rotated: pairs (a, b) -> (a cos - b sin, b cos + a sin)
+  float kreg[3][AP_HD];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int j = lane + 32 * r;
+    if (j < AP_NBAND) {
+      const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<size_t>(j) * 768 + 32);
+      const float4* cp = reinterpret_cast<const float4*>(rot_cos + j * AP_HD);
+      const float4* sp = reinterpret_cast<const float4*>(rot_sin + j * AP_HD);
+#pragma unroll
+      for (int v8 = 0; v8 < 4; ++v8) {
+        const uint4 raw = kp[v8];
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        float c[8], sn[8];
+        const float4 c0 = __ldg(cp + 2 * v8), c1 = __ldg(cp + 2 * v8 + 1), s0 = __ldg(sp + 2 * v8), s1 = __ldg(sp + 2 * v8 + 1);
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+        sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
+          kreg[r][8 * v8 + 2 * i] = a * c[2 * i] - b * sn[2 * i];
+          kreg[r][8 * v8 + 2 * i + 1] = b * c[2 * i + 1] + a * sn[2 * i + 1];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < AP_HD; ++d) kreg[r][d] = 0.f;
+    }
   }
-  __syncwarp();
+  // ---- column `lane` of V
+  float vreg[AP_NBAND];
+#pragma unroll
+  for (int j = 0; j < AP_NBAND; ++j) vreg[j] = __bfloat162float(base[static_cast<size_t>(j) * 768 + 64 + lane]);
+  const float sgn = (lane & 1) ? 1.f : -1.f;
   const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
+  const float rc = 0.f;
+  (void)rc;
+#pragma unroll 1
   for (int i = 0; i < AP_NBAND; ++i) {
     const float qv = __bfloat162float(base[static_cast<size_t>(i) * 768 + lane]);
     const float qp = __shfl_xor_sync(0xffffffffu, qv, 1);
     const float c = __ldg(rot_cos + i * AP_HD + lane), s = __ldg(rot_sin + i * AP_HD + lane);
     S.q[h][lane] = (qv * c + sgn * qp * s) * scale;
     __syncwarp();
-    float sc[3];
+    float sc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int j = lane + 32 * r;
-      float a = -INFINITY;
-      if (j < AP_NBAND) {
-        a = 0.f;
+    for (int d4 = 0; d4 < AP_HD / 4; ++d4) {
+      const float4 q4 = *reinterpret_cast<const float4*>(&S.q[h][4 * d4]);
 #pragma unroll
-        for (int d = 0; d < AP_HD; ++d) a = fmaf(S.q[h][d], S.k[h][j][d], a);
+      for (int r = 0; r < 3; ++r) {
+        sc[r] = fmaf(q4.x, kreg[r][4 * d4], sc[r]);
+        sc[r] = fmaf(q4.y, kreg[r][4 * d4 + 1], sc[r]);
+        sc[r] = fmaf(q4.z, kreg[r][4 * d4 + 2], sc[r]);
+        sc[r] = fmaf(q4.w, kreg[r][4 * d4 + 3], sc[r]);
       }
-      sc[r] = a;
     }
+    if (lane + 64 >= AP_NBAND) sc[2] = -INFINITY;
     float mx = fmaxf(fmaxf(sc[0], sc[1]), sc[2]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const float e = (lane + 32 * r) < AP_NBAND ? __expf(sc[r] - mx) : 0.f;
+      const float e = __expf(sc[r] - mx);   // exp(-inf) = 0 for the keys that do not exist
       S.p[h][lane + 32 * r] = e;
       sum += e;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     __syncwarp();
-    float acc = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < AP_NBAND; ++j) acc = fmaf(S.p[h][j], S.v[h][j][lane], acc);
-    out[(tok0 + i) * AP_N + h * AP_HD + lane] = __float2bfloat16(acc / sum);
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < AP_NBAND / 4; ++j4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&S.p[h][4 * j4]);
+      acc0 = fmaf(p4.x, vreg[4 * j4], acc0);
+      acc1 = fmaf(p4.y, vreg[4 * j4 + 1], acc1);
+      acc0 = fmaf(p4.z, vreg[4 * j4 + 2], acc0);
+      acc1 = fmaf(p4.w, vreg[4 * j4 + 3], acc1);
+    }
+    out[(tok0 + i) * AP_N + h * AP_HD + lane] = __float2bfloat16((acc0 + acc1) / sum);
     __syncwarp();
   }
 }
 
 // ConvActNorm1d head (apollo.py:143-158): y = dwconv7(x) + bias along time (zero padding 3), then RMSNorm over the
 // 256 features (the gain is folded into the following 1x1 conv) -> bf16 GEMM operand.
-// A warp walks AP_DW_RUN consecutive frames of one (row, band) with the 7-row window in registers (lane = 8 channels).
+// A warp produces AP_DW_RUN consecutive frames of one (row, band), lane = 8 channels: all AP_DW_RUN + 6 input rows are
+// requested up front (14 independent 32-byte loads per lane in flight) and the window is indexed statically.
+// (First version: a 32-frame run with a shifted register window and one row load per step - latency bound, 16 % of the
+// DRAM rate.)
 //   taps [7][256], bias [256]
-constexpr int AP_DW_RUN = 32;
-__global__ void __launch_bounds__(256) ap_dwconv_rms_kernel(const float* __restrict__ x, const float* __restrict__ taps,
-                                                            const float* __restrict__ bias, int T, int runs_per_seq,
-                                                            int64_t n_warps, __nv_bfloat16* __restrict__ u) {
+constexpr int AP_DW_RUN = 8;
+__global__ void __launch_bounds__(256, 1) ap_dwconv_rms_kernel(const float* __restrict__ x, const float* __restrict__ taps,
+                                                               const float* __restrict__ bias, int T, int runs_per_seq,
+                                                               int64_t n_warps, __nv_bfloat16* __restrict__ u) {
   const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= n_warps) return;
@@ -180,8 +217,20 @@ __global__ void __launch_bounds__(256) ap_dwconv_rms_kernel(const float* __restr
   const int run = static_cast<int>(rr % runs_per_seq);
   const int64_t r = rr / runs_per_seq;
   const int t0 = run * AP_DW_RUN;
-  const int t1 = min(t0 + AP_DW_RUN, T);
   const int c0 = lane * 8;
+  float win[AP_DW_RUN + 6][8];   // rows t0 - 3 .. t0 + AP_DW_RUN + 2
+#pragma unroll
+  for (int k = 0; k < AP_DW_RUN + 6; ++k) {
+    const int t = t0 - 3 + k;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (t >= 0 && t < T) {
+      const float* p = x + ((r * T + t) * AP_NBAND + band) * AP_N + c0;
+      a = *reinterpret_cast<const float4*>(p);
+      b = *reinterpret_cast<const float4*>(p + 4);
+    }
+    win[k][0] = a.x; win[k][1] = a.y; win[k][2] = a.z; win[k][3] = a.w;
+    win[k][4] = b.x; win[k][5] = b.y; win[k][6] = b.z; win[k][7] = b.w;
+  }
   float w[7][8], bv[8];
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
@@ -195,42 +244,27 @@ __global__ void __launch_bounds__(256) ap_dwconv_rms_kernel(const float* __restr
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
     bv[0] = a.x; bv[1] = a.y; bv[2] = a.z; bv[3] = a.w; bv[4] = b.x; bv[5] = b.y; bv[6] = b.z; bv[7] = b.w;
   }
-  auto load_row = [&](int t, float* v) {
-    if (t < 0 || t >= T) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      return;
-    }
-    const float* p = x + ((r * T + t) * AP_NBAND + band) * AP_N + c0;
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  };
-  float win[7][8];   // rows t - 3 .. t + 3
-#pragma unroll
-  for (int j = 0; j < 6; ++j) load_row(t0 - 3 + j, win[j + 1]);   // slots 1..6 hold t0 - 3 .. t0 + 2; shifted below
-  for (int t = t0; t < t1; ++t) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) win[j][i] = win[j + 1][i];
-    load_row(t + 3, win[6]);
+  for (int k = 0; k < AP_DW_RUN; ++k) {
+    const int t = t0 + k;
     float y[8];
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float a = bv[i];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) a = fmaf(w[j][i], win[j][i], a);
+      for (int j = 0; j < 7; ++j) a = fmaf(w[j][i], win[k + j][i], a);
       y[i] = a;
       q = fmaf(a, a, q);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rs = rsqrtf(q * (1.f / AP_N) + AP_EPS);
-    uint4 o4 = make_uint4(pack_bf16(y[0] * rs, y[1] * rs), pack_bf16(y[2] * rs, y[3] * rs),
-                          pack_bf16(y[4] * rs, y[5] * rs), pack_bf16(y[6] * rs, y[7] * rs));
-    *reinterpret_cast<uint4*>(u + ((r * T + t) * AP_NBAND + band) * AP_N + c0) = o4;
+    if (t < T) {
+      const uint4 o4 = make_uint4(pack_bf16(y[0] * rs, y[1] * rs), pack_bf16(y[2] * rs, y[3] * rs),
+                                  pack_bf16(y[4] * rs, y[5] * rs), pack_bf16(y[6] * rs, y[7] * rs));
+      *reinterpret_cast<uint4*>(u + ((r * T + t) * AP_NBAND + band) * AP_N + c0) = o4;
+    }
   }
 }
 
