@@ -761,6 +761,60 @@ struct LinearGLU : LinearBase<1, 256, STAGES_> {
   }
 };
 
+// Split-K form of a skinny linear layer (the embedder's Linear(40960 -> 192) on at most a few hundred rows: as one
+// tile per 128 rows it was a single CTA walking 640 k-blocks, 277 us whatever the batch).  Work item = (row tile,
+// K slice of P.tps k-blocks); the fp32 partial tile goes to out_f32[(slice * B * Sp + row) * 256 + col] and
+// splitk_reduce_kernel adds the slices in ascending order (+ bias): the summation order is fixed by K alone.
+// P.n_tiles = number of slices; N <= 256.
+template <int STAGES_>
+struct LinearSplitK : LinearBase<1, 256, STAGES_> {
+  using Params = LinearParams;
+  using Base = LinearBase<1, 256, STAGES_>;
+  static constexpr int EPI_SPLIT = 2;
+  __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
+    const int mt = tile / P.n_tiles;
+    ti.aux = tile - mt * P.n_tiles;  // K slice
+    ti.m0 = mt * GEMM_BLOCK_M;
+    ti.n0 = 0;
+    ti.b = ti.m0 / P.Sp;
+    ti.t0 = ti.m0 - ti.b * P.Sp;
+    const int total = (P.K + Base::KB - 1) / Base::KB;
+    const int left = total - ti.aux * P.tps;
+    ti.nkb = left < P.tps ? left : P.tps;
+  }
+  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
+    const int k = (ti.aux * P.tps + kb) * Base::KB;
+    tma_load_3d(sa, &P.tmA, bar, k, ti.t0, ti.b);
+    tma_load_2d(sb, &P.tmB, bar, k, 0);
+  }
+  __device__ static void epilogue(const Params& P, const TileInfo& ti, uint32_t tacc, int row, int half,
+                                  const EpiCtx&) {
+    const size_t mtot = static_cast<size_t>(P.B) * P.Sp;
+    float* dst = P.e.out_f32 + (static_cast<size_t>(ti.aux) * mtot + ti.m0 + row) * 256;
+#pragma unroll 1
+    for (int cc = 0; cc < 128; cc += 32) {
+      const int c0 = half * 128 + cc;
+      float v[32];
+      tmem_ld16(tacc + c0, v);
+      tmem_ld16(tacc + c0 + 16, v + 16);
+      tmem_ld_wait();
+      float4* o = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+};
+// out[row][col] = bias[col] + sum over slices (ascending) of part[slice][row][col]; rows < rows_valid, col < N
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, int nslice,
+                                     int64_t mtot, int rows_valid, int N, float* __restrict__ out, int out_ld) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(rows_valid) * N) return;
+  const int row = static_cast<int>(i / N), col = static_cast<int>(i - static_cast<int64_t>(row) * N);
+  float acc = 0.f;
+  for (int s = 0; s < nslice; ++s) acc += part[(static_cast<size_t>(s) * mtot + row) * 256 + col];
+  out[static_cast<size_t>(row) * out_ld + col] = acc + bias[col];
+}
+
 // Decoder: ConvTranspose1d(512 -> 1, k 16, stride 8) + overlap-by-2 add + pad / trim to T (mossformer2.py:213-257,
 // 579-589) as a skinny tf32 GEMM: D[t][j] = sum_c sep[t][c] w[c][j] (N = 16), out[8 t + j] = D[t][j] + D[t-1][8 + j].
 // A tile holds 128 frames of which the first is the halo row t0 - 1 (tiles advance by 127 frames; TMA zero-fills rows

@@ -107,8 +107,9 @@ static void sv_dims(int64_t N, int64_t frames, SvDims* d) {
   }
 }
 
+constexpr int SV_SEG1_SLICES = 64;   // Linear(40960 -> 192): 640 k-blocks in 64 slices of 10 (fixed: batch invariant)
 struct SvLayout {
-  size_t xa, xb, xs, c1, fused, cat2, mid, col, cat4, res, ds, fcat, fmid, fuse, stats, total;
+  size_t xa, xb, xs, c1, fused, cat2, mid, col, cat4, res, ds, fcat, fmid, fuse, stats, part, total;
 };
 static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
   SvDims d;
@@ -148,6 +149,7 @@ static void sv_layout(int64_t N, int64_t frames, SvLayout* L) {
   L->fmid = take(static_cast<size_t>(d.Pp[3]) * 512 * 2);
   L->fuse = take(static_cast<size_t>(d.Pp[3]) * 2048 * 4);
   L->stats = take(static_cast<size_t>((N + 127) / 128 * 128) * 40960 * 2);
+  L->part = take(static_cast<size_t>(SV_SEG1_SLICES) * ((N + 127) / 128 * 128) * 256 * 4);  // split-K partial tiles
   L->total = off;
 }
 
@@ -437,10 +439,24 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     CUDA_OK(cudaMemsetAsync(stats, 0, static_cast<size_t>(Np) * 40960 * 2, st));
     sv_tstp_kernel<<<sv_grid(N * d.H[3] * 2048), 256, 0, st>>>(fuse, stats, n, static_cast<int>(d.H[3]),
                                                                static_cast<int>(d.W[3]), 2048, 40960);
-    memset(&e, 0, sizeof e);
-    e.out_f32 = emb;
-    e.out_ld = 192;
-    if (sv_gemm(ctx, st, M.seg1, stats, 40960, N, Np, SV_LINEAR_F32, e)) return 1;
+    {
+      float* part = reinterpret_cast<float*>(base + L.part);
+      LinearParams LP;
+      memset(&LP, 0, sizeof LP);
+      if (act_map(ctx, &LP.tmA, stats, false, 40960, Np, 1, 64, 128)) return 1;
+      LP.tmB = M.seg1.map;
+      LP.B = 1;
+      LP.Sp = static_cast<int>(Np);
+      LP.S = static_cast<int>(N);
+      LP.N = 192;
+      LP.K = 40960;
+      LP.n_tiles = SV_SEG1_SLICES;
+      LP.tps = (40960 / 64 + SV_SEG1_SLICES - 1) / SV_SEG1_SLICES;
+      LP.e.out_f32 = part;
+      cudaError_t r = launch_gemm<LinearSplitK<4>>(LP, static_cast<int>(Np / 128) * SV_SEG1_SLICES, ctx->num_sms, st);
+      if (r != cudaSuccess) return fail(ctx, "tdz_embed: split-K launch failed (%s)", cudaGetErrorString(r));
+      splitk_reduce_kernel<<<sv_grid(N * 192), 256, 0, st>>>(part, M.seg1.bias, SV_SEG1_SLICES, Np, n, 192, emb, 192);
+    }
   }
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -362,7 +362,10 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   dd.B = B;
   dd.Sp = Sp;
   dd.S = S;
-  dd.seg_len = 1024;  // fixed: per-segment fp32 partial sums must not depend on the batch (bit-identical batching)
+  // a function of the chunk length alone: per-segment fp32 partial sums must not depend on the batch (bit-identical
+  // batching).  Short chunks (streaming: 600 ms = 1 199 frames) are cut finer - with 1024-frame segments a batch-1 call
+  // ran 8 / 16 CTAs that each walked up to 16 steps in sequence (30 / 37 us per launch, 19 % of the batch-1 step).
+  dd.seg_len = S <= 2048 ? 256 : 1024;
   dd.nseg = (S + dd.seg_len - 1) / dd.seg_len;
   {
     static std::atomic<unsigned long long> dd1_configured{0}, dd2_configured{0};

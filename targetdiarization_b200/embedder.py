@@ -18,8 +18,8 @@ class Embedder:
     sample_rate = 16000
     # launches of one tdz_embed call (csrc/sv_api.cuh): stem 1; per block conv1 + [subsample] + [shortcut] +
     # 4 x implicit-GEMM 3x3 conv + [AFF: 3 x (cat + 2 convs)] + conv3 = 19 + 26 + 92 + 47; layer3_ds 2 (im2col +
-    # GEMM); fuse34/TSTP/Linear 5
-    KERNELS_PER_FORWARD = 1 + 19 + 26 + 92 + 2 + 47 + 5
+    # GEMM); fuse34/TSTP/Linear (split-K + reduce) 6
+    KERNELS_PER_FORWARD = 1 + 19 + 26 + 92 + 2 + 47 + 6
 
     def __init__(self, state_dict=None, device="cuda:0", max_workspace_bytes=None, handle=None):
         self.device = torch.device(device)
