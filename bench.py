@@ -58,8 +58,8 @@ STEP_TABLE = {
     "TO_OUT": dict(bound="tensor", fmt="bf16", flops=2 * 1024 * 512, bytes=2048 + 2048 + 2048),
     "FSMN_C1": dict(bound="hbm", fmt="tf32", flops=2 * 512 * 256, bytes=2048 + 1024 + 512),
     "FSMN_UV": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 512, bytes=512 + 2048 + 512),
-    "FSMN_LIN": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 256, bytes=512 + 512),
-    "FSMN_PROJ": dict(bound="hbm", fmt="bf16", flops=2 * 256 * 256, bytes=512 + 1024),
+    # fsmn.linear -> ReLU -> fsmn.project as one back-to-back GEMM (hidden activations stay on chip)
+    "FSMN_LIN": dict(bound="hbm", fmt="bf16", flops=2 * 2 * 256 * 256, bytes=512 + 1024),
     "DD1": dict(bound="hbm", bytes=1024 + 1024),
     "DD2": dict(bound="hbm", bytes=2048 + 1024),
     "FSMN_TAIL": dict(bound="hbm", bytes=1024 + 2048 + 1024 + 1024),
@@ -71,7 +71,7 @@ STEP_TABLE = {
     "DEC1": dict(bound="hbm", fmt="tf32", flops=2 * 2 * 512 * 512, bytes=4096 + 2048 + 4096),
     "DECODER": dict(bound="hbm", bytes=4096 + 64),
 }
-LAYER_STEPS = ["FLASH_IN", "SIM", "KV", "ATT_OUT", "TO_OUT", "FSMN_C1", "FSMN_UV", "FSMN_LIN", "FSMN_PROJ", "DD1",
+LAYER_STEPS = ["FLASH_IN", "SIM", "KV", "ATT_OUT", "TO_OUT", "FSMN_C1", "FSMN_UV", "FSMN_LIN", "DD1",
                "DD2", "FSMN_TAIL", "FSMN_C2"]
 ALL_STEPS = ["ENCODER", "ENC1X1"] + LAYER_STEPS + ["FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1", "DECODER"]
 # the kernel that carries each step's time (name fragment in the ncu export), for `roofline.traffic`

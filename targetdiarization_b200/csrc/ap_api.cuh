@@ -11,6 +11,7 @@ struct ApModel {
   FftPlan plan;
   struct LayerMaps {
     CUtensorMap qkv, out, mlp1, mlp2, w1[3], w2[3];
+    CUtensorMap w1_128[3];   // 128-row boxes: hidden chunks of the back-to-back ConvActNorm1d GEMM
   } lm[TDZ_AP_LAYERS];
 };
 
@@ -71,6 +72,7 @@ static int ap_set_weights(tdz_ctx* ctx, ApModel* M, const tdz_apollo_weights* w)
     for (int b = 0; b < 3; ++b) {
       if (w_map(ctx, &m.w1[b], L.icb[b].w1, false, 1024, 256, 256)) return 1;
       if (w_map(ctx, &m.w2[b], L.icb[b].w2, false, 256, 1024, 256)) return 1;
+      if (w_map(ctx, &m.w1_128[b], L.icb[b].w1, false, 1024, 256, 128)) return 1;
     }
   }
   M->ready = true;
@@ -224,6 +226,35 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
       ap_dwconv_rms_kernel<<<static_cast<unsigned>((dw_warps * 32 + 255) / 256), 256, 0, st>>>(
           x, I.dw, I.dw_b, static_cast<int>(T), runs, dw_warps, u);
       CUDA_OK(cudaGetLastError());
+      if (!ctx->no_b2b) {
+        // Conv1d(256, 1024) -> SiLU -> Conv1d(1024, 256) + residual as one back-to-back GEMM (gemm_b2b.cuh): the
+        // 1 024-wide hidden activations never leave the SM
+        B2bParams Q;
+        memset(&Q, 0, sizeof Q);
+        Q.tmX = m_u;
+        Q.tmW1 = m.w1_128[b];
+        Q.tmW2 = m.w2[b];
+        Q.B = 1;
+        Q.Sp = static_cast<int>(Mp);
+        Q.S = static_cast<int>(tokens);
+        Q.H = 1024;
+        Q.bias1 = I.b1;
+        Q.e.bias = I.b2;
+        Q.e.resid = x;
+        Q.e.resid_ld = 256;
+        Q.e.out_f32 = x;
+        Q.e.out_ld = 256;
+        if (b < 2) {
+          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32>(Q, sms, st)));
+        } else {  // the layer output also feeds the next Roformer: bf16 copy + RMSNorm sums
+          Q.e.out_bf16 = xbf;
+          Q.e.out_bf_ld = 256;
+          Q.e.ss_out = ss;
+          Q.e.ss_out_ld = 4;
+          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT>(Q, sms, st)));
+        }
+        continue;
+      }
       ap_lin(ctx, P, m_u, m.w1[b], tokens, Mp, 1024, 256);
       P.e.bias = I.b1;
       P.e.out_bf16 = h;

@@ -1,0 +1,321 @@
+// Back-to-back GEMM: out = W2 act(W1 x + b1) (+ b2) (+ resid) for K1 = 256 inputs, H hidden units (a multiple of 128)
+// and 256 outputs, with the [rows][H] hidden activations kept ON CHIP - TMEM accumulator -> epilogue warps -> bf16 in
+// shared memory as the A operand of the second MMA - instead of a round trip through HBM between two kernels:
+//   * UniDeepFsmn linear -> ReLU -> project (look2hear/models/fsmn.py:131-139), H = 256;
+//   * the Apollo restorer's ConvActNorm1d 1x1 pair (look2hear/models/apollo.py:150-158: Conv1d(256, 1024) -> SiLU ->
+//     Conv1d(1024, 256) + residual), H = 1024: 4 KB per token of hidden traffic removed per pair.
+//
+//   warp 0 (lane 0)  TMA producer: the X tile (128 rows x 256, resident for the whole tile) and a ring of 32 KB weight
+//                    stages in the order the MMA warp consumes them
+//   warp 1 (lane 0)  tcgen05.mma issuer, software pipelined over hidden chunks of 128:
+//                    G1(j): acc1[j & 1] = X W1[j]^T (N = 128, K = 256);   G2(j): acc2 += h[j & 1] W2[:, j]^T (N = 256,
+//                    K = 128), issued as G1(0) G1(1) G2(0) G1(2) G2(1) ... so that the tensor core works on G1(j + 1)
+//                    while the epilogue warps turn acc1[j] into h[j]
+//   warps 2..9       epilogue: (1) per chunk: tcgen05.ld of acc1 -> + b1 -> activation -> bf16 -> shared memory in the
+//                    128 B-swizzled K-major layout of an A operand (fence.proxy.async + mbarrier, like the gather warps
+//                    of gemm_conv3.cuh); (2) per tile: acc2 -> + b2 + resid -> global
+// TMEM: acc2 = columns [0, 256), acc1 double buffer = [256, 384) and [384, 512).
+// Shared memory: X 64 KB | h 2 x 32 KB | weight ring 3 x 32 KB = 224 KB.
+// The arithmetic is the same as in the two-kernel form (same k order, same bf16 rounding of the hidden activations), so
+// the results are bit-identical to it.
+#pragma once
+#include "gemm_cfgs.cuh"
+
+namespace tdz {
+
+struct B2bParams {
+  CUtensorMap tmX;    // 3-D {256, Sp, B} bf16, box {64, 128, 1}
+  CUtensorMap tmW1;   // 2-D {256, H} bf16, box {64, 128}
+  CUtensorMap tmW2;   // 2-D {H, 256} bf16, box {64, 256}
+  int B, Sp, S, H;
+  const float* bias1;  // [H]
+  EpiGeneric e;        // bias (b2), resid / resid_ld, out_f32 / out_ld, out_bf16 / out_bf_ld, ss_out / ss_out_ld
+};
+
+constexpr int B2B_THREADS = 64 + 256;
+constexpr int B2B_WSTAGES = 3;
+constexpr int B2B_X_BYTES = 4 * 16384;
+constexpr int B2B_H_BYTES = 2 * 32768;
+constexpr int B2B_SMEM_BYTES = B2B_X_BYTES + B2B_H_BYTES + B2B_WSTAGES * 32768 + 1024 + 256;
+
+template <int ACT1, unsigned EF2>
+__global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_constant__ B2bParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sX = smem_base;
+  const uint32_t sH = sX + B2B_X_BYTES;
+  const uint32_t sW = sH + B2B_H_BYTES;
+  const uint32_t bar_base = sW + B2B_WSTAGES * 32768;
+  auto w_full = [&](int s) { return bar_base + 8u * s; };
+  auto w_empty = [&](int s) { return bar_base + 8u * (B2B_WSTAGES + s); };
+  const uint32_t b0 = bar_base + 8u * 2 * B2B_WSTAGES;
+  const uint32_t x_full = b0, x_empty = b0 + 8, acc2_full = b0 + 16, acc2_empty = b0 + 24;
+  auto acc1_full = [&](int b) { return b0 + 32u + 8u * b; };
+  auto acc1_empty = [&](int b) { return b0 + 48u + 8u * b; };
+  auto h_full = [&](int b) { return b0 + 64u + 8u * b; };
+  auto h_empty = [&](int b) { return b0 + 80u + 8u * b; };
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmX);
+    tma_prefetch_desc(&P.tmW1);
+    tma_prefetch_desc(&P.tmW2);
+    for (int s = 0; s < B2B_WSTAGES; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 8);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc1_full(b), 1);
+      mbar_init(acc1_empty(b), 8);
+      mbar_init(h_full(b), 8);
+      mbar_init(h_empty(b), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const int ntiles = P.B * P.Sp / GEMM_BLOCK_M;
+  const int NC = P.H / 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next_stage = [&]() {
+        if (++stage == B2B_WSTAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int m0 = tile * GEMM_BLOCK_M;
+        const int b = m0 / P.Sp, t0 = m0 - b * P.Sp;
+        mbar_wait(x_empty, (it & 1) ^ 1u);
+        mbar_arrive_expect_tx(x_full, B2B_X_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_3d(sX + kb * 16384, &P.tmX, x_full, kb * 64, t0, b);
+        for (int step = 0; step <= NC; ++step) {
+          if (step < NC) {  // G1(step): two stages of two W1 k-blocks
+            for (int s = 0; s < 2; ++s) {
+              mbar_wait(w_empty(stage), phase ^ 1u);
+              mbar_arrive_expect_tx(w_full(stage), 32768);
+              const uint32_t dst = sW + stage * 32768;
+              tma_load_2d(dst, &P.tmW1, w_full(stage), (2 * s) * 64, step * 128);
+              tma_load_2d(dst + 16384, &P.tmW1, w_full(stage), (2 * s + 1) * 64, step * 128);
+              next_stage();
+            }
+          }
+          if (step >= 1) {  // G2(step - 1): two stages of one W2 k-block
+            for (int s = 0; s < 2; ++s) {
+              mbar_wait(w_empty(stage), phase ^ 1u);
+              mbar_arrive_expect_tx(w_full(stage), 32768);
+              tma_load_2d(sW + stage * 32768, &P.tmW2, w_full(stage), (step - 1) * 128 + s * 64, 0);
+              next_stage();
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC1 = umma_idesc(1, GEMM_BLOCK_M, 128, 0, 0);
+      constexpr uint32_t IDESC2 = umma_idesc(1, GEMM_BLOCK_M, 256, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next_stage = [&]() {
+        if (++stage == B2B_WSTAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      };
+      int it = 0;
+      int c1 = 0, c2 = 0;  // running chunk counters of G1 / G2 (buffer = counter & 1, use = counter >> 1)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        mbar_wait(x_full, it & 1);
+        tc_fence_after();
+        for (int step = 0; step <= NC; ++step) {
+          if (step < NC) {
+            const int buf = c1 & 1;
+            mbar_wait(acc1_empty(buf), ((c1 >> 1) & 1) ^ 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + 256 + buf * 128;
+            for (int s = 0; s < 2; ++s) {
+              mbar_wait(w_full(stage), phase);
+              tc_fence_after();
+              const uint32_t sb = sW + stage * 32768;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da = umma_smem_desc(sX + (2 * s + kk) * 16384 + k * 32u, 16u, 1024u);
+                  const uint64_t db = umma_smem_desc(sb + kk * 16384 + k * 32u, 16u, 1024u);
+                  umma_f16(tacc, da, db, IDESC1, (s | kk | k) != 0);
+                }
+              }
+              umma_commit(w_empty(stage));
+              next_stage();
+            }
+            umma_commit(acc1_full(buf));
+            if (step == NC - 1) umma_commit(x_empty);  // the X tile may be overwritten by the next one
+            ++c1;
+          }
+          if (step >= 1) {
+            const int j = step - 1;
+            const int buf = c2 & 1;
+            mbar_wait(h_full(buf), (c2 >> 1) & 1);
+            if (j == 0) mbar_wait(acc2_empty, (it & 1) ^ 1u);
+            tc_fence_after();
+            for (int s = 0; s < 2; ++s) {
+              mbar_wait(w_full(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = sH + buf * 32768 + s * 16384;
+              const uint32_t sb = sW + stage * 32768;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_smem_desc(sa + k * 32u, 16u, 1024u);
+                const uint64_t db = umma_smem_desc(sb + k * 32u, 16u, 1024u);
+                umma_f16(tmem_base, da, db, IDESC2, (j | s | k) != 0);
+              }
+              umma_commit(w_empty(stage));
+              next_stage();
+            }
+            umma_commit(h_empty(buf));
+            if (j == NC - 1) umma_commit(acc2_full);
+            ++c2;
+          }
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    const int half = ew >> 2;         // which half of the columns
+    const int row = q * 32 + lane;
+    const uint32_t lane_t = static_cast<uint32_t>(q * 32) << 16;
+    uint8_t* hbase = smem_al + B2B_X_BYTES;
+    const uint32_t rsw = (row >> 3) * 1024 + (row & 7) * 128;   // row offset inside a k-block atom set
+    const EpiGeneric& e = P.e;
+    int it = 0, c = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int m0 = tile * GEMM_BLOCK_M;
+      const int b = m0 / P.Sp, t0 = m0 - b * P.Sp;
+      (void)b;
+      // ---- (1) hidden chunks: acc1 -> h
+      for (int j = 0; j < NC; ++j, ++c) {
+        const int buf = c & 1;
+        mbar_wait(acc1_full(buf), (c >> 1) & 1);
+        mbar_wait(h_empty(buf), ((c >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + 256 + buf * 128 + lane_t + half * 64;
+        uint8_t* hb = hbase + buf * 32768 + half * 16384 + rsw;   // this warp's 64 columns = k-block atom `half`
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 32) {
+          float v[32], bs[32];
+          tmem_ld16(tacc + cc, v);
+          tmem_ld16(tacc + cc + 16, v + 16);
+          ld_f32x16(P.bias1 + j * 128 + half * 64 + cc, bs);
+          ld_f32x16(P.bias1 + j * 128 + half * 64 + cc + 16, bs + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_apply<ACT1>(v[i] + bs[i]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int piece = cc / 8 + p;   // 16 B piece (8 columns) inside the 128 B row
+            *reinterpret_cast<uint4*>(hb + ((piece ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
+                           pack_bf16(v[8 * p + 4], v[8 * p + 5]), pack_bf16(v[8 * p + 6], v[8 * p + 7]));
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();   // generic-proxy writes of h -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(acc1_empty(buf));
+          mbar_arrive(h_full(buf));
+        }
+      }
+      // ---- (2) output tile: acc2 -> + b2 + resid -> global; this warp owns columns [128 half, 128 half + 128)
+      mbar_wait(acc2_full, it & 1);
+      tc_fence_after();
+      const bool valid = t0 + row < P.S;
+      const size_t grow = static_cast<size_t>(m0) + row;
+      float ssq0 = 0.f, ssq1 = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 128; cc += 16) {
+        const int col0 = half * 128 + cc;
+        float v[16], bs[16], rs[16];
+        tmem_ld16(tmem_base + lane_t + col0, v);
+        if constexpr ((EF2 & EF_BIAS) != 0) ld_f32x16(e.bias + col0, bs);
+        if constexpr ((EF2 & EF_RESID) != 0) {
+          if (valid) ld_f32x16_rw(e.resid + grow * e.resid_ld + col0, rs, true);
+        }
+        tmem_ld_wait();
+        if (!valid) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = v[i];
+          if constexpr ((EF2 & EF_BIAS) != 0) x += bs[i];
+          if constexpr ((EF2 & EF_RESID) != 0) x += rs[i];
+          s = fmaf(x, x, s);
+          v[i] = x;
+        }
+        if (cc < 64) ssq0 += s;
+        else ssq1 += s;
+        if constexpr ((EF2 & EF_OUT_F32) != 0) {
+          float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.out_ld + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if constexpr ((EF2 & EF_OUT_BF16) != 0) {
+          uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.out_bf_ld + col0);
+          o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                            pack_bf16(v[14], v[15]));
+        }
+      }
+      if constexpr ((EF2 & EF_SS_OUT) != 0) {   // one partial per 64 output columns, like LinearPanel
+        e.ss_out[grow * e.ss_out_ld + half * 2] = valid ? ssq0 : 0.f;
+        e.ss_out[grow * e.ss_out_ld + half * 2 + 1] = valid ? ssq1 : 0.f;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc2_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int ACT1, unsigned EF2>
+cudaError_t launch_gemm_b2b(const B2bParams& P, int num_sms, cudaStream_t st) {
+  static std::atomic<unsigned long long> configured{0};
+  if (cudaError_t err = set_max_smem_once(reinterpret_cast<const void*>(gemm_b2b_kernel<ACT1, EF2>), B2B_SMEM_BYTES, configured);
+      err != cudaSuccess)
+    return err;
+  const int ntiles = P.B * P.Sp / GEMM_BLOCK_M;
+  if (ntiles <= 0) return cudaSuccess;
+  gemm_b2b_kernel<ACT1, EF2><<<ntiles < num_sms ? ntiles : num_sms, B2B_THREADS, B2B_SMEM_BYTES, st>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace tdz

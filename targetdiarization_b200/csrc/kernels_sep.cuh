@@ -458,7 +458,9 @@ __global__ void in_finalize_kernel(const double* __restrict__ stats, const float
 // CLayerNorm(256) (norm2, :423) with its affine folded into conv2 -> tf32 operand.  One warp per group of
 // TAIL_FRAMES consecutive frames of one sample (the per-channel InstanceNorm / PReLU constants of the lane's 8
 // channels are loaded once per group, as vectors).
-constexpr int TAIL_FRAMES = 8;
+// TAIL_FRAMES = 8 amortises the constants at large batches; small calls (the streaming shape: 1 280 frames) run one
+// frame per warp - with 8 the batch-1 call was 160 warps that each walked 8 dependent rounds of loads (13 us).
+template <int TAIL_FRAMES>
 __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict__ y2, const float2* __restrict__ in2_ss,
                                                         const float* __restrict__ prelu2,
                                                         const float* __restrict__ xuv, const float* __restrict__ cres,

@@ -11,6 +11,7 @@
 #include <string>
 
 #include "gemm_cfgs.cuh"
+#include "gemm_b2b.cuh"
 #include "gemm_convt.cuh"
 #include "kernels_fbank.cuh"
 #include "kernels_misc.cuh"
@@ -36,11 +37,14 @@ struct tdz_ctx {
   // development switch, read once from the environment when the handle is created: TDZ_CONVT_SINGLE runs the
   // to_out / to_u|to_v conv GEMMs without cta_group::2 (A/B measurements)
   bool convt_single = false;
+  bool no_b2b = false;  // TDZ_NO_B2B: fsmn.linear / fsmn.project as two kernels (A/B measurements)
+  int dd_seg_len = 0;   // TDZ_DD_SEG_LEN: forces the DilatedDenseNet segment length (A/B measurements)
   tdz_mossformer2_weights sep;
   // weight tensor maps (built once per tdz_set_mossformer2_weights)
   struct LayerMaps {
     CUtensorMap w_in, w_out, w_c1, w_uv, w_lin, w_proj, w_c2;
     CUtensorMap w_in128, w_out128, w_uv128;  // 128-row boxes: M operand of the channel-major conv GEMMs
+    CUtensorMap w_lin128;                    // 128-row boxes: hidden chunks of the back-to-back linear -> project GEMM
   } lm[TDZ_NUM_LAYERS];
   CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1, m_dec;
   bool have_fbank = false;
@@ -104,6 +108,8 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
   }
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   c->convt_single = getenv("TDZ_CONVT_SINGLE") != nullptr;
+  c->no_b2b = getenv("TDZ_NO_B2B") != nullptr;
+  if (const char* e = getenv("TDZ_DD_SEG_LEN")) c->dd_seg_len = atoi(e);
   *out = c;
   return 0;
 }
@@ -179,6 +185,7 @@ extern "C" int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_w
     if (w_map(ctx, &M.w_in128, L.w_in, false, 2176, 512, 128)) return 1;
     if (w_map(ctx, &M.w_out128, L.w_out, false, 512, 1024, 128)) return 1;
     if (w_map(ctx, &M.w_uv128, L.w_uv, false, 512, 256, 128)) return 1;
+    if (w_map(ctx, &M.w_lin128, L.w_lin, false, 256, 256, 128)) return 1;
   }
   if (w_map(ctx, &ctx->m_enc1x1, w->w_enc1x1, true, 512, 512, 256)) return 1;
   if (w_map(ctx, &ctx->m_out1, w->w_out1, true, 1024, 512, 256)) return 1;
@@ -208,7 +215,9 @@ extern "C" int tdz_separate_layout(int64_t B, int64_t T, int num_sms, tdz_sep_la
   // that the summation order - and with it every output bit - does not depend on how chunks are batched.
   (void)num_sms;
   const int total_kb = static_cast<int>(Sp / 64);
-  const int kbps = 32;
+  // (chunks of up to 2048 frames - the streaming shape - are cut into 512-frame spans: with one span the batch-1 call
+  // was 8 CTAs walking 20 k-blocks each)
+  const int kbps = Sp <= 2048 ? 8 : 32;
   const int nsplit = (total_kb + kbps - 1) / kbps;
   L->kv_nsplit = nsplit;
   L->kv_kb_per_split = kbps;
@@ -366,6 +375,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   // batching).  Short chunks (streaming: 600 ms = 1 199 frames) are cut finer - with 1024-frame segments a batch-1 call
   // ran 8 / 16 CTAs that each walked up to 16 steps in sequence (30 / 37 us per launch, 19 % of the batch-1 step).
   dd.seg_len = S <= 2048 ? 256 : 1024;
+  if (ctx->dd_seg_len >= 64) dd.seg_len = ctx->dd_seg_len / 64 * 64;
   dd.nseg = (S + dd.seg_len - 1) / dd.seg_len;
   {
     static std::atomic<unsigned long long> dd1_configured{0}, dd2_configured{0};
@@ -514,7 +524,26 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
         CUDA_OK((launch_gemm_convt_cg2<CONV_UV>(P, B * tps_t * 2, sms, st)));
       }
     }
-    STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
+    // fsmn.linear -> ReLU -> fsmn.project (fsmn.py:131-139) as ONE back-to-back GEMM whose hidden activations stay on
+    // chip; the two-kernel form below runs when a test asks for one of the two steps alone (and under TDZ_NO_B2B) and
+    // gives the same bits
+    const bool b2b = step_lo <= ST_FSMN_LIN && step_hi >= ST_FSMN_PROJ && !ctx->no_b2b;
+    if (b2b) {
+      B2bParams Q;
+      memset(&Q, 0, sizeof Q);
+      Q.tmX = m_xubf;
+      Q.tmW1 = LM.w_lin128;
+      Q.tmW2 = LM.w_proj;
+      Q.B = B;
+      Q.Sp = Sp;
+      Q.S = S;
+      Q.H = 256;
+      Q.bias1 = LW.b_lin;
+      Q.e.out_f32 = p;
+      Q.e.out_ld = 256;
+      CUDA_OK((launch_gemm_b2b<ACT_RELU, EF_OUT_F32>(Q, sms, st)));
+    }
+    if (!b2b) STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;
       lin_base(P, m_xubf, LM.w_lin, 256, 256, 256);
       P.e.bias = LW.b_lin;
@@ -523,7 +552,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_BIAS | EF_OUT_BF16 | EF_ZERO_PAD, ACT_RELU, 4>>(P, mtiles, sms,
                                                                                                     st)));
     }
-    STEP(ST_FSMN_PROJ) {  // fsmn.project
+    if (!b2b) STEP(ST_FSMN_PROJ) {  // fsmn.project
       LinearParams P;
       lin_base(P, m_f1, LM.w_proj, 256, 256, 256);
       P.e.out_f32 = p;
@@ -557,8 +586,12 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
     }
     STEP(ST_FSMN_TAIL) {
       in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
-      fsmn_tail_kernel<<<static_cast<unsigned>((M / TAIL_FRAMES * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c, g,
-                                                                                   B, Sp, S);
+      if (M <= 32768)
+        fsmn_tail_kernel<1><<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c, g, B,
+                                                                                      Sp, S);
+      else
+        fsmn_tail_kernel<8><<<static_cast<unsigned>((M / 8 * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c,
+                                                                                          g, B, Sp, S);
     }
     STEP(ST_FSMN_C2) {  // conv2 + residual; also the bf16 copy and ScaleNorm sums the next FLASH layer needs
       LinearParams P;
@@ -831,7 +864,7 @@ extern "C" int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, i
 }
 
 // ------------------------------------------------------------------------------------------------ STFT + Apollo restorer
-#include "ap_api.cuh"
+#include "ap_api.cuh"  // (uses gemm_b2b.cuh, included above)
 
 static void ap_free(tdz_ctx* ctx) {
   delete ctx->ap;

@@ -38,8 +38,8 @@ def check_apollo_args(*args, **kwargs):
 class Restorer:
     sample_rate = 44100
     # launches of one forward (csrc/ap_api.cuh): stft, band split; per layer qkv GEMM + attention + 3 GEMMs +
-    # 3 x (dwconv + 2 GEMMs) = 14; band merge; istft (2)
-    KERNELS_PER_FORWARD = 2 + 6 * 14 + 1 + 2
+    # 3 x (dwconv + back-to-back GEMM) = 11; band merge; istft (2)
+    KERNELS_PER_FORWARD = 2 + 6 * 11 + 1 + 2
 
     def __init__(self, state_dict=None, device="cuda:0", handle=None):
         self.device = torch.device(device)

@@ -209,7 +209,7 @@ class Separator:
                   "FSMN_PROJ", "DD1", "DD2", "FSMN_TAIL", "FSMN_C2", "FINAL_LN", "FINAL_GN", "OUT1", "TANHSIG", "DEC1",
                   "DECODER")
     LAYER_STEPS = STEP_NAMES[2:15]
-    KERNELS_PER_FORWARD = 5 + 24 * 19 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
+    KERNELS_PER_FORWARD = 5 + 24 * 18 + 9  # launches of tdz_separate (csrc/tdz_api.cu), memsets not counted
 
     def time_steps(self, mix, reps=5):
         """CUDA-event time (ms) of every launch step of the forward run alone (layer 0 instance), after a
@@ -218,11 +218,14 @@ class Separator:
         torch.cuda.synchronize(self.device)
         out = {}
         for k, name in enumerate(self.STEP_NAMES):
-            self(mix, _debug=(1, k, k))  # warm
+            # fsmn.linear -> project run as ONE back-to-back GEMM in the forward: "FSMN_LIN" is that fused launch
+            # (steps k..k+1); "FSMN_PROJ" alone is the project kernel of the two-kernel form (tests only)
+            hi = k + 1 if name == "FSMN_LIN" else k
+            self(mix, _debug=(1, k, hi))  # warm
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
-                self(mix, _debug=(1, k, k))
+                self(mix, _debug=(1, k, hi))
             e1.record()
             torch.cuda.synchronize(self.device)
             out[name] = e0.elapsed_time(e1) / reps

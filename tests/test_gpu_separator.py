@@ -125,3 +125,27 @@ def test_too_short_input_is_an_error():
     sep = Separator(random_state_dict(seed=0), "cuda:0")
     with pytest.raises(RuntimeError):
         sep(torch.zeros(1, 15).cuda())
+
+
+@pytest.mark.parametrize("B,T", [(1, 9613), (3, 40000)])
+def test_back_to_back_linear_project_equals_two_kernels(B, T):
+    """fsmn.linear -> ReLU -> fsmn.project (fsmn.py:131-139) runs as ONE back-to-back GEMM in the forward (hidden
+    activations stay in TMEM / shared memory); asked for one step at a time the library runs the two-kernel form.
+    Same k order, same bf16 rounding of the hidden activations: the `p` buffer must agree bit for bit."""
+    import torch
+    from oracle.synth import random_state_dict
+    from targetdiarization_b200 import Separator
+    sep = Separator(random_state_dict(seed=3), "cuda:0")
+    mix = (torch.randn(B, T, generator=torch.Generator().manual_seed(1)) * 0.1).cuda()
+    sep(mix)                                   # populates the workspace (xubf of the last layer)
+    k = sep.STEP_NAMES.index("FSMN_LIN")
+    S = sep.layout(B, T).S
+    sep.debug_buffer(B, T, "p", torch.float32, 256).zero_()
+    sep(mix, _debug=(1, k, k + 1))             # fused
+    fused = sep.debug_buffer(B, T, "p", torch.float32, 256)[:, :S].clone()
+    sep.debug_buffer(B, T, "p", torch.float32, 256).zero_()
+    sep(mix, _debug=(1, k, k))
+    sep(mix, _debug=(1, k + 1, k + 1))         # linear, then project
+    two = sep.debug_buffer(B, T, "p", torch.float32, 256)[:, :S].clone()
+    assert float(two.abs().max()) > 0
+    assert torch.equal(fused, two)
