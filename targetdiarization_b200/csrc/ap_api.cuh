@@ -245,13 +245,13 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
         Q.e.out_f32 = x;
         Q.e.out_ld = 256;
         if (b < 2) {
-          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32>(Q, sms, st)));
+          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32, 1, 1024>(Q, sms, st)));
         } else {  // the layer output also feeds the next Roformer: bf16 copy + RMSNorm sums
           Q.e.out_bf16 = xbf;
           Q.e.out_bf_ld = 256;
           Q.e.ss_out = ss;
           Q.e.ss_out_ld = 4;
-          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT>(Q, sms, st)));
+          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT, 1, 1024>(Q, sms, st)));
         }
         continue;
       }

@@ -15,7 +15,14 @@
 //                    128 B-swizzled K-major layout of an A operand (fence.proxy.async + mbarrier, like the gather warps
 //                    of gemm_conv3.cuh); (2) per tile: acc2 -> + b2 + resid -> global
 // TMEM: acc2 = columns [0, 256), acc1 double buffer = [256, 384) and [384, 512).
-// Shared memory: X 64 KB | h 2 x 32 KB | weight ring 3 x 32 KB = 224 KB.
+// Shared memory: X 64 KB | h HBUF x 32 KB | weight ring 3 x 32 KB | b1 (H floats).  HBUF = 2 where it fits (H = 256:
+// measured 0.286 ms against 0.320 ms single buffered at the benchmark shape), 1 for H = 1024 (the 4 KB of b1 would not
+// fit next to two buffers): the epilogue warps then wait for G2(j) - 8 MMAs - between their arithmetic on chunk j + 1
+// and the stores of its result.
+// (ncu on the first version, Apollo shape: the epilogue warps were the serial resource - 43 % of the stall samples on
+// the first use of b1 values loaded from global memory per chunk, and two MUFU operations per SiLU (ex2 + rcp) = as
+// many XU cycles per chunk as the chunk's MMAs take.  Hence b1 in shared memory and the one-MUFU form
+// silu(x) = h + h tanh(h), h = x / 2, whose 2^-11 error is below the bf16 rounding of the stored activation.)
 // The arithmetic is the same as in the two-kernel form (same k order, same bf16 rounding of the hidden activations), so
 // the results are bit-identical to it.
 #pragma once
@@ -35,11 +42,13 @@ struct B2bParams {
 constexpr int B2B_THREADS = 64 + 256;
 constexpr int B2B_WSTAGES = 3;
 constexpr int B2B_X_BYTES = 4 * 16384;
-constexpr int B2B_H_BYTES = 2 * 32768;
-constexpr int B2B_SMEM_BYTES = B2B_X_BYTES + B2B_H_BYTES + B2B_WSTAGES * 32768 + 1024 + 256;
+constexpr int b2b_smem_bytes(int hbuf, int max_h) {
+  return B2B_X_BYTES + hbuf * 32768 + B2B_WSTAGES * 32768 + 1024 + 256 + max_h * 4;
+}
 
-template <int ACT1, unsigned EF2>
+template <int ACT1, unsigned EF2, int HBUF>
 __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_constant__ B2bParams P) {
+  constexpr int B2B_H_BYTES = HBUF * 32768;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -55,6 +64,7 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
   auto acc1_empty = [&](int b) { return b0 + 48u + 8u * b; };
   auto h_full = [&](int b) { return b0 + 64u + 8u * b; };
   auto h_empty = [&](int b) { return b0 + 80u + 8u * b; };
+  float* sbias = reinterpret_cast<float*>(smem_al + B2B_X_BYTES + B2B_H_BYTES + B2B_WSTAGES * 32768 + 256);  // [H]
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5;
@@ -74,11 +84,14 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc1_full(b), 1);
       mbar_init(acc1_empty(b), 8);
+    }
+    for (int b = 0; b < HBUF; ++b) {
       mbar_init(h_full(b), 8);
       mbar_init(h_empty(b), 1);
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < P.H; i += B2B_THREADS) sbias[i] = P.bias1[i];
   if (warp == 1) {
     tmem_alloc(smem_u32(&s_tmem_base), 512);
     tmem_relinquish();
@@ -175,14 +188,14 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
           }
           if (step >= 1) {
             const int j = step - 1;
-            const int buf = c2 & 1;
-            mbar_wait(h_full(buf), (c2 >> 1) & 1);
+            const int hb = c2 % HBUF;
+            mbar_wait(h_full(hb), (c2 / HBUF) & 1);
             if (j == 0) mbar_wait(acc2_empty, (it & 1) ^ 1u);
             tc_fence_after();
             for (int s = 0; s < 2; ++s) {
               mbar_wait(w_full(stage), phase);
               tc_fence_after();
-              const uint32_t sa = sH + buf * 32768 + s * 16384;
+              const uint32_t sa = sH + hb * 32768 + s * 16384;
               const uint32_t sb = sW + stage * 32768;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
               umma_commit(w_empty(stage));
               next_stage();
             }
-            umma_commit(h_empty(buf));
+            umma_commit(h_empty(hb));
             if (j == NC - 1) umma_commit(acc2_full);
             ++c2;
           }
@@ -218,35 +231,49 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
       for (int j = 0; j < NC; ++j, ++c) {
         const int buf = c & 1;
         mbar_wait(acc1_full(buf), (c >> 1) & 1);
-        mbar_wait(h_empty(buf), ((c >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + 256 + buf * 128 + lane_t + half * 64;
-        uint8_t* hb = hbase + buf * 32768 + half * 16384 + rsw;   // this warp's 64 columns = k-block atom `half`
+        const float* bs = sbias + j * 128 + half * 64;
+        uint4 packed[8];
 #pragma unroll
         for (int cc = 0; cc < 64; cc += 32) {
-          float v[32], bs[32];
+          float v[32];
           tmem_ld16(tacc + cc, v);
           tmem_ld16(tacc + cc + 16, v + 16);
-          ld_f32x16(P.bias1 + j * 128 + half * 64 + cc, bs);
-          ld_f32x16(P.bias1 + j * 128 + half * 64 + cc + 16, bs + 16);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply<ACT1>(v[i] + bs[i]);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + cc + i);   // same address in every lane: broadcast
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int piece = cc / 8 + p;   // 16 B piece (8 columns) inside the 128 B row
-            *reinterpret_cast<uint4*>(hb + ((piece ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
-                           pack_bf16(v[8 * p + 4], v[8 * p + 5]), pack_bf16(v[8 * p + 6], v[8 * p + 7]));
+            for (int k = 0; k < 4; ++k) {
+              float x = v[i + k] + bb[k];
+              if constexpr (ACT1 == ACT_SILU) {
+                const float hx = 0.5f * x;
+                x = fmaf(hx, tanh_approx(hx), hx);
+              } else {
+                x = act_apply<ACT1>(x);
+              }
+              v[i + k] = x;
+            }
           }
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            packed[cc / 8 + p] = make_uint4(pack_bf16(v[8 * p], v[8 * p + 1]), pack_bf16(v[8 * p + 2], v[8 * p + 3]),
+                                            pack_bf16(v[8 * p + 4], v[8 * p + 5]), pack_bf16(v[8 * p + 6], v[8 * p + 7]));
         }
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc1_empty(buf));    // acc1[buf] may be overwritten by G1(j + 2)
+        const int hbuf = c % HBUF;
+        mbar_wait(h_empty(hbuf), ((c / HBUF) & 1) ^ 1u);  // G2(j - HBUF) has finished reading this h buffer
+        uint8_t* hb = hbase + hbuf * 32768 + half * 16384 + rsw;   // this warp's 64 columns = k-block atom `half`
+#pragma unroll
+        for (int piece = 0; piece < 8; ++piece)          // 16 B pieces (8 columns) of the 128 B row, swizzled
+          *reinterpret_cast<uint4*>(hb + ((piece ^ (row & 7)) << 4)) = packed[piece];
         fence_proxy_async();   // generic-proxy writes of h -> visible to the tensor core's async-proxy reads
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(acc1_empty(buf));
-          mbar_arrive(h_full(buf));
-        }
+        if (lane == 0) mbar_arrive(h_full(hbuf));
       }
       // ---- (2) output tile: acc2 -> + b2 + resid -> global; this warp owns columns [128 half, 128 half + 128)
       mbar_wait(acc2_full, it & 1);
@@ -306,15 +333,19 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
   }
 }
 
-template <int ACT1, unsigned EF2>
+// MAX_H: the largest hidden width the instance is launched with (sizes the b1 copy): 256 with HBUF = 2, 1024 with 1
+template <int ACT1, unsigned EF2, int HBUF, int MAX_H>
 cudaError_t launch_gemm_b2b(const B2bParams& P, int num_sms, cudaStream_t st) {
+  constexpr int smem = b2b_smem_bytes(HBUF, MAX_H);
+  static_assert(smem <= 232448, "back-to-back GEMM: shared memory budget");
+  if (P.H > MAX_H || P.H % 128 != 0) return cudaErrorInvalidValue;
   static std::atomic<unsigned long long> configured{0};
-  if (cudaError_t err = set_max_smem_once(reinterpret_cast<const void*>(gemm_b2b_kernel<ACT1, EF2>), B2B_SMEM_BYTES, configured);
+  if (cudaError_t err = set_max_smem_once(reinterpret_cast<const void*>(gemm_b2b_kernel<ACT1, EF2, HBUF>), smem, configured);
       err != cudaSuccess)
     return err;
   const int ntiles = P.B * P.Sp / GEMM_BLOCK_M;
   if (ntiles <= 0) return cudaSuccess;
-  gemm_b2b_kernel<ACT1, EF2><<<ntiles < num_sms ? ntiles : num_sms, B2B_THREADS, B2B_SMEM_BYTES, st>>>(P);
+  gemm_b2b_kernel<ACT1, EF2, HBUF><<<ntiles < num_sms ? ntiles : num_sms, B2B_THREADS, smem, st>>>(P);
   return cudaGetLastError();
 }
 

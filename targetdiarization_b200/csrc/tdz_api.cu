@@ -541,7 +541,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       Q.bias1 = LW.b_lin;
       Q.e.out_f32 = p;
       Q.e.out_ld = 256;
-      CUDA_OK((launch_gemm_b2b<ACT_RELU, EF_OUT_F32>(Q, sms, st)));
+      CUDA_OK((launch_gemm_b2b<ACT_RELU, EF_OUT_F32, 2, 256>(Q, sms, st)));
     }
     if (!b2b) STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;
