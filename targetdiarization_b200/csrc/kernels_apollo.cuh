@@ -97,103 +97,124 @@ __global__ void __launch_bounds__(256) ap_bandsplit_kernel(const float2* __restr
 // qkv [tokens][768] bf16, channel = head * 96 + (q 0..31 | k 32..63 | v 64..95); rotary embedding on q, k with the
 // position = band index (interleaved pairs, cos / sin tables [100][32] of the checkpoint); softmax(q k^T / sqrt(32)) v;
 // output [tokens][256] bf16, channel = head * 32 + d.
-// K and V of the head live in REGISTERS: lane l holds the rotated keys l, l + 32, l + 64 (3 x 32 values) and column l
-// of V (80 values); per query only q (32 floats) and the 80 softmax weights go through shared memory as broadcast
-// 128-bit reads.  (The first version kept K / V in shared memory: 350 LDS per query and warp, LSU bound at 845 us per
-// layer for 10 s of audio - 42 % of the forward.)
-struct ApAttnSmem {
-  float q[AP_HEADS][AP_HD];
-  float p[AP_HEADS][96];
-};
-__global__ void __launch_bounds__(256, 1) ap_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                         const float* __restrict__ rot_cos,
-                                                         const float* __restrict__ rot_sin,
-                                                         __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) ApAttnSmem S;
+// 80 x 80 x 32 per head is far too small for a tcgen05 tile (M = 128, a TMEM round trip per head), so the two products
+// run on warp-level mma.sync.m16n8k16 (bf16 operands, fp32 accumulate) entirely in registers, FlashAttention-2 style:
+// 80 = 5 x 16 query rows = 10 x 8 keys, no padding anywhere.  A fragment register holds two ADJACENT features of one
+// row - exactly a rotary pair - so the rotation is applied to the Q / K fragments in place as they are loaded from
+// global memory; the S accumulator fragments of two neighbouring key tiles are the A fragment of the P V product.
+// (History: K / V in shared memory and scalar FMAs - LSU bound, 845 us per layer for 10 s of audio; K / V in registers -
+// 379 us, 62 % of 189 M warp instructions FFMA with two warps per scheduler and three dependent chains each; this form
+// issues 200 MMAs + 200 exponentials per head instead of 14 000 FMAs.)
+__device__ __forceinline__ void mma_bf16_16x8x16(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// two adjacent bf16 features (a, b) of position `pos`, first feature index d (even): rotated, scaled, re-packed
+__device__ __forceinline__ uint32_t ap_rot_pair(uint32_t w, const float* __restrict__ rot_cos,
+                                                const float* __restrict__ rot_sin, int pos, int d, float scale) {
+  const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+  const float2 c = __ldg(reinterpret_cast<const float2*>(rot_cos + pos * AP_HD + d));
+  const float2 sn = __ldg(reinterpret_cast<const float2*>(rot_sin + pos * AP_HD + d));
+  return pack_bf16((a * c.x - b * sn.x) * scale, (b * c.y + a * sn.y) * scale);
+}
+__global__ void __launch_bounds__(256) ap_attn_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                      const float* __restrict__ rot_cos,
+                                                      const float* __restrict__ rot_sin,
+                                                      __nv_bfloat16* __restrict__ out) {
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3;
   const size_t tok0 = static_cast<size_t>(blockIdx.x) * AP_NBAND;
   const __nv_bfloat16* base = qkv + tok0 * 768 + h * 96;
-  // ---- keys lane, lane + 32, lane + 64, rotated: pairs (a, b) -> (a cos - b sin, b cos + a sin)
-  float kreg[3][AP_HD];
+  auto word = [&](int row, int col) {   // two adjacent bf16 values (col even)
+    return *reinterpret_cast<const uint32_t*>(base + static_cast<size_t>(row) * 768 + col);
+  };
+  // ---- B fragments of Q K^T: key tile nt (keys 8 nt + g), k-step ks (features 16 ks + 2 tg (+1), + 8)
+  uint32_t kf[10][2][2];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int j = lane + 32 * r;
-    if (j < AP_NBAND) {
-      const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<size_t>(j) * 768 + 32);
-      const float4* cp = reinterpret_cast<const float4*>(rot_cos + j * AP_HD);
-      const float4* sp = reinterpret_cast<const float4*>(rot_sin + j * AP_HD);
+  for (int nt = 0; nt < 10; ++nt) {
+    const int key = nt * 8 + g;
 #pragma unroll
-      for (int v8 = 0; v8 < 4; ++v8) {
-        const uint4 raw = kp[v8];
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        float c[8], sn[8];
-        const float4 c0 = __ldg(cp + 2 * v8), c1 = __ldg(cp + 2 * v8 + 1), s0 = __ldg(sp + 2 * v8), s1 = __ldg(sp + 2 * v8 + 1);
-        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-        sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = __uint_as_float(w[i] << 16), b = __uint_as_float(w[i] & 0xffff0000u);
-          kreg[r][8 * v8 + 2 * i] = a * c[2 * i] - b * sn[2 * i];
-          kreg[r][8 * v8 + 2 * i + 1] = b * c[2 * i + 1] + a * sn[2 * i + 1];
-        }
-      }
-    } else {
-#pragma unroll
-      for (int d = 0; d < AP_HD; ++d) kreg[r][d] = 0.f;
+    for (int ks = 0; ks < 2; ++ks) {
+      const int d = ks * 16 + 2 * tg;
+      kf[nt][ks][0] = ap_rot_pair(word(key, 32 + d), rot_cos, rot_sin, key, d, 1.f);
+      kf[nt][ks][1] = ap_rot_pair(word(key, 32 + d + 8), rot_cos, rot_sin, key, d + 8, 1.f);
     }
   }
-  // ---- column `lane` of V
-  float vreg[AP_NBAND];
+  // ---- B fragments of P V: feature tile dt (feature 8 dt + g), key step kk (keys 16 kk + 2 tg (+1), + 8 (+9))
+  uint32_t vf[4][5][2];
+  {
+    const unsigned short* vb = reinterpret_cast<const unsigned short*>(base) + 64;
 #pragma unroll
-  for (int j = 0; j < AP_NBAND; ++j) vreg[j] = __bfloat162float(base[static_cast<size_t>(j) * 768 + 64 + lane]);
-  const float sgn = (lane & 1) ? 1.f : -1.f;
-  const float scale = 0.17677669529663687f;   // 1 / sqrt(32)
-  const float rc = 0.f;
-  (void)rc;
-#pragma unroll 1
-  for (int i = 0; i < AP_NBAND; ++i) {
-    const float qv = __bfloat162float(base[static_cast<size_t>(i) * 768 + lane]);
-    const float qp = __shfl_xor_sync(0xffffffffu, qv, 1);
-    const float c = __ldg(rot_cos + i * AP_HD + lane), s = __ldg(rot_sin + i * AP_HD + lane);
-    S.q[h][lane] = (qv * c + sgn * qp * s) * scale;
-    __syncwarp();
-    float sc[3] = {0.f, 0.f, 0.f};
+    for (int dt = 0; dt < 4; ++dt) {
+      const int n = dt * 8 + g;
 #pragma unroll
-    for (int d4 = 0; d4 < AP_HD / 4; ++d4) {
-      const float4 q4 = *reinterpret_cast<const float4*>(&S.q[h][4 * d4]);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        sc[r] = fmaf(q4.x, kreg[r][4 * d4], sc[r]);
-        sc[r] = fmaf(q4.y, kreg[r][4 * d4 + 1], sc[r]);
-        sc[r] = fmaf(q4.z, kreg[r][4 * d4 + 2], sc[r]);
-        sc[r] = fmaf(q4.w, kreg[r][4 * d4 + 3], sc[r]);
+      for (int kk = 0; kk < 5; ++kk) {
+        const int k = kk * 16 + 2 * tg;
+        const uint32_t v0 = vb[static_cast<size_t>(k) * 768 + n], v1 = vb[static_cast<size_t>(k + 1) * 768 + n];
+        const uint32_t v2 = vb[static_cast<size_t>(k + 8) * 768 + n], v3 = vb[static_cast<size_t>(k + 9) * 768 + n];
+        vf[dt][kk][0] = v0 | (v1 << 16);
+        vf[dt][kk][1] = v2 | (v3 << 16);
       }
     }
-    if (lane + 64 >= AP_NBAND) sc[2] = -INFINITY;
-    float mx = fmaxf(fmaxf(sc[0], sc[1]), sc[2]);
+  }
+  const float scale = 0.17677669529663687f;   // 1 / sqrt(32), folded into q
+#pragma unroll 1
+  for (int mt = 0; mt < 5; ++mt) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    uint32_t qf[2][4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float e = __expf(sc[r] - mx);   // exp(-inf) = 0 for the keys that do not exist
-      S.p[h][lane + 32 * r] = e;
-      sum += e;
+    for (int ks = 0; ks < 2; ++ks) {
+      const int d = ks * 16 + 2 * tg;
+      qf[ks][0] = ap_rot_pair(word(r0, d), rot_cos, rot_sin, r0, d, scale);
+      qf[ks][1] = ap_rot_pair(word(r1, d), rot_cos, rot_sin, r1, d, scale);
+      qf[ks][2] = ap_rot_pair(word(r0, d + 8), rot_cos, rot_sin, r0, d + 8, scale);
+      qf[ks][3] = ap_rot_pair(word(r1, d + 8), rot_cos, rot_sin, r1, d + 8, scale);
     }
+    float sc[10][4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncwarp();
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int j4 = 0; j4 < AP_NBAND / 4; ++j4) {
-      const float4 p4 = *reinterpret_cast<const float4*>(&S.p[h][4 * j4]);
-      acc0 = fmaf(p4.x, vreg[4 * j4], acc0);
-      acc1 = fmaf(p4.y, vreg[4 * j4 + 1], acc1);
-      acc0 = fmaf(p4.z, vreg[4 * j4 + 2], acc0);
-      acc1 = fmaf(p4.w, vreg[4 * j4 + 3], acc1);
+    for (int nt = 0; nt < 10; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      mma_bf16_16x8x16(sc[nt], qf[0], kf[nt][0]);
+      mma_bf16_16x8x16(sc[nt], qf[1], kf[nt][1]);
     }
-    out[(tok0 + i) * AP_N + h * AP_HD + lane] = __float2bfloat16((acc0 + acc1) / sum);
-    __syncwarp();
+    // softmax of rows r0 (elements 0, 1 of every tile) and r1 (elements 2, 3): the 4 threads of a group share a row
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 10; ++nt) {
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t pf[5][4];
+#pragma unroll
+    for (int nt = 0; nt < 10; ++nt) {
+      const float e0 = __expf(sc[nt][0] - m0), e1 = __expf(sc[nt][1] - m0);
+      const float e2 = __expf(sc[nt][2] - m1), e3 = __expf(sc[nt][3] - m1);
+      s0 += e0 + e1;
+      s1 += e2 + e3;
+      // key tiles 2 kk, 2 kk + 1 -> A fragment registers (0, 1) and (2, 3) of key step kk
+      pf[nt >> 1][(nt & 1) * 2] = pack_bf16(e0, e1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = 1.f / s0, i1 = 1.f / s1;
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) mma_bf16_16x8x16(o, pf[kk], vf[dt][kk]);
+      __nv_bfloat16* op = out + (tok0 + r0) * AP_N + h * AP_HD + dt * 8 + 2 * tg;
+      *reinterpret_cast<uint32_t*>(op) = pack_bf16(o[0] * i0, o[1] * i0);
+      *reinterpret_cast<uint32_t*>(op + 8 * AP_N) = pack_bf16(o[2] * i1, o[3] * i1);
+    }
   }
 }
 
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(256) ap_bandmerge_kernel(const float* __restri
     const int band = min(p / (2 * AP_BW), AP_NBAND - 1);
     const float* xr = xs + band * AP_XLD;
     float a = __ldg(bv + p), gt = __ldg(bg + p);
-#pragma unroll 4
+#pragma unroll 16
     for (int k = 0; k < AP_N; ++k) {
       const float xv = xr[k];
       a = fmaf(__ldg(wv + static_cast<size_t>(k) * AP_PAIRS + p), xv, a);
