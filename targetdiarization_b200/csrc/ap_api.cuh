@@ -12,6 +12,7 @@ struct ApModel {
   struct LayerMaps {
     CUtensorMap qkv, out, mlp1, mlp2, w1[3], w2[3];
     CUtensorMap w1_128[3];   // 128-row boxes: hidden chunks of the back-to-back ConvActNorm1d GEMM
+    CUtensorMap w1_64[3], w2_128[3];   // its cta_group::2 form: each CTA stages half of every weight tile
   } lm[TDZ_AP_LAYERS];
 };
 
@@ -73,6 +74,8 @@ static int ap_set_weights(tdz_ctx* ctx, ApModel* M, const tdz_apollo_weights* w)
       if (w_map(ctx, &m.w1[b], L.icb[b].w1, false, 1024, 256, 256)) return 1;
       if (w_map(ctx, &m.w2[b], L.icb[b].w2, false, 256, 1024, 256)) return 1;
       if (w_map(ctx, &m.w1_128[b], L.icb[b].w1, false, 1024, 256, 128)) return 1;
+      if (w_map(ctx, &m.w1_64[b], L.icb[b].w1, false, 1024, 256, 64)) return 1;
+      if (w_map(ctx, &m.w2_128[b], L.icb[b].w2, false, 256, 1024, 128)) return 1;
     }
   }
   M->ready = true;
@@ -244,14 +247,21 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
         Q.e.resid_ld = 256;
         Q.e.out_f32 = x;
         Q.e.out_ld = 256;
-        if (b < 2) {
-          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32, 1, 1024>(Q, sms, st)));
-        } else {  // the layer output also feeds the next Roformer: bf16 copy + RMSNorm sums
+        constexpr unsigned EF_MID = EF_BIAS | EF_RESID | EF_OUT_F32, EF_LAST = EF_MID | EF_OUT_BF16 | EF_SS_OUT;
+        if (b == 2) {  // the layer output also feeds the next Roformer: bf16 copy + RMSNorm sums
           Q.e.out_bf16 = xbf;
           Q.e.out_bf_ld = 256;
           Q.e.ss_out = ss;
           Q.e.ss_out_ld = 4;
-          CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_BIAS | EF_RESID | EF_OUT_F32 | EF_OUT_BF16 | EF_SS_OUT, 1, 1024>(Q, sms, st)));
+        }
+        if (!ctx->b2b_cg2) {
+          if (b < 2) CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_MID, 1, 1024, false>(Q, sms, st)));
+          else CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_LAST, 1, 1024, false>(Q, sms, st)));
+        } else {
+          Q.tmW1 = m.w1_64[b];
+          Q.tmW2 = m.w2_128[b];
+          if (b < 2) CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_MID, 1, 1024, true>(Q, sms, st)));
+          else CUDA_OK((launch_gemm_b2b<ACT_SILU, EF_LAST, 1, 1024, true>(Q, sms, st)));
         }
         continue;
       }

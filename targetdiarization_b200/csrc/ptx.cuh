@@ -66,6 +66,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
+// Acquire at CLUSTER scope: for barriers whose arrivals come from the peer CTA of a pair and publish shared-memory data.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (done) return;
+#if TDZ_HANG_GUARD
+    if (clock64() - t0 > 4000000000ll) __trap();
+#endif
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -214,6 +235,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
 // outstanding global store of the warp (MEMBAR + ERRBAR, 12 % of the epilogue's stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// Release form: orders this thread's earlier shared-memory writes (made visible to the async proxy by a preceding
+// fence.proxy.async) before the arrival - used where generic-proxy writes feed a tcgen05.mma issued by the peer CTA.
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
   asm volatile(

@@ -38,6 +38,7 @@ struct tdz_ctx {
   // to_out / to_u|to_v conv GEMMs without cta_group::2 (A/B measurements)
   bool convt_single = false;
   bool no_b2b = false;  // TDZ_NO_B2B: fsmn.linear / fsmn.project as two kernels (A/B measurements)
+  bool b2b_cg2 = false; // TDZ_B2B_CG2: the back-to-back GEMMs in their cta_group::2 form (measured 6 % slower: off)
   int dd_seg_len = 0;   // TDZ_DD_SEG_LEN: forces the DilatedDenseNet segment length (A/B measurements)
   tdz_mossformer2_weights sep;
   // weight tensor maps (built once per tdz_set_mossformer2_weights)
@@ -45,6 +46,7 @@ struct tdz_ctx {
     CUtensorMap w_in, w_out, w_c1, w_uv, w_lin, w_proj, w_c2;
     CUtensorMap w_in128, w_out128, w_uv128;  // 128-row boxes: M operand of the channel-major conv GEMMs
     CUtensorMap w_lin128;                    // 128-row boxes: hidden chunks of the back-to-back linear -> project GEMM
+    CUtensorMap w_lin64, w_proj128;          // the cta_group::2 form of it: each CTA stages half of every weight tile
   } lm[TDZ_NUM_LAYERS];
   CUtensorMap m_enc1x1, m_out1, m_tg, m_dec1, m_dec;
   bool have_fbank = false;
@@ -109,6 +111,7 @@ extern "C" int tdz_create(int device, tdz_ctx** out) {
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   c->convt_single = getenv("TDZ_CONVT_SINGLE") != nullptr;
   c->no_b2b = getenv("TDZ_NO_B2B") != nullptr;
+  c->b2b_cg2 = getenv("TDZ_B2B_CG2") != nullptr;
   if (const char* e = getenv("TDZ_DD_SEG_LEN")) c->dd_seg_len = atoi(e);
   *out = c;
   return 0;
@@ -186,6 +189,8 @@ extern "C" int tdz_set_mossformer2_weights(tdz_ctx* ctx, const tdz_mossformer2_w
     if (w_map(ctx, &M.w_out128, L.w_out, false, 512, 1024, 128)) return 1;
     if (w_map(ctx, &M.w_uv128, L.w_uv, false, 512, 256, 128)) return 1;
     if (w_map(ctx, &M.w_lin128, L.w_lin, false, 256, 256, 128)) return 1;
+    if (w_map(ctx, &M.w_lin64, L.w_lin, false, 256, 256, 64)) return 1;
+    if (w_map(ctx, &M.w_proj128, L.w_proj, false, 256, 256, 128)) return 1;
   }
   if (w_map(ctx, &ctx->m_enc1x1, w->w_enc1x1, true, 512, 512, 256)) return 1;
   if (w_map(ctx, &ctx->m_out1, w->w_out1, true, 1024, 512, 256)) return 1;
@@ -541,7 +546,13 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       Q.bias1 = LW.b_lin;
       Q.e.out_f32 = p;
       Q.e.out_ld = 256;
-      CUDA_OK((launch_gemm_b2b<ACT_RELU, EF_OUT_F32, 2, 256>(Q, sms, st)));
+      if (!ctx->b2b_cg2) {
+        CUDA_OK((launch_gemm_b2b<ACT_RELU, EF_OUT_F32, 2, 256, false>(Q, sms, st)));
+      } else {
+        Q.tmW1 = LM.w_lin64;
+        Q.tmW2 = LM.w_proj128;
+        CUDA_OK((launch_gemm_b2b<ACT_RELU, EF_OUT_F32, 2, 256, true>(Q, sms, st)));
+      }
     }
     if (!b2b) STEP(ST_FSMN_LIN) {  // fsmn.linear + ReLU
       LinearParams P;

@@ -149,3 +149,14 @@ def test_back_to_back_linear_project_equals_two_kernels(B, T):
     two = sep.debug_buffer(B, T, "p", torch.float32, 256)[:, :S].clone()
     assert float(two.abs().max()) > 0
     assert torch.equal(fused, two)
+    # the cta_group::2 form of the same kernel (a CTA pair per 256 rows; opt-in, read when the handle is created)
+    import os
+    os.environ["TDZ_B2B_CG2"] = "1"
+    try:
+        sep2 = Separator(random_state_dict(seed=3), "cuda:0")
+    finally:
+        del os.environ["TDZ_B2B_CG2"]
+    sep2(mix)
+    sep2.debug_buffer(B, T, "p", torch.float32, 256).zero_()
+    sep2(mix, _debug=(1, k, k + 1))
+    assert torch.equal(sep2.debug_buffer(B, T, "p", torch.float32, 256)[:, :S], two)
