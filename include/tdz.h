@@ -302,7 +302,11 @@ typedef struct tdz_apollo_weights {
   tdz_stft_plan plan;    /* n_fft 882, hop 441 */
 } tdz_apollo_weights;
 int tdz_set_apollo_weights(tdz_ctx* ctx, const tdz_apollo_weights* w);
+/* Workspace of a single pass over the whole input.  Any size from tdz_apollo_min_workspace_bytes() up is accepted:
+ * with less than the single-pass size the network runs over frame chunks with a 54-frame halo (the receptive field of
+ * the 54 depthwise k7 convolutions) - same bits, bounded memory (the single pass needs 493 KB per 10 ms frame). */
 size_t tdz_apollo_workspace_bytes(int64_t rows, int64_t nsample);
+size_t tdz_apollo_min_workspace_bytes(int64_t rows, int64_t nsample);
 /* self.restorer(tensor[B, nch, nsample]) (AudioProcessor.py:970; Apollo.forward, apollo.py:278-297):
  * wav_dev fp32 [rows = B * nch][nsample] -> out_dev fp32 [rows][nsample]. */
 int tdz_apollo_restore(tdz_ctx* ctx, const float* wav_dev, int64_t rows, int64_t nsample, float* out_dev,

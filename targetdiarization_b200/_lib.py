@@ -112,6 +112,7 @@ SIGNATURES = {
                          _vp]),
     "tdz_set_apollo_weights": (_int, [_vp, ctypes.POINTER(ApolloWeights)]),
     "tdz_apollo_workspace_bytes": (_sz, [_i64, _i64]),
+    "tdz_apollo_min_workspace_bytes": (_sz, [_i64, _i64]),
     "tdz_apollo_restore": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "tdz_apollo_debug": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _int]),
 }

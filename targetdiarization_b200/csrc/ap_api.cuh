@@ -83,15 +83,31 @@ static int ap_set_weights(tdz_ctx* ctx, ApModel* M, const tdz_apollo_weights* w)
 }
 
 // ---------------------------------------------------------------------------------------------- workspace
+// Fixed part: spectrogram, estimated spectrogram, inverse-STFT frames (10.6 KB per frame).  Token part (6 160 B per
+// token, 80 tokens per frame): sized for `Tl` frames per row.  Only the depthwise k7 convolutions mix frames - 3 taps
+// each side x 3 blocks x 6 layers = 54 frames of receptive field - so a long input is processed in frame chunks with a
+// 54-frame halo on either side, the halo results discarded: same bits as one pass (every token's arithmetic is the
+// same), bounded memory (an hour of 44.1 kHz audio would need 180 GB of token buffers in one pass).
+constexpr int AP_HALO = 54;
+constexpr size_t AP_TOKEN_BYTES = 256 * 4 + 256 * 2 + 4 * 4 + 768 * 2 + 256 * 2 + 1024 * 2 + 256 * 2;
 struct ApLayout {
   size_t spec, est, frames, x, xbf, ss, qkv, att, h, u, total;
-  int64_t T, tokens, Mp;
+  int64_t T, Tl, Mp;   // frames per row, frames per row the token buffers hold, token rows padded to the GEMM tile
 };
-static void ap_layout(int64_t rows, int64_t nsample, ApLayout* L) {
+static size_t ap_fixed_bytes(int64_t rows, int64_t T) {
+  const size_t fr = static_cast<size_t>(rows * T);
+  auto up = [](size_t b) { return (b + 1023) / 1024 * 1024; };
+  return 2 * up(fr * AP_BINS * 8) + up(fr * 882 * 4);
+}
+static size_t ap_token_bytes(int64_t rows, int64_t Tl) {
+  const size_t m = static_cast<size_t>((rows * Tl * AP_NBAND + 127) / 128 * 128);
+  return m * AP_TOKEN_BYTES + 7 * 1024;
+}
+static void ap_layout(int64_t rows, int64_t nsample, int64_t Tl, ApLayout* L) {
   const int64_t T = 1 + nsample / 441;
   L->T = T;
-  L->tokens = rows * T * AP_NBAND;
-  L->Mp = (L->tokens + 127) / 128 * 128;
+  L->Tl = Tl;
+  L->Mp = (rows * Tl * AP_NBAND + 127) / 128 * 128;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -107,9 +123,18 @@ static void ap_layout(int64_t rows, int64_t nsample, ApLayout* L) {
   L->ss = take(m * 4 * 4);       // per-row partial sums of squares of x (RMSNorm)
   L->qkv = take(m * 768 * 2);
   L->att = take(m * 256 * 2);
-  L->h = take(m * 1024 * 2);     // MLP / ICB hidden activations
+  L->h = take(m * 1024 * 2);     // gated-MLP hidden activations
   L->u = take(m * 256 * 2);      // dwconv7 + RMSNorm output
   L->total = off;
+}
+// Largest number of frames per row the token buffers may hold in `ws_bytes` (0: not even the smallest chunk fits)
+static int64_t ap_frames_that_fit(int64_t rows, int64_t T, size_t ws_bytes) {
+  const size_t fixed = ap_fixed_bytes(rows, T);
+  if (ws_bytes <= fixed) return 0;
+  int64_t Tl = static_cast<int64_t>((ws_bytes - fixed) / (static_cast<size_t>(rows) * AP_NBAND * AP_TOKEN_BYTES));
+  while (Tl > 0 && fixed + ap_token_bytes(rows, Tl) > ws_bytes) --Tl;
+  if (Tl >= T) return T;
+  return Tl > 2 * AP_HALO ? Tl : 0;
 }
 
 // ---------------------------------------------------------------------------------------------- GEMMs
@@ -139,10 +164,15 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
                       void* ws, size_t ws_bytes, cudaStream_t st, int tap = AP_RUN_ALL) {
   if (!M.ready) return fail(ctx, "tdz_apollo_restore: weights not set");
   if (rows <= 0 || nsample <= 441) return fail(ctx, "tdz_apollo_restore: need more than 441 samples per row (reflect padding)");
+  const int64_t T = 1 + nsample / 441;
+  const int64_t Tl_max = ap_frames_that_fit(rows, T, ws_bytes);
+  if (Tl_max == 0)
+    return fail(ctx, "tdz_apollo_restore: workspace too small (%zu bytes; the smallest chunked form needs %zu)", ws_bytes,
+                ap_fixed_bytes(rows, T) + ap_token_bytes(rows, 2 * AP_HALO + 1));
+  if (Tl_max < T && tap != AP_RUN_ALL) return fail(ctx, "tdz_apollo_debug: the taps need a workspace for the whole input");
   ApLayout L;
-  ap_layout(rows, nsample, &L);
-  if (ws_bytes < L.total) return fail(ctx, "tdz_apollo_restore: workspace too small (%zu < %zu)", ws_bytes, L.total);
-  if (L.Mp > 0x7fffff00ll) return fail(ctx, "tdz_apollo_restore: input too long for one call");
+  ap_layout(rows, nsample, Tl_max, &L);
+  if (L.Mp > 0x7fffff00ll) return fail(ctx, "tdz_apollo_restore: chunk too long for one call");
   uint8_t* base = static_cast<uint8_t*>(ws);
   float2* spec = reinterpret_cast<float2*>(base + L.spec);
   float2* est = reinterpret_cast<float2*>(base + L.est);
@@ -155,9 +185,8 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(base + L.h);
   __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(base + L.u);
   const tdz_apollo_weights& W = M.w;
-  const int64_t T = L.T, tokens = L.tokens, Mp = L.Mp, nframes = rows * T;
+  const int64_t nframes = rows * T;
   const int sms = ctx->num_sms;
-  const int mtiles = static_cast<int>(Mp / 128);
   auto copy_out = [&](const void* src, size_t bytes) -> int {
     CUDA_OK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -167,8 +196,21 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
   const SpecStrides SS{T * AP_BINS * 2, 2, AP_BINS * 2, 1};
   if (stft_launch(ctx, M.plan, wav, rows, nsample, AP_BINS, reinterpret_cast<float*>(spec), SS, st)) return 1;
   if (tap == AP_TAP_SPEC) return copy_out(spec, static_cast<size_t>(nframes) * AP_BINS * 8);
+  static std::atomic<unsigned long long> merge_cfg{0};
+  constexpr int merge_smem = AP_NBAND * AP_XLD * 4;
+  CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(ap_bandmerge_kernel), merge_smem, merge_cfg));
+  // frame chunks: results are final for frames [k0, k1), computed from frames [t_lo, t_hi) = the chunk + its halo
+  const int64_t keep_max = L.Tl >= T ? T : L.Tl - 2 * AP_HALO;
+  for (int64_t k0 = 0; k0 < T; k0 += keep_max) {
+  const int64_t k1 = std::min(T, k0 + keep_max);
+  const int64_t t_lo = std::max<int64_t>(0, k0 - AP_HALO), t_hi = std::min(T, k1 + AP_HALO);
+  const int64_t Tc = t_hi - t_lo;                 // frames per row in the token buffers for this chunk
+  const int64_t tokens = rows * Tc * AP_NBAND, Mp = (tokens + 127) / 128 * 128;
+  const int mtiles = static_cast<int>(Mp / 128);
   // band split + per-band bottleneck
-  ap_bandsplit_kernel<<<static_cast<unsigned>(nframes), 256, 0, st>>>(spec, W.bn_g, W.bn_w, W.bn_b, x, xbf, ss);
+  ap_bandsplit_kernel<<<static_cast<unsigned>(rows * Tc), 256, 0, st>>>(spec, W.bn_g, W.bn_w, W.bn_b, x, xbf, ss,
+                                                                       static_cast<int>(T), static_cast<int>(t_lo),
+                                                                       static_cast<int>(Tc));
   CUDA_OK(cudaGetLastError());
   if (tap == AP_TAP_FEAT) return copy_out(x, static_cast<size_t>(tokens) * 256 * 4);
 
@@ -177,7 +219,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
   if (act_map(ctx, &m_att, att, false, 256, Mp, 1, 64, 128)) return 1;
   if (act_map(ctx, &m_h, h, false, 1024, Mp, 1, 64, 128)) return 1;
   if (act_map(ctx, &m_u, u, false, 256, Mp, 1, 64, 128)) return 1;
-  const int runs = static_cast<int>((T + AP_DW_RUN - 1) / AP_DW_RUN);
+  const int runs = static_cast<int>((Tc + AP_DW_RUN - 1) / AP_DW_RUN);
   const int64_t dw_warps = rows * runs * AP_NBAND;
 
   for (int l = 0; l < TDZ_AP_LAYERS; ++l) {
@@ -191,7 +233,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     P.e.out_bf16 = qkv;
     P.e.out_bf_ld = 768;
     CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_RMS4 | EF_OUT_BF16, ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));
-    ap_attn_kernel<<<static_cast<unsigned>(nframes), 256, 0, st>>>(qkv, W.rot_cos, W.rot_sin, att);
+    ap_attn_kernel<<<static_cast<unsigned>(rows * Tc), 256, 0, st>>>(qkv, W.rot_cos, W.rot_sin, att);
     CUDA_OK(cudaGetLastError());
     if (l == 0 && tap == AP_TAP_ATT0) {
       ap_widen_kernel<<<static_cast<unsigned>((tokens * 256 + 255) / 256), 256, 0, st>>>(att, out, tokens * 256);
@@ -227,7 +269,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     for (int b = 0; b < 3; ++b) {
       const tdz_apollo_icb& I = LW.icb[b];
       ap_dwconv_rms_kernel<<<static_cast<unsigned>((dw_warps * 32 + 255) / 256), 256, 0, st>>>(
-          x, I.dw, I.dw_b, static_cast<int>(T), runs, dw_warps, u);
+          x, I.dw, I.dw_b, static_cast<int>(Tc), runs, dw_warps, u);
       CUDA_OK(cudaGetLastError());
       if (!ctx->no_b2b) {
         // Conv1d(256, 1024) -> SiLU -> Conv1d(1024, 256) + residual as one back-to-back GEMM (gemm_b2b.cuh): the
@@ -290,13 +332,12 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     }
     if (tap == AP_TAP_LAYER0 + l) return copy_out(x, static_cast<size_t>(tokens) * 256 * 4);
   }
-  // band merge -> estimated spectrogram -> waveform
-  static std::atomic<unsigned long long> merge_cfg{0};
-  constexpr int merge_smem = AP_NBAND * AP_XLD * 4;
-  CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(ap_bandmerge_kernel), merge_smem, merge_cfg));
-  ap_bandmerge_kernel<<<static_cast<unsigned>(nframes), 256, merge_smem, st>>>(x, W.out_g, W.out_wv, W.out_wg, W.out_bv,
-                                                                              W.out_bg, est);
+  // band merge -> estimated spectrogram (the chunk's own frames only)
+  ap_bandmerge_kernel<<<static_cast<unsigned>(rows * (k1 - k0)), 256, merge_smem, st>>>(
+      x, W.out_g, W.out_wv, W.out_wg, W.out_bv, W.out_bg, est, static_cast<int>(T), static_cast<int>(t_lo),
+      static_cast<int>(Tc), static_cast<int>(k0 - t_lo), static_cast<int>(k1 - k0));
   CUDA_OK(cudaGetLastError());
+  }  // frame chunks
   if (tap == AP_TAP_EST) return copy_out(est, static_cast<size_t>(nframes) * AP_BINS * 8);
   return istft_launch(ctx, M.plan, reinterpret_cast<const float*>(est), rows, T, AP_BINS, SS, frames, out, nsample, st);
 }

@@ -32,13 +32,15 @@ __device__ __forceinline__ int ap_feat_off(int band) { return band * (2 * AP_BW 
 __global__ void __launch_bounds__(256) ap_bandsplit_kernel(const float2* __restrict__ spec, const float* __restrict__ g,
                                                            const float* __restrict__ w, const float* __restrict__ b,
                                                            float* __restrict__ x, __nv_bfloat16* __restrict__ xbf,
-                                                           float* __restrict__ ss) {
+                                                           float* __restrict__ ss, int T, int t_lo, int Tl) {
   __shared__ float2 s_spec[AP_BINS];
   __shared__ float s_feat[AP_FEAT];
   __shared__ float s_ss[8][AP_NBAND];   // per-warp partial sums of squares (added in warp order: no atomics)
+  // block = local frame (row r, frame t_lo + tl of the T frames of the row): the token buffers hold Tl frames per row
   const int64_t frame = blockIdx.x;
+  const int64_t src_frame = (frame / Tl) * T + t_lo + (frame % Tl);
   const int tid = threadIdx.x;
-  for (int k = tid; k < AP_BINS; k += 256) s_spec[k] = spec[frame * AP_BINS + k];
+  for (int k = tid; k < AP_BINS; k += 256) s_spec[k] = spec[src_frame * AP_BINS + k];
   __syncthreads();
   // per band: power, normalised (re | im | log power), RMSNorm over the 2 BW + 1 features - a warp per band
   const int warp = tid >> 5, lane = tid & 31;
@@ -299,11 +301,15 @@ constexpr int AP_XLD = AP_N + 1;   // padded rows: threads of a warp may address
 __global__ void __launch_bounds__(256) ap_bandmerge_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                            const float* __restrict__ wv, const float* __restrict__ wg,
                                                            const float* __restrict__ bv, const float* __restrict__ bg,
-                                                           float2* __restrict__ est) {
+                                                           float2* __restrict__ est, int T, int t_lo, int Tl, int keep_lo,
+                                                           int keep_n) {
   extern __shared__ uint8_t ap_smem_raw[];
   float* xs = reinterpret_cast<float*>(ap_smem_raw);   // [80][AP_XLD]
   __shared__ float s_out[AP_PAIRS];
-  const int64_t frame = blockIdx.x;
+  // block = one of the keep_n frames per row whose result is final (local frames [keep_lo, keep_lo + keep_n))
+  const int64_t r = blockIdx.x / keep_n, kf = blockIdx.x % keep_n;
+  const int64_t frame = r * Tl + keep_lo + kf;              // in the token buffers
+  const int64_t dst_frame = r * T + t_lo + keep_lo + kf;    // in the spectrogram
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int band = warp; band < AP_NBAND; band += 8) {
     const float* xr = x + (static_cast<size_t>(frame) * AP_NBAND + band) * AP_N;
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(256) ap_bandmerge_kernel(const float* __restri
     const int band = min(k / AP_BW, AP_NBAND - 1);
     const int k0 = ap_band_k0(band), bw = ap_band_bw(band);
     const int j = k - k0;
-    est[frame * AP_BINS + k] = make_float2(s_out[2 * k0 + j], s_out[2 * k0 + bw + j]);
+    est[dst_frame * AP_BINS + k] = make_float2(s_out[2 * k0 + j], s_out[2 * k0 + bw + j]);
   }
 }
 

@@ -911,9 +911,13 @@ extern "C" int tdz_set_apollo_weights(tdz_ctx* ctx, const tdz_apollo_weights* w)
 }
 extern "C" size_t tdz_apollo_workspace_bytes(int64_t rows, int64_t nsample) {
   if (rows <= 0 || nsample <= 441) return 0;
-  ApLayout L;
-  ap_layout(rows, nsample, &L);
-  return L.total;
+  const int64_t T = 1 + nsample / 441;
+  return ap_fixed_bytes(rows, T) + ap_token_bytes(rows, T);
+}
+extern "C" size_t tdz_apollo_min_workspace_bytes(int64_t rows, int64_t nsample) {
+  if (rows <= 0 || nsample <= 441) return 0;
+  const int64_t T = 1 + nsample / 441;
+  return ap_fixed_bytes(rows, T) + ap_token_bytes(rows, std::min<int64_t>(T, 4 * AP_HALO));
 }
 extern "C" int tdz_apollo_debug(tdz_ctx* ctx, const float* wav_dev, int64_t rows, int64_t nsample, float* out_dev,
                                 void* ws, size_t ws_bytes, void* stream, int tap) {

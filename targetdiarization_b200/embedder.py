@@ -72,15 +72,28 @@ class Embedder:
             return max(held - 1024, 0)
         return min(24 << 30, max(_lib.free_device_bytes(self.device, held) // 4, held - 1024))
 
-    def max_batch(self, frames):
-        """Largest sub-batch whose workspace fits max_workspace_bytes (at least 1)."""
+    def max_batch(self, frames, n=None):
+        """Largest sub-batch whose workspace fits max_workspace_bytes (at least 1).  With `n` (the batch about to run):
+        if the workspace already held fits min(n, 256) utterances that is the answer, without the driver query of the
+        free memory behind the default budget (milliseconds per call, and it waits for the device)."""
         lib = self._h.lib
+        if n is not None and self._ws is not None:
+            want = max(1, min(256, int(n)))
+            if int(lib.tdz_embed_workspace_bytes(want, frames)) <= self._ws.numel():
+                return want
+            hit = self.__dict__.get("_plan")            # the decision taken for this shape with this workspace
+            if hit is not None and hit[0] == (frames, self._ws_generation):
+                return hit[1]
         budget = self.max_workspace_bytes
         per1 = int(lib.tdz_embed_workspace_bytes(1, frames))
-        n = max(1, min(256, budget // max(per1, 1)))
-        while n > 1 and int(lib.tdz_embed_workspace_bytes(n, frames)) > budget:
-            n -= 1
-        return n
+        nb = max(1, min(256, budget // max(per1, 1)))
+        while nb > 1 and int(lib.tdz_embed_workspace_bytes(nb, frames)) > budget:
+            nb -= 1
+        if n is not None:
+            need = int(lib.tdz_embed_workspace_bytes(min(int(n), nb), frames))
+            grows = self._ws is None or need > self._ws.numel()
+            self._plan = ((frames, self._ws_generation + (1 if grows else 0)), nb)
+        return nb
 
     def embed_features(self, feat):
         """feat float32 [N, frames, 80] -> [N,192] (ERes2NetV2 forward)."""
@@ -88,7 +101,7 @@ class Embedder:
             raise RuntimeError("Embedder has no weights; call load_state_dict first")
         N, frames, _ = feat.shape
         emb = torch.empty(N, EMBED_DIM, dtype=torch.float32, device=self.device)
-        nb = self.max_batch(frames)
+        nb = self.max_batch(frames, N)
         lib, h = self._h.lib, self._h
         for i in range(0, N, nb):
             n = min(nb, N - i)

@@ -62,16 +62,32 @@ class CudaKernels:
     def zeros(self, *shape):
         return torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
-    def max_batch(self, T):
-        per1 = self.sep.workspace_bytes(1, T)
+    def max_batch(self, T, n=None):
+        """Largest sub-batch the workspace budget allows.  With `n` (the batch about to run): if the workspace that is
+        ALREADY held fits it, that is the answer - the budget is derived from a driver query of the free memory
+        (cudaMemGetInfo: milliseconds, and it waits for the device), which must not sit on the steady-state path."""
         frames = -(-max(T // 8, 1) // 256) * 256
-        return int(max(1, min(4096, self.max_workspace_bytes // max(per1, 1), (1 << 23) // frames)))
+        cap = max(1, min(4096, (1 << 23) // frames))
+        if n is not None and self.sep._ws is not None:
+            want = min(int(n), cap)
+            if self.sep.workspace_bytes(want, T) <= self.sep._ws.numel():
+                return want
+            hit = self.__dict__.get("_plan")        # the decision taken for this length with this workspace
+            if hit is not None and hit[0] == (T, self.sep._ws_generation):
+                return hit[1]
+        per1 = self.sep.workspace_bytes(1, T)
+        nb = int(max(1, min(cap, self.max_workspace_bytes // max(per1, 1))))
+        if n is not None:
+            # the workspace grows to nb items in the call that follows (generation + 1 if it has to be reallocated)
+            grows = self.sep._ws is None or self.sep.workspace_bytes(min(int(n), nb), T) > self.sep._ws.numel()
+            self._plan = ((T, self.sep._ws_generation + (1 if grows else 0)), nb)
+        return nb
 
     def separate(self, chunks, out=None, out_strides=None):
         """[n,T] -> [n,2,T] (or into `out` with `out_strides`, see Separator.__call__), in sub-batches that fit the
         workspace budget."""
         n, T = chunks.shape
-        nb = self.max_batch(T)
+        nb = self.max_batch(T, n)
         if out is None:
             out = self.empty(n, 2, T)
             out_strides = (2 * T, T)

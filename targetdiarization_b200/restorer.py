@@ -41,7 +41,7 @@ class Restorer:
     # 3 x (dwconv + back-to-back GEMM) = 11; band merge; istft (2)
     KERNELS_PER_FORWARD = 2 + 6 * 11 + 1 + 2
 
-    def __init__(self, state_dict=None, device="cuda:0", handle=None):
+    def __init__(self, state_dict=None, device="cuda:0", handle=None, max_workspace_bytes=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("tdz.Restorer runs on a CUDA (sm_100a) device only; there is no CPU fallback")
@@ -50,6 +50,10 @@ class Restorer:
         self._packed = None
         self._ws = None
         self._ws_raw = None
+        # None: up to 60 % of the memory that is free when a call is sized.  A single pass needs 493 KB per 10 ms frame
+        # (an hour of audio: 180 GB); with less the library runs the network over frame chunks with a 54-frame halo -
+        # the receptive field of the depthwise convolutions - which gives the same bits.
+        self.max_workspace_bytes = None if max_workspace_bytes is None else int(max_workspace_bytes)
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -104,6 +108,13 @@ class Restorer:
             raise ValueError(f"input of {ns} samples is too short for the reflect-padded STFT (needs more than {HOP})")
         lib, h = self._h.lib, self._h
         nbytes = int(lib.tdz_apollo_workspace_bytes(rows, ns))
+        held = self._ws.numel() if self._ws is not None else 0
+        if tap is None and nbytes > held:      # the workspace would have to grow: is there room for a single pass?
+            budget = self.max_workspace_bytes
+            if budget is None:                 # (a driver query: only when a call does not fit what is already held)
+                budget = int(0.6 * _lib.free_device_bytes(self.device, held))
+            if nbytes > budget:
+                nbytes = max(int(lib.tdz_apollo_min_workspace_bytes(rows, ns)), min(budget, nbytes), held)
         ws = self._workspace(nbytes)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         T = 1 + ns // HOP

@@ -63,6 +63,9 @@ def test_restorer_tables_without_gpu(lib):
     assert so.tdz_apollo_workspace_bytes(1, 441) == 0          # too short for the reflect padding
     n = so.tdz_apollo_workspace_bytes(2, 44100)                # 2 rows x 101 frames x 80 bands = 16 160 tokens
     assert n % 1024 == 0 and n > 16160 * 6000
+    assert so.tdz_apollo_min_workspace_bytes(2, 44100) == n    # shorter than the smallest chunk: one pass
+    hour = 3600 * 44100
+    assert so.tdz_apollo_workspace_bytes(1, hour) > 170e9 and so.tdz_apollo_min_workspace_bytes(1, hour) < 4.5e9
     # tdz_stft_plan = 2 int32 + 2 pointers; per layer 4 + 3*6 pointers; model 5 + 6*22 + 5 pointers + the plan
     assert ctypes.sizeof(lib.StftPlan) == 24
     assert ctypes.sizeof(lib.ApolloLayer) == 22 * 8

@@ -149,6 +149,24 @@ def test_apollo_batch_equals_singles_and_longer_input(env):
     assert snr >= 40, snr
 
 
+def test_apollo_chunked_equals_single_pass(env):
+    """Bounded memory: with a workspace below the single-pass size the library runs the network over frame chunks with a
+    54-frame halo (only the depthwise k7 convolutions mix frames: 3 taps x 3 blocks x 6 layers).  Same bits."""
+    torch, AP, synth, sd, rest, _ = env
+    from targetdiarization_b200 import Restorer
+    x = synth.synthetic_fullband(2, 4 * 44100 + 17, seed=21).reshape(2, 1, -1).cuda()     # 401 frames per row
+    full = rest(x)
+    lib = rest._h.lib
+    need = int(lib.tdz_apollo_workspace_bytes(2, x.shape[-1]))
+    low = int(lib.tdz_apollo_min_workspace_bytes(2, x.shape[-1]))
+    assert low < need // 1.5
+    for budget in (low, (low + need) // 2):
+        small = Restorer(sd, "cuda:0", max_workspace_bytes=budget)
+        out = small(x)
+        assert small._ws.numel() <= max(budget, low)
+        assert torch.equal(out, full), budget
+
+
 def test_restorer_from_pretrain_round_trip(env, tmp_path):
     """BaseModel.serialize layout (base_model.py:132-146) -> from_pretrain with the reference's keyword arguments
     (AudioProcessor.py:279); other architectures are refused."""
