@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
   auto leader = [&](uint32_t bar) { return CG2 ? mapa_shared(bar, 0) : bar; };
   __shared__ uint32_t s_tmem_base;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches become uniform
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmX);

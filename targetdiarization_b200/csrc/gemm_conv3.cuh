@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
   int* tapc = reinterpret_cast<int*>(smem_al + STAGES * STAGE_BYTES + 256 + 128 * 8);     // [K/8] (dh, dw, channel)
   __shared__ uint32_t s_tmem_base;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches become uniform
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {

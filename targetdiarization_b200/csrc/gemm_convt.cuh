@@ -252,7 +252,7 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * CT_STAGES + 2 + s); };
   __shared__ uint32_t s_tmem_base;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches become uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
 

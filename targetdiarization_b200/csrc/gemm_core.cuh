@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   __shared__ uint32_t s_tmem_base;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches become uniform
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -227,7 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   __shared__ uint32_t s_tmem_base;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role branches become uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
 
