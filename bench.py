@@ -180,7 +180,7 @@ def cpu_leg(steps, warmup, sample_items=1):
     threads.  Bounded sample: `sample_items` 4 s mixtures per step."""
     import torch
     from oracle.mossformer2_port import mossformer2_forward
-    from oracle.synth import random_state_dict, synthetic_mixture
+    from targetdiarization_b200.synth import random_state_dict, synthetic_mixture
     from oracle import eres2netv2_port as E
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -213,7 +213,7 @@ def gpu_eager_leg(dev, items=16):
     per call keep it well inside memory; the rate does not grow with a larger batch)."""
     import torch
     from oracle.mossformer2_port import mossformer2_forward
-    from oracle.synth import random_state_dict, synthetic_mixture
+    from targetdiarization_b200.synth import random_state_dict, synthetic_mixture
     from oracle import eres2netv2_port as E
     sd = {k: v.to(dev) for k, v in random_state_dict(seed=0).items()}
     esd = {k: v.to(dev) for k, v in E.random_state_dict(seed=0).items()}

@@ -42,7 +42,7 @@ class Harness:
     def __init__(self):
         import torch
         from oracle.mossformer2_port import mossformer2_forward
-        from oracle.synth import random_state_dict
+        from targetdiarization_b200.synth import random_state_dict
         from targetdiarization_b200 import Separator
         self.torch = torch
         torch.backends.cuda.matmul.allow_tf32 = False

@@ -44,7 +44,7 @@ def test_c1_chat_mix_whole_file_against_reference_run():
     output; then get_speaker_embedding of both streams and of female_a.wav, cosine_similarity and the pick, against
     the oracle embedder run on the REFERENCE-separated streams."""
     import torch
-    from oracle.synth import random_eres2netv2_state_dict, random_state_dict
+    from targetdiarization_b200.synth import random_eres2netv2_state_dict, random_state_dict
     from targetdiarization_b200 import SeparationScoringStage, plan
     gd = np.load(os.path.join(GOLDEN, "c1_chat_mix.npz"))
     st = SeparationScoringStage.from_state_dicts(random_state_dict(seed=0, perturb=True),
@@ -174,7 +174,7 @@ def test_c5_streaming_chunk_shapes_against_oracle(stage):
     batch 256 == 256 single calls bit for bit (concurrent streams must not influence each other)."""
     torch, st = stage
     from oracle.mossformer2_port import mossformer2_forward, snr_db
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200.synth import synthetic_mixture
     sd = random_state_dict(seed=0)
     mix = synthetic_mixture(256, 9600, seed=51)
@@ -202,7 +202,7 @@ def test_from_pretrain_round_trip(tmp_path):
     reference's call form `from_pretrain(path, **cfg.model)` and gives the same bits as the state dict itself;
     another architecture - by config, by model_args or by tensor shapes - is refused."""
     import torch
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     from targetdiarization_b200.separator import MODEL_ARGS
     sd = random_state_dict(seed=5, perturb=True)
@@ -235,7 +235,7 @@ def test_strided_output_and_device_resolution():
     """tdz_separate_strided writes windows straight into the stitched [2, L] layout; 'cuda' means the current
     device; creating a handle does not change the caller's current device."""
     import torch
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     sep = Separator(random_state_dict(seed=0), "cuda")
     assert sep.device == torch.device("cuda", torch.cuda.current_device())

@@ -38,7 +38,7 @@ def _record(name, value):
 def setup():
     import torch
     from oracle import eres2netv2_port as E
-    from oracle.synth import synthetic_mixture
+    from targetdiarization_b200.synth import synthetic_mixture
     from targetdiarization_b200.embedder import Embedder
     sd = E.random_state_dict(seed=0)
     emb = Embedder(sd, "cuda:0")

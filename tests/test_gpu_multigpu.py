@@ -1,0 +1,30 @@
+"""On-hardware check of the sharded (one recording, several ranks) path, SURVEY.md section 8e: two NCCL ranks run
+tools/multi_gpu_check.py - spans + halos separated per rank, one gather of the waveform, per-segment scores dealt to
+the ranks and all-gathered - and the result must equal the single-rank run bit for bit.  Skipped on a one-GPU box
+(the CPU coverage of the same host logic is tests/test_sharding_gloo.py; bench.py asserts the same identity under
+torchrun for the strong_c3 record)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_ranks_equal_single_rank_bit_for_bit():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on the box")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "multi_gpu_check.py"),
+           "60"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
+    rec = json.loads(line)
+    assert rec["world"] == 2
+    for part in ("concat", "ola", "scores"):
+        assert rec[part]["bit_identical_to_single_rank"] is True, rec

@@ -26,7 +26,7 @@ def test_step_parity(step_results, step):
 def _full(B, T, seed, min_db=40.0):
     import torch
     from oracle.mossformer2_port import mossformer2_forward, snr_db
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     sd = random_state_dict(seed=seed)
     g = torch.Generator().manual_seed(1234 + seed)
@@ -67,7 +67,7 @@ def test_batch_equals_singles(T):
     """Chunks are independent units: a batch of 2 equals two single calls bit for bit (T = 140 000 spans several
     fixed-size splits of the linear-attention sum, whose order must not depend on the batch)."""
     import torch
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     sd = random_state_dict(seed=2)
     g = torch.Generator().manual_seed(7)
@@ -86,7 +86,7 @@ def test_real_speech_excerpt_against_reference_run():
     import numpy as np
     import torch
     from oracle.mossformer2_port import snr_db
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     gd = np.load(os.path.join(ROOT, "tests", "golden", "chat_mix_excerpt.npz"))
     sep = Separator(random_state_dict(seed=0, perturb=True), "cuda:0")
@@ -120,7 +120,7 @@ def test_one_frame_inputs_are_finite(T):
 
 def test_too_short_input_is_an_error():
     import torch
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     sep = Separator(random_state_dict(seed=0), "cuda:0")
     with pytest.raises(RuntimeError):
@@ -133,7 +133,7 @@ def test_back_to_back_linear_project_equals_two_kernels(B, T):
     activations stay in TMEM / shared memory); asked for one step at a time the library runs the two-kernel form.
     Same k order, same bf16 rounding of the hidden activations: the `p` buffer must agree bit for bit."""
     import torch
-    from oracle.synth import random_state_dict
+    from targetdiarization_b200.synth import random_state_dict
     from targetdiarization_b200 import Separator
     sep = Separator(random_state_dict(seed=3), "cuda:0")
     mix = (torch.randn(B, T, generator=torch.Generator().manual_seed(1)) * 0.1).cuda()

@@ -5,7 +5,8 @@
 
 Every rank separates its share of the windows of one long synthetic input (concat mode and overlap-add mode), the
 spans are gathered with one all_gather, and rank 0 compares the result bit for bit with the same input processed by
-a single rank (the sharding must not change a single output bit), then prints timings as one JSON line."""
+a single rank (the sharding must not change a single output bit); the per-segment scores are checked the same way
+(segments dealt to the ranks, one all_gather).  Prints timings as one JSON line; exit code 1 on any mismatch."""
 import json
 import os
 import sys
@@ -31,11 +32,11 @@ def main():
     out = {}
     for mode in ("concat", "ola"):
         fn = pipeline.separate_concat if mode == "concat" else pipeline.separate_ola
-        fn(stage.kern, audio, group=None)  # warm-up (allocations, first-use attributes)
+        fn(stage.kern, audio, group=None)  # warm-up (allocations, first-use attributes); group=None never shards
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        sharded = fn(stage.kern, audio, group=None)          # default group = all ranks
+        sharded = fn(stage.kern, audio, group=dist.group.WORLD)   # sharding is opt-in: the ranks that share the input
         torch.cuda.synchronize()
         dist.barrier()
         dt = time.perf_counter() - t0
@@ -52,10 +53,24 @@ def main():
             torch.cuda.synchronize()
             ok = bool(torch.equal(single, sharded))
         out[mode] = dict(seconds=dt, xrt=L / 16000 / dt, bit_identical_to_single_rank=ok)
+    # per-segment scores: segments dealt to the ranks, one all_gather of the [n_seg] scores
+    seg = 64000
+    clips = audio[:(L // seg) * seg].view(-1, seg)
+    target = stage.embed(synthetic_mixture(1, seg, seed=99).to(dev))[0]
+    stage.group = dist.group.WORLD
+    sharded_scores = stage.score_segments(clips, target)
+    stage.group = None
+    single_scores = stage.score_segments(clips, target)
+    torch.cuda.synchronize()
+    out["scores"] = dict(segments=int(clips.shape[0]),
+                         bit_identical_to_single_rank=bool(torch.equal(sharded_scores, single_scores)))
+    ok = torch.tensor([int(all(v["bit_identical_to_single_rank"] is not False for v in out.values()))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps(dict(world=world, audio_seconds=L / 16000, **out)))
-        if not all(v["bit_identical_to_single_rank"] for v in out.values()):
-            sys.exit(1)
+    if int(ok.item()) != 1:
+        dist.destroy_process_group()
+        sys.exit(1)
     dist.destroy_process_group()
 
 

@@ -5,7 +5,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from oracle.synth import random_state_dict, synthetic_mixture  # noqa: E402
+from targetdiarization_b200.synth import random_state_dict, synthetic_mixture  # noqa: E402
 from targetdiarization_b200 import Separator  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
