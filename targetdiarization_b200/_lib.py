@@ -155,6 +155,42 @@ def free_device_bytes(device, held=0):
     return int(free + max(cached, 0) + held)
 
 
+class CallGuard:
+    """Serialises the calls into one host object (the reference shares ONE global model between
+    the main thread and the ThreadPoolExecutor workers of its WebSocket server without any locking, main.py:42,338-367).
+
+    A Separator / Embedder owns mutable state - the workspace its kernels scribble in, the static buffers of its
+    captured CUDA graphs - so two Python threads must not interleave inside a call (lock), and a call on another CUDA
+    stream than the previous one must not start before that one's kernels are done with the workspace (the new stream
+    waits for the old one; nothing is recorded on the normal same-stream path)."""
+
+    def __init__(self, device):
+        import threading
+        self.device = device
+        self.lock = threading.RLock()
+        self.depth = 0
+        self.stream = None
+
+    def __enter__(self):
+        import torch
+        self.lock.acquire()
+        self.depth += 1
+        if self.depth == 1:
+            cur = torch.cuda.current_stream(self.device)
+            last = self.stream
+            if last is not None and last.cuda_stream != cur.cuda_stream and not torch.cuda.is_current_stream_capturing():
+                cur.wait_stream(last)
+            if last is None or last.cuda_stream != cur.cuda_stream:
+                if not torch.cuda.is_current_stream_capturing():
+                    self.stream = cur
+        return self
+
+    def __exit__(self, *exc):
+        self.depth -= 1
+        self.lock.release()
+        return False
+
+
 class Handle:
     """Owns one tdz_ctx.  check() turns non-zero return codes into RuntimeError (the reference's convention
     is Python exceptions caught at init, AudioProcessor.py:187-194)."""

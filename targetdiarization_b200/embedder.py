@@ -33,6 +33,7 @@ class Embedder:
         # None: a share of the memory that is free when a batch is sized (capped at 24 GiB: larger sub-batches buy
         # nothing, 128 x 4 s utterances need 9 GB)
         self._max_workspace_bytes = None if max_workspace_bytes is None else int(max_workspace_bytes)
+        self._guard = _lib.CallGuard(self.device)    # one call at a time per object, any Python thread / stream
         win, tw = fbank.povey_window(), fbank.twiddles()
         mel, lo, hi = fbank.mel_banks()
         self._tables = [torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in (win, tw, mel, lo, hi)]
@@ -99,6 +100,10 @@ class Embedder:
         """feat float32 [N, frames, 80] -> [N,192] (ERes2NetV2 forward)."""
         if self._packed is None:
             raise RuntimeError("Embedder has no weights; call load_state_dict first")
+        with self._guard:
+            return self._embed_features(feat)
+
+    def _embed_features(self, feat):
         N, frames, _ = feat.shape
         emb = torch.empty(N, EMBED_DIM, dtype=torch.float32, device=self.device)
         nb = self.max_batch(frames, N)

@@ -358,6 +358,8 @@ class SeparationScoringStage:
         self.group = group
         self.gather_dst = gather_dst
         self.kern = CudaKernels(separator)
+        from . import _lib
+        self._guard = _lib.CallGuard(self.device)    # the static buffers of the captured run() graphs
         self.similarity_threshold = similarity_threshold
         self.is_separate_audio = True
 
@@ -667,6 +669,10 @@ class SeparationScoringStage:
         return est, scores.view(B, 2)
 
     def _run_graphed(self, mix_dev, target_embedding, B, T):
+        with self._guard, self.separator._guard, self.embedder._guard:
+            return self._run_graphed_locked(mix_dev, target_embedding, B, T)
+
+    def _run_graphed_locked(self, mix_dev, target_embedding, B, T):
         cache = self.__dict__.setdefault("_run_graphs", {})
         gen = (self.separator._ws_generation, self.embedder._ws_generation)
         ent = cache.get((B, T))
@@ -683,7 +689,7 @@ class SeparationScoringStage:
             try:
                 torch.cuda.current_stream(self.device).synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):  # other threads may allocate meanwhile
                     est = self.kern.separate(s_in)
                     scores = self.embedder.score_many(est.view(2 * B, T), s_tgt)
             finally:

@@ -54,6 +54,7 @@ class Restorer:
         # (an hour of audio: 180 GB); with less the library runs the network over frame chunks with a 54-frame halo -
         # the receptive field of the depthwise convolutions - which gives the same bits.
         self.max_workspace_bytes = None if max_workspace_bytes is None else int(max_workspace_bytes)
+        self._guard = _lib.CallGuard(self.device)    # one call at a time per object, any Python thread / stream
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -130,10 +131,12 @@ class Restorer:
         return out
 
     def __call__(self, x):
-        return self._run(x)
+        with self._guard:
+            return self._run(x)
 
     forward = __call__
 
     def tap(self, x, name):
         """Test hook: an intermediate of the forward in the oracle's layout (oracle/apollo_port.py `taps`)."""
-        return self._run(x, name)
+        with self._guard:
+            return self._run(x, name)

@@ -58,6 +58,7 @@ class Separator:
         self._ws_generation = 0      # bumped when the workspace moves: captured CUDA graphs hold its address
         self._graphs = {}            # (B, T) -> [times seen, CUDAGraph | None, static input, static output]
         self.graph_max_frames = GRAPH_MAX_FRAMES
+        self._guard = _lib.CallGuard(self.device)    # one call at a time per object, any Python thread / stream
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -142,7 +143,7 @@ class Separator:
             lib, h = self._h.lib, self._h
             g = torch.cuda.CUDAGraph()
             torch.cuda.current_stream(self.device).synchronize()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):  # other threads may allocate meanwhile
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 rc = lib.tdz_separate(h.ptr, s_in.data_ptr(), B, T, s_out.data_ptr(), ws.data_ptr(), nbytes, stream)
             h.check(rc, "tdz_separate (graph capture)")
@@ -167,6 +168,10 @@ class Separator:
         the stitched [2, L] streams."""
         if self._packed is None:
             raise RuntimeError("Separator has no weights; call load_state_dict first")
+        with self._guard:
+            return self._forward(mix, _debug, out, out_strides)
+
+    def _forward(self, mix, _debug, out, out_strides):
         x = mix
         if x.ndim == 1:
             x = x.unsqueeze(0)

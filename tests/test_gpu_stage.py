@@ -208,3 +208,46 @@ def test_same_speaker_batch_equals_per_stream_rule4(stage):
         want = plan.is_same_person(sim, 0.4, verbose_result=True)
         assert got[i]["is_same"] == want["is_same"] and abs(got[i]["score"] - want["score"]) <= 0.002
     assert got[1]["is_same"] and got[1]["score"] >= 0.999
+
+
+@pytest.mark.timeout(600)
+def test_concurrent_python_threads_share_one_stage(stage):
+    """SURVEY.md 8b threading: the reference shares ONE global model between its main thread and ThreadPoolExecutor
+    workers without locking (main.py:42,338-367).  Four threads, each on its own CUDA stream, call the same stage -
+    the graph-replayed small-call path (static buffers), the eager path (shared workspace) and the numpy call surface -
+    and every result equals the serial one bit for bit."""
+    torch, st = stage
+    from concurrent.futures import ThreadPoolExecutor
+    from targetdiarization_b200.synth import synthetic_mixture
+    tgt = st.embed(synthetic_mixture(1, 64000, seed=32).cuda())[0]
+    small = [synthetic_mixture(2, 9600, seed=200 + i).cuda() for i in range(4)]       # graphed: 2 x 1 199 frames
+    big = [synthetic_mixture(24, 32000, seed=300 + i).cuda() for i in range(4)]       # eager: 24 x 4 096 frames
+    host = [synthetic_mixture(1, 40000 + 1000 * i, seed=400 + i)[0].numpy() for i in range(4)]
+    for _ in range(2):                                   # second pass captures the graphs of the small shape
+        want_small = [tuple(t.clone() for t in st.run(m, tgt)) for m in small]
+    want_big = [tuple(t.clone() for t in st.run(m, tgt)) for m in big]
+    want_host = [st.separate_and_score(h, tgt, loudness=None) for h in host]
+    torch.cuda.synchronize()
+
+    def work(i):
+        torch.cuda.set_device(0)
+        s = torch.cuda.Stream()
+        out = []
+        with torch.cuda.stream(s):
+            for rep in range(3):
+                a = st.run(small[i], tgt)
+                b = st.run(big[i], tgt)
+                c = st.separate_and_score(host[i], tgt, loudness=None)
+                out.append((a, b, c))
+            s.synchronize()
+        return out
+
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        results = list(pool.map(work, range(4)))
+    torch.cuda.synchronize()
+    for i, reps in enumerate(results):
+        for a, b, c in reps:
+            assert torch.equal(a[0], want_small[i][0]) and torch.equal(a[1], want_small[i][1]), f"thread {i}: graphed path"
+            assert torch.equal(b[0], want_big[i][0]) and torch.equal(b[1], want_big[i][1]), f"thread {i}: eager path"
+            assert np.array_equal(c["spk1_audio"], want_host[i]["spk1_audio"]), f"thread {i}: numpy surface"
+            assert c["spk1_score"] == want_host[i]["spk1_score"] and c["target"] == want_host[i]["target"]
