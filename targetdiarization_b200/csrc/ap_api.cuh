@@ -36,7 +36,7 @@ static int stft_launch(tdz_ctx* ctx, const FftPlan& f, const float* x, int64_t r
   const int smem = 2 * f.n * 8;
   static std::atomic<unsigned long long> configured{0};
   CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(stft_kernel), 200 * 1024, configured));
-  stft_kernel<<<dim3(static_cast<unsigned>((T + 1) / 2), static_cast<unsigned>(rows)), FFT_THREADS, smem, st>>>(
+  pdl(stft_kernel, dim3(static_cast<unsigned>((T + 1) / 2), static_cast<unsigned>(rows)), FFT_THREADS, smem, st)(
       f, x, L, static_cast<int>(T), static_cast<int>(n_keep), spec, S);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -50,9 +50,9 @@ static int istft_launch(tdz_ctx* ctx, const FftPlan& f, const float* spec, int64
   const int smem = 2 * f.n * 8;
   static std::atomic<unsigned long long> configured{0};
   CUDA_OK(set_max_smem_once(reinterpret_cast<const void*>(istft_frames_kernel), 200 * 1024, configured));
-  istft_frames_kernel<<<dim3(static_cast<unsigned>((T + 1) / 2), static_cast<unsigned>(rows)), FFT_THREADS, smem, st>>>(
+  pdl(istft_frames_kernel, dim3(static_cast<unsigned>((T + 1) / 2), static_cast<unsigned>(rows)), FFT_THREADS, smem, st)(
       f, spec, S, static_cast<int>(T), static_cast<int>(n_keep), frames);
-  istft_ola_kernel<<<dim3(static_cast<unsigned>((out_len + 255) / 256), static_cast<unsigned>(rows)), 256, 0, st>>>(
+  pdl(istft_ola_kernel, dim3(static_cast<unsigned>((out_len + 255) / 256), static_cast<unsigned>(rows)), 256, 0, st)(
       frames, f.window, f.n, f.hop, static_cast<int>(T), out_len, out);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -156,6 +156,7 @@ enum ApTap { AP_TAP_SPEC = 0, AP_TAP_FEAT = 1, AP_TAP_ATT0 = 2, AP_TAP_BAND0 = 3
              AP_RUN_ALL = 1000 };
 
 __global__ void ap_widen_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ o, int64_t n) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) o[i] = __bfloat162float(a[i]);
 }
@@ -208,7 +209,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
   const int64_t tokens = rows * Tc * AP_NBAND, Mp = (tokens + 127) / 128 * 128;
   const int mtiles = static_cast<int>(Mp / 128);
   // band split + per-band bottleneck
-  ap_bandsplit_kernel<<<static_cast<unsigned>(rows * Tc), 256, 0, st>>>(spec, W.bn_g, W.bn_w, W.bn_b, x, xbf, ss,
+  pdl(ap_bandsplit_kernel, static_cast<unsigned>(rows * Tc), 256, 0, st)(spec, W.bn_g, W.bn_w, W.bn_b, x, xbf, ss,
                                                                        static_cast<int>(T), static_cast<int>(t_lo),
                                                                        static_cast<int>(Tc));
   CUDA_OK(cudaGetLastError());
@@ -233,10 +234,10 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     P.e.out_bf16 = qkv;
     P.e.out_bf_ld = 768;
     CUDA_OK((launch_gemm<LinearPanel<1, 256, 3, EF_RMS4 | EF_OUT_BF16, ACT_NONE, 4>>(P, mtiles * P.n_tiles, sms, st)));
-    ap_attn_kernel<<<static_cast<unsigned>(rows * Tc), 256, 0, st>>>(qkv, W.rot_cos, W.rot_sin, att);
+    pdl(ap_attn_kernel, static_cast<unsigned>(rows * Tc), 256, 0, st)(qkv, W.rot_cos, W.rot_sin, att);
     CUDA_OK(cudaGetLastError());
     if (l == 0 && tap == AP_TAP_ATT0) {
-      ap_widen_kernel<<<static_cast<unsigned>((tokens * 256 + 255) / 256), 256, 0, st>>>(att, out, tokens * 256);
+      pdl(ap_widen_kernel, static_cast<unsigned>((tokens * 256 + 255) / 256), 256, 0, st)(att, out, tokens * 256);
       CUDA_OK(cudaGetLastError());
       return 0;
     }
@@ -268,7 +269,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     // ---- seq_net: three ConvActNorm1d blocks along time
     for (int b = 0; b < 3; ++b) {
       const tdz_apollo_icb& I = LW.icb[b];
-      ap_dwconv_rms_kernel<<<static_cast<unsigned>((dw_warps * 32 + 255) / 256), 256, 0, st>>>(
+      pdl(ap_dwconv_rms_kernel, static_cast<unsigned>((dw_warps * 32 + 255) / 256), 256, 0, st)(
           x, I.dw, I.dw_b, static_cast<int>(Tc), runs, dw_warps, u);
       CUDA_OK(cudaGetLastError());
       if (!ctx->no_b2b) {
@@ -333,7 +334,7 @@ static int ap_forward(tdz_ctx* ctx, const ApModel& M, const float* wav, int64_t 
     if (tap == AP_TAP_LAYER0 + l) return copy_out(x, static_cast<size_t>(tokens) * 256 * 4);
   }
   // band merge -> estimated spectrogram (the chunk's own frames only)
-  ap_bandmerge_kernel<<<static_cast<unsigned>(rows * (k1 - k0)), 256, merge_smem, st>>>(
+  pdl(ap_bandmerge_kernel, static_cast<unsigned>(rows * (k1 - k0)), 256, merge_smem, st)(
       x, W.out_g, W.out_wv, W.out_wg, W.out_bv, W.out_bg, est, static_cast<int>(T), static_cast<int>(t_lo),
       static_cast<int>(Tc), static_cast<int>(k0 - t_lo), static_cast<int>(k1 - k0));
   CUDA_OK(cudaGetLastError());

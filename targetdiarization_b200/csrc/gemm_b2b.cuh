@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();  // (the biases staged above are weights, not another kernel's output)
   const int ntiles = P.B * P.Sp / GEMM_BLOCK_M;
   const int NC = P.H / 128;
   // work items: row tiles, or pairs of row tiles (tile = 2 w + rank; a pair's second tile may lie past the end: its
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
       };
       int it = 0;
       for (int w = w_first; w < nwork; w += w_step, ++it) {
+        if (w + w_step >= nwork) pdl_trigger();  // last row tile of this CTA: the next kernel may be launched
         const int m0 = (w * NCTA + static_cast<int>(rank)) * GEMM_BLOCK_M;
         const int b = m0 / P.Sp, t0 = m0 - b * P.Sp;
         mbar_wait(x_empty, (it & 1) ^ 1u);
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(B2B_THREADS, 1) gemm_b2b_kernel(const __grid_c
       }
     };
     for (int w = w_first; w < nwork; w += w_step, ++it) {
+      if (w + w_step >= nwork) pdl_trigger();
       const int m0 = (w * NCTA + static_cast<int>(rank)) * GEMM_BLOCK_M;
       const int b = m0 / P.Sp, t0 = m0 - b * P.Sp;
       const bool in_range = m0 < P.B * P.Sp;   // false only for the second tile of an odd last pair
@@ -424,7 +427,7 @@ cudaError_t launch_gemm_b2b(const B2bParams& P, int num_sms, cudaStream_t st) {
   const int ntiles = P.B * P.Sp / GEMM_BLOCK_M;
   if (ntiles <= 0) return cudaSuccess;
   if constexpr (!CG2) {
-    kernel<<<ntiles < num_sms ? ntiles : num_sms, B2B_THREADS, smem, st>>>(P);
+    pdl(kernel, ntiles < num_sms ? ntiles : num_sms, B2B_THREADS, smem, st)(P);
     return cudaGetLastError();
   } else {
     const int npairs = (ntiles + 1) / 2;

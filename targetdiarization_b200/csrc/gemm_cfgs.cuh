@@ -807,6 +807,7 @@ struct LinearSplitK : LinearBase<1, 256, STAGES_> {
 // out[row][col] = bias[col] + sum over slices (ascending) of part[slice][row][col]; rows < rows_valid, col < N
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, int nslice,
                                      int64_t mtot, int rows_valid, int N, float* __restrict__ out, int out_ld) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(rows_valid) * N) return;
   const int row = static_cast<int>(i / N), col = static_cast<int>(i - static_cast<int64_t>(row) * N);

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();
   const int ntiles = Cfg::num_tiles(P);
   const int nkb = (P.K + 63) / 64;
 
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tile + static_cast<int>(gridDim.x) >= ntiles) pdl_trigger();  // last tile: the next kernel may be launched
         TileInfo ti;
         Cfg::tile_info(P, tile, ti);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
     constexpr int COLS = BLOCK_N / Cfg::EPI_SPLIT;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if (tile + static_cast<int>(gridDim.x) >= ntiles) pdl_trigger();
       TileInfo ti;
       Cfg::tile_info(P, tile, ti);
       const int as = it & 1;
@@ -250,6 +253,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
     int rh[RPT], rw[RPT];
     const __nv_bfloat16* rbase[RPT];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tile + static_cast<int>(gridDim.x) >= ntiles) pdl_trigger();
       TileInfo ti;
       Cfg::tile_info(P, tile, ti);
       if (ti.m0 != last_m0) {  // (n-tiles of the same pixel tile follow each other)
@@ -326,7 +330,7 @@ cudaError_t launch_gemm_conv3(const Conv3Params& CP, int ntiles, int num_sms, cu
     return e;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  gemm_conv3_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_WARPS, smem, st>>>(CP);
+  pdl(gemm_conv3_kernel<Cfg>, grid, gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_WARPS, smem, st)(CP);
   return cudaGetLastError();
 }
 

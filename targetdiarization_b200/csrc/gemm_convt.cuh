@@ -283,6 +283,7 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();
   // work items: (channel tile, time tile); CG2: (pair of channel tiles, time tile), one per cluster
   const int nct = CG2 ? P.n_tiles / 2 : P.n_tiles;
   const int ntiles = P.B * P.tps * nct;
@@ -300,6 +301,7 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
       convt_tile(P, nct, first, ti);
       [[maybe_unused]] const uint32_t leader_bars = CG2 ? mapa_shared(bar_base, 0) : 0u;
       for (int tile = first; tile < ntiles; tile += stride, convt_next(P, tstep, ti)) {
+        if (tile + stride >= ntiles) pdl_trigger();  // last tile of this CTA: the next kernel may be launched
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * CT_STAGE_BYTES;
@@ -378,6 +380,7 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
     [[maybe_unused]] const uint32_t leader_tempty = CG2 ? mapa_shared(tempty_bar(0), 0) : 0u;
     convt_tile(P, nct, first, ti);
     for (int tile = first; tile < ntiles; tile += stride, ++it, ti = tn) {
+      if (tile + stride >= ntiles) pdl_trigger();
       tn = ti;
       convt_next(P, tstep, tn);
       const int c = chan_tile(ti) * 128 + q * 32 + lane;  // output channel of this thread
@@ -452,7 +455,7 @@ cudaError_t launch_gemm_convt(const LinearParams& P, int ntiles, int num_sms, cu
     return e;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  gemm_convt_kernel<MODE><<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(P);
+  pdl(gemm_convt_kernel<MODE>, grid, CT_THREADS, CT_SMEM_BYTES, st)(P);
   return cudaGetLastError();
 }
 
@@ -465,7 +468,7 @@ cudaError_t launch_gemm_convt_cg2(const LinearParams& P, int npairs, int num_sms
     return e;
   if (npairs <= 0) return cudaSuccess;
   const int grid = 2 * npairs < num_sms ? 2 * npairs : (num_sms & ~1);
-  gemm_convt_cg2_kernel<MODE><<<grid, CT_THREADS, smem, st>>>(P);
+  pdl(gemm_convt_cg2_kernel<MODE>, grid, CT_THREADS, smem, st)(P);
   return cudaGetLastError();
 }
 

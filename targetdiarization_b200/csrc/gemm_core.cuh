@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();  // barriers, TMEM and descriptors are ready; from here on the producer kernel's data is visible
 
   const int ntiles = Cfg::num_tiles(P);
 
@@ -109,6 +110,10 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // last tile of this CTA: the next kernel of the stream may be launched (its CTAs take the SMs that go idle in
+        // this grid's tail and run their prologue there).  Not earlier: a dependent grid of small CTAs that sits next
+        // to this one for its whole duration costs the epilogue warps issue slots (measured: +4 % per forward).
+        if (tile + static_cast<int>(gridDim.x) >= ntiles) pdl_trigger();
         TileInfo ti;
         Cfg::tile_info(P, tile, ti);
         for (int kb = 0; kb < ti.nkb; ++kb) {
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
                      : nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      if (tile + static_cast<int>(gridDim.x) >= ntiles) pdl_trigger();
       TileInfo ti;
       Cfg::tile_info(P, tile, ti);
       const int as = it & 1;
@@ -251,6 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();
 
   const int nwork = Cfg::num_pair_tiles(P);
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
@@ -261,6 +268,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < nwork; w += nclusters) {
+        if (w + nclusters >= nwork) pdl_trigger();  // last work item of this CTA pair (see gemm_kernel)
         TileInfo ti;
         Cfg::pair_tile_info(P, w, rank, ti);
         for (int kb = 0; kb < ti.nkb; ++kb) {
@@ -331,6 +339,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(Cfg::CG
     }
     for (int it = 0; w < nwork; w += nclusters, ++it) {
       const bool has_next = w + nclusters < nwork;
+      if (!has_next) pdl_trigger();
       if (has_next) Cfg::pair_tile_info(P, w + nclusters, rank, nx);
       const int as = it & 1;
       mbar_wait(tfull_bar(as), (it >> 1) & 1);
@@ -359,7 +368,7 @@ cudaError_t launch_gemm_cg2(const typename Cfg::Params& P, int nwork, int num_sm
     return e;
   if (nwork <= 0) return cudaSuccess;
   int grid = 2 * nwork < num_sms ? 2 * nwork : (num_sms & ~1);
-  gemm_cg2_kernel<Cfg><<<grid, gemm_threads(Cfg::CG2_EPI_SPLIT), smem, st>>>(P);
+  pdl(gemm_cg2_kernel<Cfg>, grid, gemm_threads(Cfg::CG2_EPI_SPLIT), smem, st)(P);
   return cudaGetLastError();
 }
 
@@ -371,7 +380,7 @@ cudaError_t launch_gemm(const typename Cfg::Params& P, int ntiles, int num_sms, 
     return e;
   if (ntiles <= 0) return cudaSuccess;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  gemm_kernel<Cfg><<<grid, gemm_threads(Cfg::EPI_SPLIT), smem, st>>>(P);
+  pdl(gemm_kernel<Cfg>, grid, gemm_threads(Cfg::EPI_SPLIT), smem, st)(P);
   return cudaGetLastError();
 }
 

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) ap_bandsplit_kernel(const float2* __restr
                                                            const float* __restrict__ w, const float* __restrict__ b,
                                                            float* __restrict__ x, __nv_bfloat16* __restrict__ xbf,
                                                            float* __restrict__ ss, int T, int t_lo, int Tl) {
+  pdl_enter();
   __shared__ float2 s_spec[AP_BINS];
   __shared__ float s_feat[AP_FEAT];
   __shared__ float s_ss[8][AP_NBAND];   // per-warp partial sums of squares (added in warp order: no atomics)
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) ap_attn_kernel(const __nv_bfloat16* __res
                                                       const float* __restrict__ rot_cos,
                                                       const float* __restrict__ rot_sin,
                                                       __nv_bfloat16* __restrict__ out) {
+  pdl_enter();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tg = lane & 3;
   const size_t tok0 = static_cast<size_t>(blockIdx.x) * AP_NBAND;
@@ -231,6 +233,7 @@ constexpr int AP_DW_RUN = 8;
 __global__ void __launch_bounds__(256, 1) ap_dwconv_rms_kernel(const float* __restrict__ x, const float* __restrict__ taps,
                                                                const float* __restrict__ bias, int T, int runs_per_seq,
                                                                int64_t n_warps, __nv_bfloat16* __restrict__ u) {
+  pdl_enter();
   const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= n_warps) return;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(256) ap_bandmerge_kernel(const float* __restri
                                                            const float* __restrict__ bv, const float* __restrict__ bg,
                                                            float2* __restrict__ est, int T, int t_lo, int Tl, int keep_lo,
                                                            int keep_n) {
+  pdl_enter();
   extern __shared__ uint8_t ap_smem_raw[];
   float* xs = reinterpret_cast<float*>(ap_smem_raw);   // [80][AP_XLD]
   __shared__ float s_out[AP_PAIRS];

@@ -20,6 +20,7 @@ struct FbankTables {
 
 __global__ void __launch_bounds__(128) fbank_kernel(const float* __restrict__ wav, int64_t T, int64_t frames,
                                                     int64_t total_frames, FbankTables tb, float* __restrict__ feat) {
+  pdl_enter();
   __shared__ float2 fft[4][FB_NFFT];
   __shared__ float raw[4][FB_WIN];
   __shared__ float2 tw[256];
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(128) fbank_kernel(const float* __restrict__ wa
 
 // feature - feature.mean(dim=0): one block per utterance, 240 threads = 80 bins x 3 frame phases.
 __global__ void __launch_bounds__(240) fbank_meannorm_kernel(float* __restrict__ feat, int64_t frames) {
+  pdl_enter();
   __shared__ float part[3][FB_NMEL];
   const int bin = threadIdx.x % FB_NMEL, ph = threadIdx.x / FB_NMEL;
   float* base = feat + static_cast<int64_t>(blockIdx.x) * frames * FB_NMEL;

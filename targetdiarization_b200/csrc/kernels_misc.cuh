@@ -7,6 +7,7 @@ namespace tdz {
 // look2hear/utils/separator.py:95-112 -- segment i of the zero-padded mixture.
 __global__ void gather_segments_kernel(const float* __restrict__ mix, int64_t L, int64_t session, int64_t hop,
                                        int64_t seg_begin, int64_t n_seg, float* __restrict__ seg) {
+  pdl_enter();
   const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n_seg * session) return;
   const int64_t pad = session - hop;
@@ -25,6 +26,7 @@ __global__ void gather_segments_kernel(const float* __restrict__ mix, int64_t L,
 __global__ void stitch_ola_kernel(const float* __restrict__ est, int64_t session, int64_t hop, int64_t seg_begin,
                                   int64_t n_seg, int64_t L, int64_t out_begin, int64_t n_out, float ratio,
                                   float* __restrict__ out) {
+  pdl_enter();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= 2 * n_out) return;
   const int64_t trk = idx / n_out;
@@ -50,6 +52,7 @@ __global__ void stitch_ola_kernel(const float* __restrict__ est, int64_t session
 // TargetASR.cosine_similarity (TargetASR.py:144-152): zero vector -> 1.0, clamp to [0,1]. Warp per row.
 __global__ void cosine_scores_kernel(const float* __restrict__ emb, const float* __restrict__ target, int N, int dim,
                                      float* __restrict__ scores) {
+  pdl_enter();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -92,6 +95,7 @@ struct KWeight {
 };
 __global__ void __launch_bounds__(128) kweight_sq_kernel(const float* __restrict__ x, int64_t L, int64_t n_streams,
                                                          KWeight kw, double* __restrict__ ysq) {
+  pdl_enter();
   const int64_t seg = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t segs_per_stream = (L + LK_SEG - 1) / LK_SEG;
   if (seg >= segs_per_stream * n_streams) return;
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(256) loudness_blocks_kernel(const double* __re
                                                               const int64_t* __restrict__ hi, int64_t nblk,
                                                               int64_t n_streams, double inv_len,
                                                               double* __restrict__ z) {
+  pdl_enter();
   const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nblk * n_streams) return;

@@ -14,6 +14,7 @@ constexpr int ENC_FRAMES = 64;
 __global__ void __launch_bounds__(512) encoder_kernel(const float* __restrict__ mix, int T, const float* __restrict__ w,
                                                       float* __restrict__ enc, double* __restrict__ gn_stats, int B,
                                                       int Sp, int S) {
+  pdl_enter();
   __shared__ __align__(16) float xs[ENC_FRAMES * 8 + 8];
   __shared__ float red[2][16];
   const int strips = Sp / ENC_FRAMES;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(512) encoder_kernel(const float* __restrict__ 
 // GroupNorm(1,C,eps) statistics -> per-sample scale/shift (mossformer2.py:152).  A = rstd, Bv = -rstd*mean.
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, float* __restrict__ sampA,
                                    float* __restrict__ sampB, int B, double count, double eps) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double mean = stats[2 * b] / count;
@@ -85,6 +87,7 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, float* __re
 
 // Rotary angle table (rotary_embedding_torch: angle[t,j] = t * freqs[j]); fp32 positions.
 __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __restrict__ tab, int Sp) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Sp * 16) return;
   const int t = i >> 4, j = i & 15;
@@ -97,6 +100,7 @@ __global__ void rotary_table_kernel(const float* __restrict__ freqs, float2* __r
 // GEMM epilogue that adds it reads a float4 instead of evaluating four sinf / cosf per output.
 __global__ void posenc_table_kernel(const float* __restrict__ inv_freq, const float* __restrict__ scale,
                                     float* __restrict__ tab, int Sp, int N) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Sp * N) return;
   const int t = i / N, c = i - t * N, hlf = N >> 1;
@@ -116,6 +120,7 @@ constexpr int QKH_FRAMES = 8;
 __global__ void __launch_bounds__(256) qk_heads_kernel(const float* __restrict__ qkf, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float2* __restrict__ rot,
                                                        __nv_bfloat16* __restrict__ qk4, int Sp, int S, size_t rows) {
+  pdl_enter();
   const int c = (threadIdx.x & 63) * 2;
   float2 g[4], bt[4];
 #pragma unroll
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(256) qk_heads_kernel(const float* __restrict__
 template <bool SHIFT>
 __global__ void rowscale_kernel(const float* __restrict__ parts, float* __restrict__ out, int Sp, int S, size_t rows,
                                 float dim_rsqrt) {
+  pdl_enter();
   const size_t row = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const int t = static_cast<int>(row % Sp);
@@ -228,6 +234,7 @@ struct DdParams {
 
 template <int STAGE>
 __global__ void __launch_bounds__(DD_THREADS, DD_CTAS_PER_SM) dd_stream_kernel(const __grid_constant__ DdParams P) {
+  pdl_enter();
   constexpr int NCG = (STAGE == 1 ? 256 : 512) / DD_CH;  // channel groups: stage 2 reads y1 (first half) and p
   constexpr int HALO = STAGE == 1 ? 19 : 38;
   constexpr int STEP = STAGE == 1 ? 1 : 2;   // dilation
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(DD_THREADS, DD_CTAS_PER_SM) dd_stream_kernel(c
 // eps 1e-5 (fsmn.py:93,103).  out[b*256+c] = (rstd*g, beta - mean*rstd*g).
 __global__ void in_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ g,
                                    const float* __restrict__ bt, float2* __restrict__ out, int n, double count) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = i & 255;
@@ -465,6 +473,7 @@ __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict_
                                                         const float* __restrict__ prelu2,
                                                         const float* __restrict__ xuv, const float* __restrict__ cres,
                                                         float* __restrict__ gout, int B, int Sp, int S) {
+  pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int groups = Sp / TAIL_FRAMES;  // Sp is a multiple of 256
@@ -537,6 +546,7 @@ __global__ void __launch_bounds__(256) fsmn_tail_kernel(const float* __restrict_
 // qk_heads_kernel).
 __global__ void kv_reduce_kernel(const float* __restrict__ part, __half* __restrict__ kv, int nsplit,
                                  float inv_n, size_t per_sample /*128*2048*/, size_t total4) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const size_t e = i * 4;
@@ -561,6 +571,7 @@ __global__ void kv_reduce_kernel(const float* __restrict__ part, __half* __restr
 __global__ void __launch_bounds__(256) final_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                        const float* __restrict__ bta, float* __restrict__ out,
                                                        double* __restrict__ gn_stats, int B, int Sp, int S) {
+  pdl_enter();
   __shared__ float red[2][8];
   const int warp_in_block = threadIdx.x >> 5;
   const int warp = blockIdx.x * 8 + warp_in_block;
@@ -624,6 +635,7 @@ __global__ void final_gn_kernel(const float* __restrict__ ln, const float* __res
                                 const float* __restrict__ bta, const float* __restrict__ x0,
                                 const float* __restrict__ alpha, float* __restrict__ out, int Sp, int S,
                                 size_t total4) {
+  pdl_enter();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const size_t e = i * 4;

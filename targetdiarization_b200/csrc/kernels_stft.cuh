@@ -128,6 +128,7 @@ __device__ float2* fft_cta(const FftPlan& P, float2* buf0, float2* buf1) {
 __global__ void __launch_bounds__(FFT_THREADS) stft_kernel(const __grid_constant__ FftPlan P, const float* __restrict__ x,
                                                            int64_t L, int T, int n_keep, float* __restrict__ out,
                                                            SpecStrides S) {
+  pdl_enter();
   extern __shared__ float2 fft_smem[];
   float2* buf0 = fft_smem;
   float2* buf1 = fft_smem + P.n;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(FFT_THREADS) stft_kernel(const __grid_constant
 __global__ void __launch_bounds__(FFT_THREADS) istft_frames_kernel(const __grid_constant__ FftPlan P,
                                                                    const float* __restrict__ spec, SpecStrides S, int T,
                                                                    int n_keep, float* __restrict__ frames) {
+  pdl_enter();
   extern __shared__ float2 fft_smem[];
   float2* buf0 = fft_smem;
   float2* buf1 = fft_smem + P.n;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(FFT_THREADS) istft_frames_kernel(const __grid_
 // longer than the transform's support).
 __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window, int n, int hop,
                                  int T, int64_t out_len, float* __restrict__ out) {
+  pdl_enter();
   const int64_t m = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t row = blockIdx.y;
   if (m >= out_len) return;

@@ -23,6 +23,7 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* v) {
 __global__ void __launch_bounds__(256) sv_stem_kernel(const float* __restrict__ feat, const float* __restrict__ w,
                                                       const float* __restrict__ bias,
                                                       __nv_bfloat16* __restrict__ out_bf, int N, int H, int W) {
+  pdl_enter();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(N) * H * W * 8;
   if (idx >= total) return;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) sv_stem_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) sv_subsample_kernel(const __nv_bfloat16* __restrict__ in,
                                                            __nv_bfloat16* __restrict__ out, int N, int Hin, int Win,
                                                            int Hout, int Wout, int C) {
+  pdl_enter();
   const int c8 = C / 8;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(N) * Hout * Wout * c8;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) sv_im2col_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ b, int ldb, int offb,
                                                         __nv_bfloat16* __restrict__ col, int N, int Hin, int Win,
                                                         int Hout, int Wout, int C, int stride) {
+  pdl_enter();
   const int c8 = C >> 3;
   const int per_pix = 9 * c8;
   const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;  // position inside the output row
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(256) sv_im2col_kernel(const __nv_bfloat16* __r
 __global__ void __launch_bounds__(256) sv_cat2_kernel(const __nv_bfloat16* __restrict__ a, int lda, int offa,
                                                       const __nv_bfloat16* __restrict__ b, int ldb, int offb,
                                                       __nv_bfloat16* __restrict__ out, int64_t P, int C) {
+  pdl_enter();
   const int c8 = C / 8;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= P * 2 * c8) return;
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(256) sv_cat2_kernel(const __nv_bfloat16* __res
 // operand of the embedding Linear, matching reshape(N, C*F, T) of an NCHW tensor.  Thread = (n, h, c).
 __global__ void __launch_bounds__(256) sv_tstp_kernel(const float* __restrict__ fuse, __nv_bfloat16* __restrict__ stats,
                                                       int N, int H, int W, int C, int ld_stats) {
+  pdl_enter();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(N) * H * C) return;
   const int c = static_cast<int>(idx % C);
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256) sv_tstp_kernel(const float* __restrict__ 
 }
 
 __global__ void sv_fill_kernel(float* __restrict__ dst, int64_t n, float value) {
+  pdl_enter();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = value;
 }

@@ -278,7 +278,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     // Fewer than 9 fbank frames leave ONE time step after the three stride-2 stages; TSTP's unbiased variance over
     // one step is 0/0, so the reference model returns an all-NaN embedding (dropped by the enrolment path,
     // TargetASR.py:235-236; scored 0.0 by cosine_similarity, :151).  Same result here, without running the network.
-    sv_fill_kernel<<<sv_grid(N * TDZ_SV_EMBED_DIM), 256, 0, st>>>(emb, N * TDZ_SV_EMBED_DIM, nanf(""));
+    pdl(sv_fill_kernel, sv_grid(N * TDZ_SV_EMBED_DIM), 256, 0, st)(emb, N * TDZ_SV_EMBED_DIM, nanf(""));
     CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -299,7 +299,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
   // columns N..63 of `mid` are never written but are read (against zero weights) by the second AFF conv
   CUDA_OK(cudaMemsetAsync(mid, 0, static_cast<size_t>(d.Pp[2]) * 64 * 2, st));
   // stem
-  sv_stem_kernel<<<sv_grid(d.P[0] * 8), 256, 0, st>>>(feat, M.stem_w, M.stem_b, x, n, static_cast<int>(d.H[0]),
+  pdl(sv_stem_kernel, sv_grid(d.P[0] * 8), 256, 0, st)(feat, M.stem_w, M.stem_b, x, n, static_cast<int>(d.H[0]),
                                                       static_cast<int>(d.W[0]));
   if (stop_block == -1) {
     CUDA_OK(cudaMemcpyAsync(emb, x, static_cast<size_t>(d.P[0]) * 64 * 2, cudaMemcpyDeviceToDevice, st));
@@ -315,7 +315,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     const int Hc = static_cast<int>(d.H[layer]), Wc = static_cast<int>(d.W[layer]);
     const __nv_bfloat16* a_in = x;
     if (s.stride == 2) {
-      sv_subsample_kernel<<<sv_grid(P * (s.in_planes / 8)), 256, 0, st>>>(
+      pdl(sv_subsample_kernel, sv_grid(P * (s.in_planes / 8)), 256, 0, st)(
           x, xs, n, static_cast<int>(d.H[lin]), static_cast<int>(d.W[lin]), Hc, Wc, s.in_planes);
       a_in = xs;
     }
@@ -348,7 +348,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
         ioffb = i * wd;
       } else if (i > 0) {
         // AFF(sp, x_i): two 1x1 convs on cat(sp, x_i), then the gate in the second epilogue
-        sv_cat2_kernel<<<sv_grid(P * 2 * (wd / 8)), 256, 0, st>>>(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, cat2,
+        pdl(sv_cat2_kernel, sv_grid(P * 2 * (wd / 8)), 256, 0, st)(cat4, 4 * wd, (i - 1) * wd, c1, 4 * wd, i * wd, cat2,
                                                                  P, wd);
         memset(&e, 0, sizeof e);
         e.out_bf16 = mid;
@@ -384,7 +384,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
                      chain ? c1 : nullptr, 4 * wd, (i + 1) * wd, chain ? sum_buf[i & 1] : nullptr, wd))
           return 1;
       } else {
-        sv_im2col_kernel<<<dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st>>>(
+        pdl(sv_im2col_kernel, dim3(sv_grid(static_cast<int64_t>(Wc) * 9 * (wd / 8)), n * Hc), 256, 0, st)(
             ia, ilda, ioffa, ib, ildb, ioffb, col, n, Hc, Wc, Hc, Wc, wd, 1);
         if (sv_gemm(ctx, st, M.convs[k][i], col, 9 * wd, P, Pp, SV_HT20, e)) return 1;
       }
@@ -404,7 +404,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     if (k == 12) {
       // end of layer3: out3_ds = Conv2d(1024, 2048, 3, stride 2, pad 1)(out3), needed after layer4
       const int64_t P4 = d.P[3], Pp4 = d.Pp[3];
-      sv_im2col_kernel<<<dim3(sv_grid(d.W[3] * 9 * (1024 / 8)), n * static_cast<int>(d.H[3])), 256, 0, st>>>(x, 1024, 0, nullptr, 0, 0, col, n, Hc, Wc,
+      pdl(sv_im2col_kernel, dim3(sv_grid(d.W[3] * 9 * (1024 / 8)), n * static_cast<int>(d.H[3])), 256, 0, st)(x, 1024, 0, nullptr, 0, 0, col, n, Hc, Wc,
                                                                     static_cast<int>(d.H[3]),
                                                                     static_cast<int>(d.W[3]), 1024, 2);
       memset(&e, 0, sizeof e);
@@ -417,7 +417,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
   {
     const int64_t P4 = d.P[3], Pp4 = d.Pp[3];
     EpiGeneric e;
-    sv_cat2_kernel<<<sv_grid(P4 * 2 * (2048 / 8)), 256, 0, st>>>(x, 2048, 0, ds, 2048, 0, fcat, P4, 2048);
+    pdl(sv_cat2_kernel, sv_grid(P4 * 2 * (2048 / 8)), 256, 0, st)(x, 2048, 0, ds, 2048, 0, fcat, P4, 2048);
     memset(&e, 0, sizeof e);
     e.out_bf16 = fmid;
     e.out_bf_ld = 512;
@@ -437,7 +437,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
     // TSTP + embedding Linear
     const int64_t Np = (N + 127) / 128 * 128;
     CUDA_OK(cudaMemsetAsync(stats, 0, static_cast<size_t>(Np) * 40960 * 2, st));
-    sv_tstp_kernel<<<sv_grid(N * d.H[3] * 2048), 256, 0, st>>>(fuse, stats, n, static_cast<int>(d.H[3]),
+    pdl(sv_tstp_kernel, sv_grid(N * d.H[3] * 2048), 256, 0, st)(fuse, stats, n, static_cast<int>(d.H[3]),
                                                                static_cast<int>(d.W[3]), 2048, 40960);
     {
       float* part = reinterpret_cast<float*>(base + L.part);
@@ -455,7 +455,7 @@ static int sv_embed(tdz_ctx* ctx, const SvModel& M, const float* feat, int64_t N
       LP.e.out_f32 = part;
       cudaError_t r = launch_gemm<LinearSplitK<4>>(LP, static_cast<int>(Np / 128) * SV_SEG1_SLICES, ctx->num_sms, st);
       if (r != cudaSuccess) return fail(ctx, "tdz_embed: split-K launch failed (%s)", cudaGetErrorString(r));
-      splitk_reduce_kernel<<<sv_grid(N * 192), 256, 0, st>>>(part, M.seg1.bias, SV_SEG1_SLICES, Np, n, 192, emb, 192);
+      pdl(splitk_reduce_kernel, sv_grid(N * 192), 256, 0, st)(part, M.seg1.bias, SV_SEG1_SLICES, Np, n, 192, emb, 192);
     }
   }
   CUDA_OK(cudaGetLastError());

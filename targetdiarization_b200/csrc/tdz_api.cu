@@ -296,6 +296,11 @@ enum Step : int {
   ST_DECODER, ST_COUNT
 };
 
+// Calls of at most this many padded frames (the shapes the host side replays as CUDA graphs) launch their kernels
+// with the programmatic-dependent-launch attribute (ptx.cuh); 4 s of fbank frames per utterance for the embedder.
+constexpr size_t TDZ_PDL_MAX_FRAMES = 32768;
+constexpr int64_t TDZ_PDL_MAX_SV_FRAMES = 4096;
+
 static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64, float* out, int64_t out_cs,
                         int64_t out_ss, void* ws, size_t ws_bytes, cudaStream_t st, int num_layers, int step_lo,
                         int step_hi) {
@@ -310,6 +315,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   const int S = static_cast<int>(L.S), Sp = static_cast<int>(L.Sp);
   const size_t M = static_cast<size_t>(L.Mtot);
   if (M > (1ull << 24)) return fail(ctx, "tdz_separate: batch too large for one call (more than 2^24 padded frames)");
+  PdlScope pdl_scope(M <= TDZ_PDL_MAX_FRAMES);  // small (latency-bound) calls: programmatic dependent launches
   const int sms = ctx->num_sms;
   const tdz_mossformer2_weights& W = ctx->sep;
   uint8_t* base = static_cast<uint8_t*>(ws);
@@ -413,12 +419,12 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       CUDA_OK(cudaMemset2DAsync(qk4 + static_cast<size_t>(S) * 512, static_cast<size_t>(Sp) * 512 * 2, 0,
                                 static_cast<size_t>(Sp - S) * 512 * 2, B, st));
     }
-    encoder_kernel<<<B * (Sp / ENC_FRAMES), 512, 0, st>>>(mix, T, W.enc_w, enc, gn_stats, B, Sp, S);
-    gn_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(gn_stats, samp, samp + B, B, 512.0 * S, 1e-8);
-    rotary_table_kernel<<<(Sp * 16 + 255) / 256, 256, 0, st>>>(W.rot_freqs, rot, Sp);
+    pdl(encoder_kernel, B * (Sp / ENC_FRAMES), 512, 0, st)(mix, T, W.enc_w, enc, gn_stats, B, Sp, S);
+    pdl(gn_finalize_kernel, (B + 127) / 128, 128, 0, st)(gn_stats, samp, samp + B, B, 512.0 * S, 1e-8);
+    pdl(rotary_table_kernel, (Sp * 16 + 255) / 256, 256, 0, st)(W.rot_freqs, rot, Sp);
   }
   STEP(ST_ENC1X1) {
-    posenc_table_kernel<<<(Sp * 512 + 255) / 256, 256, 0, st>>>(W.pos_inv_freq, W.pos_scale, pos_tab, Sp, 512);
+    pdl(posenc_table_kernel, (Sp * 512 + 255) / 256, 256, 0, st)(W.pos_inv_freq, W.pos_scale, pos_tab, Sp, 512);
     LinearParams P;
     lin_base(P, m_enc, ctx->m_enc1x1, 512, 512, 256);
     P.e.sampA = samp;
@@ -453,7 +459,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 2176;
       P.cv.vu = vu;
       P.cv.qkf = qkf;
-      rowscale_kernel<true><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(ss, hrs, Sp, S, M,
+      pdl(rowscale_kernel<true>, static_cast<unsigned>((M + 255) / 256), 256, 0, st)(ss, hrs, Sp, S, M,
                                                                                    0.044194173824159216f);
       P.e.ss_in = hrs;
       P.tmA = m_xbf256;
@@ -461,13 +467,13 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.n_tiles = 17;
       P.tps = tps_t;
       CUDA_OK((launch_gemm_convt<CONV_VUQK>(P, B * tps_t * P.n_tiles, sms, st)));
-      qk_heads_kernel<<<static_cast<unsigned>((M + 4 * QKH_FRAMES - 1) / (4 * QKH_FRAMES)), 256, 0, st>>>(qkf, LW.os_gamma, LW.os_beta, rot, qk4, Sp, S, M);
+      pdl(qk_heads_kernel, static_cast<unsigned>((M + 4 * QKH_FRAMES - 1) / (4 * QKH_FRAMES)), 256, 0, st)(qkf, LW.os_gamma, LW.os_beta, rot, qk4, Sp, S, M);
     }
     STEP(ST_SIM) CUDA_OK((launch_gemm<AttnSim>(AP, mtiles, sms, st)));
     STEP(ST_KV) {
       CUDA_OK((launch_gemm<AttnKV>(AP, B * AP.nsplit * 8, sms, st)));
       const size_t total4 = static_cast<size_t>(B) * 128 * 2048 / 4;
-      kv_reduce_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
+      pdl(kv_reduce_kernel, static_cast<unsigned>((total4 + 255) / 256), 256, 0, st)(
           kv_part, kv, AP.nsplit, 1.f / static_cast<float>(S), static_cast<size_t>(128) * 2048, total4);
     }
     STEP(ST_ATT_OUT) {
@@ -483,7 +489,7 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       P.cv.ldw = 512;
       P.cv.x_in = x_in;
       P.cv.x_out = x;
-      rowscale_kernel<false><<<static_cast<unsigned>((M + 255) / 256), 256, 0, st>>>(o_ss, hrs, Sp, S, M, 0.03125f);
+      pdl(rowscale_kernel<false>, static_cast<unsigned>((M + 255) / 256), 256, 0, st)(o_ss, hrs, Sp, S, M, 0.03125f);
       P.e.ss_in = hrs;
       P.tmA = m_o256;
       P.tmAh = m_o;
@@ -579,12 +585,12 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       D.out = y1;
       D.stats = st1;
       D.tmA = m_p;
-      dd_stream_kernel<1><<<B * dd.nseg * (256 / DD_CH), DD_THREADS, DD_SMEM_BYTES, st>>>(D);
+      pdl(dd_stream_kernel<1>, B * dd.nseg * (256 / DD_CH), DD_THREADS, DD_SMEM_BYTES, st)(D);
     }
     float2* in_ss1 = in_ss;
     float2* in_ss2 = in_ss + static_cast<size_t>(B) * 256;
     STEP(ST_DD2) {
-      in_finalize_kernel<<<B, 256, 0, st>>>(st1, LW.in1_g, LW.in1_b, in_ss1, B * 256, static_cast<double>(S));
+      pdl(in_finalize_kernel, B, 256, 0, st)(st1, LW.in1_g, LW.in1_b, in_ss1, B * 256, static_cast<double>(S));
       DdParams D = dd;
       D.taps = LW.dd_w2;
       D.in_ss = in_ss1;
@@ -593,15 +599,15 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
       D.stats = st2;
       D.tmA = m_y1;
       D.tmB = m_p;
-      dd_stream_kernel<2><<<B * dd.nseg * (512 / DD_CH), DD_THREADS, DD_SMEM_BYTES, st>>>(D);
+      pdl(dd_stream_kernel<2>, B * dd.nseg * (512 / DD_CH), DD_THREADS, DD_SMEM_BYTES, st)(D);
     }
     STEP(ST_FSMN_TAIL) {
-      in_finalize_kernel<<<B, 256, 0, st>>>(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
+      pdl(in_finalize_kernel, B, 256, 0, st)(st2, LW.in2_g, LW.in2_b, in_ss2, B * 256, static_cast<double>(S));
       if (M <= 32768)
-        fsmn_tail_kernel<1><<<static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c, g, B,
+        pdl(fsmn_tail_kernel<1>, static_cast<unsigned>((M * 32 + 255) / 256), 256, 0, st)(y2, in_ss2, LW.dd_prelu2, xuv, c, g, B,
                                                                                       Sp, S);
       else
-        fsmn_tail_kernel<8><<<static_cast<unsigned>((M / 8 * 32 + 255) / 256), 256, 0, st>>>(y2, in_ss2, LW.dd_prelu2, xuv, c,
+        pdl(fsmn_tail_kernel<8>, static_cast<unsigned>((M / 8 * 32 + 255) / 256), 256, 0, st)(y2, in_ss2, LW.dd_prelu2, xuv, c,
                                                                                           g, B, Sp, S);
     }
     STEP(ST_FSMN_C2) {  // conv2 + residual; also the bf16 copy and ScaleNorm sums the next FLASH layer needs
@@ -626,14 +632,14 @@ static int run_separate(tdz_ctx* ctx, const float* mix, int64_t B64, int64_t T64
   const float* x_fin = (num_layers == 0) ? x0 : x;
   STEP(ST_FINAL_LN) {
     CUDA_OK(cudaMemsetAsync(gn_stats + 2 * B, 0, static_cast<size_t>(B) * 2 * 8, st));
-    final_ln_kernel<<<static_cast<unsigned>(M / 8), 256, 0, st>>>(x_fin, W.fln_g, W.fln_b, lnb, gn_stats + 2 * B, B, Sp,
+    pdl(final_ln_kernel, static_cast<unsigned>(M / 8), 256, 0, st)(x_fin, W.fln_g, W.fln_b, lnb, gn_stats + 2 * B, B, Sp,
                                                                   S);
-    gn_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(gn_stats + 2 * B, samp + 2 * B, samp + 3 * B, B, 512.0 * S,
+    pdl(gn_finalize_kernel, (B + 127) / 128, 128, 0, st)(gn_stats + 2 * B, samp + 2 * B, samp + 3 * B, B, 512.0 * S,
                                                         1e-8);
   }
   STEP(ST_FINAL_GN) {
     const size_t total4 = M * 512 / 4;
-    final_gn_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, st>>>(
+    pdl(final_gn_kernel, static_cast<unsigned>((total4 + 255) / 256), 256, 0, st)(
         lnb, samp + 2 * B, samp + 3 * B, W.fgn_g, W.fgn_b, x0, W.mask_prelu, ab, Sp, S, total4);
   }
   STEP(ST_OUT1) {  // conv1d_out 512 -> 1024 (+bias)
@@ -742,7 +748,7 @@ extern "C" int tdz_gather_segments_span(tdz_ctx* ctx, const float* mix_dev, int6
                 (long long)need_lo, (long long)need_hi, (long long)mix_origin, (long long)(mix_origin + mix_len));
   const size_t total = static_cast<size_t>(n_seg) * session;
   const size_t threads = (total + 3) / 4;  // one thread per 4 outputs, the last one possibly partial
-  gather_segments_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl(gather_segments_kernel, static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream))(
       mix_dev - mix_origin, L, session, hop, seg_begin, n_seg, seg_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -758,7 +764,7 @@ extern "C" int tdz_stitch_ola(tdz_ctx* ctx, const float* est_dev, int64_t sessio
   DeviceScope dev_scope(ctx->device);
   if (n_out <= 0) return 0;
   const size_t total = static_cast<size_t>(n_out) * 2;
-  stitch_ola_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl(stitch_ola_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream))(
       est_dev, session, hop, seg_begin, n_seg, L, out_begin, n_out, ratio, out_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -778,7 +784,8 @@ extern "C" int tdz_cosine_scores(tdz_ctx* ctx, const float* emb_dev, const float
   if (!ctx) return 1;
   DeviceScope dev_scope(ctx->device);
   if (N <= 0) return 0;
-  cosine_scores_kernel<<<static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  PdlScope pdl_scope(N <= 64);
+  pdl(cosine_scores_kernel, static_cast<unsigned>((N * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream))(
       emb_dev, target_dev, static_cast<int>(N), static_cast<int>(dim), scores_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -799,8 +806,8 @@ extern "C" int tdz_loudness_blocks(tdz_ctx* ctx, const float* x_dev, int64_t n_s
     }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t segs = (L + LK_SEG - 1) / LK_SEG * n_streams;
-  kweight_sq_kernel<<<static_cast<unsigned>((segs + 127) / 128), 128, 0, st>>>(x_dev, L, n_streams, kw, ysq_dev);
-  loudness_blocks_kernel<<<static_cast<unsigned>((nblk * n_streams * 32 + 255) / 256), 256, 0, st>>>(
+  pdl(kweight_sq_kernel, static_cast<unsigned>((segs + 127) / 128), 128, 0, st)(x_dev, L, n_streams, kw, ysq_dev);
+  pdl(loudness_blocks_kernel, static_cast<unsigned>((nblk * n_streams * 32 + 255) / 256), 256, 0, st)(
       ysq_dev, L, lo_dev, hi_dev, nblk, n_streams, inv_len, z_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -829,8 +836,9 @@ extern "C" int tdz_fbank(tdz_ctx* ctx, const float* wav_dev, int64_t N, int64_t 
   if (N <= 0 || frames <= 0) return fail(ctx, "tdz_fbank: input shorter than one 25 ms window");
   const int64_t total = N * frames;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  fbank_kernel<<<static_cast<unsigned>((total + 3) / 4), 128, 0, st>>>(wav_dev, T, frames, total, ctx->fb, feat_dev);
-  fbank_meannorm_kernel<<<static_cast<unsigned>(N), 240, 0, st>>>(feat_dev, frames);
+  PdlScope pdl_scope(total <= TDZ_PDL_MAX_SV_FRAMES);
+  pdl(fbank_kernel, static_cast<unsigned>((total + 3) / 4), 128, 0, st)(wav_dev, T, frames, total, ctx->fb, feat_dev);
+  pdl(fbank_meannorm_kernel, static_cast<unsigned>(N), 240, 0, st)(feat_dev, frames);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -862,6 +870,7 @@ extern "C" int tdz_embed(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->sv) return fail(ctx, "tdz_embed: weights not set");
   if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(ctx, "tdz_embed: workspace must be 1024 B aligned");
+  PdlScope pdl_scope(N * frames <= TDZ_PDL_MAX_SV_FRAMES);
   return sv_embed(ctx, *ctx->sv, feat_dev, N, frames, emb_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 extern "C" int tdz_embed_debug(tdz_ctx* ctx, const float* feat_dev, int64_t N, int64_t frames, float* out_dev, void* ws,
