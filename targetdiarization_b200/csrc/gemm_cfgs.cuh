@@ -113,15 +113,25 @@ struct LinearBase {
     ti.nkb = (P.K + KB - 1) / KB;  // a partial last k-block is zero-filled by TMA
     ti.aux = nt;
   }
-  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
+  // The B operand is a weight matrix: its k-blocks may be requested before griddepcontrol.wait (gemm_kernel asks for
+  // the first ring of them while the producer kernel is still running).  Configurations that override load() or
+  // read another kernel's output through B set this to false.
+  static constexpr bool PREFETCH_B = true;
+  __device__ static void load_a(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t bar) {
     const int trow = ti.t0 - (kb < P.shift_kblocks ? 1 : 0);
     tma_load_3d(sa, &P.tmA, bar, P.a_k0 + kb * KB, trow, ti.b);
+  }
+  __device__ static void load_b(const Params& P, const TileInfo& ti, int kb, uint32_t sb, uint32_t bar) {
     if (P.split_n == 0) {
       tma_load_2d(sb, &P.tmB, bar, kb * KB, ti.n0);
     } else {
       tma_load_2d(sb, &P.tmB, bar, kb * KB, ti.n0 / 2);
       tma_load_2d(sb + (BLOCK_N / 2) * 128, &P.tmB, bar, kb * KB, P.split_n + ti.n0 / 2);
     }
+  }
+  __device__ static void load(const Params& P, const TileInfo& ti, int kb, uint32_t sa, uint32_t sb, uint32_t bar) {
+    load_a(P, ti, kb, sa, bar);
+    load_b(P, ti, kb, sb, bar);
   }
 };
 
@@ -771,6 +781,7 @@ struct LinearSplitK : LinearBase<1, 256, STAGES_> {
   using Params = LinearParams;
   using Base = LinearBase<1, 256, STAGES_>;
   static constexpr int EPI_SPLIT = 2;
+  static constexpr bool PREFETCH_B = false;  // (own load(): K-sliced coordinates)
   __device__ static void tile_info(const Params& P, int tile, TileInfo& ti) {
     const int mt = tile / P.n_tiles;
     ti.aux = tile - mt * P.n_tiles;  // K slice
@@ -834,6 +845,7 @@ constexpr int DEC_TILE_FRAMES = 127;
 struct DecoderGemm {
   using Params = DecParams;
   static constexpr int FMT = 2, BLOCK_N = 16, STAGES = 8, A_MN = 0, B_MN = 0, EPI_SPLIT = 1, PANEL_BYTES = 0;
+  static constexpr bool PREFETCH_B = false;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmA);
     tma_prefetch_desc(&P.tmB);
@@ -915,6 +927,7 @@ struct AttnSim {
   using Params = AttnParams;
   static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 0, EPI_SPLIT = 2;
+  static constexpr bool PREFETCH_B = false;  // both operands are activations
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmQK);
     tma_prefetch_desc(&P.tmQKb);
@@ -963,6 +976,7 @@ struct AttnKV {
   using Params = AttnParams;
   static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 1, B_MN = 1, EPI_SPLIT = 2;
+  static constexpr bool PREFETCH_B = false;
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmQKmn);
     tma_prefetch_desc(&P.tmVUmn);
@@ -1015,6 +1029,7 @@ struct AttnOut {
   using Params = AttnParams;
   static constexpr int PANEL_BYTES = 0;
   static constexpr int FMT = 1, BLOCK_N = 256, STAGES = 4, A_MN = 0, B_MN = 1, EPI_SPLIT = 2;
+  static constexpr bool PREFETCH_B = false;
   static constexpr int F16_FROM_KB = 4;  // k-blocks from this one on use fp16 operands (instruction descriptor fmt 0)
   __device__ static void prefetch(const Params& P) {
     tma_prefetch_desc(&P.tmP);

@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT) + 32 * C3_GATHER_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  pdl_wait();
+  // Warp 0 streams WEIGHT k-blocks only (the activation half of a stage is assembled by the gather warps): it does not
+  // wait for the producer kernel - under a programmatic dependent launch the first ring of weights is in shared memory
+  // when the gather warps are released.  Every other warp waits (and keeps the CTA alive until the producer is done).
+  if (warp != 0) pdl_wait();
   const int ntiles = Cfg::num_tiles(P);
   const int nkb = (P.K + 63) / 64;
 

@@ -283,7 +283,6 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  pdl_wait();
   // work items: (channel tile, time tile); CG2: (pair of channel tiles, time tile), one per cluster
   const int nct = CG2 ? P.n_tiles / 2 : P.n_tiles;
   const int ntiles = P.B * P.tps * nct;
@@ -292,6 +291,26 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
   const int stride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const ConvTStep tstep = convt_step(nct, stride);
   auto chan_tile = [&](const ConvTTile& t) { return CG2 ? 2 * t.ct + static_cast<int>(rank) : t.ct; };
+  // Weight k-blocks of this CTA's first tile (one ring of them) are requested BEFORE the wait for the producer kernel:
+  // under a programmatic dependent launch they stream in while that kernel is still running.
+  int pre_kb = 0;
+  if (warp == 0 && lane == 0 && first < ntiles) {
+    ConvTTile ti;
+    convt_tile(P, nct, first, ti);
+    pre_kb = nkb < CT_STAGES ? nkb : CT_STAGES;
+    [[maybe_unused]] const uint32_t leader_bars = CG2 ? mapa_shared(bar_base, 0) : 0u;
+    for (int kb = 0; kb < pre_kb; ++kb) {
+      const uint32_t sa = smem_base + kb * CT_STAGE_BYTES;
+      if constexpr (CG2) {
+        if (rank == 0) mbar_arrive_expect_tx(full_bar(kb), 2 * CT_STAGE_BYTES);
+        tma_load_2d_cg2(sa, &P.tmB, leader_bars + 8u * kb, kb * 64, chan_tile(ti) * 128);
+      } else {
+        mbar_arrive_expect_tx(full_bar(kb), CT_STAGE_BYTES);
+        tma_load_2d(sa, &P.tmB, full_bar(kb), kb * 64, ti.ct * 128);
+      }
+    }
+  }
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -303,18 +322,21 @@ __device__ __forceinline__ void gemm_convt_body(const LinearParams& P) {
       for (int tile = first; tile < ntiles; tile += stride, convt_next(P, tstep, ti)) {
         if (tile + stride >= ntiles) pdl_trigger();  // last tile of this CTA: the next kernel may be launched
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const bool armed = tile == first && kb < pre_kb;  // barrier armed, weight tile requested before the wait
+          if (!armed) mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * CT_STAGE_BYTES;
           const int trow = ti.t0 - (kb < P.shift_kblocks ? 1 : 0);  // token shift (mossformer_block.py:204-207)
           if constexpr (CG2) {
             // both CTAs' bytes are counted on the leader's barrier; each CTA: its weight tile + its half of X
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * CT_STAGE_BYTES);
+            if (rank == 0 && !armed) mbar_arrive_expect_tx(full_bar(stage), 2 * CT_STAGE_BYTES);
             const uint32_t fb = leader_bars + 8u * stage;
-            tma_load_2d_cg2(sa, &P.tmB, fb, kb * 64, chan_tile(ti) * 128);
+            if (!armed) tma_load_2d_cg2(sa, &P.tmB, fb, kb * 64, chan_tile(ti) * 128);
             tma_load_3d_cg2(sa + GEMM_STAGE_A_BYTES, &P.tmAh, fb, kb * 64, trow + 128 * static_cast<int>(rank), ti.b);
           } else {
-            mbar_arrive_expect_tx(full_bar(stage), CT_STAGE_BYTES);
-            tma_load_2d(sa, &P.tmB, full_bar(stage), kb * 64, ti.ct * 128);                 // weights: M operand
+            if (!armed) {
+              mbar_arrive_expect_tx(full_bar(stage), CT_STAGE_BYTES);
+              tma_load_2d(sa, &P.tmB, full_bar(stage), kb * 64, ti.ct * 128);               // weights: M operand
+            }
             tma_load_3d(sa + GEMM_STAGE_A_BYTES, &P.tmA, full_bar(stage), kb * 64, trow, ti.b);  // frames: N operand
           }
           if (++stage == CT_STAGES) {

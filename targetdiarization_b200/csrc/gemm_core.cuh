@@ -101,9 +101,22 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  pdl_wait();  // barriers, TMEM and descriptors are ready; from here on the producer kernel's data is visible
-
   const int ntiles = Cfg::num_tiles(P);
+  // Weight k-blocks of this CTA's first tile (as many as the ring holds) are requested BEFORE the wait for the
+  // producer kernel: with a programmatic dependent launch they stream in while that kernel is still running.
+  int pre_kb = 0;
+  if constexpr (Cfg::PREFETCH_B) {
+    if (warp == 0 && lane == 0 && static_cast<int>(blockIdx.x) < ntiles) {
+      TileInfo ti;
+      Cfg::tile_info(P, blockIdx.x, ti);
+      pre_kb = ti.nkb < STAGES ? ti.nkb : STAGES;
+      for (int kb = 0; kb < pre_kb; ++kb) {
+        mbar_arrive_expect_tx(full_bar(kb), STAGE_BYTES);   // (the A half arrives after the wait)
+        Cfg::load_b(P, ti, kb, smem_base + kb * STAGE_BYTES + GEMM_STAGE_A_BYTES, full_bar(kb));
+      }
+    }
+  }
+  pdl_wait();  // barriers, TMEM and descriptors are ready; from here on the producer kernel's data is visible
 
   if (warp == 0) {
     if (lane == 0) {
@@ -117,10 +130,16 @@ __global__ void __launch_bounds__(gemm_threads(Cfg::EPI_SPLIT), 1) gemm_kernel(c
         TileInfo ti;
         Cfg::tile_info(P, tile, ti);
         for (int kb = 0; kb < ti.nkb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          Cfg::load(P, ti, kb, sa, sa + GEMM_STAGE_A_BYTES, full_bar(stage));
+          bool armed = false;  // first ring of the first tile: barrier armed and weights requested before the wait
+          if constexpr (Cfg::PREFETCH_B) armed = tile == static_cast<int>(blockIdx.x) && kb < pre_kb;
+          if (armed) {
+            if constexpr (Cfg::PREFETCH_B) Cfg::load_a(P, ti, kb, sa, full_bar(stage));
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            Cfg::load(P, ti, kb, sa, sa + GEMM_STAGE_A_BYTES, full_bar(stage));
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
