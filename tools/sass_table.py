@@ -3,7 +3,8 @@
     python tools/sass_table.py > profiles/r2_sass_opcodes.md
 
 For every kernel: instructions, UTC*MMA (tcgen05.mma; `.2CTA` = cta_group::2), LDTM (tcgen05.ld), UTMALDG (TMA loads),
-LDGSTS (cp.async), FFMA2 (packed fp32 FMA), MUFU, HMMA (legacy mma.sync - must be 0)."""
+LDGSTS (cp.async), FFMA2 (packed fp32 FMA), MUFU, HMMA (legacy mma.sync: only the restorer's 80 x 80 attention),
+ACQBULK / PREEXIT (griddepcontrol.wait / .launch_dependents: programmatic dependent launch)."""
 import collections
 import os
 import re
@@ -12,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "targetdiarization_b200", "libtdz.so")
-COLS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "LDGSTS", "FFMA2", "FFMA", "MUFU", "HMMA"]
+COLS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "LDGSTS", "FFMA2", "FFMA", "MUFU", "HMMA", "ACQBULK", "PREEXIT"]
 
 
 def main():
@@ -30,7 +31,7 @@ def main():
             cur["_n"] += 1
             if op.startswith("UTC") and "MMA" in op:
                 cur["UTCHMMA.2CTA" if ".2CTA" in op else "UTCHMMA"] += 1
-            for key in ("LDTM", "UTMALDG", "LDGSTS", "FFMA2", "MUFU", "HMMA"):
+            for key in ("LDTM", "UTMALDG", "LDGSTS", "FFMA2", "MUFU", "HMMA", "ACQBULK", "PREEXIT"):
                 if op.startswith(key):
                     cur[key] += 1
             if op == "FFMA" or op.startswith("FFMA."):
@@ -44,7 +45,8 @@ def main():
         print(f"| `{short}` | {c['_n']} | " + " | ".join(str(c[k]) for k in COLS) + " |")
     n_mma = sum(1 for c in kernels.values() if c["UTCHMMA"] + c["UTCHMMA.2CTA"])
     print(f"\n{len(kernels)} kernels, {n_mma} with tcgen05.mma; legacy HMMA instructions in the library: "
-          f"{sum(c['HMMA'] for c in kernels.values())}")
+          f"{sum(c['HMMA'] for c in kernels.values())}; kernels with griddepcontrol.wait: "
+          f"{sum(1 for c in kernels.values() if c['ACQBULK'])}")
 
 
 if __name__ == "__main__":
