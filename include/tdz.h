@@ -25,7 +25,12 @@
  * the library never allocates on the hot path, the caller passes a workspace sized by the matching
  * *_workspace_bytes().  Every call returns 0 on success or a non-zero code, with text in
  * tdz_last_error(); there is no CPU fallback.  `stream` is a cudaStream_t passed as void*.
- * A handle serialises its own calls; different handles may be used from different threads.
+ * A handle serialises its own calls; different handles may be used from different threads.  A workspace
+ * is scratch memory of one call at a time: calls that share a workspace must be ordered by the caller (same
+ * stream, or an event between streams) - the Python host objects do that (targetdiarization_b200/_lib.py::CallGuard).
+ * Small calls (at most 32 768 padded frames per tdz_separate, 4 096 fbank frames per tdz_embed) launch their kernels
+ * with the programmatic-stream-serialization attribute; every kernel of the library orders itself behind its
+ * producer with griddepcontrol.wait, so this needs nothing from the caller (environment: TDZ_NO_PDL=1 turns it off).
  */
 #ifndef TDZ_H_
 #define TDZ_H_
