@@ -488,10 +488,45 @@ class SeparationScoringStage:
         """TargetASR.multi_speakers_separate_asr lines 609-625: separate, embed both streams, cosine vs the target,
         pick.  Returns dict(target=1|2|None, spk1_score, spk2_score, spk1_audio, spk2_audio)."""
         threshold = self.similarity_threshold if threshold is None else threshold
-        spk1, spk2 = self.separate_speaker(audio_data, **kw)
-        scores = self.embedder.score_many([spk1, spk2], target_embedding).cpu().tolist()
+        one = self._separate_and_score_one_window(audio_data, target_embedding, **kw)
+        if one is not None:
+            spk1, spk2, scores = one
+        else:
+            spk1, spk2 = self.separate_speaker(audio_data, **kw)
+            scores = self.embedder.score_many([spk1, spk2], target_embedding).cpu().tolist()
         return dict(target=P.pick_target(scores[0], scores[1], threshold), spk1_score=scores[0],
                     spk2_score=scores[1], spk1_audio=spk1, spk2_audio=spk2)
+
+    def _separate_and_score_one_window(self, audio_data, target_embedding, sampling_rate=16000, low_gpu_ram=False,
+                                       mode="concat", loudness="device", **other):
+        """The common case of separate_and_score - a 16 kHz recording the chunk rule keeps as ONE window (up to 15 s) -
+        as one upload, one run() (separation, fbank, ERes2NetV2 and cosine of both streams: a single CUDA-graph replay
+        from the second call of a length on) and one download, instead of a download of the streams followed by their
+        upload for scoring.  Same kernels on the same data as the general path, so the same bits.  Returns None when
+        the call is not of that kind (the general path then also produces the reference's errors)."""
+        if (other or not self.is_separate_audio or self.group is not None or sampling_rate != 16000 or low_gpu_ram
+                or mode != "concat" or not (loudness is None or loudness == "device" or callable(loudness))):
+            return None
+        if not (isinstance(audio_data, np.ndarray) or torch.is_tensor(audio_data)):
+            return None
+        L = int(audio_data.size if isinstance(audio_data, np.ndarray) else audio_data.numel())
+        if L < 6400 or len(P.chunk_bounds(L, P.WINDOW)) != 1:     # (under 0.4 s the loudness meter refuses the input)
+            return None
+        mix = self.kern.to_device(audio_data).reshape(1, L)
+        est, scores = self.run(mix, target_embedding)
+        est = est[0]
+        swap = False
+        if loudness == "device":
+            l1, l2 = self.meter_loudness_device(est, sampling_rate)
+            swap = l1 < l2
+        host = self.kern.to_host(est)
+        sc = scores[0].cpu().tolist()
+        spk1, spk2 = host[0], host[1]
+        if callable(loudness):
+            swap = loudness(spk1, sampling_rate) < loudness(spk2, sampling_rate)
+        if swap:
+            spk1, spk2, sc = spk2, spk1, [sc[1], sc[0]]
+        return spk1, spk2, sc
 
     def score_segments(self, segments, target_embedding):
         """Batched form of the per-segment loops (TargetDiarization.py:581-629): [N] cosine scores on the device
