@@ -63,6 +63,36 @@ def main():
     for r in data[:first_sv]:
         t, b, p = vals(r)
         print(line(short(r[col["Kernel Name"]]), 1, t, b, p))
+    # ---- per launch step: DRAM traffic of its kernels against the algorithmic bytes of bench.py::STEP_TABLE
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    # kernels of each step in the launch order of tools/run_all_steps.py (Separator.STEP_NAMES)
+    step_kernels = [("ENCODER", 3), ("ENC1X1", 2), ("FLASH_IN", 3), ("SIM", 1), ("KV", 2), ("ATT_OUT", 1), ("TO_OUT", 2),
+                    ("FSMN_C1", 1), ("FSMN_UV", 1), ("FSMN_LIN", 1), ("FSMN_PROJ", 1), ("DD1", 1), ("DD2", 2),
+                    ("FSMN_TAIL", 2), ("FSMN_C2", 1), ("FINAL_LN", 2), ("FINAL_GN", 1), ("OUT1", 1), ("TANHSIG", 2),
+                    ("DEC1", 2), ("DECODER", 1)]
+    if sum(n for _, n in step_kernels) == first_sv:
+        frames = 16 * 8192          # padded frames of the capture (B = 16, T = 64 000 -> Sp = 8 192)
+        print("\n## Separator steps: measured DRAM traffic against the algorithmic bytes (`bench.py::STEP_TABLE`)\n")
+        print("Algorithmic = compulsory read + write bytes per frame x 131 072 padded frames.  The capture is small enough "
+              "(268 MB per 2 KB/frame tensor) for the 126 MB L2 to keep part of a producer's output for its consumer and to "
+              "hold dirty lines past the end of a kernel, so measured traffic BELOW the algorithmic figure is L2 reuse, not "
+              "an accounting error; traffic well above it would be wasted re-reads (none: the largest ratio is listed "
+              "first).  FSMN_LIN = the back-to-back GEMM (linear + project); FSMN_PROJ alone is the two-kernel test form.\n")
+        print("| step | kernels | us | measured MB | algorithmic MB | measured / algorithmic |")
+        print("|---|---|---|---|---|---|")
+        out, i = [], 0
+        for name, n in step_kernels:
+            t = sum(vals(r)[0] for r in data[i:i + n])
+            b = sum(vals(r)[1] for r in data[i:i + n])
+            i += n
+            if name in bench.STEP_TABLE:
+                alg = bench.STEP_TABLE[name]["bytes"] * frames
+                out.append((b / alg, f"| {name} | {n} | {t * 1e6:.1f} | {b / 1e6:.0f} | {alg / 1e6:.0f} | {b / alg:.2f} |"))
+        for _, l in sorted(out, reverse=True):
+            print(l)
     print("\n## fbank + ERes2NetV2 (one call, 32 utterances of 4 s), aggregated per kernel\n")
     print(hdr)
     print(sep)
